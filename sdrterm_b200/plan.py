@@ -1,0 +1,322 @@
+"""Host-side plan for the B200 decimation chain: every table the CUDA kernels consume.
+
+The reference filters each 131072-byte chunk independently with SciPy's
+``decimate(x, q)`` = zero-phase ``sosfiltfilt`` of a Chebyshev-I order-8 low-pass followed by
+``[::q]`` (src/dsp/dsp_processor.py:147; SciPy _signaltools.py:5091-5203, 5206-5369).  A
+sample-serial IIR is a poor fit for a GPU, and only every q-th output is kept, so the device
+path evaluates the *same linear operator* in block form:
+
+* the cascade is diagonalised once, here, in 50-digit arithmetic (mpmath): poles ``p_i``,
+  normalised modal output weights ``c_i``, ``kappa_i = H(1/p_i)``, ``rho_i = c_i*kappa_i``;
+* forward modal states ``w_i[n+1] = p_i w_i[n] + x[n]`` and anticausal states
+  ``T_i[n] = p_i T_i[n+1] + x[n]`` are advanced one *block* of q samples at a time,
+  ``W <- p^q W + F``, ``T <- p^q T + G`` with ``F = sum_j p^(q-1-j) u_j``, ``G = sum_j p^j u_j``;
+  both come from one pass over the block through the even/odd split
+  ``F,G = S +- D``, ``S = sum_j Ec_j (u_j + u_(q-1-j))``, ``D = sum_j Oc_j (u_j - u_(q-1-j))``;
+* the decimated output at a block start is
+  ``y[n] = sum_i rho_i w_i[n] + sum_i (rho_i/p_i) T_i[n] + g0 x[n] + sum_i c_i p_i^(L-1-n) zeta_i``
+  where the last term carries sosfiltfilt's finite-length / ``zi`` boundary condition.
+
+Filter *design* (cheby1, sosfilt_zi, ellip) is SciPy's, exactly as in the reference, so the
+coefficients are identical to the oracle's.  Nothing here touches the GPU.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+
+import mpmath as mp
+import numpy as np
+from scipy import signal as _sig
+
+TILE_BLOCKS = 32          # one warp: lane <-> block
+CHUNK_BYTES = 131072      # src/misc/read_file.py:38
+_ITEMSIZE = {'b': 1, 'B': 1, 'h': 2, 'H': 2, 'i': 4, 'I': 4, 'f': 4, 'd': 8, 'Z': 16}
+
+
+def _c(x) -> complex:
+    return complex(mp.re(x), mp.im(x))
+
+
+def _cascade_state_space(sos):
+    """Exact (A, b, c, d) of the DF2T cascade, state = [z0_1, z1_1, z0_2, z1_2, ...] -- the
+    same variables SciPy's _sosfilt carries, so sosfilt_zi maps onto it directly."""
+    ns = len(sos)
+    n = 2 * ns
+    A = mp.zeros(n, n)
+    b = mp.zeros(n, 1)
+    # u (section input) as a linear form over [state..., x]
+    u = [mp.mpf(0)] * n + [mp.mpf(1)]
+    for k in range(ns):
+        b0, b1, b2, a0, a1, a2 = [mp.mpf(float(v)) for v in sos[k]]
+        assert a0 == 1
+        y = [b0 * t for t in u]
+        y[2 * k] += 1
+        z0 = [b1 * t - a1 * s for t, s in zip(u, y)]
+        z0[2 * k + 1] += 1
+        z1 = [b2 * t - a2 * s for t, s in zip(u, y)]
+        for j in range(n):
+            A[2 * k, j] = z0[j]
+            A[2 * k + 1, j] = z1[j]
+        b[2 * k] = z0[n]
+        b[2 * k + 1] = z1[n]
+        u = y
+    c = mp.matrix(1, n)
+    for j in range(n):
+        c[0, j] = u[j]
+    return A, b, c, u[n]
+
+
+@dataclass
+class FilterModes:
+    """Normalised modal form of the decimation low-pass (poles 0..3 upper half plane, 4..7 their
+    conjugates, same order)."""
+    p: np.ndarray          # (8,) complex
+    c: np.ndarray          # (8,) normalised output weights c_i (input weight 1 per mode)
+    kappa: np.ndarray      # (8,) H(1/p_i)
+    rho: np.ndarray        # (8,) c_i * kappa_i
+    rho_p: np.ndarray      # (8,) rho_i / p_i
+    zhat: np.ndarray       # (8,) sosfilt_zi in normalised modal coordinates
+    xi: np.ndarray         # (8,8) c_l / (1 - p_i p_l)   [i, l]
+    d: float
+    g0: float
+    mp_p: list = field(repr=False, default=None)   # high-precision poles for table building
+    mp_c: list = field(repr=False, default=None)
+
+
+def filter_modes(sos: np.ndarray, zi: np.ndarray, dps: int = 50) -> FilterModes:
+    mp.mp.dps = dps
+    A, b, c, d = _cascade_state_space(sos)
+    n = A.rows
+    E, ER = mp.eig(A)
+    idx_up = sorted([i for i in range(n) if mp.im(E[i]) > 0], key=lambda i: -abs(mp.im(E[i])))
+    if 2 * len(idx_up) != n:
+        raise ValueError('decimation filter must have complex-conjugate pole pairs only')
+    order = list(idx_up)
+    for i in idx_up:  # conjugate partner
+        j = min((j for j in range(n) if mp.im(E[j]) < 0), key=lambda j: abs(E[j] - mp.conj(E[i])))
+        order.append(j)
+    p = [E[i] for i in order]
+    V = mp.matrix(n, n)
+    for col, i in enumerate(order):
+        for r in range(n):
+            V[r, col] = ER[r, i]
+    beta = mp.lu_solve(V, b)
+    zflat = mp.matrix([mp.mpf(float(v)) for v in np.asarray(zi).reshape(-1)])
+    zmod = mp.lu_solve(V, zflat)
+    cV = c * V
+    chat = [cV[0, i] * beta[i] for i in range(n)]
+    zhat = [zmod[i] / beta[i] for i in range(n)]
+    kappa = [d + p[i] * sum(chat[l] / (1 - p[i] * p[l]) for l in range(n)) for i in range(n)]
+    rho = [chat[i] * kappa[i] for i in range(n)]
+    chi = [(kappa[l] - d) / p[l] for l in range(n)]
+    g0 = d * d + sum(chi[l] * chat[l] for l in range(n)) - sum(rho[i] / p[i] for i in range(n))
+    xi = np.array([[_c(chat[l] / (1 - p[i] * p[l])) for l in range(n)] for i in range(n)])
+    return FilterModes(p=np.array([_c(v) for v in p]), c=np.array([_c(v) for v in chat]),
+                       kappa=np.array([_c(v) for v in kappa]), rho=np.array([_c(v) for v in rho]),
+                       rho_p=np.array([_c(rho[i] / p[i]) for i in range(n)]),
+                       zhat=np.array([_c(v) for v in zhat]), xi=xi, d=float(d),
+                       g0=float(mp.re(g0)), mp_p=p, mp_c=chat)
+
+
+def _phasor(w: float, n) -> np.ndarray:
+    """exp(1j*w*n) with the product formed in 80-bit arithmetic (w is the reference's rounded
+    double; the reference itself rounds w*n to double before exp, so it deviates from these
+    values by <= ulp(w*n)/2 in phase -- DESIGN.md section 5)."""
+    ph = np.longdouble(w) * np.asarray(n, dtype=np.longdouble)
+    return (np.cos(ph) + 1j * np.sin(ph)).astype(np.complex128)
+
+
+@dataclass
+class Plan:
+    # geometry
+    enc: str
+    swap: bool
+    fs: int
+    q: int
+    N: int
+    edge: int
+    L: int
+    Mf: int            # full blocks
+    rem: int           # samples in the trailing partial block
+    M: int             # outputs per chunk-row = ceil(N/q)
+    ntiles: int
+    cnt_last: int      # blocks in the last tile
+    Hq: int            # pairs per block = ceil(q/2)
+    rows_hz: list
+    R: int
+    # filter
+    sos: np.ndarray
+    zi: np.ndarray
+    modes: FilterModes
+    P: np.ndarray          # (8,) p^q
+    Ec: np.ndarray         # (4, Hq) complex: even-part coefficients, upper poles
+    Oc: np.ndarray         # (4, Hq) complex: odd-part coefficients
+    Ppow: np.ndarray       # (TILE_BLOCKS+1, 8) P^l
+    bnd: np.ndarray        # (M, 8) c_i p_i^(L-1-n_k)
+    k_bnd: int             # first k whose boundary term is not negligible
+    # IQ corrector
+    correct_iq: bool
+    Liq: float
+    lam: float
+    lam_j: np.ndarray      # (q+1,) lam^j
+    lam_q: float
+    # normalisation (read_file.py:82-96), None when off
+    norm: tuple | None
+    # per row
+    w: np.ndarray          # (R,) phase increment per sample (reference's rounded double)
+    use_nco: np.ndarray    # (R,) bool: False reproduces "no shift when centre == 0"
+    T2: np.ndarray         # (R, q)
+    T3: np.ndarray         # (R, TILE_BLOCKS+1)
+    T1: np.ndarray         # (R, ntiles)
+    Ehead: np.ndarray      # (R, edge+1)  phases of samples 0..edge
+    Eend: np.ndarray       # (R, nend)    phases of samples ws..N-1
+    ws: int
+    nend: int
+    PhiF: np.ndarray       # (R, 8)  sum_j p^(q-1-j) lam^j T2[j]
+    PhiG: np.ndarray       # (R, 8)  sum_j p^j lam^j T2[j]
+    PsiW: np.ndarray       # (2, R, 8)  deferred tile-start offset -> forward aggregate (full / last tile)
+    PsiT: np.ndarray       # (2, R, 8)
+    psiY: np.ndarray       # (2, R, TILE_BLOCKS)
+    lam_tile: np.ndarray   # (2,) lam^(q*cnt)
+    # demod / output
+    demod: str
+    out_sos: np.ndarray | None
+    big_endian_out: bool
+
+    @property
+    def chunk_bytes(self) -> int:
+        return self.N * 2 * _ITEMSIZE[self.enc]
+
+
+def reference_w(f_hz: int, fs: int) -> float:
+    """Phase increment per sample exactly as the reference forms it:
+    ``-2j * pi * (f / fs)`` (dsp_processor.py:187, vfo_processor.py:48)."""
+    return float((-2j * np.pi * (f_hz / fs)).imag)
+
+
+def build_plan(fs: int, enc: str, dec: int, rows_hz, *, simo: bool = False, swap: bool = False,
+               correct_iq: bool = False, normalize: bool = False, impedance: int = 50,
+               demod: str = 'fm', omega_out: int = 12500, chunk_bytes: int = CHUNK_BYTES,
+               big_endian_out: bool | None = None) -> Plan:
+    if dec < 2:
+        raise ValueError('Decimation must be at least 2.')
+    if enc not in _ITEMSIZE:
+        raise ValueError(f'unknown encoding {enc!r}')
+    q = int(dec)
+    N = chunk_bytes // (2 * _ITEMSIZE[enc])
+    sos = np.ascontiguousarray(_sig.cheby1(8, 0.05, 0.8 / q, output='sos'), dtype=np.float64)
+    zi = np.ascontiguousarray(_sig.sosfilt_zi(sos), dtype=np.float64)
+    nsec = sos.shape[0]
+    edge = 3 * (2 * nsec + 1 - min(int((sos[:, 2] == 0).sum()), int((sos[:, 5] == 0).sum())))
+    if N <= edge + 1:
+        raise ValueError(f'chunk of {N} samples is not longer than the filter pad ({edge})')
+    L = N + 2 * edge
+    Mf, rem = divmod(N, q)
+    M = Mf + (1 if rem else 0)
+    ntiles = max(1, -(-Mf // TILE_BLOCKS))
+    cnt_last = Mf - (ntiles - 1) * TILE_BLOCKS
+    Hq = (q + 1) // 2
+
+    modes = filter_modes(sos, zi)
+    pm = modes.mp_p
+    n8 = len(pm)
+    nu = n8 // 2
+    P = np.array([_c(pm[i] ** q) for i in range(n8)])
+    Ec = np.zeros((nu, Hq), dtype=np.complex128)
+    Oc = np.zeros((nu, Hq), dtype=np.complex128)
+    for m in range(nu):
+        for j in range(Hq):
+            if 2 * j == q - 1:          # middle sample of an odd block
+                Ec[m, j] = _c(pm[m] ** j)
+            else:
+                Ec[m, j] = _c((pm[m] ** (q - 1 - j) + pm[m] ** j) / 2)
+                Oc[m, j] = _c((pm[m] ** (q - 1 - j) - pm[m] ** j) / 2)
+    Ppow = np.array([[_c(pm[i] ** (q * l)) for i in range(n8)] for l in range(TILE_BLOCKS + 1)])
+    # boundary weights c_i p_i^(L-1-n_k), n_k = edge + q k
+    bnd = np.zeros((M, n8), dtype=np.complex128)
+    rmax = max(abs(v) for v in pm)
+    k_bnd = M
+    for k in range(M - 1, -1, -1):
+        e = L - 1 - (edge + q * k)
+        if rmax ** e < mp.mpf(10) ** -30:
+            break
+        k_bnd = k
+        for i in range(n8):
+            bnd[k, i] = _c(modes.mp_c[i] * pm[i] ** e)
+
+    Liq = impedance / fs if correct_iq else 0.0
+    lam = 1.0 - Liq
+    mlam = mp.mpf(1) - mp.mpf(Liq)
+    lam_j = np.array([float(mlam ** j) for j in range(q + 1)])
+    lam_q = float(mlam ** q)
+    norm = None
+    if normalize:
+        dom = {'B': (0, 255), 'h': (-32768, 32767), 'b': (-128, 127),
+               'i': (-2147483648, 2147483647), 'H': (0, 65536), 'I': (0, 4294967295)}.get(enc)
+        if dom is not None:
+            norm = (float(dom[0]), 1 / (-dom[0] + dom[1]))
+
+    rows_hz = [int(f) for f in rows_hz]
+    R = len(rows_hz)
+    w = np.array([reference_w(f, fs) for f in rows_hz])
+    # standard mode skips the shift entirely when centre == 0 (dsp_processor.py:185-187);
+    # exp(0) == 1 exactly, so a zero phase increment is the same thing.
+    use_nco = np.array([bool(simo or f) for f in rows_hz])
+    ws = min(q * Mf, N - 1 - edge)
+    nend = N - ws
+    T2 = np.stack([_phasor(wr, np.arange(q)) for wr in w])
+    T3 = np.stack([_phasor(wr, q * np.arange(TILE_BLOCKS + 1)) for wr in w])
+    T1 = np.stack([_phasor(wr, q * TILE_BLOCKS * np.arange(ntiles)) for wr in w])
+    Ehead = np.stack([_phasor(wr, np.arange(edge + 1)) for wr in w])
+    Eend = np.stack([_phasor(wr, ws + np.arange(nend)) for wr in w])
+
+    # IQ / constant-offset block vectors: geometric sums, closed form in high precision
+    PhiF = np.zeros((R, n8), dtype=np.complex128)
+    PhiG = np.zeros((R, n8), dtype=np.complex128)
+    PsiW = np.zeros((2, R, n8), dtype=np.complex128)
+    PsiT = np.zeros((2, R, n8), dtype=np.complex128)
+    psiY = np.zeros((2, R, TILE_BLOCKS), dtype=np.complex128)
+    lam_tile = np.array([float(mlam ** (q * TILE_BLOCKS)), float(mlam ** (q * cnt_last))])
+    if correct_iq:
+        g0 = mp.mpf(modes.g0)
+        rho = [mp.mpc(v) for v in modes.rho]
+        rho_p = [mp.mpc(v) for v in modes.rho_p]
+        for r in range(R):
+            mu = mlam * mp.expj(mp.mpf(w[r]))              # lam * e^{jw}
+            muq = mu ** q
+            phiF = [(pm[i] ** q - muq) / (pm[i] - mu) for i in range(n8)]
+            phiG = [(1 - (pm[i] * mu) ** q) / (1 - pm[i] * mu) for i in range(n8)]
+            PhiF[r] = [_c(v) for v in phiF]
+            PhiG[r] = [_c(v) for v in phiG]
+            for kind, cnt in ((0, TILE_BLOCKS), (1, cnt_last)):
+                # block l of the tile sees the deferred offset scaled by muq^l (lam^(ql) T3[l])
+                fl = [[phiF[i] * muq ** l for i in range(n8)] for l in range(cnt)]
+                gl = [[phiG[i] * muq ** l for i in range(n8)] for l in range(cnt)]
+                Wl = [[mp.mpc(0)] * n8]
+                for l in range(cnt):
+                    Wl.append([pm[i] ** q * Wl[l][i] + fl[l][i] for i in range(n8)])
+                Tl = [[mp.mpc(0)] * n8 for _ in range(cnt + 1)]
+                for l in range(cnt - 1, -1, -1):
+                    Tl[l] = [pm[i] ** q * Tl[l + 1][i] + gl[l][i] for i in range(n8)]
+                PsiW[kind, r] = [_c(v) for v in Wl[cnt]]
+                PsiT[kind, r] = [_c(v) for v in Tl[0]]
+                for l in range(cnt):
+                    y = sum(rho[i] * Wl[l][i] + rho_p[i] * Tl[l][i] for i in range(n8)) \
+                        + g0 * muq ** l
+                    psiY[kind, r, l] = _c(y)
+
+    out_sos = None
+    if demod in ('fm', 'am'):
+        out_sos = np.ascontiguousarray(
+            _sig.ellip(3, 1, 30, omega_out, btype='lowpass', analog=False, output='sos',
+                       fs=fs // q), dtype=np.float64)
+    elif demod not in ('re', 'im'):
+        raise ValueError(f'Invalid demod type {demod}')
+    return Plan(enc=enc, swap=bool(swap), fs=fs, q=q, N=N, edge=edge, L=L, Mf=Mf, rem=rem, M=M,
+                ntiles=ntiles, cnt_last=cnt_last, Hq=Hq, rows_hz=rows_hz, R=R, sos=sos, zi=zi,
+                modes=modes, P=P, Ec=Ec, Oc=Oc, Ppow=Ppow, bnd=bnd, k_bnd=k_bnd,
+                correct_iq=bool(correct_iq), Liq=Liq, lam=lam, lam_j=lam_j, lam_q=lam_q,
+                norm=norm, w=w, use_nco=use_nco, T2=T2, T3=T3, T1=T1, Ehead=Ehead, Eend=Eend,
+                ws=ws, nend=nend, PhiF=PhiF, PhiG=PhiG, PsiW=PsiW, PsiT=PsiT, psiY=psiY,
+                lam_tile=lam_tile, demod=demod, out_sos=out_sos,
+                big_endian_out=bool(simo if big_endian_out is None else big_endian_out))

@@ -1,0 +1,268 @@
+"""numpy emulation of the CUDA kernels' arithmetic, driven by the same ``Plan`` tables
+(sdrterm_b200/plan.py).  TEST INFRASTRUCTURE: it lets the CPU suite validate the block-modal
+algorithm and every table against the oracle without a GPU.  Structure mirrors the kernels:
+
+  emu_main    <-> k_main   (per chunk x tile [x row]: decode, block-local IQ, NCO, even/odd block
+                            sums, tile-local scans, partial outputs + tile aggregates)
+  emu_iq_scan <-> k_iqscan (offset at every tile start, carried across chunks and calls)
+  emu_fixup   <-> k_fixup  (head / end segments, cross-tile carries, boundary term -> decimated y)
+  emu_demod   <-> k_demod  (fm pair-phase + 2x FFT interpolation | am | re | im, output SOS)
+"""
+import numpy as np
+
+from sdrterm_b200.plan import TILE_BLOCKS, Plan
+
+_BASE = {'b': 'i1', 'B': 'u1', 'h': 'i2', 'H': 'u2', 'i': 'i4', 'I': 'u4', 'f': 'f4', 'd': 'f8'}
+
+
+def decode(pl: Plan, raw: np.ndarray) -> np.ndarray:
+    dt = np.dtype(_BASE[pl.enc])
+    if dt.itemsize > 1:
+        dt = dt.newbyteorder('>' if (pl.swap == np.little_endian) else '<')
+    v = np.frombuffer(raw, dtype=dt).astype(np.float64)
+    z = v[0::2] + 1j * v[1::2]
+    if pl.norm is not None:
+        xmin, k = pl.norm
+        z = (((1.6 * (z.real - xmin)) * k) - 0.8) + 1j * ((1.6 * z.imag) * k)
+    return z
+
+
+def emu_main(pl: Plan, z: np.ndarray):
+    """z: decoded chunk (N,).  Returns dict of per-chunk arrays written by the main kernel."""
+    q, Mf, nt = pl.q, pl.Mf, pl.ntiles
+    m = pl.modes
+    zb = z[:q * Mf].reshape(Mf, q)
+    # ---- phase 0: block-local IQ (zero offset at block start)
+    zp = np.empty_like(zb)
+    acc = np.zeros(Mf, dtype=np.complex128)
+    for j in range(q):
+        zp[:, j] = zb[:, j] - pl.Liq * acc
+        acc = pl.lam * acc + zb[:, j]
+    blk_agg = pl.Liq * acc                     # offset gained over one block from zero
+    # tile-local block offsets (zero at tile start) and tile aggregates
+    off_loc = np.zeros(Mf, dtype=np.complex128)
+    tile_agg = np.zeros(nt, dtype=np.complex128)
+    for t in range(nt):
+        k0 = t * TILE_BLOCKS
+        cnt = min(TILE_BLOCKS, Mf - k0)
+        o = 0j
+        for l in range(cnt):
+            off_loc[k0 + l] = o
+            o = pl.lam_q * o + blk_agg[k0 + l]
+        tile_agg[t] = o
+    # tail window: tile-local-corrected samples n in [N-1-edge, q*Mf)
+    n0 = pl.N - 1 - pl.edge
+    tailwin = np.zeros(pl.edge + 1, dtype=np.complex128)
+    for n in range(n0, q * Mf):
+        k, j = divmod(n, q)
+        tailwin[n - n0] = zp[k, j] - pl.lam_j[j] * off_loc[k]
+
+    ypart = np.zeros((pl.R, Mf), dtype=np.complex128)
+    Wout = np.zeros((pl.R, nt, 8), dtype=np.complex128)
+    Tin = np.zeros((pl.R, nt, 8), dtype=np.complex128)
+    H = q // 2
+    for r in range(pl.R):
+        u = zp * pl.T2[r][None, :]
+        a = u[:, :H] + u[:, ::-1][:, :H]
+        d = u[:, :H] - u[:, ::-1][:, :H]
+        if q & 1:
+            a = np.concatenate([a, u[:, H:H + 1]], axis=1)
+            d = np.concatenate([d, np.zeros((Mf, 1))], axis=1)
+        F = np.empty((Mf, 8), dtype=np.complex128)
+        G = np.empty((Mf, 8), dtype=np.complex128)
+        for mm in range(4):
+            Er, Ei = pl.Ec[mm].real, pl.Ec[mm].imag
+            Or, Oi = pl.Oc[mm].real, pl.Oc[mm].imag
+            # four real sums per mode and per part, exactly what the kernel accumulates
+            s1, s2, s3, s4 = a.real @ Er, a.real @ Ei, a.imag @ Er, a.imag @ Ei
+            d1, d2, d3, d4 = d.real @ Or, d.real @ Oi, d.imag @ Or, d.imag @ Oi
+            S_up = (s1 - s4) + 1j * (s3 + s2)
+            S_lo = (s1 + s4) + 1j * (s3 - s2)
+            D_up = (d1 - d4) + 1j * (d3 + d2)
+            D_lo = (d1 + d4) + 1j * (d3 - d2)
+            F[:, mm], G[:, mm] = S_up + D_up, S_up - D_up
+            F[:, mm + 4], G[:, mm + 4] = S_lo + D_lo, S_lo - D_lo
+        # local IQ offsets, then block rotation
+        F -= off_loc[:, None] * pl.PhiF[r][None, :]
+        G -= off_loc[:, None] * pl.PhiG[r][None, :]
+        x0 = zp[:, 0] - off_loc                  # first sample of each block (T2[0] == 1)
+        for t in range(nt):
+            k0 = t * TILE_BLOCKS
+            cnt = min(TILE_BLOCKS, Mf - k0)
+            rot = pl.T3[r][:cnt]
+            Fl = F[k0:k0 + cnt] * rot[:, None]
+            Gl = G[k0:k0 + cnt] * rot[:, None]
+            W = np.zeros((cnt + 1, 8), dtype=np.complex128)
+            for l in range(cnt):
+                W[l + 1] = pl.P * W[l] + Fl[l]
+            T = np.zeros((cnt + 1, 8), dtype=np.complex128)
+            for l in range(cnt - 1, -1, -1):
+                T[l] = pl.P * T[l + 1] + Gl[l]
+            ypart[r, k0:k0 + cnt] = (W[:cnt] @ m.rho + T[:cnt] @ m.rho_p
+                                      + m.g0 * x0[k0:k0 + cnt] * rot)
+            Wout[r, t] = W[cnt]
+            Tin[r, t] = T[0]
+    return dict(ypart=ypart, Wout=Wout, Tin=Tin, tile_agg=tile_agg, tailwin=tailwin)
+
+
+def emu_iq_scan(pl: Plan, tile_aggs: np.ndarray, off0: complex):
+    """tile_aggs: (nchunks, ntiles).  Returns off at every tile start (nchunks, ntiles+1)
+    [last column = offset at sample q*Mf], off at every chunk start, and the state after the
+    batch.  The partial block + nothing else remains: its samples advance the state too."""
+    nch = tile_aggs.shape[0]
+    off_tile = np.zeros((nch, pl.ntiles + 1), dtype=np.complex128)
+    return off_tile
+
+
+def emu_fixup(pl: Plan, z: np.ndarray, mo: dict, off_chunk: complex):
+    """One chunk, all rows: (R, M) decimated complex + offset after the chunk."""
+    q, Mf, nt, edge, N = pl.q, pl.Mf, pl.ntiles, pl.edge, pl.N
+    m = pl.modes
+    p, P = m.p, pl.P
+    # offsets at tile starts
+    off_tile = np.zeros(nt + 1, dtype=np.complex128)
+    off_tile[0] = off_chunk
+    for t in range(nt):
+        kind = 1 if t == nt - 1 else 0
+        cnt = pl.cnt_last if kind else TILE_BLOCKS
+        off_tile[t + 1] = pl.lam_tile[kind] * off_tile[t] + mo['tile_agg'][t] if Mf else off_chunk
+        _ = cnt
+    # corrected head samples 0..edge (reference recurrence from the chunk-start offset)
+    o = off_chunk
+    xh = np.empty(edge + 1, dtype=np.complex128)
+    for n in range(edge + 1):
+        xh[n] = z[n] - o
+        o = o + xh[n] * pl.Liq
+    # corrected end-window samples ws..N-1
+    n0 = N - 1 - edge
+    xe = np.empty(pl.nend, dtype=np.complex128)
+    o = off_tile[nt]                       # offset at sample q*Mf
+    for i in range(pl.nend):
+        n = pl.ws + i
+        if n < q * Mf:
+            t = (n // q) // TILE_BLOCKS
+            nt0 = t * TILE_BLOCKS * q
+            xe[i] = mo['tailwin'][n - n0] - off_tile[t] * pl.lam ** (n - nt0)
+        else:
+            xe[i] = z[n] - o
+            o = o + xe[i] * pl.Liq
+    off_after = o
+    if pl.rem == 0:
+        off_after = off_tile[nt]
+    y = np.zeros((pl.R, pl.M), dtype=np.complex128)
+    for r in range(pl.R):
+        xs_h = xh * pl.Ehead[r]
+        xs_e = xe * pl.Eend[r]
+        # head: odd extension, zi, edge samples
+        ext = 2 * xs_h[0] - xs_h[edge:0:-1]
+        w = m.zhat * ext[0]
+        for j in range(edge):
+            w = p * w + ext[j]
+        # forward across tiles
+        Win = np.zeros((nt + 1, 8), dtype=np.complex128)
+        Win[0] = w
+        s = -off_tile[:nt]
+        for t in range(nt):
+            kind = 1 if t == nt - 1 else 0
+            cnt = pl.cnt_last if kind else TILE_BLOCKS
+            Win[t + 1] = pl.Ppow[cnt] * Win[t] + pl.T1[r, t] * (mo['Wout'][r, t]
+                                                                + s[t] * pl.PsiW[kind, r])
+        # end segment: partial block (rem samples) + tail extension
+        xN1 = xs_e[-1]
+        tail = 2 * xN1 - xs_e[-2:-(edge + 2):-1]
+        part = xs_e[pl.nend - pl.rem:] if pl.rem else xs_e[:0]
+        seq = np.concatenate([part, tail])
+        w = Win[nt].copy()
+        wL1 = None
+        for i, v in enumerate(seq):
+            if i == len(seq) - 1:
+                wL1 = w.copy()
+            w = p * w + v
+        wL = w
+        yfL1 = np.sum(m.c * wL1) + m.d * seq[-1]
+        zeta = m.zhat * yfL1 - m.xi @ wL
+        T = np.zeros(8, dtype=np.complex128)
+        for v in seq[::-1]:
+            T = p * T + v
+        Tend = T                                   # anticausal state at n = edge + q*Mf
+        if pl.rem:
+            k = Mf
+            y[r, k] = (np.sum(m.rho * Win[nt]) + np.sum(m.rho_p * Tend) + m.g0 * part[0]
+                       + np.sum(pl.bnd[k] * zeta))
+        # backward across tiles
+        Tn = np.zeros((nt + 1, 8), dtype=np.complex128)
+        Tn[nt] = Tend
+        for t in range(nt - 1, -1, -1):
+            kind = 1 if t == nt - 1 else 0
+            cnt = pl.cnt_last if kind else TILE_BLOCKS
+            Tn[t] = pl.Ppow[cnt] * Tn[t + 1] + pl.T1[r, t] * (mo['Tin'][r, t]
+                                                              + s[t] * pl.PsiT[kind, r])
+        for t in range(nt):
+            kind = 1 if t == nt - 1 else 0
+            cnt = pl.cnt_last if kind else TILE_BLOCKS
+            k0 = t * TILE_BLOCKS
+            for l in range(cnt):
+                k = k0 + l
+                v = pl.T1[r, t] * (mo['ypart'][r, k] + s[t] * pl.psiY[kind, r, l])
+                v += np.sum(m.rho * pl.Ppow[l] * Win[t])
+                v += np.sum(m.rho_p * pl.Ppow[cnt - l] * Tn[t + 1])
+                if k >= pl.k_bnd:
+                    v += np.sum(pl.bnd[k] * zeta)
+                y[r, k] = v
+    return y, off_after
+
+
+def emu_demod(pl: Plan, y: np.ndarray) -> np.ndarray:
+    """(R, M) complex -> (R, M) float64, as k_demod does it."""
+    M = y.shape[1]
+    if pl.demod == 'fm':
+        h = M >> 1
+        pr = y[:, 0:2 * h:2] * np.conj(y[:, 1:2 * h:2])
+        r = np.arctan2(pr.imag, pr.real)
+        z = np.empty((y.shape[0], M))
+        # 2x trigonometric interpolation: rfft -> halve the unpaired bin -> irfft(n=M) * 2
+        X = np.fft.rfft(r, axis=1)
+        m2 = h // 2 + 1
+        X = X[:, :m2].copy()
+        if h % 2 == 0 and M != h:
+            X[:, h // 2] *= 0.5
+        z[:] = np.fft.irfft(X / (h / M), n=M, axis=1)
+    elif pl.demod == 'am':
+        sq = y * y
+        z = np.hypot(sq.real, sq.imag)
+    elif pl.demod == 're':
+        z = y.real.copy()
+    else:
+        z = y.imag.copy()
+    if pl.out_sos is not None:
+        for s in range(pl.out_sos.shape[0]):
+            b0, b1, b2, _, a1, a2 = pl.out_sos[s]
+            z0 = np.zeros(z.shape[0])
+            z1 = np.zeros(z.shape[0])
+            for i in range(M):
+                xc = z[:, i]
+                xn = b0 * xc + z0
+                z0 = (b1 * xc - a1 * xn) + z1
+                z1 = b2 * xc - a2 * xn
+                z[:, i] = xn
+    return z
+
+
+def emu_stream(pl: Plan, stream: bytes, off0: complex = 0j, stale_tail: bool = True):
+    """Whole byte stream -> ((R, nchunks*M) float64, (nchunks, R, M) decimated complex)."""
+    raw = np.frombuffer(stream, dtype=np.uint8)
+    cb = pl.chunk_bytes
+    buf = np.zeros(cb, dtype=np.uint8)
+    outs, ys = [], []
+    off = off0
+    for o in range(0, raw.size, cb):
+        part = raw[o:o + cb]
+        buf[:part.size] = part
+        if not stale_tail and part.size < cb:
+            buf[part.size:] = 0
+        z = decode(pl, buf)
+        mo = emu_main(pl, z)
+        y, off = emu_fixup(pl, z, mo, off)
+        ys.append(y)
+        outs.append(emu_demod(pl, y))
+    return np.concatenate(outs, axis=1), np.stack(ys), off
