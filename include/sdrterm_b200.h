@@ -1,0 +1,151 @@
+/*
+ * sdrterm_b200.h -- C ABI of libsdrterm_b200.so: the B200 (sm_100a) implementation of
+ * peads/sdrterm's streamed IQ demodulation chain.
+ *
+ * The reference has no C ABI; its boundary is Python.  Each entry point
+ * below names the reference interface it stands in for (paths relative to the reference tree).
+ * All pointers are caller-owned; every function returns 0 on success and a negative code on
+ * failure with a message available from sdrb_last_error(); nothing throws across the boundary.
+ * A handle is not thread-safe: one handle per processor object, called from one thread.
+ */
+#ifndef SDRTERM_B200_H
+#define SDRTERM_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SDRB_ABI_VERSION 1
+#define SDRB_TILE_BLOCKS 32
+#define SDRB_NPOLES 8
+#define SDRB_MAX_DECIMATION 256
+
+enum sdrb_status {
+    SDRB_OK = 0,
+    SDRB_ERR_ARG = -1,      /* bad argument / unsupported configuration */
+    SDRB_ERR_CUDA = -2,     /* CUDA runtime error, see sdrb_last_error  */
+    SDRB_ERR_NOMEM = -3,
+    SDRB_ERR_STATE = -4
+};
+
+enum sdrb_demod { SDRB_FM = 0, SDRB_AM = 1, SDRB_RE = 2, SDRB_IM = 3 };
+
+/* Geometry and switches of one processor.  Mirrors the keyword arguments that
+ * src/misc/io_args.py:97-141 passes to DspProcessor/VfoProcessor and to readFile
+ * (src/misc/read_file.py:31-44). */
+typedef struct sdrb_config {
+    int32_t abi_version;     /* SDRB_ABI_VERSION */
+    int32_t device;          /* CUDA device ordinal */
+    char enc;                /* 'b','B','h','H','i','I','f','d' (file_util.py:46-60) or 'Z' =
+                                already-decoded complex128 chunks (the Queue payload of
+                                read_file.py:112) */
+    uint8_t swap;            /* stored byte order differs from the host's (read_file.py:48-49,
+                                file_util.py:92-95,106-107) */
+    uint8_t correct_iq;      /* --correct-iq (read_file.py:55-77) */
+    uint8_t normalize;       /* --normalize-input (read_file.py:79-96) */
+    uint8_t demod;           /* enum sdrb_demod (io_args.py:37-47) */
+    uint8_t big_endian_out;  /* SIMO framing '!d' (vfo_processor.py:84) vs '@d' (dsp_processor.py:162) */
+    uint8_t reserved[2];
+    int32_t q;               /* -d decimation, 2..SDRB_MAX_DECIMATION */
+    int32_t N;               /* complex samples per chunk = 131072 / (2*itemsize) */
+    int32_t edge;            /* sosfiltfilt pad length (27) */
+    int32_t R;               /* rows: 1, or K+1 in --simo (vfo_processor.py:42-47) */
+    int32_t n_out_sections;  /* output low-pass SOS sections (0 for re/im) */
+    int32_t max_chunks;      /* largest number of chunks one sdrb_process* call will carry */
+    double iq_L;             /* impedance / fs (read_file.py:65) */
+    double norm_xmin;        /* read_file.py:177-196 */
+    double norm_k;
+} sdrb_config;
+
+/* Host-computed tables (sdrterm_b200/plan.py; filter design is SciPy's as in
+ * dsp_processor.py:39-45 and scipy.signal.decimate, the modal block form is derived from those
+ * coefficients in extended precision).  Complex arrays are interleaved (re, im) doubles. */
+typedef struct sdrb_tables {
+    /* filter modes, SDRB_NPOLES each */
+    const double *p, *P, *rho, *rho_p, *c, *zhat;
+    const double *xi;        /* [8][8] complex */
+    double g0, d;
+    const double *Ec, *Oc;   /* [4][Hq] complex, Hq = ceil(q/2) */
+    const double *Ppow;      /* [TILE_BLOCKS+1][8] complex */
+    const double *bnd;       /* [M][8] complex */
+    int32_t k_bnd;
+    /* IQ corrector */
+    double lam, lam_q, lam_N;
+    const double *lam_j;     /* [q+1] */
+    double lam_tile[2];
+    /* per row */
+    const double *T2;        /* [R][q] complex */
+    const double *T3;        /* [R][TILE_BLOCKS+1] complex */
+    const double *T1;        /* [R][ntiles] complex */
+    const double *Ehead;     /* [R][edge+1] complex */
+    const double *Eend;      /* [R][nend] complex */
+    const double *PhiF, *PhiG;   /* [R][8] complex */
+    const double *PsiW, *PsiT;   /* [2][R][8] complex */
+    const double *psiY;          /* [2][R][TILE_BLOCKS] complex */
+    /* demodulation */
+    const double *out_sos;   /* [n_out_sections][6] */
+    const double *fm_interp; /* optional dense [M][M/2] matrix for non-power-of-two FM resample */
+} sdrb_tables;
+
+typedef struct sdrb_handle sdrb_handle;
+
+/* Stands in for constructing a DspProcessor/VfoProcessor and selecting its demodulation
+ * (src/dsp/dsp_processor.py:51-138, src/dsp/vfo_processor.py:38-69). */
+int sdrb_create(const sdrb_config *cfg, const sdrb_tables *tab, sdrb_handle **out);
+int sdrb_destroy(sdrb_handle *h);
+const char *sdrb_last_error(const sdrb_handle *h);
+
+/* Geometry derived from the config: outputs per chunk-row M = ceil(N/q), bytes per chunk. */
+int sdrb_outputs_per_chunk(const sdrb_handle *h);
+size_t sdrb_chunk_bytes(const sdrb_handle *h);
+
+/* The hot path: feedBuffers' decode/normalise/IQ-correct (src/misc/read_file.py:100-103) +
+ * DspProcessor._processChunk (src/dsp/dsp_processor.py:140-149) + framing (:162,
+ * vfo_processor.py:84) over `nchunks` whole chunks.
+ *   raw : nchunks * chunk_bytes bytes
+ *   out : R * nchunks * M doubles, row-major [row][chunk][M] (each row is one output stream);
+ *         byte-swapped to big-endian when cfg.big_endian_out
+ * sdrb_process takes HOST buffers (pinned or pageable) and includes H2D/D2H; it returns after
+ * the results are in `out`.  sdrb_process_device takes DEVICE buffers and only enqueues work on
+ * `stream` (a cudaStream_t, may be NULL). */
+int sdrb_process(sdrb_handle *h, const void *raw, size_t nchunks, double *out);
+int sdrb_process_device(sdrb_handle *h, const void *raw_dev, size_t nchunks, double *out_dev,
+                        void *stream);
+
+/* Double-buffered streaming from pinned host memory: sdrb_submit enqueues H2D + kernels + D2H for
+ * one batch on slot (0 or 1) and returns; sdrb_wait blocks until that slot's `out` is complete.
+ * Batches must be submitted in stream order; the IQ-corrector state chains through them. */
+int sdrb_submit(sdrb_handle *h, int slot, const void *raw_host, size_t nchunks, double *out_host);
+int sdrb_wait(sdrb_handle *h, int slot);
+
+/* The one piece of state that crosses chunks: the IQ corrector's complex offset
+ * (src/misc/read_file.py:53).  Used for time-segment sharding across GPUs. */
+int sdrb_get_iq_state(sdrb_handle *h, double off[2]);
+int sdrb_set_iq_state(sdrb_handle *h, const double off[2]);
+
+/* Test/diagnostic access: complex decimator output of the last batch, [chunk][row][M]
+ * interleaved doubles (what `y` holds after dsp_processor.py:147). */
+int sdrb_read_decimated(sdrb_handle *h, size_t nchunks, double *y_host);
+
+/* Kernel launches issued by this handle since creation (bench.py's gpu_launches). */
+long long sdrb_launch_count(const sdrb_handle *h);
+
+/* Module-level operators of src/dsp/demodulation.py (caller-owned in/out host arrays):
+ *   sdrb_fm_demod   fmDemod(data(R,M) c128, out(R,M) f64)        demodulation.py:25-38
+ *   sdrb_am_demod   amDemod                                       demodulation.py:41-48
+ *   sdrb_real_output / sdrb_imag_output                           demodulation.py:51-68
+ *   sdrb_shift_freq shiftFreq(y(N), shift(R,N), res(R,N))         demodulation.py:71-79 */
+int sdrb_fm_demod(int device, const double *y, int R, int M, double *out);
+int sdrb_am_demod(int device, const double *y, int R, int M, double *out);
+int sdrb_real_output(int device, const double *y, int R, int M, double *out);
+int sdrb_imag_output(int device, const double *y, int R, int M, double *out);
+int sdrb_shift_freq(int device, const double *y, const double *shift, int R, int N, double *res);
+const char *sdrb_global_error(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SDRTERM_B200_H */

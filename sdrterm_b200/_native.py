@@ -1,0 +1,114 @@
+"""ctypes binding of libsdrterm_b200.so (include/sdrterm_b200.h).
+
+There is no CPU fallback: importing works anywhere (so the CPU test-suite can check that the
+library loads and exports its symbols), but every compute entry point needs a CUDA device and
+raises ``SdrbError`` otherwise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(_HERE)
+LIB_PATH = os.path.join(_HERE, 'libsdrterm_b200.so')
+HEADER = os.path.join(ROOT, 'include', 'sdrterm_b200.h')
+SOURCES = [os.path.join(_HERE, 'csrc', f) for f in ('sdrb_api.cu', 'sdrb_kernels.cuh', 'sdrb_device.cuh')]
+
+ABI_VERSION = 1
+FM, AM, RE, IM = 0, 1, 2, 3
+DEMOD_CODE = {'fm': FM, 'am': AM, 're': RE, 'im': IM}
+
+
+class SdrbError(RuntimeError):
+    pass
+
+
+class Config(C.Structure):
+    _fields_ = [('abi_version', C.c_int32), ('device', C.c_int32), ('enc', C.c_char),
+                ('swap', C.c_uint8), ('correct_iq', C.c_uint8), ('normalize', C.c_uint8),
+                ('demod', C.c_uint8), ('big_endian_out', C.c_uint8), ('reserved', C.c_uint8 * 2),
+                ('q', C.c_int32), ('N', C.c_int32), ('edge', C.c_int32), ('R', C.c_int32),
+                ('n_out_sections', C.c_int32), ('max_chunks', C.c_int32), ('iq_L', C.c_double),
+                ('norm_xmin', C.c_double), ('norm_k', C.c_double)]
+
+
+_DP = C.POINTER(C.c_double)
+
+
+class Tables(C.Structure):
+    _fields_ = [('p', _DP), ('P', _DP), ('rho', _DP), ('rho_p', _DP), ('c', _DP), ('zhat', _DP),
+                ('xi', _DP), ('g0', C.c_double), ('d', C.c_double), ('Ec', _DP), ('Oc', _DP),
+                ('Ppow', _DP), ('bnd', _DP), ('k_bnd', C.c_int32), ('lam', C.c_double),
+                ('lam_q', C.c_double), ('lam_N', C.c_double), ('lam_j', _DP),
+                ('lam_tile', C.c_double * 2), ('T2', _DP), ('T3', _DP), ('T1', _DP),
+                ('Ehead', _DP), ('Eend', _DP), ('PhiF', _DP), ('PhiG', _DP), ('PsiW', _DP),
+                ('PsiT', _DP), ('psiY', _DP), ('out_sos', _DP), ('fm_interp', _DP)]
+
+
+EXPORTS = ['sdrb_create', 'sdrb_destroy', 'sdrb_last_error', 'sdrb_outputs_per_chunk',
+           'sdrb_chunk_bytes', 'sdrb_process', 'sdrb_process_device', 'sdrb_submit', 'sdrb_wait',
+           'sdrb_get_iq_state', 'sdrb_set_iq_state', 'sdrb_read_decimated', 'sdrb_launch_count',
+           'sdrb_fm_demod', 'sdrb_am_demod', 'sdrb_real_output', 'sdrb_imag_output',
+           'sdrb_shift_freq', 'sdrb_global_error']
+
+
+def nvcc_command(out: str = LIB_PATH) -> list[str]:
+    nvcc = os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc')
+    return [nvcc, '-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17',
+            '-Xcompiler', '-fPIC', '-shared', '-o', out, SOURCES[0]]
+
+
+def build(force: bool = False) -> str:
+    """Compile the CUDA library in-tree for sm_100a (nvcc cross-compiles without a GPU)."""
+    stale = force or not os.path.exists(LIB_PATH) or any(
+        os.path.getmtime(s) > os.path.getmtime(LIB_PATH) for s in SOURCES + [HEADER])
+    if stale:
+        env = dict(os.environ)
+        env.pop('CC', None), env.pop('CXX', None)
+        subprocess.run(nvcc_command(), check=True, env=env)
+    return LIB_PATH
+
+
+_lib = None
+
+
+def lib():
+    """The loaded library; raises SdrbError (never falls back) when it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise SdrbError(f'{LIB_PATH} is missing: run `python -c "import __graft_entry__ as g; '
+                            f'g.build()"` (there is no CPU fallback)')
+        L = C.CDLL(LIB_PATH)
+        vp, sz = C.c_void_p, C.c_size_t
+        L.sdrb_create.argtypes = [C.POINTER(Config), C.POINTER(Tables), C.POINTER(vp)]
+        L.sdrb_destroy.argtypes = [vp]
+        L.sdrb_last_error.argtypes = [vp]
+        L.sdrb_last_error.restype = C.c_char_p
+        L.sdrb_global_error.restype = C.c_char_p
+        L.sdrb_outputs_per_chunk.argtypes = [vp]
+        L.sdrb_chunk_bytes.argtypes = [vp]
+        L.sdrb_chunk_bytes.restype = sz
+        L.sdrb_process.argtypes = [vp, vp, sz, vp]
+        L.sdrb_process_device.argtypes = [vp, vp, sz, vp, vp]
+        L.sdrb_submit.argtypes = [vp, C.c_int, vp, sz, vp]
+        L.sdrb_wait.argtypes = [vp, C.c_int]
+        L.sdrb_get_iq_state.argtypes = [vp, _DP]
+        L.sdrb_set_iq_state.argtypes = [vp, _DP]
+        L.sdrb_read_decimated.argtypes = [vp, sz, vp]
+        L.sdrb_launch_count.argtypes = [vp]
+        L.sdrb_launch_count.restype = C.c_longlong
+        for name in ('sdrb_fm_demod', 'sdrb_am_demod', 'sdrb_real_output', 'sdrb_imag_output'):
+            getattr(L, name).argtypes = [C.c_int, vp, C.c_int, C.c_int, vp]
+        L.sdrb_shift_freq.argtypes = [C.c_int, vp, vp, C.c_int, C.c_int, vp]
+        _lib = L
+    return _lib
+
+
+def check(rc: int, handle=None) -> None:
+    if rc != 0:
+        L = lib()
+        msg = L.sdrb_last_error(handle) if handle else L.sdrb_global_error()
+        raise SdrbError(f'libsdrterm_b200 error {rc}: {(msg or b"").decode(errors="replace")}')

@@ -1,0 +1,534 @@
+// sdrb_api.cu -- C ABI of libsdrterm_b200.so (see include/sdrterm_b200.h).
+// Host side: table upload, scratch, kernel launch sequence, double-buffered host streaming.
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/sdrterm_b200.h"
+#include "sdrb_kernels.cuh"
+
+namespace {
+
+thread_local std::string g_error;
+
+struct Slot {
+    uint8_t *raw = nullptr;   // device staging for host-path input
+    double *out = nullptr;    // device staging for host-path output
+    cudaStream_t stream = nullptr;
+    cudaEvent_t done = nullptr;
+    double *host_out = nullptr;
+    size_t nchunks = 0;
+};
+
+}  // namespace
+
+struct sdrb_handle {
+    sdrb_config cfg{};
+    DevPlan pl{};
+    Scratch sc{};
+    std::vector<void *> owned;      // device allocations to free
+    Slot slot[2];
+    cudaEvent_t iq_done = nullptr;  // orders the IQ-state chain between slots
+    size_t max_chunks = 0;
+    int enc_code = 0;
+    int tpc = 1, warps = 4;
+    size_t main_smem = 0, demod_smem = 0;
+    long long launches = 0;
+    size_t last_nchunks = 0;
+    std::string error;
+};
+
+namespace {
+
+int fail(sdrb_handle *h, int code, const char *fmt, ...)
+{
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (h) h->error = buf;
+    g_error = buf;
+    return code;
+}
+
+#define CK(h, call)                                                                        \
+    do {                                                                                   \
+        cudaError_t e_ = (call);                                                           \
+        if (e_ != cudaSuccess)                                                             \
+            return fail(h, SDRB_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), \
+                        __FILE__, __LINE__);                                               \
+    } while (0)
+
+int enc_code_of(char c)
+{
+    switch (c) {
+    case 'b': return ENC_b; case 'B': return ENC_B; case 'h': return ENC_h; case 'H': return ENC_H;
+    case 'i': return ENC_i; case 'I': return ENC_I; case 'f': return ENC_f; case 'd': return ENC_d;
+    case 'Z': return ENC_Z; default: return -1;
+    }
+}
+int itemsize_of(int code)
+{
+    static const int sz[] = {1, 1, 2, 2, 4, 4, 4, 8, 8};
+    return sz[code];
+}
+
+template <typename T>
+int upload(sdrb_handle *h, const T *src, size_t count, const T **dst)
+{
+    void *d = nullptr;
+    if (count == 0) count = 1;
+    CK(h, cudaMalloc(&d, count * sizeof(T)));
+    h->owned.push_back(d);
+    if (src) CK(h, cudaMemcpy(d, src, count * sizeof(T), cudaMemcpyHostToDevice));
+    else CK(h, cudaMemset(d, 0, count * sizeof(T)));
+    *dst = static_cast<const T *>(d);
+    return 0;
+}
+template <typename T>
+int dalloc(sdrb_handle *h, size_t count, T **dst)
+{
+    void *d = nullptr;
+    if (count == 0) count = 1;
+    CK(h, cudaMalloc(&d, count * sizeof(T)));
+    h->owned.push_back(d);
+    *dst = static_cast<T *>(d);
+    return 0;
+}
+
+inline double2 c2(const double *a, size_t i) { return make_double2(a[2 * i], a[2 * i + 1]); }
+inline double2 hmul(double2 a, double2 b) { return make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
+
+bool is_pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
+
+std::vector<double2> make_twiddles(int n)
+{
+    std::vector<double2> tw(n > 0 ? n : 1);
+    const long double two_pi = 6.283185307179586476925286766559005768L;
+    for (int k = 0; k < n; k++) {
+        long double a = -two_pi * (long double)k / (long double)n;
+        tw[k] = make_double2((double)cosl(a), (double)sinl(a));
+    }
+    return tw;
+}
+
+template <int ENC>
+int launch_chain_t(sdrb_handle *h, const uint8_t *raw, size_t nch, double *out, cudaStream_t st)
+{
+    const DevPlan &pl = h->pl;
+    const int groups = (pl.ntiles + h->tpc - 1) / h->tpc;
+    k_main<ENC><<<(unsigned)(nch * groups), 32 * h->warps, h->main_smem, st>>>(pl, h->sc, raw, (int)nch, h->tpc);
+    h->launches++;
+    if (pl.correct_iq) {
+        int nth = 1024;
+        while (nth > 32 && (size_t)nth / 2 >= nch) nth /= 2;
+        k_iqscan<ENC><<<1, nth, 0, st>>>(pl, h->sc, raw, (int)nch);
+        h->launches++;
+    }
+    k_fixup<ENC><<<(unsigned)(nch * pl.R), 128, 0, st>>>(pl, h->sc, raw, (int)nch);
+    h->launches++;
+    k_demod<<<(unsigned)(nch * pl.R), 128, h->demod_smem, st>>>(pl, h->sc.y, out, h->sc.fftbuf, h->sc.zrow,
+                                                                (int)nch, pl.demod, 1, pl.be_out);
+    h->launches++;
+    CK(h, cudaGetLastError());
+    return 0;
+}
+
+int launch_chain(sdrb_handle *h, const uint8_t *raw, size_t nch, double *out, cudaStream_t st)
+{
+    switch (h->enc_code) {
+    case ENC_b: return launch_chain_t<ENC_b>(h, raw, nch, out, st);
+    case ENC_B: return launch_chain_t<ENC_B>(h, raw, nch, out, st);
+    case ENC_h: return launch_chain_t<ENC_h>(h, raw, nch, out, st);
+    case ENC_H: return launch_chain_t<ENC_H>(h, raw, nch, out, st);
+    case ENC_i: return launch_chain_t<ENC_i>(h, raw, nch, out, st);
+    case ENC_I: return launch_chain_t<ENC_I>(h, raw, nch, out, st);
+    case ENC_f: return launch_chain_t<ENC_f>(h, raw, nch, out, st);
+    case ENC_d: return launch_chain_t<ENC_d>(h, raw, nch, out, st);
+    case ENC_Z: return launch_chain_t<ENC_Z>(h, raw, nch, out, st);
+    }
+    return fail(h, SDRB_ERR_ARG, "bad encoding code %d", h->enc_code);
+}
+
+template <int ENC>
+int set_smem_attr_t(sdrb_handle *h)
+{
+    CK(h, cudaFuncSetAttribute(k_main<ENC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->main_smem));
+    return 0;
+}
+int set_smem_attr(sdrb_handle *h)
+{
+    switch (h->enc_code) {
+    case ENC_b: return set_smem_attr_t<ENC_b>(h); case ENC_B: return set_smem_attr_t<ENC_B>(h);
+    case ENC_h: return set_smem_attr_t<ENC_h>(h); case ENC_H: return set_smem_attr_t<ENC_H>(h);
+    case ENC_i: return set_smem_attr_t<ENC_i>(h); case ENC_I: return set_smem_attr_t<ENC_I>(h);
+    case ENC_f: return set_smem_attr_t<ENC_f>(h); case ENC_d: return set_smem_attr_t<ENC_d>(h);
+    case ENC_Z: return set_smem_attr_t<ENC_Z>(h);
+    }
+    return SDRB_ERR_ARG;
+}
+
+int env_int(const char *name, int dflt)
+{
+    const char *v = getenv(name);
+    return (v && *v) ? atoi(v) : dflt;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char *sdrb_global_error(void) { return g_error.c_str(); }
+const char *sdrb_last_error(const sdrb_handle *h) { return h ? h->error.c_str() : g_error.c_str(); }
+
+int sdrb_create(const sdrb_config *cfg, const sdrb_tables *tab, sdrb_handle **out)
+{
+    if (!cfg || !tab || !out) return fail(nullptr, SDRB_ERR_ARG, "null argument");
+    if (cfg->abi_version != SDRB_ABI_VERSION) return fail(nullptr, SDRB_ERR_ARG, "ABI version mismatch");
+    const int code = enc_code_of(cfg->enc);
+    if (code < 0) return fail(nullptr, SDRB_ERR_ARG, "unknown encoding '%c'", cfg->enc);
+    if (cfg->q < 2 || cfg->q > SDRB_MAX_DECIMATION)
+        return fail(nullptr, SDRB_ERR_ARG, "decimation %d outside 2..%d", cfg->q, SDRB_MAX_DECIMATION);
+    if (cfg->R < 1 || cfg->N <= cfg->edge + 1 || cfg->max_chunks < 1 || cfg->n_out_sections > 4)
+        return fail(nullptr, SDRB_ERR_ARG, "bad geometry");
+    if (cfg->N / cfg->q < 1) return fail(nullptr, SDRB_ERR_ARG, "chunk shorter than one block");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        return fail(nullptr, SDRB_ERR_CUDA, "no CUDA device: libsdrterm_b200 has no CPU fallback");
+    if (cfg->device < 0 || cfg->device >= ndev) return fail(nullptr, SDRB_ERR_ARG, "bad device ordinal");
+
+    sdrb_handle *h = new sdrb_handle();
+    h->cfg = *cfg;
+    h->enc_code = code;
+    h->max_chunks = (size_t)cfg->max_chunks;
+    int rc = 0;
+    auto bail = [&](int c) { std::string e = h->error; sdrb_destroy(h); g_error = e; return c; };
+    if (cudaSetDevice(cfg->device) != cudaSuccess) return bail(fail(h, SDRB_ERR_CUDA, "cudaSetDevice failed"));
+
+    DevPlan &pl = h->pl;
+    pl.enc = code; pl.itemsize = itemsize_of(code); pl.swap = cfg->swap; pl.correct_iq = cfg->correct_iq;
+    pl.normalize = cfg->normalize; pl.demod = cfg->demod; pl.be_out = cfg->big_endian_out;
+    pl.q = cfg->q; pl.N = cfg->N; pl.edge = cfg->edge; pl.L = cfg->N + 2 * cfg->edge;
+    pl.Mf = cfg->N / cfg->q; pl.rem = cfg->N - pl.Mf * cfg->q; pl.M = pl.Mf + (pl.rem ? 1 : 0);
+    pl.ntiles = (pl.Mf + SDRB_TB - 1) / SDRB_TB; pl.cnt_last = pl.Mf - (pl.ntiles - 1) * SDRB_TB;
+    pl.Hq = (cfg->q + 1) / 2; pl.KS = (pl.Hq + 3) / 4; pl.R = cfg->R;
+    pl.ws = std::min(pl.q * pl.Mf, pl.N - 1 - pl.edge); pl.nend = pl.N - pl.ws;
+    pl.k_bnd = tab->k_bnd; pl.nsec_out = cfg->n_out_sections;
+    pl.Liq = cfg->correct_iq ? cfg->iq_L : 0.0; pl.lam = tab->lam; pl.lam_q = tab->lam_q; pl.lam_N = tab->lam_N;
+    pl.g0 = tab->g0; pl.d = tab->d; pl.norm_xmin = cfg->norm_xmin; pl.norm_k = cfg->norm_k;
+    pl.lam_tile[0] = tab->lam_tile[0]; pl.lam_tile[1] = tab->lam_tile[1];
+    {
+        double v = tab->lam_q;
+        for (int i = 0; i < 5; i++) { pl.lamq_pow[i] = v; v *= v; }
+    }
+    for (int i = 0; i < SDRB_NP; i++) {
+        pl.p[i] = c2(tab->p, i); pl.P[i] = c2(tab->P, i); pl.rho[i] = c2(tab->rho, i);
+        pl.rho_p[i] = c2(tab->rho_p, i); pl.c[i] = c2(tab->c, i); pl.zhat[i] = c2(tab->zhat, i);
+    }
+    for (int i = 0; i < SDRB_NP * SDRB_NP; i++) pl.xi[i] = c2(tab->xi, i);
+    for (int i = 0; i < 6 * cfg->n_out_sections; i++) pl.out_sos[i] = tab->out_sos[i];
+
+    const int q = pl.q, R = pl.R, Hq = pl.Hq, KS = pl.KS, nt = pl.ntiles, M = pl.M;
+    // DMMA A fragments: lane -> (row o = lane>>2: mode o>>1, Re/Im o&1 ; col k = lane&3)
+    std::vector<double> afrag((size_t)KS * 2 * 32, 0.0);
+    for (int s = 0; s < KS; s++)
+        for (int lane = 0; lane < 32; lane++) {
+            const int o = lane >> 2, k = lane & 3, j = 4 * s + k, m = o >> 1, e = o & 1;
+            if (j < Hq) {
+                afrag[((size_t)2 * s) * 32 + lane] = tab->Ec[2 * ((size_t)m * Hq + j) + e];
+                afrag[((size_t)2 * s + 1) * 32 + lane] = tab->Oc[2 * ((size_t)m * Hq + j) + e];
+            }
+        }
+    std::vector<double2> rw((size_t)(SDRB_TB + 1) * 8), rt((size_t)(SDRB_TB + 1) * 8);
+    for (int l = 0; l <= SDRB_TB; l++)
+        for (int i = 0; i < 8; i++) {
+            const double2 pp = c2(tab->Ppow, (size_t)l * 8 + i);
+            rw[(size_t)l * 8 + i] = hmul(pl.rho[i], pp);
+            rt[(size_t)l * 8 + i] = hmul(pl.rho_p[i], pp);
+        }
+    std::vector<double2> prot((size_t)R * 16);
+    for (int r = 0; r < R; r++) {
+        const double2 eps = c2(tab->T3, (size_t)r * (SDRB_TB + 1) + 1);
+        for (int i = 0; i < 8; i++) {
+            prot[(size_t)r * 16 + i] = hmul(make_double2(eps.x, -eps.y), pl.P[i]);
+            prot[(size_t)r * 16 + 8 + i] = hmul(eps, pl.P[i]);
+        }
+    }
+    const int h2 = M >> 1;
+    pl.fft_ok = (M == 2 * h2) && is_pow2(h2) ? 1 : 0;
+    pl.fft_n = pl.fft_ok ? M : 0;
+    if (cfg->demod == SDRB_FM && !pl.fft_ok && !tab->fm_interp)
+        return bail(fail(h, SDRB_ERR_ARG, "FM with M=%d needs the dense interpolation table", M));
+    std::vector<double2> tw = make_twiddles(pl.fft_n);
+
+#define UP(expr) do { rc = (expr); if (rc) return bail(rc); } while (0)
+    UP(upload(h, afrag.data(), afrag.size(), &pl.Afrag));
+    UP(upload(h, tab->lam_j, (size_t)q + 1, &pl.lam_j));
+    UP(upload(h, reinterpret_cast<const double2 *>(tab->Ppow), (size_t)(SDRB_TB + 1) * 8, &pl.Ppow));
+    UP(upload(h, rw.data(), rw.size(), &pl.RW));
+    UP(upload(h, rt.data(), rt.size(), &pl.RT));
+    UP(upload(h, reinterpret_cast<const double2 *>(tab->bnd), (size_t)M * 8, &pl.bnd));
+    UP(upload(h, reinterpret_cast<const double2 *>(tab->T2), (size_t)R * q, &pl.T2));
+    UP(upload(h, reinterpret_cast<const double2 *>(tab->T3), (size_t)R * (SDRB_TB + 1), &pl.T3));
+    UP(upload(h, reinterpret_cast<const double2 *>(tab->T1), (size_t)R * nt, &pl.T1));
+    UP(upload(h, reinterpret_cast<const double2 *>(tab->Ehead), (size_t)R * (pl.edge + 1), &pl.Ehead));
+    UP(upload(h, reinterpret_cast<const double2 *>(tab->Eend), (size_t)R * pl.nend, &pl.Eend));
+    UP(upload(h, reinterpret_cast<const double2 *>(tab->PhiF), (size_t)R * 8, &pl.PhiF));
+    UP(upload(h, reinterpret_cast<const double2 *>(tab->PhiG), (size_t)R * 8, &pl.PhiG));
+    UP(upload(h, reinterpret_cast<const double2 *>(tab->PsiW), (size_t)2 * R * 8, &pl.PsiW));
+    UP(upload(h, reinterpret_cast<const double2 *>(tab->PsiT), (size_t)2 * R * 8, &pl.PsiT));
+    UP(upload(h, reinterpret_cast<const double2 *>(tab->psiY), (size_t)2 * R * SDRB_TB, &pl.psiY));
+    UP(upload(h, prot.data(), prot.size(), &pl.Prot));
+    UP(upload(h, tw.data(), tw.size(), &pl.tw));
+    pl.fm_interp = nullptr;
+    if (cfg->demod == SDRB_FM && !pl.fft_ok) UP(upload(h, tab->fm_interp, (size_t)M * h2, &pl.fm_interp));
+
+    // launch geometry
+    h->tpc = env_int("SDRB_TPC", R == 1 ? 2 : 1);
+    h->warps = env_int("SDRB_WARPS", R == 1 ? h->tpc : (R >= 8 ? 8 : 4));
+    if (h->tpc < 1) h->tpc = 1;
+    if (h->warps < 1) h->warps = 1;
+    if (h->warps > 8) h->warps = 8;
+    const size_t tile_bytes = (size_t)q * (SDRB_TB + SDRB_ZPAD) * sizeof(double2);
+    auto smem_for = [&](int tpc, int w) {
+        return tpc * (tile_bytes + SDRB_TB * sizeof(double2)) + (size_t)w * 32 * SDRB_XSTRIDE * sizeof(double);
+    };
+    while (h->tpc > 1 && smem_for(h->tpc, h->warps) > 220 * 1024) h->tpc--;
+    while (h->warps > 1 && smem_for(h->tpc, h->warps) > 220 * 1024) h->warps--;
+    h->main_smem = smem_for(h->tpc, h->warps);
+    if (h->main_smem > 227 * 1024) return bail(fail(h, SDRB_ERR_ARG, "decimation %d needs too much shared memory", q));
+    UP(set_smem_attr(h));
+    const size_t dsm = (size_t)M * (2 * sizeof(double2) + sizeof(double));
+    pl.demod_in_smem = dsm <= 96 * 1024 ? 1 : 0;
+    h->demod_smem = pl.demod_in_smem ? dsm : 0;
+    if (h->demod_smem > 48 * 1024)
+        if (cudaFuncSetAttribute(k_demod, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->demod_smem) != cudaSuccess)
+            return bail(fail(h, SDRB_ERR_CUDA, "cudaFuncSetAttribute(k_demod) failed"));
+
+    // scratch for max_chunks
+    const size_t nch = h->max_chunks;
+    Scratch &sc = h->sc;
+    UP(dalloc(h, nch * R * pl.Mf, &sc.ypart));
+    UP(dalloc(h, nch * R * nt * 16, &sc.agg));
+    UP(dalloc(h, nch * nt, &sc.tile_agg));
+    UP(dalloc(h, nch * (pl.edge + 1), &sc.tailwin));
+    UP(dalloc(h, nch * (nt + 1), &sc.off_tile));
+    UP(dalloc(h, nch * R * (nt + 1) * 16, &sc.carry));
+    UP(dalloc(h, nch * R * M, &sc.y));
+    UP(dalloc(h, (size_t)1, &sc.iq_state));
+    if (cudaMemset(sc.iq_state, 0, sizeof(double2)) != cudaSuccess) return bail(fail(h, SDRB_ERR_CUDA, "memset failed"));
+    sc.fftbuf = nullptr; sc.zrow = nullptr;
+    if (!pl.demod_in_smem) {
+        UP(dalloc(h, nch * R * 2 * M, &sc.fftbuf));
+        UP(dalloc(h, nch * R * M, &sc.zrow));
+    }
+#undef UP
+    for (int s = 0; s < 2; s++) {
+        if (cudaStreamCreateWithFlags(&h->slot[s].stream, cudaStreamNonBlocking) != cudaSuccess ||
+            cudaEventCreateWithFlags(&h->slot[s].done, cudaEventDisableTiming) != cudaSuccess)
+            return bail(fail(h, SDRB_ERR_CUDA, "stream/event creation failed"));
+    }
+    if (cudaEventCreateWithFlags(&h->iq_done, cudaEventDisableTiming) != cudaSuccess)
+        return bail(fail(h, SDRB_ERR_CUDA, "event creation failed"));
+    *out = h;
+    return SDRB_OK;
+}
+
+int sdrb_destroy(sdrb_handle *h)
+{
+    if (!h) return SDRB_OK;
+    cudaSetDevice(h->cfg.device);
+    cudaDeviceSynchronize();
+    for (void *p : h->owned) cudaFree(p);
+    for (int s = 0; s < 2; s++) {
+        if (h->slot[s].raw) cudaFree(h->slot[s].raw);
+        if (h->slot[s].out) cudaFree(h->slot[s].out);
+        if (h->slot[s].stream) cudaStreamDestroy(h->slot[s].stream);
+        if (h->slot[s].done) cudaEventDestroy(h->slot[s].done);
+    }
+    if (h->iq_done) cudaEventDestroy(h->iq_done);
+    delete h;
+    return SDRB_OK;
+}
+
+int sdrb_outputs_per_chunk(const sdrb_handle *h) { return h ? h->pl.M : SDRB_ERR_ARG; }
+size_t sdrb_chunk_bytes(const sdrb_handle *h) { return h ? (size_t)h->pl.N * 2 * h->pl.itemsize : 0; }
+long long sdrb_launch_count(const sdrb_handle *h) { return h ? h->launches : 0; }
+
+int sdrb_process_device(sdrb_handle *h, const void *raw_dev, size_t nchunks, double *out_dev, void *stream)
+{
+    if (!h || !raw_dev || !out_dev) return fail(h, SDRB_ERR_ARG, "null argument");
+    if (nchunks == 0) return SDRB_OK;
+    if (nchunks > h->max_chunks) return fail(h, SDRB_ERR_ARG, "nchunks %zu > max_chunks %zu", nchunks, h->max_chunks);
+    CK(h, cudaSetDevice(h->cfg.device));
+    h->last_nchunks = nchunks;
+    return launch_chain(h, static_cast<const uint8_t *>(raw_dev), nchunks, out_dev, static_cast<cudaStream_t>(stream));
+}
+
+static int ensure_slot(sdrb_handle *h, int s)
+{
+    Slot &sl = h->slot[s];
+    if (!sl.raw) CK(h, cudaMalloc(&sl.raw, h->max_chunks * sdrb_chunk_bytes(h)));
+    if (!sl.out) CK(h, cudaMalloc(&sl.out, h->max_chunks * (size_t)h->pl.R * h->pl.M * sizeof(double)));
+    return 0;
+}
+
+int sdrb_submit(sdrb_handle *h, int s, const void *raw_host, size_t nchunks, double *out_host)
+{
+    if (!h || !raw_host || !out_host || s < 0 || s > 1) return fail(h, SDRB_ERR_ARG, "bad argument");
+    if (nchunks == 0 || nchunks > h->max_chunks) return fail(h, SDRB_ERR_ARG, "nchunks %zu outside 1..%zu", nchunks, h->max_chunks);
+    CK(h, cudaSetDevice(h->cfg.device));
+    int rc = ensure_slot(h, s);
+    if (rc) return rc;
+    Slot &sl = h->slot[s];
+    const size_t cb = sdrb_chunk_bytes(h);
+    CK(h, cudaMemcpyAsync(sl.raw, raw_host, nchunks * cb, cudaMemcpyHostToDevice, sl.stream));
+    // the scratch and the IQ state are shared between slots: kernels of consecutive batches
+    // serialise on iq_done, while this batch's H2D overlaps the previous batch's kernels/D2H
+    CK(h, cudaStreamWaitEvent(sl.stream, h->iq_done, 0));
+    h->last_nchunks = nchunks;
+    rc = launch_chain(h, sl.raw, nchunks, sl.out, sl.stream);
+    if (rc) return rc;
+    CK(h, cudaEventRecord(h->iq_done, sl.stream));
+    CK(h, cudaMemcpyAsync(out_host, sl.out, nchunks * (size_t)h->pl.R * h->pl.M * sizeof(double),
+                          cudaMemcpyDeviceToHost, sl.stream));
+    CK(h, cudaEventRecord(sl.done, sl.stream));
+    sl.host_out = out_host; sl.nchunks = nchunks;
+    return SDRB_OK;
+}
+
+int sdrb_wait(sdrb_handle *h, int s)
+{
+    if (!h || s < 0 || s > 1) return fail(h, SDRB_ERR_ARG, "bad argument");
+    CK(h, cudaSetDevice(h->cfg.device));
+    CK(h, cudaStreamSynchronize(h->slot[s].stream));
+    return SDRB_OK;
+}
+
+int sdrb_process(sdrb_handle *h, const void *raw, size_t nchunks, double *out)
+{
+    if (!h || (!raw && nchunks) || (!out && nchunks)) return fail(h, SDRB_ERR_ARG, "null argument");
+    const size_t cb = sdrb_chunk_bytes(h), M = (size_t)h->pl.M, R = (size_t)h->pl.R;
+    if (nchunks <= h->max_chunks) {
+        if (nchunks == 0) return SDRB_OK;
+        int rc = sdrb_submit(h, 0, raw, nchunks, out);
+        if (rc) return rc;
+        return sdrb_wait(h, 0);
+    }
+    // more chunks than one batch holds: rows of `out` are nchunks*M long, so each batch is
+    // staged through a per-batch buffer and scattered row by row
+    std::vector<double> tmp(h->max_chunks * R * M);
+    size_t done = 0;
+    while (done < nchunks) {
+        const size_t n = std::min(h->max_chunks, nchunks - done);
+        int rc = sdrb_submit(h, 0, static_cast<const uint8_t *>(raw) + done * cb, n, tmp.data());
+        if (rc) return rc;
+        rc = sdrb_wait(h, 0);
+        if (rc) return rc;
+        for (size_t r = 0; r < R; r++)
+            memcpy(out + r * nchunks * M + done * M, tmp.data() + r * n * M, n * M * sizeof(double));
+        done += n;
+    }
+    return SDRB_OK;
+}
+
+int sdrb_get_iq_state(sdrb_handle *h, double off[2])
+{
+    if (!h || !off) return fail(h, SDRB_ERR_ARG, "null argument");
+    CK(h, cudaSetDevice(h->cfg.device));
+    CK(h, cudaDeviceSynchronize());
+    CK(h, cudaMemcpy(off, h->sc.iq_state, sizeof(double2), cudaMemcpyDeviceToHost));
+    return SDRB_OK;
+}
+
+int sdrb_set_iq_state(sdrb_handle *h, const double off[2])
+{
+    if (!h || !off) return fail(h, SDRB_ERR_ARG, "null argument");
+    CK(h, cudaSetDevice(h->cfg.device));
+    CK(h, cudaDeviceSynchronize());
+    CK(h, cudaMemcpy(h->sc.iq_state, off, sizeof(double2), cudaMemcpyHostToDevice));
+    return SDRB_OK;
+}
+
+int sdrb_read_decimated(sdrb_handle *h, size_t nchunks, double *y_host)
+{
+    if (!h || !y_host) return fail(h, SDRB_ERR_ARG, "null argument");
+    if (nchunks > h->last_nchunks) return fail(h, SDRB_ERR_STATE, "only %zu chunks in the last batch", h->last_nchunks);
+    CK(h, cudaSetDevice(h->cfg.device));
+    CK(h, cudaDeviceSynchronize());
+    CK(h, cudaMemcpy(y_host, h->sc.y, nchunks * (size_t)h->pl.R * h->pl.M * sizeof(double2), cudaMemcpyDeviceToHost));
+    return SDRB_OK;
+}
+
+// ---------------------------------------------------------------- module-level operators
+static int demod_op(int device, const double *y, int R, int M, double *out, int demod)
+{
+    if (!y || !out || R < 1 || M < 1) return fail(nullptr, SDRB_ERR_ARG, "bad argument");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        return fail(nullptr, SDRB_ERR_CUDA, "no CUDA device: libsdrterm_b200 has no CPU fallback");
+    CK(nullptr, cudaSetDevice(device));
+    DevPlan pl{};
+    pl.M = M; pl.R = R; pl.nsec_out = 0;
+    const int h2 = M >> 1;
+    pl.fft_ok = (M == 2 * h2) && is_pow2(h2);
+    pl.fft_n = pl.fft_ok ? M : 0;
+    if (demod == SDRB_FM && !pl.fft_ok)
+        return fail(nullptr, SDRB_ERR_ARG, "fmDemod operator needs a row length of 2*2^k (got %d)", M);
+    std::vector<double2> tw = make_twiddles(pl.fft_n);
+    double2 *d_tw = nullptr, *d_y = nullptr, *d_fft = nullptr;
+    double *d_out = nullptr, *d_z = nullptr;
+    const size_t dsm = (size_t)M * (2 * sizeof(double2) + sizeof(double));
+    pl.demod_in_smem = dsm <= 48 * 1024;
+    CK(nullptr, cudaMalloc(&d_tw, tw.size() * sizeof(double2)));
+    CK(nullptr, cudaMalloc(&d_y, (size_t)R * M * sizeof(double2)));
+    CK(nullptr, cudaMalloc(&d_out, (size_t)R * M * sizeof(double)));
+    if (!pl.demod_in_smem) {
+        CK(nullptr, cudaMalloc(&d_fft, (size_t)R * 2 * M * sizeof(double2)));
+        CK(nullptr, cudaMalloc(&d_z, (size_t)R * M * sizeof(double)));
+    }
+    CK(nullptr, cudaMemcpy(d_tw, tw.data(), tw.size() * sizeof(double2), cudaMemcpyHostToDevice));
+    CK(nullptr, cudaMemcpy(d_y, y, (size_t)R * M * sizeof(double2), cudaMemcpyHostToDevice));
+    pl.tw = d_tw;
+    // rows are laid out [R][M]: run as R "rows" of a single chunk
+    k_demod<<<R, 128, pl.demod_in_smem ? dsm : 0>>>(pl, d_y, d_out, d_fft, d_z, 1, demod, 0, 0);
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e == cudaSuccess) e = cudaMemcpy(out, d_out, (size_t)R * M * sizeof(double), cudaMemcpyDeviceToHost);
+    cudaFree(d_tw); cudaFree(d_y); cudaFree(d_out); cudaFree(d_fft); cudaFree(d_z);
+    if (e != cudaSuccess) return fail(nullptr, SDRB_ERR_CUDA, "demod operator failed: %s", cudaGetErrorString(e));
+    return SDRB_OK;
+}
+
+int sdrb_fm_demod(int device, const double *y, int R, int M, double *out) { return demod_op(device, y, R, M, out, SDRB_FM); }
+int sdrb_am_demod(int device, const double *y, int R, int M, double *out) { return demod_op(device, y, R, M, out, SDRB_AM); }
+int sdrb_real_output(int device, const double *y, int R, int M, double *out) { return demod_op(device, y, R, M, out, SDRB_RE); }
+int sdrb_imag_output(int device, const double *y, int R, int M, double *out) { return demod_op(device, y, R, M, out, SDRB_IM); }
+
+int sdrb_shift_freq(int device, const double *y, const double *shift, int R, int N, double *res)
+{
+    if (!y || !shift || !res || R < 1 || N < 1) return fail(nullptr, SDRB_ERR_ARG, "bad argument");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        return fail(nullptr, SDRB_ERR_CUDA, "no CUDA device: libsdrterm_b200 has no CPU fallback");
+    CK(nullptr, cudaSetDevice(device));
+    double2 *d_y = nullptr, *d_s = nullptr, *d_r = nullptr;
+    CK(nullptr, cudaMalloc(&d_y, (size_t)N * sizeof(double2)));
+    CK(nullptr, cudaMalloc(&d_s, (size_t)R * N * sizeof(double2)));
+    CK(nullptr, cudaMalloc(&d_r, (size_t)R * N * sizeof(double2)));
+    CK(nullptr, cudaMemcpy(d_y, y, (size_t)N * sizeof(double2), cudaMemcpyHostToDevice));
+    CK(nullptr, cudaMemcpy(d_s, shift, (size_t)R * N * sizeof(double2), cudaMemcpyHostToDevice));
+    k_shift<<<148 * 4, 256>>>(d_y, d_s, d_r, R, N);
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e == cudaSuccess) e = cudaMemcpy(res, d_r, (size_t)R * N * sizeof(double2), cudaMemcpyDeviceToHost);
+    cudaFree(d_y); cudaFree(d_s); cudaFree(d_r);
+    if (e != cudaSuccess) return fail(nullptr, SDRB_ERR_CUDA, "shiftFreq operator failed: %s", cudaGetErrorString(e));
+    return SDRB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,142 @@
+"""Engine: one libsdrterm_b200 handle built from a Plan (sdrterm_b200/plan.py).
+
+This is the thin host layer between the reference-shaped processors (dsp/*.py) and the C ABI.
+Inputs are whole 131072-byte chunks of raw IQ bytes; outputs are float64 rows
+``[row][chunk][M]`` framed as the reference frames them (native doubles, or big-endian in SIMO).
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _native as nat
+from .plan import Plan
+
+
+def _dp(a: np.ndarray):
+    return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+class Engine:
+    def __init__(self, plan: Plan, max_chunks: int = 256, device: int = 0):
+        self.plan = plan
+        self.max_chunks = int(max_chunks)
+        self.device = int(device)
+        self._h = C.c_void_p()
+        self._keep = []
+        L = nat.lib()
+        pl = plan
+        cfg = nat.Config()
+        cfg.abi_version = nat.ABI_VERSION
+        cfg.device = self.device
+        cfg.enc = pl.enc.encode()
+        cfg.swap = int(pl.swap)
+        cfg.correct_iq = int(pl.correct_iq)
+        cfg.normalize = int(pl.norm is not None)
+        cfg.demod = nat.DEMOD_CODE[pl.demod]
+        cfg.big_endian_out = int(pl.big_endian_out)
+        cfg.q, cfg.N, cfg.edge, cfg.R = pl.q, pl.N, pl.edge, pl.R
+        cfg.n_out_sections = 0 if pl.out_sos is None else pl.out_sos.shape[0]
+        cfg.max_chunks = self.max_chunks
+        cfg.iq_L = pl.Liq
+        cfg.norm_xmin, cfg.norm_k = pl.norm if pl.norm is not None else (0.0, 0.0)
+        tab = nat.Tables()
+
+        def put(name, arr):
+            a = np.ascontiguousarray(arr)
+            if a.dtype == np.complex128:
+                a = a.view(np.float64)
+            a = np.ascontiguousarray(a, dtype=np.float64)
+            self._keep.append(a)
+            setattr(tab, name, _dp(a))
+
+        m = pl.modes
+        for name, arr in (('p', m.p), ('P', pl.P), ('rho', m.rho), ('rho_p', m.rho_p), ('c', m.c),
+                          ('zhat', m.zhat), ('xi', m.xi), ('Ec', pl.Ec), ('Oc', pl.Oc),
+                          ('Ppow', pl.Ppow), ('bnd', pl.bnd), ('lam_j', pl.lam_j), ('T2', pl.T2),
+                          ('T3', pl.T3), ('T1', pl.T1), ('Ehead', pl.Ehead), ('Eend', pl.Eend),
+                          ('PhiF', pl.PhiF), ('PhiG', pl.PhiG), ('PsiW', pl.PsiW),
+                          ('PsiT', pl.PsiT), ('psiY', pl.psiY)):
+            put(name, arr)
+        put('out_sos', pl.out_sos if pl.out_sos is not None else np.zeros(6))
+        tab.g0, tab.d, tab.k_bnd = m.g0, m.d, int(pl.k_bnd)
+        tab.lam, tab.lam_q = pl.lam, pl.lam_q
+        tab.lam_N = float(pl.lam_N)
+        tab.lam_tile[0], tab.lam_tile[1] = float(pl.lam_tile[0]), float(pl.lam_tile[1])
+        if pl.fm_interp is not None:
+            put('fm_interp', pl.fm_interp)
+        nat.check(L.sdrb_create(C.byref(cfg), C.byref(tab), C.byref(self._h)))
+        self.M = int(L.sdrb_outputs_per_chunk(self._h))
+        self.chunk_bytes = int(L.sdrb_chunk_bytes(self._h))
+        self.R = pl.R
+
+    # ------------------------------------------------------------------ lifetime
+    def close(self):
+        if self._h:
+            nat.lib().sdrb_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    # ------------------------------------------------------------------ hot path
+    def _nchunks(self, nbytes: int) -> int:
+        n, r = divmod(nbytes, self.chunk_bytes)
+        if r:
+            raise ValueError(f'input of {nbytes} bytes is not a whole number of '
+                             f'{self.chunk_bytes}-byte chunks')
+        return n
+
+    def process(self, raw, out: np.ndarray | None = None) -> np.ndarray:
+        """Host bytes in, (R, nchunks*M) float64 out (H2D + kernels + D2H, synchronous).  With
+        big-endian framing the returned array holds the byte-swapped doubles (dtype '>f8')."""
+        buf = np.frombuffer(raw, dtype=np.uint8) if not isinstance(raw, np.ndarray) else raw
+        buf = np.ascontiguousarray(buf).view(np.uint8).reshape(-1)
+        n = self._nchunks(buf.size)
+        dt = np.dtype('>f8') if self.plan.big_endian_out else np.dtype('=f8')
+        if out is None:
+            out = np.empty((self.R, n * self.M), dtype=dt)
+        if n:
+            nat.check(nat.lib().sdrb_process(self._h, buf.ctypes.data, n, out.ctypes.data), self._h)
+        return out
+
+    def submit(self, slot: int, raw_ptr: int, nchunks: int, out_ptr: int) -> None:
+        nat.check(nat.lib().sdrb_submit(self._h, slot, raw_ptr, nchunks, out_ptr), self._h)
+
+    def wait(self, slot: int) -> None:
+        nat.check(nat.lib().sdrb_wait(self._h, slot), self._h)
+
+    def process_device(self, raw_ptr: int, nchunks: int, out_ptr: int, stream: int = 0) -> None:
+        """Device pointers in/out; only enqueues work on ``stream``."""
+        nat.check(nat.lib().sdrb_process_device(self._h, raw_ptr, nchunks, out_ptr, stream), self._h)
+
+    def decimated(self, nchunks: int) -> np.ndarray:
+        """Complex decimator output of the last batch: (nchunks, R, M)."""
+        y = np.empty((nchunks, self.R, self.M), dtype=np.complex128)
+        nat.check(nat.lib().sdrb_read_decimated(self._h, nchunks, y.ctypes.data), self._h)
+        return y
+
+    @property
+    def iq_state(self) -> complex:
+        v = (C.c_double * 2)()
+        nat.check(nat.lib().sdrb_get_iq_state(self._h, v), self._h)
+        return complex(v[0], v[1])
+
+    @iq_state.setter
+    def iq_state(self, off: complex) -> None:
+        v = (C.c_double * 2)(off.real, off.imag)
+        nat.check(nat.lib().sdrb_set_iq_state(self._h, v), self._h)
+
+    @property
+    def launches(self) -> int:
+        return int(nat.lib().sdrb_launch_count(self._h))

@@ -160,6 +160,7 @@ class Plan:
     lam: float
     lam_j: np.ndarray      # (q+1,) lam^j
     lam_q: float
+    lam_N: float
     # normalisation (read_file.py:82-96), None when off
     norm: tuple | None
     # per row
@@ -182,6 +183,7 @@ class Plan:
     demod: str
     out_sos: np.ndarray | None
     big_endian_out: bool
+    fm_interp: np.ndarray | None = None   # (M, M>>1) dense resample matrix, non-power-of-two FM only
 
     @property
     def chunk_bytes(self) -> int:
@@ -249,6 +251,7 @@ def build_plan(fs: int, enc: str, dec: int, rows_hz, *, simo: bool = False, swap
     mlam = mp.mpf(1) - mp.mpf(Liq)
     lam_j = np.array([float(mlam ** j) for j in range(q + 1)])
     lam_q = float(mlam ** q)
+    lam_N = float(mlam ** N)
     norm = None
     if normalize:
         dom = {'B': (0, 255), 'h': (-32768, 32767), 'b': (-128, 127),
@@ -312,11 +315,17 @@ def build_plan(fs: int, enc: str, dec: int, rows_hz, *, simo: bool = False, swap
                        fs=fs // q), dtype=np.float64)
     elif demod not in ('re', 'im'):
         raise ValueError(f'Invalid demod type {demod}')
+    fm_interp = None
+    h = M >> 1
+    if demod == 'fm' and not (M == 2 * h and h & (h - 1) == 0):
+        # scipy.signal.resample(r, M) is linear in r: its matrix, column by column
+        fm_interp = np.ascontiguousarray(_sig.resample(np.eye(h), M, axis=0))
     return Plan(enc=enc, swap=bool(swap), fs=fs, q=q, N=N, edge=edge, L=L, Mf=Mf, rem=rem, M=M,
                 ntiles=ntiles, cnt_last=cnt_last, Hq=Hq, rows_hz=rows_hz, R=R, sos=sos, zi=zi,
                 modes=modes, P=P, Ec=Ec, Oc=Oc, Ppow=Ppow, bnd=bnd, k_bnd=k_bnd,
-                correct_iq=bool(correct_iq), Liq=Liq, lam=lam, lam_j=lam_j, lam_q=lam_q,
+                correct_iq=bool(correct_iq), Liq=Liq, lam=lam, lam_j=lam_j, lam_q=lam_q, lam_N=lam_N,
                 norm=norm, w=w, use_nco=use_nco, T2=T2, T3=T3, T1=T1, Ehead=Ehead, Eend=Eend,
                 ws=ws, nend=nend, PhiF=PhiF, PhiG=PhiG, PsiW=PsiW, PsiT=PsiT, psiY=psiY,
                 lam_tile=lam_tile, demod=demod, out_sos=out_sos,
-                big_endian_out=bool(simo if big_endian_out is None else big_endian_out))
+                big_endian_out=bool(simo if big_endian_out is None else big_endian_out),
+                fm_interp=fm_interp)
