@@ -1,0 +1,450 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the B200 demodulation chain (see the contract in DESIGN.md).
+
+Metric (BASELINE.json): input Msamples/s through the single-VFO FM chain, -d 64.
+Workload at every N: configuration 1/5 of BASELINE.json -- int16 IQ at 1.024 MS/s,
+`-c 15k -w 5k -d 64 --correct-iq -m fm` -- 2^28 complex samples (8192 chunks of 131072 bytes,
+1 GiB of raw input) per GPU per step; for N > 1 the stream is time-segment sharded (one
+contiguous segment per rank, IQ-corrector state handed off through an all-gather, weak scaling).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference ...                     # the reference's CPU path (oracle port)
+
+One JSON line on stdout (rank 0).  `value`: device-resident input, CUDA-event timed, max over
+ranks.  `e2e`: the same through the C ABI's host entry points (pinned host buffers, H2D and D2H
+inside the timed region, double-buffered).  `roofline`: k_main's algorithmic bytes over its
+CUDA-event duration vs the measured HBM copy bandwidth.  `cpu_baseline`: the oracle port on this
+box's host cores over a bounded sample.  `simo`: config 3 (16 VFOs + centre, 17 rows) measured the
+same way, rows sharded across ranks with an NCCL broadcast of each raw batch.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for _p in (ROOT, os.path.join(ROOT, 'tests')):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+CB = 131072
+FS, CENTER, OMEGA, DEC = 1_024_000, 15_000, 5_000, 64
+METRIC = 'input Msamples/s through FM chain (d=64)'
+WORKLOAD = ('config 1/5: single-VFO FM chain, int16 IQ, fs 1.024 MS/s, -c 15k -w 5k -d 64 '
+            '--correct-iq, 2^28 samples (8192 chunks) per GPU per step')
+
+
+# ------------------------------------------------------------------------------ CPU (oracle) arm
+def cpu_chain_rate(nchunks_hint: int, target_s: float, nthreads: int):
+    """Time the oracle port (decode + IQ + NCO + decimate + fm + LPF + pack) on host cores over
+    a bounded sample of the same synthetic workload.  Returns (Msamples/s, sample description)."""
+    import numpy as np
+    import signals
+    from oracle import oracle as orc
+    kw = dict(fs=FS, enc='h', center=CENTER, dec=DEC, demod='fm', omega_out=OMEGA, correct_iq=True,
+              nthreads=nthreads)
+    base = signals.c1_bytes(16 * 32768, seed=0, header=False)
+
+    def run(nch):
+        body = (base * (-(-nch // 16)))[:nch * CB]
+        ch = orc.Chain(**kw)
+        t0 = time.perf_counter()
+        out = ch.run_fast(body)
+        _ = np.ascontiguousarray(out[0], dtype='=f8').tobytes()
+        return time.perf_counter() - t0
+
+    run(8)                                     # warm-up (library load, page faults)
+    t = run(nchunks_hint)
+    nch = int(max(nchunks_hint, min(16384, nchunks_hint * target_s / max(t, 1e-3))))
+    best = min(run(nch) for _ in range(2))
+    return nch * 32768 / best / 1e6, f'{nch} chunks ({nch * 32768} samples) of the workload, best of 2'
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    from oracle import oracle as orc
+    nthreads = orc.max_threads()
+    import numpy as np
+    import signals
+    kw = dict(fs=FS, enc='h', center=CENTER, dec=DEC, demod='fm', omega_out=OMEGA, correct_iq=True,
+              nthreads=nthreads)
+    nch = args.ref_chunks
+    base = signals.c1_bytes(16 * 32768, seed=0, header=False)
+    body = (base * (-(-nch // 16)))[:nch * CB]
+    times = []
+    for it in range(args.warmup + args.steps):
+        ch = orc.Chain(**kw)
+        t0 = time.perf_counter()
+        out = ch.run_fast(body)
+        _ = np.ascontiguousarray(out[0], dtype='=f8').tobytes()
+        dt = time.perf_counter() - t0
+        if it >= args.warmup:
+            times.append(dt)
+    t = sum(times) / len(times)
+    val = nch * 32768 / t / 1e6
+    sample = f'{nch} chunks ({nch * 32768} samples) per step'
+    line = {'impl': 'reference', 'metric': METRIC, 'value': val, 'unit': 'Msamples/s',
+            'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup,
+            'ms_per_step': t * 1e3, 'higher_is_better': True, 'scaling': 'weak',
+            'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+            'config': {'workload': WORKLOAD, 'note': 'reference CPU path = oracle port '
+                       '(oracle/, numpy + C restatement of src/dsp + SciPy recurrences); the '
+                       'Python reference itself cannot travel to the GPU box'},
+            'cpu_baseline': {'value': val, 'unit': 'Msamples/s', 'cores': nthreads, 'kind': 'port',
+                             'sample': sample},
+            'e2e': {'value': val, 'unit': 'Msamples/s', 'h2d_bytes_per_step': 0,
+                    'd2h_bytes_per_step': 0},
+            'gpu_launches': 0}
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------ clocks sampler
+class Clocks:
+    Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
+         'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+         'clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index: int):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ['nvidia-smi', f'--id={self.index}', f'--query-gpu={self.Q}',
+                 '--format=csv,noheader,nounits', '-lms', '100'],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(',')])
+
+    def stop(self):
+        if self.proc is not None:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self):
+        sm, mx, reasons = [], 0.0, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                mx = max(mx, float(r[2]))
+                for name, v in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown',
+                                    'sw_power_cap'), r[4:8]):
+                    if v.lower().startswith('active'):
+                        reasons.add(name)
+            except Exception:
+                pass
+        sm.sort()
+        return {'sm_mhz': sm[len(sm) // 2] if sm else None, 'sm_max_mhz': mx or None,
+                'reasons': sorted(reasons), 'samples': len(sm)}
+
+
+# ------------------------------------------------------------------------------ synthetic input
+def synth_c1_device(torch, nsamples: int, seed: int, device):
+    """Config-1 signal generated on the device (not timed): FM carrier at +15 kHz, 1 kHz tone,
+    +-2.5 kHz deviation, amplitude 8000, AWGN sigma 200, DC (+37,-21), rounded to int16 I,Q."""
+    g = torch.Generator(device=device)
+    g.manual_seed(seed)
+    out = torch.empty((nsamples, 2), dtype=torch.int16, device=device)
+    step = 1 << 22
+    for s in range(0, nsamples, step):
+        n = min(step, nsamples - s)
+        t = (torch.arange(s, s + n, device=device, dtype=torch.float64)) / FS
+        ph = 2 * torch.pi * 15_000 * t + 2.5 * torch.sin(2 * torch.pi * 1_000 * t)
+        re = 8000.0 * torch.cos(ph) + 200.0 * torch.randn(n, generator=g, device=device, dtype=torch.float64) + 37.0
+        im = 8000.0 * torch.sin(ph) + 200.0 * torch.randn(n, generator=g, device=device, dtype=torch.float64) - 21.0
+        out[s:s + n, 0] = torch.clamp(torch.round(re), -32768, 32767).to(torch.int16)
+        out[s:s + n, 1] = torch.clamp(torch.round(im), -32768, 32767).to(torch.int16)
+    return out.view(torch.uint8).reshape(-1)
+
+
+def synth_c3_device(torch, nsamples: int, seed: int, device, offs):
+    g = torch.Generator(device=device)
+    g.manual_seed(seed)
+    fs = 2_400_000
+    out = torch.empty((nsamples, 2), dtype=torch.int16, device=device)
+    step = 1 << 21
+    for s in range(0, nsamples, step):
+        n = min(step, nsamples - s)
+        t = (torch.arange(s, s + n, device=device, dtype=torch.float64)) / fs
+        re = 100.0 * torch.randn(n, generator=g, device=device, dtype=torch.float64)
+        im = 100.0 * torch.randn(n, generator=g, device=device, dtype=torch.float64)
+        for i, f in enumerate(list(offs) + [0]):
+            ph = 2 * torch.pi * f * t + (2000.0 / (700 + 40 * i)) * torch.sin(2 * torch.pi * (700 + 40 * i) * t) + 0.37 * i
+            re += 1500.0 * torch.cos(ph)
+            im += 1500.0 * torch.sin(ph)
+        out[s:s + n, 0] = torch.clamp(torch.round(re), -32768, 32767).to(torch.int16)
+        out[s:s + n, 1] = torch.clamp(torch.round(im), -32768, 32767).to(torch.int16)
+    # big-endian on the wire (config 3): swap the two bytes of every int16
+    b = out.view(torch.uint8).reshape(-1, 2)
+    return b.flip(1).contiguous().reshape(-1)
+
+
+# ------------------------------------------------------------------------------ CUDA arm
+def measure_e2e(torch, Engine, pl, raw, sub, e2e_ch, local, args, barrier, max_over_ranks, world):
+    """Host pinned buffers through sdrb_submit / sdrb_wait, H2D and D2H inside the timed region."""
+    eng2 = Engine(pl, max_chunks=sub, device=local)
+    host_raw = torch.empty(e2e_ch * CB, dtype=torch.uint8).pin_memory()
+    host_raw.copy_(raw[:e2e_ch * CB].cpu())
+    nb = -(-e2e_ch // sub)
+    host_out = [torch.empty(sub * pl.M, dtype=torch.float64).pin_memory() for _ in range(2)]
+
+    def step_e2e():
+        pend = [None, None]
+        for b in range(nb):
+            s = b & 1
+            if pend[s] is not None:
+                eng2.wait(s)
+            n = min(sub, e2e_ch - b * sub)
+            eng2.submit(s, host_raw.data_ptr() + b * sub * CB, n, host_out[s].data_ptr())
+            pend[s] = n
+        eng2.wait(0)
+        eng2.wait(1)
+
+    for _ in range(max(1, args.warmup // 2)):
+        step_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    e2e_steps = max(1, min(args.steps, 3))
+    for _ in range(e2e_steps):
+        step_e2e()
+    torch.cuda.synchronize()
+    dt = max_over_ranks(time.perf_counter() - t0)
+    return world * e2e_ch * 32768 * e2e_steps / dt / 1e6
+
+
+
+def run_cuda_arm(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from sdrterm_b200.engine import Engine
+    from sdrterm_b200.plan import build_plan
+
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    if not torch.cuda.is_available():
+        raise SystemExit('bench.py: no CUDA device (the CUDA arm has no CPU fallback)')
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+    if world != args.gpus and rank == 0:
+        print(f'# note: --gpus {args.gpus} but WORLD_SIZE {world}', file=sys.stderr)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+
+    def max_over_ranks(v: float) -> float:
+        if world == 1:
+            return v
+        t = torch.tensor([v], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    nch = args.chunks
+    nsamp = nch * 32768
+    pl = build_plan(FS, 'h', DEC, [CENTER], correct_iq=True, demod='fm', omega_out=OMEGA)
+    eng = Engine(pl, max_chunks=nch, device=local)
+    raw = synth_c1_device(torch, nsamp, seed=5 + rank, device=dev)
+    out = torch.empty((1, nch * pl.M), dtype=torch.float64, device=dev)
+    stream = torch.cuda.current_stream().cuda_stream
+    decay_seg = pl.lam ** nsamp            # IQ-offset decay over one rank's segment
+
+    def step_device():
+        if world == 1:
+            eng.process_device(raw.data_ptr(), nch, out.data_ptr(), stream)
+            return
+        # time-segment sharding: block kernel + offset gain from zero, exchange, finish
+        eng.iq_state = 0j
+        eng.process_device_phases(raw.data_ptr(), nch, 0, 1 | 2, stream)
+        g = eng.iq_state
+        mine = torch.tensor([g.real, g.imag], dtype=torch.float64, device=dev)
+        allg = torch.empty((world, 2), dtype=torch.float64, device=dev)
+        dist.all_gather_into_tensor(allg, mine)
+        gains = allg.cpu().numpy()
+        off = 0j
+        for i in range(rank):
+            off = decay_seg * off + complex(gains[i, 0], gains[i, 1])
+        eng.iq_state = off
+        eng.process_device_phases(raw.data_ptr(), nch, out.data_ptr(), 2 | 4, stream)
+
+    clocks = Clocks(local)
+    eng.set_profiling(world == 1)
+    for _ in range(args.warmup):
+        step_device()
+    barrier()
+    if rank == 0:
+        clocks.start()
+    l0 = eng.launches
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ktimes = []
+    ev0.record()
+    for _ in range(args.steps):
+        step_device()
+        if world == 1:
+            ktimes.append(None)   # read after the loop's final sync for the last step only
+    ev1.record()
+    barrier()
+    ms_total = max_over_ranks(ev0.elapsed_time(ev1))
+    launches = eng.launches - l0
+    kt = eng.kernel_times() if world == 1 else None
+    # a few extra profiled steps for a steadier per-kernel average
+    kavg = None
+    if world == 1:
+        acc = np.zeros(4)
+        reps = max(3, args.steps)
+        for _ in range(reps):
+            step_device()
+            torch.cuda.synchronize()
+            acc += np.array(eng.kernel_times())
+        kavg = (acc / reps).tolist()
+    if rank == 0:
+        clocks.stop()
+    ms_step = ms_total / args.steps
+    value = world * nsamp / (ms_step * 1e-3) / 1e6
+
+    # ---------------- e2e: host pinned buffers through sdrb_submit / sdrb_wait
+    sub = min(args.e2e_batch, nch)
+    e2e_ch = min(nch, args.e2e_chunks)
+    e2e_val = None
+    if e2e_ch > 0:
+        e2e_val = measure_e2e(torch, Engine, pl, raw, sub, e2e_ch, local, args, barrier, max_over_ranks, world)
+    # ---------------- SIMO (config 3): rows sharded, raw batch broadcast
+    simo = None
+    if args.simo_chunks > 0:
+        import signals
+        offs = signals.vfo_grid(16, 100_000)
+        rows_all = [o for o in offs] + [0]
+        per = -(-len(rows_all) // world)
+        mine = rows_all[rank * per:(rank + 1) * per]
+        sch = args.simo_chunks
+        if mine:
+            pls = build_plan(2_400_000, 'h', 64, mine, simo=True, swap=True, demod='fm', omega_out=5000)
+            engs = Engine(pls, max_chunks=sch, device=local)
+            outs = torch.empty((len(mine), sch * pls.M), dtype=torch.float64, device=dev)
+        raws = synth_c3_device(torch, sch * 32768, 3, dev, offs) if rank == 0 else \
+            torch.empty(sch * CB, dtype=torch.uint8, device=dev)
+
+        def step_simo():
+            if world > 1:
+                dist.broadcast(raws, src=0)
+            if mine:
+                engs.process_device(raws.data_ptr(), sch, outs.data_ptr(), stream)
+
+        for _ in range(2):
+            step_simo()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        ss = 3
+        for _ in range(ss):
+            step_simo()
+        e1.record()
+        barrier()
+        ms = max_over_ranks(e0.elapsed_time(e1)) / ss
+        in_msps = sch * 32768 / (ms * 1e-3) / 1e6
+        bps = 4 + 8 * len(rows_all) / 64
+        simo = {'workload': 'config 3: 16 VFOs + centre (17 rows), int16 big-endian IQ, fs 2.4 MS/s, '
+                            f'FM, -d 64, {sch} chunks per step; rows sharded over ranks, raw batch '
+                            'broadcast over NCCL inside the timed region when n_gpus > 1',
+                'rows': len(rows_all), 'input_msps': in_msps, 'vfo_msps': in_msps * len(rows_all),
+                'ms_per_step': ms, 'bytes_per_sample': bps}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peaks_path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(peaks_path):
+        peak = json.load(open(peaks_path))['hbm_gbs']
+        peak_src = 'measured (MEASURED_PEAKS.json hbm_gbs, burst copy)'
+    else:
+        peak, peak_src = 6650.0, 'fallback (B200_PROFILING.md)'
+    bytes_per_sample = 4 + 8 * 1 / 64
+    roof = None
+    if kavg is not None:
+        ach = bytes_per_sample * nsamp / (kavg[0] * 1e-3) / 1e9
+        traffic = None
+        tpath = os.path.join(ROOT, 'profiles', 'traffic.json')
+        if os.path.exists(tpath):
+            try:
+                traffic = json.load(open(tpath)).get('k_main_dram_bytes_per_launch')
+            except Exception:
+                traffic = None
+        roof = {'bound': 'hbm', 'kernel': 'k_main', 'achieved': ach, 'peak': peak, 'unit': 'GB/s',
+                'frac': ach / peak, 'traffic': traffic, 'peak_source': peak_src,
+                'algorithmic_bytes_per_sample': bytes_per_sample,
+                'kernel_ms': {'k_main': kavg[0], 'k_iqscan': kavg[1], 'k_fixup': kavg[2], 'k_demod': kavg[3]},
+                'note': 'the chain is FP64-issue-bound (DFMA/DMMA pipe ~17 TFMA/s measured), see DESIGN.md'}
+        if simo is not None:
+            simo['frac_hbm'] = simo['input_msps'] * 1e6 * simo['bytes_per_sample'] / 1e9 / peak
+    cpu = None
+    if world == 1 and not args.no_cpu:
+        from oracle import oracle as orc
+        nth = orc.max_threads()
+        v, sample = cpu_chain_rate(64, args.cpu_seconds, nth)
+        cpu = {'value': v, 'unit': 'Msamples/s', 'cores': nth, 'kind': 'port', 'sample': sample}
+    line = {'metric': METRIC, 'value': value, 'unit': 'Msamples/s', 'n_gpus': world, 'steps': args.steps,
+            'warmup': args.warmup, 'ms_per_step': ms_step, 'higher_is_better': True, 'scaling': 'weak',
+            'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+            'config': {'workload': WORKLOAD, 'chunks_per_gpu_per_step': nch,
+                       'l2': 'inputs larger than L2 (1 GiB per step per GPU)',
+                       'parallelism': 'time-segment sharding, IQ state via all-gather' if world > 1 else 'single GPU'},
+            'e2e': None if e2e_val is None else {'value': e2e_val, 'unit': 'Msamples/s', 'h2d_bytes_per_step': e2e_ch * CB,
+                    'd2h_bytes_per_step': e2e_ch * pl.M * 8,
+                    'note': f'{e2e_ch} chunks per step in batches of {sub}, double-buffered sdrb_submit/sdrb_wait'},
+            'gpu_launches': launches, 'clocks': clocks.summary()}
+    if roof is not None:
+        line['roofline'] = roof
+    if cpu is not None:
+        line['cpu_baseline'] = cpu
+    if simo is not None:
+        line['simo'] = simo
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=5)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--chunks', type=int, default=8192, help='chunks per GPU per step')
+    ap.add_argument('--e2e-chunks', type=int, default=4096)
+    ap.add_argument('--e2e-batch', type=int, default=512)
+    ap.add_argument('--simo-chunks', type=int, default=512)
+    ap.add_argument('--ref-chunks', type=int, default=1024, help='chunks per step of the reference arm')
+    ap.add_argument('--cpu-seconds', type=float, default=10.0)
+    ap.add_argument('--no-cpu', action='store_true')
+    args = ap.parse_args()
+    if args.impl == 'reference':
+        run_reference_arm(args)
+    else:
+        run_cuda_arm(args)
+
+
+if __name__ == '__main__':
+    main()

@@ -73,9 +73,12 @@ typedef struct sdrb_tables {
     const double *bnd;       /* [M][8] complex */
     int32_t k_bnd;
     /* IQ corrector */
-    double lam, lam_q, lam_N;
+    double lam, lam_q, lam_N, lam_inv;
     const double *lam_j;     /* [q+1] */
     double lam_tile[2];
+    int32_t RL;              /* pairs per DMMA k-lane = ceil(Hq/4) */
+    int32_t run_len[8];      /* samples per run of a block, sample order */
+    double lam_run[8];       /* lam^run_len */
     /* per row */
     const double *T2;        /* [R][q] complex */
     const double *T3;        /* [R][TILE_BLOCKS+1] complex */
@@ -85,9 +88,13 @@ typedef struct sdrb_tables {
     const double *PhiF, *PhiG;   /* [R][8] complex */
     const double *PsiW, *PsiT;   /* [2][R][8] complex */
     const double *psiY;          /* [2][R][TILE_BLOCKS] complex */
+    const uint8_t *use_nco;      /* [R] 0 = no shift for this row (centre == 0, dsp_processor.py:185-187) */
     /* demodulation */
     const double *out_sos;   /* [n_out_sections][6] */
     const double *fm_interp; /* optional dense [M][M/2] matrix for non-power-of-two FM resample */
+    int32_t sos_Lseg;        /* output SOS evaluated in 32 segments of this many samples */
+    const double *sos_AL;    /* [ns][ns], ns = 2*n_out_sections: A^Lseg of the output cascade */
+    const double *sos_CA;    /* [sos_Lseg][ns]: c A^i */
 } sdrb_tables;
 
 typedef struct sdrb_handle sdrb_handle;
@@ -114,6 +121,21 @@ size_t sdrb_chunk_bytes(const sdrb_handle *h);
 int sdrb_process(sdrb_handle *h, const void *raw, size_t nchunks, double *out);
 int sdrb_process_device(sdrb_handle *h, const void *raw_dev, size_t nchunks, double *out_dev,
                         void *stream);
+
+/* The same chain split for time-segment sharding across GPUs: phase bits
+ * 1 = block kernel, 2 = IQ-offset scan from the handle's IQ state, 4 = fix-up + demodulation.
+ * A rank runs (1|2) from a zero state, reads its segment's offset gain with sdrb_get_iq_state,
+ * exchanges gains, sets its true initial state and runs (2|4); the raw data is read once. */
+#define SDRB_PHASE_MAIN 1
+#define SDRB_PHASE_IQSCAN 2
+#define SDRB_PHASE_FINISH 4
+int sdrb_process_device_phases(sdrb_handle *h, const void *raw_dev, size_t nchunks, double *out_dev,
+                               void *stream, int phases);
+
+/* CUDA-event timing of the four kernels of the last full sdrb_process_device call
+ * (ms[0..3] = block kernel, IQ scan, fix-up, demodulation), for bench.py's roofline. */
+int sdrb_set_profiling(sdrb_handle *h, int on);
+int sdrb_kernel_times(sdrb_handle *h, float ms[4]);
 
 /* Double-buffered streaming from pinned host memory: sdrb_submit enqueues H2D + kernels + D2H for
  * one batch on slot (0 or 1) and returns; sdrb_wait blocks until that slot's `out` is complete.

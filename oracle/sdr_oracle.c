@@ -266,6 +266,47 @@ long orc_batch(const double *sos, int nsec, const double *zi0, int edge, const d
     return fail ? -1 : M;
 }
 
+/* Batched helpers for the CPU baseline: same arithmetic, chunk/row-parallel where the reference's
+ * data flow allows it (decode is element-wise; the IQ recurrence stays serial). */
+int orc_decode_batch(const uint8_t *raw, long n_total, char enc, int swap, double *z, int nthreads)
+{
+    int sz = orc_itemsize(enc);
+    if (sz < 0) return -1;
+    const long blk = 1 << 16;
+    long nblk = (n_total + blk - 1) / blk;
+#ifdef _OPENMP
+#pragma omp parallel for num_threads(nthreads > 0 ? nthreads : 1) schedule(static)
+#endif
+    for (long b = 0; b < nblk; b++) {
+        long lo = b * blk, hi = lo + blk < n_total ? lo + blk : n_total;
+        orc_decode(raw + 2 * lo * sz, hi - lo, enc, swap, z + 2 * lo);
+    }
+    (void)nthreads;
+    return 0;
+}
+
+void orc_fm_pairs_rows(const double *y, long rows, long m, double *res, int nthreads)
+{
+#ifdef _OPENMP
+#pragma omp parallel for num_threads(nthreads > 0 ? nthreads : 1) schedule(static)
+#endif
+    for (long r = 0; r < rows; r++) orc_fm_pairs(y + 2 * r * m, (m >> 1) * 2, res + r * (m >> 1));
+    (void)nthreads;
+}
+
+void orc_sosfilt_rows(const double *sos, int nsec, double *x, long rows, long n, int nthreads)
+{
+#ifdef _OPENMP
+#pragma omp parallel for num_threads(nthreads > 0 ? nthreads : 1) schedule(static)
+#endif
+    for (long r = 0; r < rows; r++) {
+        double zi[2 * 16];
+        memset(zi, 0, sizeof zi);
+        orc_sosfilt_r(sos, nsec, x + r * n, n, zi);
+    }
+    (void)nthreads;
+}
+
 int orc_max_threads(void)
 {
 #ifdef _OPENMP

@@ -41,17 +41,20 @@ class Tables(C.Structure):
     _fields_ = [('p', _DP), ('P', _DP), ('rho', _DP), ('rho_p', _DP), ('c', _DP), ('zhat', _DP),
                 ('xi', _DP), ('g0', C.c_double), ('d', C.c_double), ('Ec', _DP), ('Oc', _DP),
                 ('Ppow', _DP), ('bnd', _DP), ('k_bnd', C.c_int32), ('lam', C.c_double),
-                ('lam_q', C.c_double), ('lam_N', C.c_double), ('lam_j', _DP),
-                ('lam_tile', C.c_double * 2), ('T2', _DP), ('T3', _DP), ('T1', _DP),
+                ('lam_q', C.c_double), ('lam_N', C.c_double), ('lam_inv', C.c_double),
+                ('lam_j', _DP), ('lam_tile', C.c_double * 2), ('RL', C.c_int32),
+                ('run_len', C.c_int32 * 8), ('lam_run', C.c_double * 8), ('T2', _DP), ('T3', _DP), ('T1', _DP),
                 ('Ehead', _DP), ('Eend', _DP), ('PhiF', _DP), ('PhiG', _DP), ('PsiW', _DP),
-                ('PsiT', _DP), ('psiY', _DP), ('out_sos', _DP), ('fm_interp', _DP)]
+                ('PsiT', _DP), ('psiY', _DP), ('use_nco', C.POINTER(C.c_uint8)), ('out_sos', _DP),
+                ('fm_interp', _DP), ('sos_Lseg', C.c_int32), ('sos_AL', _DP), ('sos_CA', _DP)]
 
 
 EXPORTS = ['sdrb_create', 'sdrb_destroy', 'sdrb_last_error', 'sdrb_outputs_per_chunk',
            'sdrb_chunk_bytes', 'sdrb_process', 'sdrb_process_device', 'sdrb_submit', 'sdrb_wait',
            'sdrb_get_iq_state', 'sdrb_set_iq_state', 'sdrb_read_decimated', 'sdrb_launch_count',
            'sdrb_fm_demod', 'sdrb_am_demod', 'sdrb_real_output', 'sdrb_imag_output',
-           'sdrb_shift_freq', 'sdrb_global_error']
+           'sdrb_shift_freq', 'sdrb_global_error', 'sdrb_process_device_phases',
+           'sdrb_set_profiling', 'sdrb_kernel_times']
 
 
 def nvcc_command(out: str = LIB_PATH) -> list[str]:
@@ -93,6 +96,9 @@ def lib():
         L.sdrb_chunk_bytes.restype = sz
         L.sdrb_process.argtypes = [vp, vp, sz, vp]
         L.sdrb_process_device.argtypes = [vp, vp, sz, vp, vp]
+        L.sdrb_process_device_phases.argtypes = [vp, vp, sz, vp, vp, C.c_int]
+        L.sdrb_set_profiling.argtypes = [vp, C.c_int]
+        L.sdrb_kernel_times.argtypes = [vp, C.POINTER(C.c_float)]
         L.sdrb_submit.argtypes = [vp, C.c_int, vp, sz, vp]
         L.sdrb_wait.argtypes = [vp, C.c_int]
         L.sdrb_get_iq_state.argtypes = [vp, _DP]

@@ -40,6 +40,9 @@ struct sdrb_handle {
     size_t main_smem = 0, demod_smem = 0;
     long long launches = 0;
     size_t last_nchunks = 0;
+    bool profiling = false;
+    cudaEvent_t pev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    bool pev_valid[5] = {false, false, false, false, false};
     std::string error;
 };
 
@@ -118,58 +121,77 @@ std::vector<double2> make_twiddles(int n)
     return tw;
 }
 
-template <int ENC>
-int launch_chain_t(sdrb_handle *h, const uint8_t *raw, size_t nch, double *out, cudaStream_t st)
+enum { PH_MAIN = 1, PH_IQSCAN = 2, PH_FINISH = 4, PH_ALL = 7 };
+
+template <int ENC, bool IQ>
+int launch_chain_t(sdrb_handle *h, const uint8_t *raw, size_t nch, double *out, cudaStream_t st, int phases)
 {
     const DevPlan &pl = h->pl;
-    const int groups = (pl.ntiles + h->tpc - 1) / h->tpc;
-    k_main<ENC><<<(unsigned)(nch * groups), 32 * h->warps, h->main_smem, st>>>(pl, h->sc, raw, (int)nch, h->tpc);
-    h->launches++;
-    if (pl.correct_iq) {
-        int nth = 1024;
-        while (nth > 32 && (size_t)nth / 2 >= nch) nth /= 2;
-        k_iqscan<ENC><<<1, nth, 0, st>>>(pl, h->sc, raw, (int)nch);
+    const bool prof = h->profiling && phases == PH_ALL;
+    auto mark = [&](int i) {
+        if (prof) { cudaEventRecord(h->pev[i], st); h->pev_valid[i] = true; }
+    };
+    if (prof) for (int i = 0; i < 5; i++) h->pev_valid[i] = false;
+    mark(0);
+    if (phases & PH_MAIN) {
+        const int groups = (pl.ntiles + h->tpc - 1) / h->tpc;
+        k_main<ENC, IQ><<<(unsigned)(nch * groups), 32 * h->warps, h->main_smem, st>>>(pl, h->sc, raw, (int)nch, h->tpc);
         h->launches++;
     }
-    k_fixup<ENC><<<(unsigned)(nch * pl.R), 128, 0, st>>>(pl, h->sc, raw, (int)nch);
-    h->launches++;
-    k_demod<<<(unsigned)(nch * pl.R), 128, h->demod_smem, st>>>(pl, h->sc.y, out, h->sc.fftbuf, h->sc.zrow,
-                                                                (int)nch, pl.demod, 1, pl.be_out);
-    h->launches++;
+    mark(1);
+    if ((phases & PH_IQSCAN) && IQ) {
+        const unsigned gb = (unsigned)((nch + 127) / 128);
+        k_iqgain<ENC><<<gb, 128, 0, st>>>(pl, h->sc, raw, (int)nch);
+        int nth = 1024;
+        while (nth > 32 && (size_t)nth / 2 >= nch) nth /= 2;
+        k_iqscan<<<1, nth, 0, st>>>(pl, h->sc, (int)nch);
+        k_iqtiles<<<gb, 128, 0, st>>>(pl, h->sc, (int)nch);
+        h->launches += 3;
+    }
+    mark(2);
+    if (phases & PH_FINISH) {
+        k_fixup<ENC><<<(unsigned)(nch * pl.R), 128, 0, st>>>(pl, h->sc, raw, (int)nch);
+        h->launches++;
+        mark(3);
+        k_demod<<<(unsigned)(nch * pl.R), 128, h->demod_smem, st>>>(pl, h->sc.y, out, h->sc.fftbuf, h->sc.zrow,
+                                                                    (int)nch, pl.demod, 1, pl.be_out);
+        h->launches++;
+        mark(4);
+    }
     CK(h, cudaGetLastError());
     return 0;
 }
 
-int launch_chain(sdrb_handle *h, const uint8_t *raw, size_t nch, double *out, cudaStream_t st)
+int launch_chain(sdrb_handle *h, const uint8_t *raw, size_t nch, double *out, cudaStream_t st, int phases = PH_ALL)
 {
     switch (h->enc_code) {
-    case ENC_b: return launch_chain_t<ENC_b>(h, raw, nch, out, st);
-    case ENC_B: return launch_chain_t<ENC_B>(h, raw, nch, out, st);
-    case ENC_h: return launch_chain_t<ENC_h>(h, raw, nch, out, st);
-    case ENC_H: return launch_chain_t<ENC_H>(h, raw, nch, out, st);
-    case ENC_i: return launch_chain_t<ENC_i>(h, raw, nch, out, st);
-    case ENC_I: return launch_chain_t<ENC_I>(h, raw, nch, out, st);
-    case ENC_f: return launch_chain_t<ENC_f>(h, raw, nch, out, st);
-    case ENC_d: return launch_chain_t<ENC_d>(h, raw, nch, out, st);
-    case ENC_Z: return launch_chain_t<ENC_Z>(h, raw, nch, out, st);
+    case ENC_b: return h->pl.correct_iq ? launch_chain_t<ENC_b, true>(h, raw, nch, out, st, phases) : launch_chain_t<ENC_b, false>(h, raw, nch, out, st, phases);
+    case ENC_B: return h->pl.correct_iq ? launch_chain_t<ENC_B, true>(h, raw, nch, out, st, phases) : launch_chain_t<ENC_B, false>(h, raw, nch, out, st, phases);
+    case ENC_h: return h->pl.correct_iq ? launch_chain_t<ENC_h, true>(h, raw, nch, out, st, phases) : launch_chain_t<ENC_h, false>(h, raw, nch, out, st, phases);
+    case ENC_H: return h->pl.correct_iq ? launch_chain_t<ENC_H, true>(h, raw, nch, out, st, phases) : launch_chain_t<ENC_H, false>(h, raw, nch, out, st, phases);
+    case ENC_i: return h->pl.correct_iq ? launch_chain_t<ENC_i, true>(h, raw, nch, out, st, phases) : launch_chain_t<ENC_i, false>(h, raw, nch, out, st, phases);
+    case ENC_I: return h->pl.correct_iq ? launch_chain_t<ENC_I, true>(h, raw, nch, out, st, phases) : launch_chain_t<ENC_I, false>(h, raw, nch, out, st, phases);
+    case ENC_f: return h->pl.correct_iq ? launch_chain_t<ENC_f, true>(h, raw, nch, out, st, phases) : launch_chain_t<ENC_f, false>(h, raw, nch, out, st, phases);
+    case ENC_d: return h->pl.correct_iq ? launch_chain_t<ENC_d, true>(h, raw, nch, out, st, phases) : launch_chain_t<ENC_d, false>(h, raw, nch, out, st, phases);
+    case ENC_Z: return h->pl.correct_iq ? launch_chain_t<ENC_Z, true>(h, raw, nch, out, st, phases) : launch_chain_t<ENC_Z, false>(h, raw, nch, out, st, phases);
     }
     return fail(h, SDRB_ERR_ARG, "bad encoding code %d", h->enc_code);
 }
 
-template <int ENC>
+template <int ENC, bool IQ>
 int set_smem_attr_t(sdrb_handle *h)
 {
-    CK(h, cudaFuncSetAttribute(k_main<ENC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->main_smem));
+    CK(h, cudaFuncSetAttribute(k_main<ENC, IQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->main_smem));
     return 0;
 }
 int set_smem_attr(sdrb_handle *h)
 {
     switch (h->enc_code) {
-    case ENC_b: return set_smem_attr_t<ENC_b>(h); case ENC_B: return set_smem_attr_t<ENC_B>(h);
-    case ENC_h: return set_smem_attr_t<ENC_h>(h); case ENC_H: return set_smem_attr_t<ENC_H>(h);
-    case ENC_i: return set_smem_attr_t<ENC_i>(h); case ENC_I: return set_smem_attr_t<ENC_I>(h);
-    case ENC_f: return set_smem_attr_t<ENC_f>(h); case ENC_d: return set_smem_attr_t<ENC_d>(h);
-    case ENC_Z: return set_smem_attr_t<ENC_Z>(h);
+    case ENC_b: return h->pl.correct_iq ? set_smem_attr_t<ENC_b, true>(h) : set_smem_attr_t<ENC_b, false>(h); case ENC_B: return h->pl.correct_iq ? set_smem_attr_t<ENC_B, true>(h) : set_smem_attr_t<ENC_B, false>(h);
+    case ENC_h: return h->pl.correct_iq ? set_smem_attr_t<ENC_h, true>(h) : set_smem_attr_t<ENC_h, false>(h); case ENC_H: return h->pl.correct_iq ? set_smem_attr_t<ENC_H, true>(h) : set_smem_attr_t<ENC_H, false>(h);
+    case ENC_i: return h->pl.correct_iq ? set_smem_attr_t<ENC_i, true>(h) : set_smem_attr_t<ENC_i, false>(h); case ENC_I: return h->pl.correct_iq ? set_smem_attr_t<ENC_I, true>(h) : set_smem_attr_t<ENC_I, false>(h);
+    case ENC_f: return h->pl.correct_iq ? set_smem_attr_t<ENC_f, true>(h) : set_smem_attr_t<ENC_f, false>(h); case ENC_d: return h->pl.correct_iq ? set_smem_attr_t<ENC_d, true>(h) : set_smem_attr_t<ENC_d, false>(h);
+    case ENC_Z: return h->pl.correct_iq ? set_smem_attr_t<ENC_Z, true>(h) : set_smem_attr_t<ENC_Z, false>(h);
     }
     return SDRB_ERR_ARG;
 }
@@ -218,6 +240,17 @@ int sdrb_create(const sdrb_config *cfg, const sdrb_tables *tab, sdrb_handle **ou
     pl.Mf = cfg->N / cfg->q; pl.rem = cfg->N - pl.Mf * cfg->q; pl.M = pl.Mf + (pl.rem ? 1 : 0);
     pl.ntiles = (pl.Mf + SDRB_TB - 1) / SDRB_TB; pl.cnt_last = pl.Mf - (pl.ntiles - 1) * SDRB_TB;
     pl.Hq = (cfg->q + 1) / 2; pl.KS = (pl.Hq + 3) / 4; pl.R = cfg->R;
+    pl.RL = tab->RL;
+    if (pl.RL != pl.KS) return bail(fail(h, SDRB_ERR_ARG, "RL %d does not match ceil(Hq/4) = %d", pl.RL, pl.KS));
+    pl.sb = 2 * pl.itemsize; pl.rowb = pl.q * pl.sb + (pl.sb <= 4 ? 4 : pl.sb);
+    for (int i = 0; i < 8; i++) { pl.run_len[i] = tab->run_len[i]; pl.lam_run[i] = tab->lam_run[i]; }
+    pl.lam_inv = tab->lam_inv;
+    pl.sos_ns = 2 * cfg->n_out_sections; pl.sos_Lseg = tab->sos_Lseg;
+    if (cfg->n_out_sections > 0) {
+        if (!tab->sos_AL || !tab->sos_CA || tab->sos_Lseg * 32 < pl.M)
+            return bail(fail(h, SDRB_ERR_ARG, "output SOS segment tables missing or too short"));
+        for (int i = 0; i < pl.sos_ns * pl.sos_ns; i++) pl.sos_AL[i] = tab->sos_AL[i];
+    }
     pl.ws = std::min(pl.q * pl.Mf, pl.N - 1 - pl.edge); pl.nend = pl.N - pl.ws;
     pl.k_bnd = tab->k_bnd; pl.nsec_out = cfg->n_out_sections;
     pl.Liq = cfg->correct_iq ? cfg->iq_L : 0.0; pl.lam = tab->lam; pl.lam_q = tab->lam_q; pl.lam_N = tab->lam_N;
@@ -239,8 +272,8 @@ int sdrb_create(const sdrb_config *cfg, const sdrb_tables *tab, sdrb_handle **ou
     std::vector<double> afrag((size_t)KS * 2 * 32, 0.0);
     for (int s = 0; s < KS; s++)
         for (int lane = 0; lane < 32; lane++) {
-            const int o = lane >> 2, k = lane & 3, j = 4 * s + k, m = o >> 1, e = o & 1;
-            if (j < Hq) {
+            const int o = lane >> 2, k = lane & 3, j = k * KS + s, m = o >> 1, e = o & 1;
+            if (j < Hq && j < (k + 1) * KS) {
                 afrag[((size_t)2 * s) * 32 + lane] = tab->Ec[2 * ((size_t)m * Hq + j) + e];
                 afrag[((size_t)2 * s + 1) * 32 + lane] = tab->Oc[2 * ((size_t)m * Hq + j) + e];
             }
@@ -286,18 +319,21 @@ int sdrb_create(const sdrb_config *cfg, const sdrb_tables *tab, sdrb_handle **ou
     UP(upload(h, reinterpret_cast<const double2 *>(tab->psiY), (size_t)2 * R * SDRB_TB, &pl.psiY));
     UP(upload(h, prot.data(), prot.size(), &pl.Prot));
     UP(upload(h, tw.data(), tw.size(), &pl.tw));
+    UP(upload(h, tab->use_nco, (size_t)R, &pl.use_nco));
+    pl.sos_CA = nullptr;
+    if (cfg->n_out_sections > 0) UP(upload(h, tab->sos_CA, (size_t)pl.sos_Lseg * pl.sos_ns, &pl.sos_CA));
     pl.fm_interp = nullptr;
     if (cfg->demod == SDRB_FM && !pl.fft_ok) UP(upload(h, tab->fm_interp, (size_t)M * h2, &pl.fm_interp));
 
     // launch geometry
     h->tpc = env_int("SDRB_TPC", R == 1 ? 2 : 1);
+    if (h->tpc > pl.ntiles) h->tpc = pl.ntiles;
     h->warps = env_int("SDRB_WARPS", R == 1 ? h->tpc : (R >= 8 ? 8 : 4));
     if (h->tpc < 1) h->tpc = 1;
     if (h->warps < 1) h->warps = 1;
     if (h->warps > 8) h->warps = 8;
-    const size_t tile_bytes = (size_t)q * (SDRB_TB + SDRB_ZPAD) * sizeof(double2);
     auto smem_for = [&](int tpc, int w) {
-        return tpc * (tile_bytes + SDRB_TB * sizeof(double2)) + (size_t)w * 32 * SDRB_XSTRIDE * sizeof(double);
+        return (size_t)tpc * main_tile_bytes(pl.rowb, pl.correct_iq != 0) + (size_t)w * main_warp_bytes();
     };
     while (h->tpc > 1 && smem_for(h->tpc, h->warps) > 220 * 1024) h->tpc--;
     while (h->warps > 1 && smem_for(h->tpc, h->warps) > 220 * 1024) h->warps--;
@@ -353,6 +389,7 @@ int sdrb_destroy(sdrb_handle *h)
         if (h->slot[s].done) cudaEventDestroy(h->slot[s].done);
     }
     if (h->iq_done) cudaEventDestroy(h->iq_done);
+    for (int i = 0; i < 5; i++) if (h->pev[i]) cudaEventDestroy(h->pev[i]);
     delete h;
     return SDRB_OK;
 }
@@ -435,6 +472,34 @@ int sdrb_process(sdrb_handle *h, const void *raw, size_t nchunks, double *out)
             memcpy(out + r * nchunks * M + done * M, tmp.data() + r * n * M, n * M * sizeof(double));
         done += n;
     }
+    return SDRB_OK;
+}
+
+int sdrb_process_device_phases(sdrb_handle *h, const void *raw_dev, size_t nchunks, double *out_dev, void *stream, int phases)
+{
+    if (!h || !raw_dev || (!out_dev && (phases & PH_FINISH))) return fail(h, SDRB_ERR_ARG, "null argument");
+    if (nchunks == 0) return SDRB_OK;
+    if (nchunks > h->max_chunks) return fail(h, SDRB_ERR_ARG, "nchunks %zu > max_chunks %zu", nchunks, h->max_chunks);
+    CK(h, cudaSetDevice(h->cfg.device));
+    h->last_nchunks = nchunks;
+    return launch_chain(h, static_cast<const uint8_t *>(raw_dev), nchunks, out_dev, static_cast<cudaStream_t>(stream), phases);
+}
+
+int sdrb_set_profiling(sdrb_handle *h, int on)
+{
+    if (!h) return fail(h, SDRB_ERR_ARG, "null argument");
+    CK(h, cudaSetDevice(h->cfg.device));
+    if (on) for (int i = 0; i < 5; i++) if (!h->pev[i]) CK(h, cudaEventCreate(&h->pev[i]));
+    h->profiling = on != 0;
+    return SDRB_OK;
+}
+
+int sdrb_kernel_times(sdrb_handle *h, float ms[4])
+{
+    if (!h || !ms) return fail(h, SDRB_ERR_ARG, "null argument");
+    for (int i = 0; i < 5; i++) if (!h->pev_valid[i]) return fail(h, SDRB_ERR_STATE, "no profiled batch");
+    CK(h, cudaEventSynchronize(h->pev[4]));
+    for (int i = 0; i < 4; i++) CK(h, cudaEventElapsedTime(&ms[i], h->pev[i], h->pev[i + 1]));
     return SDRB_OK;
 }
 

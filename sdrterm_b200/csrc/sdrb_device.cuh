@@ -6,7 +6,6 @@
 
 #define SDRB_TB 32          // blocks per tile == warp width (lane <-> block)
 #define SDRB_NP 8           // poles of the cheby1 order-8 decimation low-pass
-#define SDRB_ZPAD 2         // zT row stride = TB + ZPAD double2 (conflict-free DMMA-order reads)
 #define SDRB_XSTRIDE 33     // exchange buffer row stride in doubles
 
 enum { ENC_b = 0, ENC_B, ENC_h, ENC_H, ENC_i, ENC_I, ENC_f, ENC_d, ENC_Z };
@@ -14,10 +13,16 @@ enum { ENC_b = 0, ENC_B, ENC_h, ENC_H, ENC_i, ENC_I, ENC_f, ENC_d, ENC_Z };
 struct DevPlan {
     int enc, itemsize, swap, correct_iq, normalize, demod, be_out;
     int q, N, edge, L, Mf, rem, M, ntiles, cnt_last, Hq, KS, R, nend, ws, k_bnd, nsec_out;
+    int RL;                // pairs per DMMA k-lane (== KS): lane k owns pairs [k*RL, (k+1)*RL)
+    int sb, rowb;          // bytes per complex sample; padded bytes per block row of the raw tile
+    int run_len[8];        // samples per run, sample order (4 ascending + 4 descending)
+    int sos_ns, sos_Lseg;  // output SOS evaluated in 32 segments of sos_Lseg samples
     int fft_ok;            // FM resample by FFT (M == 2h, h power of two)
     int fft_n;             // twiddle table length (== M when fft_ok)
     int demod_in_smem;     // FFT / row buffers fit shared memory
-    double Liq, lam, lam_q, lam_N, g0, d, norm_xmin, norm_k;
+    double Liq, lam, lam_q, lam_N, lam_inv, g0, d, norm_xmin, norm_k;
+    double lam_run[8];     // lam^run_len
+    double sos_AL[64];     // [ns][ns] A^Lseg of the output cascade
     double lamq_pow[5];    // lam_q^(1,2,4,8,16)
     double lam_tile[2];
     double2 p[SDRB_NP], P[SDRB_NP], rho[SDRB_NP], rho_p[SDRB_NP], c[SDRB_NP], zhat[SDRB_NP];
@@ -42,6 +47,8 @@ struct DevPlan {
     const double2 *Prot;   // [R][16]  rotating-frame block multipliers (8 forward, 8 backward)
     const double2 *tw;     // [fft_n]  exp(-2 pi i k / fft_n)
     const double *fm_interp;  // [M][M/2] or null
+    const double *sos_CA;     // [sos_Lseg][ns]  c A^i
+    const unsigned char *use_nco;  // [R]
 };
 
 // ---------------------------------------------------------------- complex helpers (double2)

@@ -1,15 +1,17 @@
 // sdrb_kernels.cuh -- the sm_100a kernels of the demodulation chain.
 //
-//   k_main    decode + block-local IQ + NCO + even/odd block sums on the FP64 tensor pipe (DMMA)
-//             + tile-local modal scans -> partial outputs and tile aggregates
-//   k_iqscan  IQ-corrector offset at every tile start (carried across chunks and calls)
-//   k_fixup   head/end segments, cross-tile carries, boundary term -> decimated complex y
-//   k_demod   fm (pair phase + 2x FFT interpolation) | am | re | im, output SOS, framing
+//   k_main     raw tile -> shared memory; run-wise IQ correction, NCO and the even/odd block sums
+//              on the FP64 tensor pipe (DMMA.8x8x4), all from registers; tile-local modal scans
+//              -> partial outputs + tile aggregates
+//   k_iqgain / k_iqscan / k_iqtiles   IQ-corrector offset at every tile start, carried across
+//              chunks and calls
+//   k_fixup    head / end segments, cross-tile carries, boundary term -> decimated complex y
+//   k_demod    fm (pair phase + 2x FFT interpolation) | am | re | im, segmented output SOS, framing
 //
 // Reference behaviour being reproduced: src/misc/read_file.py:100-103 (decode, normalise, IQ
 // correction), src/dsp/demodulation.py:71-79 (NCO), src/dsp/dsp_processor.py:147 (scipy
 // decimate), demodulation.py:25-68, dsp_processor.py:32-36,149,162, vfo_processor.py:84.
-// tests/emulator.py is the line-by-line numpy twin of these kernels.
+// tests/emulator.py is the numpy twin of these kernels (same tables, same decomposition).
 #pragma once
 #include "sdrb_device.cuh"
 
@@ -27,137 +29,213 @@ struct Scratch {
     double *zrow;       // [nch*R][M]     "
 };
 
+// Shared-memory carve-up of k_main (host mirrors this in sdrb_api.cu: main_smem_bytes()).
+__host__ __device__ inline size_t main_tile_bytes(int rowb, bool iq)
+{
+    size_t b = (size_t)SDRB_TB * rowb;                       // raw tile, padded rows
+    b = (b + 15) & ~(size_t)15;
+    b += 2 * SDRB_TB * sizeof(double2);                      // cl[32], blkagg[32]
+    if (iq) b += (size_t)SDRB_TB * 4 * 2 * sizeof(double2);  // runA[32][4][2]
+    return b;
+}
+__host__ __device__ inline size_t main_warp_bytes()
+{
+    return (size_t)32 * SDRB_XSTRIDE * sizeof(double) + SDRB_TB * sizeof(double2);  // xb + x0s
+}
+
 // ------------------------------------------------------------------------------------ k_main
-// grid.x = nchunks * ceil(ntiles / TPC); block = 32*W threads.  A CTA decodes TPC consecutive
-// tiles of one chunk into shared memory (phase 0, once, shared by all rows) and its warps then
-// take (tile, row) items.
-template <int ENC>
+// grid.x = nchunks * ceil(ntiles / TPC); block = 32*W threads.  A CTA stages TPC consecutive
+// tiles of one chunk in shared memory (raw bytes, once, shared by all rows); its warps then take
+// (tile, row) items.  Lane roles follow the DMMA fragments: k = lane&3 owns the pairs
+// [k*RL, (k+1)*RL) of block 8g + (lane>>2) in group g (B operand), and accumulates output row
+// lane>>2 for blocks 8g + 2k, 8g + 2k + 1 (C operand).
+template <int ENC, bool IQ>
 __global__ void __launch_bounds__(256)
 k_main(const __grid_constant__ DevPlan pl, Scratch sc, const uint8_t *__restrict__ raw, int nchunks, int TPC)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, W = blockDim.x >> 5;
-    const int q = pl.q, zs = SDRB_TB + SDRB_ZPAD;
+    const int q = pl.q, sb = pl.sb, rowb = pl.rowb;
     const int groups = (pl.ntiles + TPC - 1) / TPC;
     const int chunk = blockIdx.x / groups, tg = blockIdx.x % groups;
     if (chunk >= nchunks) return;
-    double2 *zT = reinterpret_cast<double2 *>(smem_raw);                 // [TPC][q][zs]
-    double2 *cl = zT + (size_t)TPC * q * zs;                              // [TPC][32]
-    double *xball = reinterpret_cast<double *>(cl + TPC * SDRB_TB);       // [W][32][XSTRIDE]
-    const uint8_t *rawc = raw + (size_t)chunk * pl.N * 2 * pl.itemsize;
+    const size_t tileb = main_tile_bytes(rowb, IQ);
+    unsigned char *warp_base = smem_raw + (size_t)TPC * tileb;
+    const uint8_t *rawc = raw + (size_t)chunk * pl.N * sb;
     const int t0 = tg * TPC;
     const int ntl = min(TPC, pl.ntiles - t0);
+    const int kq = lane & 3, nq = lane >> 2;
+    // this lane's pair range and the two sample runs it owns inside a block
+    const int a0 = min(kq * pl.RL, pl.Hq), a1 = min((kq + 1) * pl.RL, pl.Hq);
+    const int d0 = max(q - a1, pl.Hq), d1 = q - a0;
 
-    // ---------------- phase 0: decode + block-local IQ correction, lane <-> block
+    // ---------------- stage the raw tiles, then (IQ) run aggregates and block offsets
     for (int tl = warp; tl < ntl; tl += W) {
         const int t = t0 + tl;
         const int cnt = (t == pl.ntiles - 1) ? pl.cnt_last : SDRB_TB;
-        const bool active = lane < cnt;
-        const long base = ((long)t * SDRB_TB + lane) * q;
-        double2 *zTt = zT + (size_t)tl * q * zs;
-        double2 acc = make_double2(0.0, 0.0);
-        for (int j = 0; j < q; j++) {
-            double2 z = make_double2(0.0, 0.0);
-            if (active) z = decode_sample<ENC>(pl, rawc, base + j);
-            double2 zp = z;
-            if (pl.correct_iq) {
-                zp.x = fma(-pl.Liq, acc.x, z.x);
-                zp.y = fma(-pl.Liq, acc.y, z.y);
-                acc.x = fma(pl.lam, acc.x, z.x);
-                acc.y = fma(pl.lam, acc.y, z.y);
+        unsigned char *tb = smem_raw + (size_t)tl * tileb;
+        const uint8_t *src = rawc + (size_t)t * SDRB_TB * q * sb;
+        for (int row = 0; row < SDRB_TB; row++) {
+            unsigned char *dst = tb + (size_t)row * rowb;
+            if (row < cnt) {
+                const uint8_t *s = src + (size_t)row * q * sb;
+                for (int col = lane; col < q; col += 32) {
+                    if (sb == 2) *reinterpret_cast<uint16_t *>(dst + col * 2) = *reinterpret_cast<const uint16_t *>(s + col * 2);
+                    else if (sb == 4) *reinterpret_cast<uint32_t *>(dst + col * 4) = *reinterpret_cast<const uint32_t *>(s + col * 4);
+                    else if (sb == 8) *reinterpret_cast<uint2 *>(dst + col * 8) = *reinterpret_cast<const uint2 *>(s + col * 8);
+                    else *reinterpret_cast<uint4 *>(dst + col * 16) = *reinterpret_cast<const uint4 *>(s + col * 16);
+                }
+            } else {
+                for (int col = lane; col < q * sb / 2; col += 32) *reinterpret_cast<uint16_t *>(dst + col * 2) = 0;
             }
-            zTt[j * zs + lane] = zp;
         }
+    }
+    __syncthreads();
+    for (int tl = warp; tl < ntl; tl += W) {
+        const int t = t0 + tl;
+        const int cnt = (t == pl.ntiles - 1) ? pl.cnt_last : SDRB_TB;
+        unsigned char *tb = smem_raw + (size_t)tl * tileb;
+        double2 *cl = reinterpret_cast<double2 *>(tb + (((size_t)SDRB_TB * rowb + 15) & ~(size_t)15));
+        double2 *blkagg = cl + SDRB_TB;
         double2 excl = make_double2(0.0, 0.0);
-        if (pl.correct_iq) {
-            double2 inc = active ? cscale(pl.Liq, acc) : make_double2(0.0, 0.0);
+        if (IQ) {
+            double2 *runA = blkagg + SDRB_TB;
+            for (int g = 0; g < 4; g++) {
+                const int b = 8 * g + nq;
+                const unsigned char *rowp = tb + (size_t)b * rowb;
+                double2 agg_a = make_double2(0.0, 0.0), agg_d = make_double2(0.0, 0.0);
+                for (int j = a0; j < a1; j++) {
+                    const double2 z = decode_sample<ENC>(pl, rowp, j);
+                    agg_a.x = fma(pl.lam, agg_a.x, z.x); agg_a.y = fma(pl.lam, agg_a.y, z.y);
+                }
+                for (int j = d0; j < d1; j++) {
+                    const double2 z = decode_sample<ENC>(pl, rowp, j);
+                    agg_d.x = fma(pl.lam, agg_d.x, z.x); agg_d.y = fma(pl.lam, agg_d.y, z.y);
+                }
+                // EMA state at the 9 run boundaries of this block (all four lanes of the block
+                // compute the same chain from the gathered run aggregates)
+                const int base = lane & ~3;
+                double2 A[9];
+                A[0] = make_double2(0.0, 0.0);
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    const double2 v = shfl_c(agg_a, base + i);
+                    A[i + 1] = make_double2(fma(pl.lam_run[i], A[i].x, v.x), fma(pl.lam_run[i], A[i].y, v.y));
+                }
+#pragma unroll
+                for (int i = 4; i < 8; i++) {
+                    const double2 v = shfl_c(agg_d, base + (7 - i));
+                    A[i + 1] = make_double2(fma(pl.lam_run[i], A[i].x, v.x), fma(pl.lam_run[i], A[i].y, v.y));
+                }
+                const double2 As = kq == 0 ? A[0] : kq == 1 ? A[1] : kq == 2 ? A[2] : A[3];   // at ascending-run start
+                const double2 Ae = kq == 0 ? A[8] : kq == 1 ? A[7] : kq == 2 ? A[6] : A[5];   // at descending-run end
+                runA[(b * 4 + kq) * 2] = As;
+                runA[(b * 4 + kq) * 2 + 1] = Ae;
+                if (kq == 0) blkagg[b] = A[8];
+            }
+            __syncwarp();
+            const bool active = lane < cnt;
+            double2 inc = active ? cscale(pl.Liq, blkagg[lane]) : make_double2(0.0, 0.0);
 #pragma unroll
             for (int i = 0; i < 5; i++) {
-                double2 tt = shfl_up_c(inc, 1 << i);
+                const double2 tt = shfl_up_c(inc, 1 << i);
                 if (lane >= (1 << i)) { inc.x = fma(pl.lamq_pow[i], tt.x, inc.x); inc.y = fma(pl.lamq_pow[i], tt.y, inc.y); }
             }
             excl = shfl_up_c(inc, 1);
             if (lane == 0) excl = make_double2(0.0, 0.0);
-            double2 tagg = shfl_c(inc, cnt - 1);
+            const double2 tagg = shfl_c(inc, cnt - 1);
             if (lane == 0) sc.tile_agg[(size_t)chunk * pl.ntiles + t] = tagg;
-            // tail window: tile-local-corrected samples n in [N-1-edge, q*Mf)
-            const long n0 = pl.N - 1 - pl.edge;
-            if (active && base + q > n0) {
-                for (int j = 0; j < q; j++) {
-                    long n = base + j;
-                    if (n >= n0) {
-                        double2 v = zTt[j * zs + lane];
-                        double lj = pl.lam_j[j];
-                        sc.tailwin[(size_t)chunk * (pl.edge + 1) + (n - n0)] =
-                            make_double2(fma(-lj, excl.x, v.x), fma(-lj, excl.y, v.y));
-                    }
-                }
-            }
-        } else {
-            const long n0 = pl.N - 1 - pl.edge;
-            if (active && base + q > n0)
-                for (int j = 0; j < q; j++)
-                    if (base + j >= n0)
-                        sc.tailwin[(size_t)chunk * (pl.edge + 1) + (base + j - n0)] = zTt[j * zs + lane];
         }
-        cl[tl * SDRB_TB + lane] = excl;
+        cl[lane] = excl;
+        // tail window: tile-local-corrected samples n in [N-1-edge, q*Mf), lane <-> block
+        const long n0 = pl.N - 1 - pl.edge;
+        const long base_n = ((long)t * SDRB_TB + lane) * q;
+        if (lane < cnt && base_n + q > n0) {
+            const unsigned char *rowp = tb + (size_t)lane * rowb;
+            double2 acc = make_double2(0.0, 0.0);
+            for (int j = 0; j < q; j++) {
+                const double2 z = decode_sample<ENC>(pl, rowp, j);
+                double2 zp = z;
+                if (IQ) {
+                    zp.x = fma(-pl.Liq, acc.x, z.x); zp.y = fma(-pl.Liq, acc.y, z.y);
+                    acc.x = fma(pl.lam, acc.x, z.x); acc.y = fma(pl.lam, acc.y, z.y);
+                    const double lj = pl.lam_j[j];
+                    zp.x = fma(-lj, excl.x, zp.x); zp.y = fma(-lj, excl.y, zp.y);
+                }
+                if (base_n + j >= n0) sc.tailwin[(size_t)chunk * (pl.edge + 1) + (base_n + j - n0)] = zp;
+            }
+        }
     }
     __syncthreads();
 
     // ---------------- items: (tile, row)
-    double *xb = xball + (size_t)warp * 32 * SDRB_XSTRIDE;
+    double *xb = reinterpret_cast<double *>(warp_base + (size_t)warp * main_warp_bytes());
+    double2 *x0s = reinterpret_cast<double2 *>(xb + 32 * SDRB_XSTRIDE);
     const int e = (lane >> 2) & 1, m = lane >> 3;
     for (int item = warp; item < ntl * pl.R; item += W) {
         const int tl = item % ntl, r = item / ntl;
         const int t = t0 + tl;
         const int cnt = (t == pl.ntiles - 1) ? pl.cnt_last : SDRB_TB;
-        const double2 *zTt = zT + (size_t)tl * q * zs;
+        const unsigned char *tb = smem_raw + (size_t)tl * tileb;
+        const double2 *cl = reinterpret_cast<const double2 *>(tb + (((size_t)SDRB_TB * rowb + 15) & ~(size_t)15));
+        const double2 *runA = cl + 2 * SDRB_TB;
         const double2 *T2r = pl.T2 + (size_t)r * q;
-        double acc[4][4][2];
-#pragma unroll
-        for (int g = 0; g < 4; g++)
-#pragma unroll
-            for (int ty = 0; ty < 4; ty++) { acc[g][ty][0] = 0.0; acc[g][ty][1] = 0.0; }
-
-        for (int s = 0; s < pl.KS; s++) {
-            int j = 4 * s + (lane & 3);
-            if (j >= pl.Hq) j = 0;                      // padded pair: coefficient is zero
-            const int jm = q - 1 - j;
-            const bool mid = (j == jm);
-            const double aE = __ldg(pl.Afrag + (size_t)(2 * s) * 32 + lane);
-            const double aO = __ldg(pl.Afrag + (size_t)(2 * s + 1) * 32 + lane);
-            const double2 t2a = __ldg(T2r + j), t2b = __ldg(T2r + jm);
-#pragma unroll
-            for (int g = 0; g < 4; g++) {
-                const int bB = 8 * g + (lane >> 2);
-                const double2 za = zTt[j * zs + bB], zb = zTt[jm * zs + bB];
-                const double2 ua = cmul(t2a, za), ub = cmul(t2b, zb);
-                double2 a, d;
-                if (mid) { a = ua; d = make_double2(0.0, 0.0); }
-                else { a = cadd(ua, ub); d = csub(ua, ub); }
-                dmma884(acc[g][0][0], acc[g][0][1], aE, a.x);
-                dmma884(acc[g][1][0], acc[g][1][1], aE, a.y);
-                dmma884(acc[g][2][0], acc[g][2][1], aO, d.x);
-                dmma884(acc[g][3][0], acc[g][3][1], aO, d.y);
-            }
-        }
-        // combine the four real sums into F/G (part e of poles m and m+4), local IQ, exchange
+        const bool nco = pl.use_nco[r] != 0;
         const double2 phFu = pl.PhiF[(size_t)r * 8 + m], phFl = pl.PhiF[(size_t)r * 8 + m + 4];
         const double2 phGu = pl.PhiG[(size_t)r * 8 + m], phGl = pl.PhiG[(size_t)r * 8 + m + 4];
-#pragma unroll
+
         for (int g = 0; g < 4; g++) {
+            const int bB = 8 * g + nq;
+            const unsigned char *rowp = tb + (size_t)bB * rowb;
+            double2 acc_a = make_double2(0.0, 0.0), acc_d = make_double2(0.0, 0.0);
+            if (IQ) { acc_a = runA[(bB * 4 + kq) * 2]; acc_d = runA[(bB * 4 + kq) * 2 + 1]; }
+            double Sr0 = 0, Sr1 = 0, Si0 = 0, Si1 = 0, Dr0 = 0, Dr1 = 0, Di0 = 0, Di1 = 0;
+            for (int s = 0; s < pl.RL; s++) {
+                const int j = a0 + s;
+                const bool valid = j < a1;
+                double2 a = make_double2(0.0, 0.0), d = make_double2(0.0, 0.0);
+                if (valid) {
+                    const int jm = q - 1 - j;
+                    const bool mid = (j == jm);
+                    double2 za = decode_sample<ENC>(pl, rowp, j);
+                    if (IQ) {
+                        const double2 z = za;
+                        za.x = fma(-pl.Liq, acc_a.x, z.x); za.y = fma(-pl.Liq, acc_a.y, z.y);
+                        acc_a.x = fma(pl.lam, acc_a.x, z.x); acc_a.y = fma(pl.lam, acc_a.y, z.y);
+                    }
+                    if (s == 0 && kq == 0) x0s[bB] = za;          // first sample of the block
+                    const double2 ua = nco ? cmul(__ldg(T2r + j), za) : za;
+                    if (mid) { a = ua; }
+                    else {
+                        double2 zb = decode_sample<ENC>(pl, rowp, jm);
+                        if (IQ) {
+                            acc_d.x = (acc_d.x - zb.x) * pl.lam_inv; acc_d.y = (acc_d.y - zb.y) * pl.lam_inv;
+                            zb.x = fma(-pl.Liq, acc_d.x, zb.x); zb.y = fma(-pl.Liq, acc_d.y, zb.y);
+                        }
+                        const double2 ub = nco ? cmul(__ldg(T2r + jm), zb) : zb;
+                        a = cadd(ua, ub); d = csub(ua, ub);
+                    }
+                }
+                const double aE = __ldg(pl.Afrag + (size_t)(2 * s) * 32 + lane);
+                const double aO = __ldg(pl.Afrag + (size_t)(2 * s + 1) * 32 + lane);
+                dmma884(Sr0, Sr1, aE, a.x);
+                dmma884(Si0, Si1, aE, a.y);
+                dmma884(Dr0, Dr1, aO, d.x);
+                dmma884(Di0, Di1, aO, d.y);
+            }
+            // combine the four real sums into F/G (part e of poles m and m+4), local IQ, exchange
 #pragma unroll
             for (int i = 0; i < 2; i++) {
-                const int b = 8 * g + 2 * (lane & 3) + i;
-                const double Sr = acc[g][0][i], Si = acc[g][1][i], Dr = acc[g][2][i], Di = acc[g][3][i];
+                const int b = 8 * g + 2 * kq + i;
+                const double Sr = i ? Sr1 : Sr0, Si = i ? Si1 : Si0, Dr = i ? Dr1 : Dr0, Di = i ? Di1 : Di0;
                 const double oS = __shfl_xor_sync(0xffffffffu, Si, 4);
                 const double oD = __shfl_xor_sync(0xffffffffu, Di, 4);
                 double Sup, Slo, Dup, Dlo;
                 if (e == 0) { Sup = Sr - oS; Slo = Sr + oS; Dup = Dr - oD; Dlo = Dr + oD; }
                 else        { Sup = oS + Sr; Slo = oS - Sr; Dup = oD + Dr; Dlo = oD - Dr; }
                 double Fu = Sup + Dup, Gu = Sup - Dup, Fl = Slo + Dlo, Gl = Slo - Dlo;
-                if (pl.correct_iq) {
-                    const double2 cb = cl[tl * SDRB_TB + b];
+                if (IQ) {
+                    const double2 cb = cl[b];
                     if (e == 0) {
                         Fu -= fma(cb.x, phFu.x, -cb.y * phFu.y); Fl -= fma(cb.x, phFl.x, -cb.y * phFl.y);
                         Gu -= fma(cb.x, phGu.x, -cb.y * phGu.y); Gl -= fma(cb.x, phGl.x, -cb.y * phGl.y);
@@ -202,7 +280,7 @@ k_main(const __grid_constant__ DevPlan pl, Scratch sc, const uint8_t *__restrict
                 sT = cfma(pl.rho_p[i], Tv, sT);
             }
             const double2 epsb = cconj(pl.T3[(size_t)r * (SDRB_TB + 1) + 1]);
-            double2 x0 = csub(zTt[lane], cl[tl * SDRB_TB + lane]);
+            const double2 x0 = csub(x0s[lane], cl[lane]);
             double2 ys = cfma(epsb, sw, sT);
             ys.x = fma(pl.g0, x0.x, ys.x); ys.y = fma(pl.g0, x0.y, ys.y);
             const double2 yp = cmul(pl.T3[(size_t)r * (SDRB_TB + 1) + lane], ys);
@@ -212,77 +290,132 @@ k_main(const __grid_constant__ DevPlan pl, Scratch sc, const uint8_t *__restrict
     }
 }
 
-// ---------------------------------------------------------------------------------- k_iqscan
-// Offset of the IQ corrector at every tile start of every chunk.  One CTA; thread <-> chunk
-// group.  State before the batch in sc.iq_state[0]; state after it is written back.
+// -------------------------------------------------------------------------------- IQ kernels
+// k_iqgain: thread <-> chunk, offset gained over the chunk from a zero state -> off_tile[c][nt].
 template <int ENC>
-__global__ void __launch_bounds__(1024)
-k_iqscan(const __grid_constant__ DevPlan pl, Scratch sc, const uint8_t *__restrict__ raw, int nchunks)
+__global__ void __launch_bounds__(128)
+k_iqgain(const __grid_constant__ DevPlan pl, Scratch sc, const uint8_t *__restrict__ raw, int nchunks)
 {
-    __shared__ double2 s_a[1024];   // per-thread aggregate (offset gained from zero over its chunks)
-    __shared__ double s_m[1024];    // per-thread decay multiplier
-    const int tid = threadIdx.x, nth = blockDim.x;
-    const int per = (nchunks + nth - 1) / nth;
-    const int c0 = tid * per, c1 = min(nchunks, c0 + per);
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= nchunks) return;
     const int nt = pl.ntiles;
-    // pass 1: per chunk aggregate (from zero) over tiles + partial block; thread aggregate
+    const double2 *ta = sc.tile_agg + (size_t)c * nt;
+    double2 o = make_double2(0.0, 0.0);
+    int t = 0;
+    for (; t + 8 <= nt; t += 8) {
+        double2 g[8];
+#pragma unroll
+        for (int i = 0; i < 8; i++) g[i] = ta[t + i];
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            const double lt = pl.lam_tile[(t + i) == nt - 1 ? 1 : 0];
+            o.x = fma(lt, o.x, g[i].x); o.y = fma(lt, o.y, g[i].y);
+        }
+    }
+    for (; t < nt; t++) {
+        const double lt = pl.lam_tile[t == nt - 1 ? 1 : 0];
+        const double2 g = ta[t];
+        o.x = fma(lt, o.x, g.x); o.y = fma(lt, o.y, g.y);
+    }
+    if (pl.rem) {
+        const uint8_t *rawc = raw + (size_t)c * pl.N * pl.sb;
+        double2 acc = make_double2(0.0, 0.0);
+        for (int j = 0; j < pl.rem; j++) {
+            const double2 z = decode_sample<ENC>(pl, rawc, (long)pl.q * pl.Mf + j);
+            acc.x = fma(pl.lam, acc.x, z.x); acc.y = fma(pl.lam, acc.y, z.y);
+        }
+        const double lr = pl.lam_j[pl.rem];
+        o.x = fma(lr, o.x, pl.Liq * acc.x); o.y = fma(lr, o.y, pl.Liq * acc.y);
+    }
+    sc.off_tile[(size_t)c * (nt + 1) + nt] = o;
+}
+
+// k_iqscan: one CTA; exclusive scan of the per-chunk affine maps o -> lam_N*o + gain, starting from
+// the handle's IQ state; writes the offset at every chunk start to off_tile[c][0] and the new state.
+__global__ void __launch_bounds__(1024)
+k_iqscan(const __grid_constant__ DevPlan pl, Scratch sc, int nchunks)
+{
+    __shared__ double2 s_a[1024];
+    __shared__ double s_m[1024];
+    const int tid = threadIdx.x, nth = blockDim.x, nt = pl.ntiles;
+    const int per = (nchunks + nth - 1) / nth;
+    const int c0 = min(nchunks, tid * per), c1 = min(nchunks, c0 + per);
     double2 a = make_double2(0.0, 0.0);
     double mlt = 1.0;
     for (int c = c0; c < c1; c++) {
-        double2 o = make_double2(0.0, 0.0);
-        for (int t = 0; t < nt; t++) {
-            const double lt = pl.lam_tile[t == nt - 1 ? 1 : 0];
-            const double2 g = sc.tile_agg[(size_t)c * nt + t];
-            o.x = fma(lt, o.x, g.x); o.y = fma(lt, o.y, g.y);
-        }
-        // partial block: reference recurrence from zero gives the affine part; decay lam^rem
-        if (pl.rem) {
-            const uint8_t *rawc = raw + (size_t)c * pl.N * 2 * pl.itemsize;
-            double2 acc = make_double2(0.0, 0.0);
-            for (int j = 0; j < pl.rem; j++) {
-                double2 z = decode_sample<ENC>(pl, rawc, (long)pl.q * pl.Mf + j);
-                acc.x = fma(pl.lam, acc.x, z.x); acc.y = fma(pl.lam, acc.y, z.y);
-            }
-            const double lr = pl.lam_j[pl.rem];
-            o.x = fma(lr, o.x, pl.Liq * acc.x); o.y = fma(lr, o.y, pl.Liq * acc.y);
-        }
-        // o = offset gained over chunk c from zero; stash it in off_tile[c][nt] for pass 2
-        sc.off_tile[(size_t)c * (nt + 1) + nt] = o;
-        a.x = fma(pl.lam_N, a.x, o.x); a.y = fma(pl.lam_N, a.y, o.y);
+        const double2 g = sc.off_tile[(size_t)c * (nt + 1) + nt];
+        a.x = fma(pl.lam_N, a.x, g.x); a.y = fma(pl.lam_N, a.y, g.y);
         mlt *= pl.lam_N;
     }
     s_a[tid] = a; s_m[tid] = mlt;
     __syncthreads();
-    // serial combine over threads by thread 0 (<= 1024 steps), exclusive prefix into s_a
-    if (tid == 0) {
-        double2 o = sc.iq_state[0];
-        for (int i = 0; i < nth; i++) {
-            const double2 ai = s_a[i]; const double mi = s_m[i];
-            s_a[i] = o;
-            o.x = fma(mi, o.x, ai.x); o.y = fma(mi, o.y, ai.y);
+    // Hillis-Steele inclusive scan of affine maps (m, a): later o earlier = (m2*m1, m2*a1 + a2)
+    for (int d = 1; d < nth; d <<= 1) {
+        double2 pa = make_double2(0.0, 0.0);
+        double pm = 1.0;
+        const bool has = tid >= d;
+        if (has) { pa = s_a[tid - d]; pm = s_m[tid - d]; }
+        __syncthreads();
+        if (has) {
+            const double mm = s_m[tid];
+            s_a[tid] = make_double2(fma(mm, pa.x, s_a[tid].x), fma(mm, pa.y, s_a[tid].y));
+            s_m[tid] = mm * pm;
         }
-        sc.iq_state[0] = o;
+        __syncthreads();
+    }
+    const double2 st0 = sc.iq_state[0];
+    double2 o = st0;
+    if (tid > 0) {
+        const double2 pa = s_a[tid - 1]; const double pm = s_m[tid - 1];
+        o = make_double2(fma(pm, st0.x, pa.x), fma(pm, st0.y, pa.y));
+    }
+    for (int c = c0; c < c1; c++) {
+        sc.off_tile[(size_t)c * (nt + 1)] = o;
+        const double2 g = sc.off_tile[(size_t)c * (nt + 1) + nt];
+        o.x = fma(pl.lam_N, o.x, g.x); o.y = fma(pl.lam_N, o.y, g.y);
     }
     __syncthreads();
-    // pass 2: offsets at tile starts
-    double2 o = s_a[tid];
-    for (int c = c0; c < c1; c++) {
-        const double2 gain = sc.off_tile[(size_t)c * (nt + 1) + nt];
-        double2 ot = o;
-        for (int t = 0; t < nt; t++) {
-            sc.off_tile[(size_t)c * (nt + 1) + t] = ot;
-            const double lt = pl.lam_tile[t == nt - 1 ? 1 : 0];
-            const double2 g = sc.tile_agg[(size_t)c * nt + t];
-            ot.x = fma(lt, ot.x, g.x); ot.y = fma(lt, ot.y, g.y);
-        }
-        sc.off_tile[(size_t)c * (nt + 1) + nt] = ot;      // offset at sample q*Mf
-        o.x = fma(pl.lam_N, o.x, gain.x); o.y = fma(pl.lam_N, o.y, gain.y);
+    if (tid == nth - 1) {
+        const double2 pa = s_a[tid]; const double pm = s_m[tid];
+        sc.iq_state[0] = make_double2(fma(pm, st0.x, pa.x), fma(pm, st0.y, pa.y));
     }
 }
 
+// k_iqtiles: thread <-> chunk, offsets at the tile starts from the chunk-start offset.
+__global__ void __launch_bounds__(128)
+k_iqtiles(const __grid_constant__ DevPlan pl, Scratch sc, int nchunks)
+{
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= nchunks) return;
+    const int nt = pl.ntiles;
+    const double2 *ta = sc.tile_agg + (size_t)c * nt;
+    double2 *ot = sc.off_tile + (size_t)c * (nt + 1);
+    double2 o = ot[0];
+    int t = 0;
+    for (; t + 8 <= nt; t += 8) {
+        double2 g[8];
+#pragma unroll
+        for (int i = 0; i < 8; i++) g[i] = ta[t + i];
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            ot[t + i] = o;
+            const double lt = pl.lam_tile[(t + i) == nt - 1 ? 1 : 0];
+            o.x = fma(lt, o.x, g[i].x); o.y = fma(lt, o.y, g[i].y);
+        }
+    }
+    for (; t < nt; t++) {
+        ot[t] = o;
+        const double lt = pl.lam_tile[t == nt - 1 ? 1 : 0];
+        const double2 g = ta[t];
+        o.x = fma(lt, o.x, g.x); o.y = fma(lt, o.y, g.y);
+    }
+    ot[nt] = o;      // offset at sample q*Mf
+}
+
 // ----------------------------------------------------------------------------------- k_fixup
-// One CTA per (chunk, row).  Warp 0: lanes 0..7 <-> poles run the head, the cross-tile carries,
-// the end segment and the boundary vector zeta; then all threads emit y[k].
+// One CTA per (chunk, row).  Warp 0: raw head / end-window samples are fetched by all lanes at
+// once, then lanes 0..7 <-> poles run the head, the cross-tile carries, the end segment and the
+// boundary vector zeta; then all threads emit y[k].
 template <int ENC>
 __global__ void __launch_bounds__(128)
 k_fixup(const __grid_constant__ DevPlan pl, Scratch sc, const uint8_t *__restrict__ raw, int nchunks)
@@ -292,47 +425,62 @@ k_fixup(const __grid_constant__ DevPlan pl, Scratch sc, const uint8_t *__restric
     const int chunk = blockIdx.x / pl.R, r = blockIdx.x % pl.R;
     if (chunk >= nchunks) return;
     const int nt = pl.ntiles, edge = pl.edge, q = pl.q;
-    const uint8_t *rawc = raw + (size_t)chunk * pl.N * 2 * pl.itemsize;
+    const uint8_t *rawc = raw + (size_t)chunk * pl.N * pl.sb;
     const double2 *offt = sc.off_tile + (size_t)chunk * (nt + 1);
     const double2 *aggr = sc.agg + ((size_t)chunk * pl.R + r) * nt * 16;
     double2 *carry = sc.carry + ((size_t)chunk * pl.R + r) * (nt + 1) * 16;
     double2 *yrow = sc.y + ((size_t)chunk * pl.R + r) * pl.M;
     const double2 *T1r = pl.T1 + (size_t)r * nt;
     double2 *s_h = s_x, *s_e = s_x + (edge + 1);
+    const bool iq = pl.correct_iq != 0;
 
     if (threadIdx.x < 32) {
         const int lane = threadIdx.x;
-        // corrected + shifted head and end-window samples (lane 0 and lane 1, serial recurrences)
-        if (lane == 0) {
-            double2 o = pl.correct_iq ? offt[0] : make_double2(0.0, 0.0);
-            for (int n = 0; n <= edge; n++) {
-                double2 z = decode_sample<ENC>(pl, rawc, n);
-                double2 x = csub(z, o);
-                o.x = fma(x.x, pl.Liq, o.x); o.y = fma(x.y, pl.Liq, o.y);
-                s_h[n] = cmul(x, pl.Ehead[(size_t)r * (edge + 1) + n]);
-            }
-        } else if (lane == 1) {
-            double2 o = pl.correct_iq ? offt[nt] : make_double2(0.0, 0.0);
-            const long n0 = pl.N - 1 - edge;
-            for (int i = 0; i < pl.nend; i++) {
-                const long n = pl.ws + i;
-                double2 x;
-                if (n < (long)q * pl.Mf) {
-                    x = sc.tailwin[(size_t)chunk * (edge + 1) + (n - n0)];
-                    if (pl.correct_iq) {
-                        const int t = (int)((n / q) / SDRB_TB);
-                        const double lp = pow(pl.lam, (double)(n - (long)t * SDRB_TB * q));
-                        x.x = fma(-lp, offt[t].x, x.x); x.y = fma(-lp, offt[t].y, x.y);
-                    }
-                } else {
-                    double2 z = decode_sample<ENC>(pl, rawc, n);
-                    x = csub(z, o);
-                    o.x = fma(x.x, pl.Liq, o.x); o.y = fma(x.y, pl.Liq, o.y);
+        // fetch: raw head samples, and the end window (tile-local-corrected inside full blocks,
+        // raw in the partial block); every load is independent
+        const long n0 = pl.N - 1 - edge;
+        for (int n = lane; n <= edge; n += 32) s_h[n] = decode_sample<ENC>(pl, rawc, n);
+        for (int i = lane; i < pl.nend; i += 32) {
+            const long n = pl.ws + i;
+            double2 x;
+            if (n < (long)q * pl.Mf) {
+                x = sc.tailwin[(size_t)chunk * (edge + 1) + (n - n0)];
+                if (iq) {
+                    const int t = (int)((n / q) / SDRB_TB);
+                    const double lp = pow(pl.lam, (double)(n - (long)t * SDRB_TB * q));
+                    const double2 ot = offt[t];
+                    x.x = fma(-lp, ot.x, x.x); x.y = fma(-lp, ot.y, x.y);
                 }
-                s_e[i] = cmul(x, pl.Eend[(size_t)r * pl.nend + i]);
+            } else {
+                x = decode_sample<ENC>(pl, rawc, n);
             }
+            s_e[i] = x;
         }
         __syncwarp();
+        // serial IQ recurrences over the few raw samples (head from the chunk-start offset,
+        // partial block from the offset at q*Mf), then the NCO phases
+        if (iq) {
+            if (lane == 0) {
+                double2 o = offt[0];
+                for (int n = 0; n <= edge; n++) {
+                    const double2 x = csub(s_h[n], o);
+                    o.x = fma(x.x, pl.Liq, o.x); o.y = fma(x.y, pl.Liq, o.y);
+                    s_h[n] = x;
+                }
+            } else if (lane == 1 && pl.rem) {
+                double2 o = offt[nt];
+                for (int i = pl.nend - pl.rem; i < pl.nend; i++) {
+                    const double2 x = csub(s_e[i], o);
+                    o.x = fma(x.x, pl.Liq, o.x); o.y = fma(x.y, pl.Liq, o.y);
+                    s_e[i] = x;
+                }
+            }
+            __syncwarp();
+        }
+        for (int n = lane; n <= edge; n += 32) s_h[n] = cmul(s_h[n], pl.Ehead[(size_t)r * (edge + 1) + n]);
+        for (int i = lane; i < pl.nend; i += 32) s_e[i] = cmul(s_e[i], pl.Eend[(size_t)r * pl.nend + i]);
+        __syncwarp();
+
         const int i = lane & 7;                       // pole handled by this lane (lanes >= 8 mirror)
         const double2 p = pl.p[i];
         // head: odd extension, zi, edge samples -> state at n = edge
@@ -348,7 +496,7 @@ k_fixup(const __grid_constant__ DevPlan pl, Scratch sc, const uint8_t *__restric
             const int kind = (t == nt - 1) ? 1 : 0;
             const int cnt = kind ? pl.cnt_last : SDRB_TB;
             double2 add = aggr[(size_t)t * 16 + i];
-            if (pl.correct_iq) {
+            if (iq) {
                 const double2 s = make_double2(-offt[t].x, -offt[t].y);
                 add = cfma(s, pl.PsiW[((size_t)kind * pl.R + r) * 8 + i], add);
             }
@@ -361,16 +509,16 @@ k_fixup(const __grid_constant__ DevPlan pl, Scratch sc, const uint8_t *__restric
         const double2 xN1 = s_e[pl.nend - 1];
         double2 wL1 = w, last = make_double2(0.0, 0.0);
         for (int k = 0; k < nseq; k++) {
-            double2 v = (k < pl.rem) ? s_e[pl.nend - pl.rem + k]
-                                     : csub(cscale(2.0, xN1), s_e[pl.nend - 2 - (k - pl.rem)]);
+            const double2 v = (k < pl.rem) ? s_e[pl.nend - pl.rem + k]
+                                           : csub(cscale(2.0, xN1), s_e[pl.nend - 2 - (k - pl.rem)]);
             if (k == nseq - 1) { wL1 = w; last = v; }
             w = cfma(p, w, v);
         }
         const double2 wL = w;
         double2 T = make_double2(0.0, 0.0);
         for (int k = nseq - 1; k >= 0; k--) {
-            double2 v = (k < pl.rem) ? s_e[pl.nend - pl.rem + k]
-                                     : csub(cscale(2.0, xN1), s_e[pl.nend - 2 - (k - pl.rem)]);
+            const double2 v = (k < pl.rem) ? s_e[pl.nend - pl.rem + k]
+                                           : csub(cscale(2.0, xN1), s_e[pl.nend - 2 - (k - pl.rem)]);
             T = cfma(p, T, v);
         }
         const double2 Tend = T;
@@ -381,8 +529,7 @@ k_fixup(const __grid_constant__ DevPlan pl, Scratch sc, const uint8_t *__restric
         double2 zeta = cmul(pl.zhat[i], yfL1);
         for (int l = 0; l < 8; l++) {
             const double2 wl = shfl_c(wL, l);
-            const double2 xv = pl.xi[i * 8 + l];
-            zeta = csub(zeta, cmul(xv, wl));
+            zeta = csub(zeta, cmul(pl.xi[i * 8 + l], wl));
         }
         if (lane < 8) s_zeta[i] = zeta;
         if (pl.rem) {
@@ -401,7 +548,7 @@ k_fixup(const __grid_constant__ DevPlan pl, Scratch sc, const uint8_t *__restric
             const int kind = (t == nt - 1) ? 1 : 0;
             const int cnt = kind ? pl.cnt_last : SDRB_TB;
             double2 add = aggr[(size_t)t * 16 + 8 + i];
-            if (pl.correct_iq) {
+            if (iq) {
                 const double2 s = make_double2(-offt[t].x, -offt[t].y);
                 add = cfma(s, pl.PsiT[((size_t)kind * pl.R + r) * 8 + i], add);
             }
@@ -417,7 +564,7 @@ k_fixup(const __grid_constant__ DevPlan pl, Scratch sc, const uint8_t *__restric
         const int kind = (t == nt - 1) ? 1 : 0;
         const int cnt = kind ? pl.cnt_last : SDRB_TB;
         double2 v = ypr[k];
-        if (pl.correct_iq) {
+        if (iq) {
             const double2 s = make_double2(-offt[t].x, -offt[t].y);
             v = cfma(s, pl.psiY[((size_t)kind * pl.R + r) * SDRB_TB + l], v);
         }
@@ -510,8 +657,6 @@ k_demod(const __grid_constant__ DevPlan pl, const double2 *__restrict__ yall, do
                 dst[k] = v;
             }
             __syncthreads();
-            // dst holds Y (length M); inverse FFT ping-pongs between dst and src... src has only
-            // M entries when it is bufA/bufB of size M: both buffers are M long.
             double2 *s2 = dst, *d2 = src;
             for (int Ns = 1; Ns < M; Ns <<= 1) {
                 fft_pass(s2, d2, M, Ns, true, pl);
@@ -540,19 +685,51 @@ k_demod(const __grid_constant__ DevPlan pl, const double2 *__restrict__ yall, do
         for (int k = threadIdx.x; k < M; k += blockDim.x) z[k] = y[k].y;
     }
     __syncthreads();
-    // output low-pass: scipy.signal.sosfilt, zero initial state, SciPy's operation order
-    if (apply_sos && pl.nsec_out > 0 && threadIdx.x == 0) {
-        double z0[4] = {0, 0, 0, 0}, z1[4] = {0, 0, 0, 0};
-        for (int k = 0; k < M; k++) {
+    // output low-pass (scipy.signal.sosfilt, zero initial state) in 32 segments: each lane of
+    // warp 0 runs SciPy's DF2T recurrence over its segment from a zero state, the segment-end
+    // states are chained with A^Lseg, and every sample then gets c A^i s_in of its segment.
+    if (apply_sos && pl.nsec_out > 0 && threadIdx.x < 32) {
+        const int lane = threadIdx.x, Ls = pl.sos_Lseg, ns = pl.sos_ns, nsec = pl.nsec_out;
+        const int lo = min(M, lane * Ls), hi = min(M, lo + Ls);
+        double st[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        for (int k = lo; k < hi; k++) {
             double xc = z[k];
-            for (int s = 0; s < pl.nsec_out; s++) {
-                const double *cf = pl.out_sos + 6 * s;
-                const double xn = __dadd_rn(__dmul_rn(cf[0], xc), z0[s]);
-                z0[s] = __dadd_rn(__dadd_rn(__dmul_rn(cf[1], xc), -__dmul_rn(cf[4], xn)), z1[s]);
-                z1[s] = __dadd_rn(__dmul_rn(cf[2], xc), -__dmul_rn(cf[5], xn));
-                xc = xn;
+#pragma unroll
+            for (int s = 0; s < 4; s++) {
+                if (s < nsec) {
+                    const double *cf = pl.out_sos + 6 * s;
+                    const double xn = __dadd_rn(__dmul_rn(cf[0], xc), st[2 * s]);
+                    st[2 * s] = __dadd_rn(__dadd_rn(__dmul_rn(cf[1], xc), -__dmul_rn(cf[4], xn)), st[2 * s + 1]);
+                    st[2 * s + 1] = __dadd_rn(__dmul_rn(cf[2], xc), -__dmul_rn(cf[5], xn));
+                    xc = xn;
+                }
             }
             z[k] = xc;
+        }
+        // chain: s_in(seg+1) = A^Ls s_in(seg) + s_loc(seg); every lane walks the chain and keeps
+        // the value that belongs to its own segment
+        double sin_mine[8] = {0, 0, 0, 0, 0, 0, 0, 0}, cur[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        for (int seg = 0; seg < 32; seg++) {
+            if (seg == lane) {
+#pragma unroll
+                for (int a = 0; a < 8; a++) sin_mine[a] = cur[a];
+            }
+            double nxt[8];
+#pragma unroll
+            for (int a = 0; a < 8; a++) {
+                double v = (a < ns) ? __shfl_sync(0xffffffffu, st[a], seg) : 0.0;
+                if (a < ns)
+                    for (int b = 0; b < ns; b++) v = fma(pl.sos_AL[a * ns + b], cur[b], v);
+                nxt[a] = v;
+            }
+#pragma unroll
+            for (int a = 0; a < 8; a++) cur[a] = nxt[a];
+        }
+        for (int k = lo; k < hi; k++) {
+            const double *ca = pl.sos_CA + (size_t)(k - lo) * ns;
+            double v = z[k];
+            for (int a = 0; a < ns; a++) v = fma(ca[a], sin_mine[a], v);
+            z[k] = v;
         }
     }
     __syncthreads();

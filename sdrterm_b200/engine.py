@@ -61,7 +61,18 @@ class Engine:
             put(name, arr)
         put('out_sos', pl.out_sos if pl.out_sos is not None else np.zeros(6))
         tab.g0, tab.d, tab.k_bnd = m.g0, m.d, int(pl.k_bnd)
-        tab.lam, tab.lam_q = pl.lam, pl.lam_q
+        tab.lam, tab.lam_q, tab.lam_inv = pl.lam, pl.lam_q, pl.lam_inv
+        tab.RL = int(pl.RL)
+        for i in range(8):
+            tab.run_len[i] = int(pl.run_len[i])
+            tab.lam_run[i] = float(pl.lam_run[i])
+        nco = np.ascontiguousarray(pl.use_nco, dtype=np.uint8)
+        self._keep.append(nco)
+        tab.use_nco = nco.ctypes.data_as(C.POINTER(C.c_uint8))
+        tab.sos_Lseg = int(pl.sos_Lseg)
+        if pl.sos_AL is not None:
+            put('sos_AL', pl.sos_AL)
+            put('sos_CA', pl.sos_CA)
         tab.lam_N = float(pl.lam_N)
         tab.lam_tile[0], tab.lam_tile[1] = float(pl.lam_tile[0]), float(pl.lam_tile[1])
         if pl.fm_interp is not None:
@@ -119,6 +130,19 @@ class Engine:
     def process_device(self, raw_ptr: int, nchunks: int, out_ptr: int, stream: int = 0) -> None:
         """Device pointers in/out; only enqueues work on ``stream``."""
         nat.check(nat.lib().sdrb_process_device(self._h, raw_ptr, nchunks, out_ptr, stream), self._h)
+
+    def process_device_phases(self, raw_ptr: int, nchunks: int, out_ptr: int, phases: int,
+                              stream: int = 0) -> None:
+        nat.check(nat.lib().sdrb_process_device_phases(self._h, raw_ptr, nchunks, out_ptr, stream,
+                                                       phases), self._h)
+
+    def set_profiling(self, on: bool) -> None:
+        nat.check(nat.lib().sdrb_set_profiling(self._h, int(on)), self._h)
+
+    def kernel_times(self) -> list[float]:
+        ms = (C.c_float * 4)()
+        nat.check(nat.lib().sdrb_kernel_times(self._h, ms), self._h)
+        return [float(v) for v in ms]
 
     def decimated(self, nchunks: int) -> np.ndarray:
         """Complex decimator output of the last batch: (nchunks, R, M)."""

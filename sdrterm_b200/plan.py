@@ -161,6 +161,10 @@ class Plan:
     lam_j: np.ndarray      # (q+1,) lam^j
     lam_q: float
     lam_N: float
+    lam_inv: float         # 1/lam (backward EMA over the descending half of a block)
+    RL: int                # pairs per DMMA k-lane = ceil(Hq/4): lane k owns pairs [k*RL, (k+1)*RL)
+    run_len: np.ndarray    # (8,) samples per run, in sample order (4 ascending + 4 descending runs)
+    lam_run: np.ndarray    # (8,) lam^run_len
     # normalisation (read_file.py:82-96), None when off
     norm: tuple | None
     # per row
@@ -184,6 +188,9 @@ class Plan:
     out_sos: np.ndarray | None
     big_endian_out: bool
     fm_interp: np.ndarray | None = None   # (M, M>>1) dense resample matrix, non-power-of-two FM only
+    sos_Lseg: int = 0                     # output SOS evaluated in 32 segments of this length
+    sos_AL: np.ndarray | None = None      # (ns, ns) A^Lseg of the output cascade (ns = 2*sections)
+    sos_CA: np.ndarray | None = None      # (Lseg, ns) c A^i
 
     @property
     def chunk_bytes(self) -> int:
@@ -252,6 +259,15 @@ def build_plan(fs: int, enc: str, dec: int, rows_hz, *, simo: bool = False, swap
     lam_j = np.array([float(mlam ** j) for j in range(q + 1)])
     lam_q = float(mlam ** q)
     lam_N = float(mlam ** N)
+    lam_inv = float(1 / mlam)
+    RL = -(-Hq // 4)
+    run_len = np.zeros(8, dtype=np.int64)
+    for k in range(4):
+        a0, a1 = min(k * RL, Hq), min((k + 1) * RL, Hq)
+        run_len[k] = a1 - a0
+        run_len[7 - k] = (q - a0) - max(q - a1, Hq)
+    assert run_len.sum() == q
+    lam_run = np.array([float(mlam ** int(v)) for v in run_len])
     norm = None
     if normalize:
         dom = {'B': (0, 255), 'h': (-32768, 32767), 'b': (-128, 127),
@@ -315,6 +331,19 @@ def build_plan(fs: int, enc: str, dec: int, rows_hz, *, simo: bool = False, swap
                        fs=fs // q), dtype=np.float64)
     elif demod not in ('re', 'im'):
         raise ValueError(f'Invalid demod type {demod}')
+    sos_Lseg, sos_AL, sos_CA = 0, None, None
+    if out_sos is not None:
+        sos_Lseg = -(-M // 32)
+        mp.mp.dps = 40
+        A_, b_, c_, d_ = _cascade_state_space(out_sos)
+        ns = A_.rows
+        AL = A_ ** sos_Lseg
+        sos_AL = np.array([[float(AL[i, j]) for j in range(ns)] for i in range(ns)])
+        sos_CA = np.zeros((sos_Lseg, ns))
+        cur = c_.copy()
+        for i in range(sos_Lseg):
+            sos_CA[i] = [float(cur[0, j]) for j in range(ns)]
+            cur = cur * A_
     fm_interp = None
     h = M >> 1
     if demod == 'fm' and not (M == 2 * h and h & (h - 1) == 0):
@@ -323,9 +352,9 @@ def build_plan(fs: int, enc: str, dec: int, rows_hz, *, simo: bool = False, swap
     return Plan(enc=enc, swap=bool(swap), fs=fs, q=q, N=N, edge=edge, L=L, Mf=Mf, rem=rem, M=M,
                 ntiles=ntiles, cnt_last=cnt_last, Hq=Hq, rows_hz=rows_hz, R=R, sos=sos, zi=zi,
                 modes=modes, P=P, Ec=Ec, Oc=Oc, Ppow=Ppow, bnd=bnd, k_bnd=k_bnd,
-                correct_iq=bool(correct_iq), Liq=Liq, lam=lam, lam_j=lam_j, lam_q=lam_q, lam_N=lam_N,
+                correct_iq=bool(correct_iq), Liq=Liq, lam=lam, lam_j=lam_j, lam_q=lam_q, lam_N=lam_N, lam_inv=lam_inv, RL=RL, run_len=run_len, lam_run=lam_run,
                 norm=norm, w=w, use_nco=use_nco, T2=T2, T3=T3, T1=T1, Ehead=Ehead, Eend=Eend,
                 ws=ws, nend=nend, PhiF=PhiF, PhiG=PhiG, PsiW=PsiW, PsiT=PsiT, psiY=psiY,
                 lam_tile=lam_tile, demod=demod, out_sos=out_sos,
                 big_endian_out=bool(simo if big_endian_out is None else big_endian_out),
-                fm_interp=fm_interp)
+                fm_interp=fm_interp, sos_Lseg=sos_Lseg, sos_AL=sos_AL, sos_CA=sos_CA)

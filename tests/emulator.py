@@ -27,6 +27,78 @@ def decode(pl: Plan, raw: np.ndarray) -> np.ndarray:
     return z
 
 
+def iq_runs(pl: Plan, zb: np.ndarray):
+    """Block-local IQ correction as k_main evaluates it: each block is cut into 8 runs (4 ascending
+    over the first half, 4 over the second); run aggregates are scanned to give the EMA state at
+    every run boundary; the first-half runs then advance the EMA forward from their start, the
+    second-half runs recover it BACKWARD from their end (acc_j = (acc_{j+1} - z_j)/lam), which is
+    the order in which the even/odd pairing consumes the samples."""
+    q, Hq, RL = pl.q, pl.Hq, pl.RL
+    Mf = zb.shape[0]
+    bounds = []
+    for k in range(4):
+        a0, a1 = min(k * RL, Hq), min((k + 1) * RL, Hq)
+        bounds.append((a0, a1))
+    dbounds = [(max(q - a1, Hq), q - a0) for (a0, a1) in bounds]      # per k
+    runs = bounds + [dbounds[3], dbounds[2], dbounds[1], dbounds[0]]   # sample order
+    agg = np.zeros((8, Mf), dtype=np.complex128)
+    for i, (lo, hi) in enumerate(runs):
+        a = np.zeros(Mf, dtype=np.complex128)
+        for j in range(lo, hi):
+            a = pl.lam * a + zb[:, j]
+        agg[i] = a
+        assert hi - lo == pl.run_len[i]
+    A = np.zeros((9, Mf), dtype=np.complex128)
+    for i in range(8):
+        A[i + 1] = pl.lam_run[i] * A[i] + agg[i]
+    zp = np.empty_like(zb)
+    for k in range(4):
+        acc = A[k].copy()
+        for j in range(*bounds[k]):
+            zp[:, j] = zb[:, j] - pl.Liq * acc
+            acc = pl.lam * acc + zb[:, j]
+        acc = A[8 - k].copy()
+        lo, hi = dbounds[k]
+        for j in range(hi - 1, lo - 1, -1):
+            acc = (acc - zb[:, j]) * pl.lam_inv
+            zp[:, j] = zb[:, j] - pl.Liq * acc
+    return zp, A[8]
+
+
+def sos_segments(pl: Plan, z: np.ndarray) -> np.ndarray:
+    """Output low-pass as k_demod evaluates it: 32 segments run the DF2T recurrence from a zero
+    state, the segment-end states are chained with A^Lseg, and each sample then receives the
+    zero-input response c A^i s_in of its segment's true initial state."""
+    sos, Ls = pl.out_sos, pl.sos_Lseg
+    R, M = z.shape
+    ns = 2 * sos.shape[0]
+    out = np.empty_like(z)
+    nseg = -(-M // Ls)
+    sloc = np.zeros((nseg, R, ns))
+    for g in range(nseg):
+        lo, hi = g * Ls, min(M, (g + 1) * Ls)
+        st = np.zeros((R, ns))
+        for i in range(lo, hi):
+            xc = z[:, i]
+            for s in range(sos.shape[0]):
+                b0, b1, b2, _, a1, a2 = sos[s]
+                xn = b0 * xc + st[:, 2 * s]
+                st[:, 2 * s] = (b1 * xc - a1 * xn) + st[:, 2 * s + 1]
+                st[:, 2 * s + 1] = b2 * xc - a2 * xn
+                xc = xn
+            out[:, i] = xc
+        if hi - lo == Ls:
+            sloc[g] = st
+        else:   # short last segment: its end state is never used
+            sloc[g] = st
+    sin = np.zeros((R, ns))
+    for g in range(nseg):
+        lo, hi = g * Ls, min(M, (g + 1) * Ls)
+        out[:, lo:hi] += sin @ pl.sos_CA[:hi - lo].T
+        sin = sin @ pl.sos_AL.T + sloc[g]
+    return out
+
+
 def emu_main(pl: Plan, z: np.ndarray):
     """z: decoded chunk (N,).  Returns dict of per-chunk arrays written by the main kernel."""
     q, Mf, nt = pl.q, pl.Mf, pl.ntiles
@@ -39,6 +111,11 @@ def emu_main(pl: Plan, z: np.ndarray):
         zp[:, j] = zb[:, j] - pl.Liq * acc
         acc = pl.lam * acc + zb[:, j]
     blk_agg = pl.Liq * acc                     # offset gained over one block from zero
+    if pl.correct_iq:
+        zp2, acc2 = iq_runs(pl, zb)            # the kernel's run-wise evaluation of the same thing
+        assert np.max(np.abs(zp2 - zp)) <= 1e-13 * max(1.0, np.max(np.abs(zb)))
+        assert np.max(np.abs(acc2 - acc)) <= 1e-12 * max(1.0, np.max(np.abs(acc)))
+        zp = zp2
     # tile-local block offsets (zero at tile start) and tile aggregates
     off_loc = np.zeros(Mf, dtype=np.complex128)
     tile_agg = np.zeros(nt, dtype=np.complex128)
@@ -235,6 +312,7 @@ def emu_demod(pl: Plan, y: np.ndarray) -> np.ndarray:
     else:
         z = y.imag.copy()
     if pl.out_sos is not None:
+        zseg = sos_segments(pl, z)
         for s in range(pl.out_sos.shape[0]):
             b0, b1, b2, _, a1, a2 = pl.out_sos[s]
             z0 = np.zeros(z.shape[0])
@@ -245,6 +323,8 @@ def emu_demod(pl: Plan, y: np.ndarray) -> np.ndarray:
                 z0 = (b1 * xc - a1 * xn) + z1
                 z1 = b2 * xc - a2 * xn
                 z[:, i] = xn
+        assert np.max(np.abs(zseg - z)) <= 1e-12 * max(1e-300, np.max(np.abs(z)))
+        z = zseg
     return z
 
 
