@@ -392,11 +392,12 @@ def run_cuda_arm(args):
                 traffic = json.load(open(tpath)).get('k_main_dram_bytes_per_launch')
             except Exception:
                 traffic = None
-        roof = {'bound': 'hbm', 'kernel': 'k_main', 'achieved': ach, 'peak': peak, 'unit': 'GB/s',
+        kname = 'k_tc' if eng.tc is not None else 'k_main'
+        roof = {'bound': 'hbm', 'kernel': kname, 'achieved': ach, 'peak': peak, 'unit': 'GB/s',
                 'frac': ach / peak, 'traffic': traffic, 'peak_source': peak_src,
                 'algorithmic_bytes_per_sample': bytes_per_sample,
-                'kernel_ms': {'k_main': kavg[0], 'k_iqscan': kavg[1], 'k_fixup': kavg[2], 'k_demod': kavg[3]},
-                'note': 'the chain is FP64-issue-bound (DFMA/DMMA pipe ~17 TFMA/s measured), see DESIGN.md'}
+                'kernel_ms': {kname: kavg[0], 'k_iqscan': kavg[1], 'k_fixup': kavg[2], 'k_demod': kavg[3]},
+                'note': 'dominant kernel = block front end; k_tc = tcgen05 int8 GEMM over the raw bytes + FP64 epilogue (DESIGN.md 3.4)'}
         if simo is not None:
             simo['frac_hbm'] = simo['input_msps'] * 1e6 * simo['bytes_per_sample'] / 1e9 / peak
     cpu = None

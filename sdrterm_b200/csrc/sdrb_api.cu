@@ -11,6 +11,7 @@
 
 #include "../../include/sdrterm_b200.h"
 #include "sdrb_kernels.cuh"
+#include "sdrb_tc.cuh"
 
 namespace {
 
@@ -44,6 +45,12 @@ struct sdrb_handle {
     cudaEvent_t pev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
     bool pev_valid[5] = {false, false, false, false, false};
     std::string error;
+    // tensor-core block front end (k_tc)
+    bool tc_on = false;
+    TcDev tc{};
+    CUtensorMap map_b{};
+    size_t tc_smem = 0;
+    int num_sms = 148;
 };
 
 namespace {
@@ -121,7 +128,100 @@ std::vector<double2> make_twiddles(int n)
     return tw;
 }
 
+int env_int(const char *name, int dflt);
+int launch_tc(sdrb_handle *h, const uint8_t *raw, size_t nch, cudaStream_t st, bool iq);
+
 enum { PH_MAIN = 1, PH_IQSCAN = 2, PH_FINISH = 4, PH_ALL = 7 };
+
+// ------------------------------------------------------------------ tensor-core front end
+typedef CUresult (*encode_tiled_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                    const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+encode_tiled_fn get_encode_tiled()
+{
+    static encode_tiled_fn fn = nullptr;
+    if (!fn) {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<encode_tiled_fn>(p);
+    }
+    return fn;
+}
+
+// 2-D byte tensor [rows][K] (row pitch K), box = 128 bytes x box_rows, 128B swizzle.
+int make_byte_map(sdrb_handle *h, CUtensorMap *map, const void *base, uint64_t rows, uint32_t K, uint32_t box_rows)
+{
+    encode_tiled_fn enc = get_encode_tiled();
+    if (!enc) return fail(h, SDRB_ERR_CUDA, "cuTensorMapEncodeTiled is not available");
+    cuuint64_t dims[2] = {K, rows};
+    cuuint64_t strides[1] = {K};
+    cuuint32_t box[2] = {128, box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void *>(base), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(h, SDRB_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
+    return 0;
+}
+
+template <bool IQ, int NCOL>
+int launch_tc_t(sdrb_handle *h, const CUtensorMap &map_a, size_t nch, int n_mtiles, cudaStream_t st)
+{
+    const int grid = std::min(h->num_sms, n_mtiles);
+    k_tc<IQ, NCOL><<<grid, TC_THREADS, h->tc_smem, st>>>(h->pl, h->tc, h->sc, map_a, h->map_b, (int)nch, n_mtiles);
+    return 0;
+}
+
+int launch_tc(sdrb_handle *h, const uint8_t *raw, size_t nch, cudaStream_t st, bool iq)
+{
+    const uint64_t rows = (uint64_t)nch * h->pl.Mf;
+    CUtensorMap map_a;
+    int rc = make_byte_map(h, &map_a, raw, rows, (uint32_t)h->tc.K, 128);
+    if (rc) return rc;
+    const int n_mtiles = (int)((rows + 127) / 128);
+    if (h->tc.ncol == 7) return iq ? launch_tc_t<true, 7>(h, map_a, nch, n_mtiles, st) : launch_tc_t<false, 7>(h, map_a, nch, n_mtiles, st);
+    return iq ? launch_tc_t<true, 6>(h, map_a, nch, n_mtiles, st) : launch_tc_t<false, 6>(h, map_a, nch, n_mtiles, st);
+}
+
+int setup_tc(sdrb_handle *h, const sdrb_tables *tab)
+{
+    if (!tab->tc_enable || env_int("SDRB_NO_TC", 0)) return 0;
+    if (h->pl.R != 1 || (tab->tc_K != 128 && tab->tc_K != 256) || tab->tc_nout != TC_MAX_OUT ||
+        (tab->tc_ncol != 6 && tab->tc_ncol != 7) || tab->tc_npad > 256 || tab->tc_npad % 16 ||
+        tab->tc_npad < tab->tc_nout * tab->tc_ncol || tab->tc_K != h->pl.q * h->pl.sb || h->pl.rem != 0 ||
+        h->pl.cnt_last != SDRB_TB || h->pl.q < h->pl.edge + 1 || h->pl.normalize || !tab->tc_Bq || !tab->tc_scale || !tab->tc_cst)
+        return fail(h, SDRB_ERR_ARG, "tensor-core tables do not match the configuration");
+    TcDev &tc = h->tc;
+    tc.K = tab->tc_K; tc.isz = tab->tc_isz; tc.ncol = tab->tc_ncol; tc.nout = tab->tc_nout; tc.npad = tab->tc_npad;
+    tc.nregion = tc.K / 128;
+    memcpy(&tc.xor_word, tab->tc_xor, 4);
+    for (int i = 0; i < 16; i++)
+        if (tab->tc_xor[i] != tab->tc_xor[i & 3]) return fail(h, SDRB_ERR_ARG, "XOR pattern is not 4-periodic");
+    tc.idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(tc.npad >> 3) << 17) | ((128u >> 4) << 24);
+    for (int o = 0; o < tc.nout; o++) {
+        tc.scale[o] = tab->tc_scale[o];
+        tc.scale24[o] = tab->tc_scale[o] * 16777216.0;
+        tc.cst[o] = tab->tc_cst[o];
+    }
+    const int8_t *d_bq = nullptr;
+    int rc = upload(h, tab->tc_Bq, (size_t)tc.npad * tc.K, &d_bq);
+    if (rc) return rc;
+    rc = make_byte_map(h, &h->map_b, d_bq, (uint64_t)tc.npad, (uint32_t)tc.K, (uint32_t)tc.npad);
+    if (rc) return rc;
+    h->tc_smem = tc_smem_bytes(tc.npad, tc.nregion);
+    if (h->tc_smem > 227 * 1024) return fail(h, SDRB_ERR_ARG, "k_tc needs %zu bytes of shared memory", h->tc_smem);
+    cudaDeviceProp prop;
+    CK(h, cudaGetDeviceProperties(&prop, h->cfg.device));
+    h->num_sms = prop.multiProcessorCount;
+    CK(h, cudaFuncSetAttribute(k_tc<true, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->tc_smem));
+    CK(h, cudaFuncSetAttribute(k_tc<false, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->tc_smem));
+    CK(h, cudaFuncSetAttribute(k_tc<true, 7>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->tc_smem));
+    CK(h, cudaFuncSetAttribute(k_tc<false, 7>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->tc_smem));
+    h->tc_on = true;
+    return 0;
+}
 
 template <int ENC, bool IQ>
 int launch_chain_t(sdrb_handle *h, const uint8_t *raw, size_t nch, double *out, cudaStream_t st, int phases)
@@ -134,8 +234,13 @@ int launch_chain_t(sdrb_handle *h, const uint8_t *raw, size_t nch, double *out, 
     if (prof) for (int i = 0; i < 5; i++) h->pev_valid[i] = false;
     mark(0);
     if (phases & PH_MAIN) {
-        const int groups = (pl.ntiles + h->tpc - 1) / h->tpc;
-        k_main<ENC, IQ><<<(unsigned)(nch * groups), 32 * h->warps, h->main_smem, st>>>(pl, h->sc, raw, (int)nch, h->tpc);
+        if (h->tc_on && ((uintptr_t)raw & 15) == 0) {
+            int rc = launch_tc(h, raw, nch, st, IQ);
+            if (rc) return rc;
+        } else {
+            const int groups = (pl.ntiles + h->tpc - 1) / h->tpc;
+            k_main<ENC, IQ><<<(unsigned)(nch * groups), 32 * h->warps, h->main_smem, st>>>(pl, h->sc, raw, (int)nch, h->tpc);
+        }
         h->launches++;
     }
     mark(1);
@@ -364,6 +469,7 @@ int sdrb_create(const sdrb_config *cfg, const sdrb_tables *tab, sdrb_handle **ou
         UP(dalloc(h, nch * R * 2 * M, &sc.fftbuf));
         UP(dalloc(h, nch * R * M, &sc.zrow));
     }
+    UP(setup_tc(h, tab));
 #undef UP
     for (int s = 0; s < 2; s++) {
         if (cudaStreamCreateWithFlags(&h->slot[s].stream, cudaStreamNonBlocking) != cudaSuccess ||

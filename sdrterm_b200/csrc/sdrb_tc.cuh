@@ -1,0 +1,423 @@
+// sdrb_tc.cuh -- k_tc: the block front end on the 5th-generation tensor cores (tcgen05, sm_100a).
+//
+// Every per-block quantity of the chain -- decode, byte order, block-local IQ correction, NCO and
+// the 16 modal block sums F_i, G_i plus the IQ-EMA block aggregate E -- is a real-linear functional
+// of the block's integer samples, i.e. one row of a coefficient matrix applied to the block's raw
+// bytes.  sdrterm_b200/plan.py (build_tc) rounds the coefficients to 48-bit fixed point and cuts
+// them into balanced base-256 digits, so that
+//
+//     D[block, NCOL*o + t] = sum_k  rawbyte[block, k] * digit[o, t, k]        (int8 x int8 -> int32)
+//
+// is an EXACT integer GEMM: A = the raw stream itself, viewed as [blocks][K = q*2*itemsize] bytes
+// and brought in by TMA (128B swizzle) without ever being decoded; B = the digit matrix, resident
+// in shared memory; D in tensor memory.  The epilogue warps (lane <-> TMEM lane <-> block) read
+// their rows with tcgen05.ld, recombine the digit columns in int64 -> FP64 (exact up to one
+// rounding) and continue exactly like k_main: tile-local IQ offsets, modal scans in the rotating
+// frame, partial outputs and tile aggregates for k_fixup.
+//
+// Warp roles (384 threads, one CTA per SM, persistent over MMA tiles of 128 blocks = 4 tiles):
+//   warp 0      TMA producer (one lane)
+//   warp 1      TMEM allocation; tcgen05.mma issue (one lane)
+//   warps 2-3   sign fix-up: XOR 0x80 into the bytes that are not the signed top byte, so that
+//               every byte is a valid two's-complement int8 operand (the constant this removes is
+//               added back as cst[o])
+//   warps 4-7   epilogue of accumulator stage 0, warps 8-11 of stage 1 (warp%4 = TMEM lane quarter)
+//
+// Reference behaviour reproduced: src/misc/read_file.py:100-103, src/dsp/demodulation.py:71-79,
+// the block form of scipy.signal.decimate (src/dsp/dsp_processor.py:147).  tests/emulator.py
+// (emu_main_tc) is the numpy twin.
+#pragma once
+#include <cuda.h>
+#include "sdrb_kernels.cuh"
+
+#define TC_MAX_OUT 34
+#define TC_THREADS 384
+#define TC_STAGES 2
+#define TC_REGION_BYTES 16384          // 128 rows x 128 bytes, one SWIZZLE_128B operand slab
+
+struct TcDev {
+    int K, isz, ncol, nout, npad, nregion;
+    uint32_t xor_word;                 // XOR pattern of 4 consecutive stream bytes
+    uint32_t idesc;                    // tcgen05 instruction descriptor (i8 x i8 -> s32, M=128, N=npad)
+    double scale[TC_MAX_OUT];          // 2^-S_o
+    double scale24[TC_MAX_OUT];        // 2^(24-S_o)
+    double cst[TC_MAX_OUT];
+};
+
+__host__ __device__ inline size_t tc_warp_bytes()
+{
+    return main_warp_bytes() + SDRB_TB * sizeof(double2);      // xb + x0s + cl
+}
+__host__ __device__ inline size_t tc_smem_bytes(int npad, int nregion)
+{
+    size_t b = (size_t)nregion * npad * 128;                   // B slabs
+    b += (size_t)TC_STAGES * nregion * TC_REGION_BYTES;        // A stages
+    b += 8 * tc_warp_bytes();
+    b += 32 * sizeof(double2);                                 // PhiF, PhiG
+    b += 16 * sizeof(unsigned long long);                      // mbarriers
+    return b + 1024;                                           // alignment slack
+}
+
+// ------------------------------------------------------------------------------ PTX helpers
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t a, uint32_t cnt)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(a), "r"(cnt));
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t a)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(a) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t a, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(a), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try(uint32_t a, uint32_t parity)
+{
+    uint32_t ok;
+    asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+                 : "=r"(ok) : "r"(a), "r"(parity) : "memory");
+    return ok != 0;
+}
+// Bounded wait: a protocol error traps (and surfaces as a CUDA error) instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t a, uint32_t parity)
+{
+    if (mbar_try(a, parity)) return;
+    const long long t0 = clock64();
+    while (!mbar_try(a, parity))
+        if (clock64() - t0 > 4000000000LL) __trap();
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map, int x, int y, uint32_t bar)
+{
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                 ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(x), "r"(y), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// K-major SWIZZLE_128B shared-memory operand descriptor (8-row atoms of 128 bytes, 1024 B apart).
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr)
+{
+    uint64_t d = (uint64_t)((saddr & 0x3FFFF) >> 4);
+    d |= (uint64_t)1 << 16;                  // leading byte offset (unused for swizzled K-major)
+    d |= (uint64_t)(1024 >> 4) << 32;        // stride byte offset between 8-row atoms
+    d |= (uint64_t)1 << 46;                  // descriptor version (sm_100)
+    d |= (uint64_t)2 << 61;                  // SWIZZLE_128B
+    return d;
+}
+__device__ __forceinline__ void umma_i8(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accum)
+{
+    asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+                 "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n}"
+                 ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accum) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar)
+{
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32])
+{
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                 "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                   "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+                   "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+                   "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+                 : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16])
+{
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+                 "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                   "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                 : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// Exact int64 -> double for |v| < 2^51 without the slow I2F.F64 path: bias into the mantissa of
+// 1.5 * 2^52 and subtract it again.
+__device__ __forceinline__ double i64_to_double(long long v)
+{
+    return __longlong_as_double(v + 0x4338000000000000LL) - 6755399441055744.0;
+}
+
+// Digit columns c[0..NCOL) (most significant first, weight 256 per step) -> value * scale + cst.
+template <int NCOL>
+__device__ __forceinline__ double tc_combine(const uint32_t *c, double s24, double s, double cst)
+{
+    constexpr int NHI = NCOL - 3;
+    long long vhi = (int)c[0];
+#pragma unroll
+    for (int t = 1; t < NHI; t++) vhi = vhi * 256 + (int)c[t];
+    long long vlo = (int)c[NHI];
+#pragma unroll
+    for (int t = NHI + 1; t < NCOL; t++) vlo = vlo * 256 + (int)c[t];
+    return fma(i64_to_double(vhi), s24, i64_to_double(vlo) * s) + cst;
+}
+
+// One complex sample j of tile row `row`, read back from the staged (sign-fixed, swizzled) A tile.
+__device__ __forceinline__ double2 tc_sample(const unsigned char *a_stage, int row, int j, const DevPlan &pl,
+                                             uint32_t xor_word)
+{
+    const int kb = j * pl.sb;
+    const int region = kb >> 7, kin = kb & 127;
+    const unsigned char *p = a_stage + (size_t)region * TC_REGION_BYTES + row * 128 +
+                             ((((kin >> 4) ^ (row & 7)) << 4) | (kin & 15));
+    if (pl.sb == 4) {
+        uint32_t v = *reinterpret_cast<const uint32_t *>(p) ^ xor_word;
+        if (pl.swap) v = __byte_perm(v, 0, 0x2301);
+        if (pl.enc == ENC_h) return make_double2((double)(int16_t)(v & 0xffff), (double)(int16_t)(v >> 16));
+        return make_double2((double)(v & 0xffff), (double)(v >> 16));
+    }
+    const uint32_t v = (uint32_t)(*reinterpret_cast<const uint16_t *>(p)) ^ (xor_word & 0xffffu);
+    if (pl.enc == ENC_b) return make_double2((double)(int8_t)(v & 0xff), (double)(int8_t)(v >> 8));
+    return make_double2((double)(v & 0xff), (double)(v >> 8));
+}
+
+// ------------------------------------------------------------------------------------- k_tc
+template <bool IQ, int NCOL>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+k_tc(const __grid_constant__ DevPlan pl, const __grid_constant__ TcDev tc, Scratch sc,
+     const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+     int nchunks, int n_mtiles)
+{
+    extern __shared__ unsigned char smem_dyn[];
+    unsigned char *smem = reinterpret_cast<unsigned char *>(((uintptr_t)smem_dyn + 1023) & ~(uintptr_t)1023);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nreg = tc.nregion, npad = tc.npad;
+    unsigned char *sB = smem;
+    unsigned char *sA = sB + (size_t)nreg * npad * 128;
+    unsigned char *sW = sA + (size_t)TC_STAGES * nreg * TC_REGION_BYTES;
+    double2 *sPhi = reinterpret_cast<double2 *>(sW + 8 * tc_warp_bytes());
+    unsigned long long *bars = reinterpret_cast<unsigned long long *>(sPhi + 32);
+    __shared__ uint32_t tmem_base_s;
+    // barrier indices
+    const uint32_t bar0 = smem_u32(bars);
+    auto BAR = [&](int kind, int s) { return bar0 + 8u * (uint32_t)(kind * TC_STAGES + s); };
+    enum { B_FULL_A = 0, B_XORED = 1, B_MMA_DONE = 2, B_A_FREE = 3, B_TMEM_FREE = 4, B_BFULL = 5 };
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < TC_STAGES; s++) {
+            mbar_init(BAR(B_FULL_A, s), 1);
+            mbar_init(BAR(B_XORED, s), 2);
+            mbar_init(BAR(B_MMA_DONE, s), 1);
+            mbar_init(BAR(B_A_FREE, s), 4);
+            mbar_init(BAR(B_TMEM_FREE, s), 4);
+        }
+        mbar_init(BAR(B_BFULL, 0), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (threadIdx.x < 32) {
+        if (threadIdx.x < 16) {
+            sPhi[threadIdx.x] = threadIdx.x < 8 ? pl.PhiF[threadIdx.x] : pl.PhiG[threadIdx.x - 8];
+        }
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(&tmem_base_s)) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_s;
+    const int my_iters = (n_mtiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+    const int total_tiles = nchunks * pl.ntiles;
+
+    if (warp == 0) {
+        // ===================================================================== TMA producer
+        if (lane == 0) {
+            mbar_expect_tx(BAR(B_BFULL, 0), (uint32_t)(nreg * npad * 128));
+            for (int rg = 0; rg < nreg; rg++)
+                tma_load_2d(smem_u32(sB + (size_t)rg * npad * 128), &map_b, rg * 128, 0, BAR(B_BFULL, 0));
+            for (int it = 0; it < my_iters; it++) {
+                const int s = it & 1, u = it >> 1;
+                const int mt = blockIdx.x + it * gridDim.x;
+                mbar_wait(BAR(B_A_FREE, s), (u & 1) ^ 1);
+                mbar_expect_tx(BAR(B_FULL_A, s), (uint32_t)(nreg * TC_REGION_BYTES));
+                for (int rg = 0; rg < nreg; rg++)
+                    tma_load_2d(smem_u32(sA + ((size_t)s * nreg + rg) * TC_REGION_BYTES), &map_a, rg * 128, mt * 128,
+                                BAR(B_FULL_A, s));
+            }
+        }
+    } else if (warp == 1) {
+        // ===================================================================== MMA issuer
+        if (lane == 0) {
+            mbar_wait(BAR(B_BFULL, 0), 0);
+            for (int it = 0; it < my_iters; it++) {
+                const int s = it & 1, u = it >> 1;
+                mbar_wait(BAR(B_XORED, s), u & 1);
+                mbar_wait(BAR(B_TMEM_FREE, s), (u & 1) ^ 1);
+                tc_fence_after();
+                const uint32_t d = tmem_base + (uint32_t)(s * 256);
+                const int ksteps = tc.K >> 5;
+                for (int ks = 0; ks < ksteps; ks++) {
+                    const int rg = ks >> 2, kin = (ks & 3) * 32;
+                    const uint64_t da = umma_desc(smem_u32(sA + ((size_t)s * nreg + rg) * TC_REGION_BYTES) + kin);
+                    const uint64_t db = umma_desc(smem_u32(sB + (size_t)rg * npad * 128) + kin);
+                    umma_i8(d, da, db, tc.idesc, ks > 0 ? 1u : 0u);
+                }
+                umma_commit(BAR(B_MMA_DONE, s));
+            }
+        }
+    } else if (warp < 4) {
+        // ===================================================================== sign fix-up
+        const int tx = threadIdx.x - 64;
+        const uint32_t m = tc.xor_word;
+        for (int it = 0; it < my_iters; it++) {
+            const int s = it & 1, u = it >> 1;
+            mbar_wait(BAR(B_FULL_A, s), u & 1);
+            uint4 *base = reinterpret_cast<uint4 *>(sA + (size_t)s * nreg * TC_REGION_BYTES);
+            const int n16 = nreg * (TC_REGION_BYTES / 16);
+#pragma unroll 8
+            for (int i = tx; i < n16; i += 64) {
+                uint4 v = base[i];
+                v.x ^= m; v.y ^= m; v.z ^= m; v.w ^= m;
+                base[i] = v;
+            }
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(BAR(B_XORED, s));
+        }
+    } else {
+        // ===================================================================== epilogue
+        const int g = (warp - 4) >> 2, qd = warp & 3;
+        unsigned char *wbase = sW + (size_t)(warp - 4) * tc_warp_bytes();
+        double *xb = reinterpret_cast<double *>(wbase);
+        double2 *x0s = reinterpret_cast<double2 *>(xb + 32 * SDRB_XSTRIDE);
+        double2 *cl = x0s + SDRB_TB;
+        const int q = pl.q;
+        const int r = 0;
+        for (int it = g; it < my_iters; it += 2) {
+            const int s = it & 1, u = it >> 1;
+            const int mt = blockIdx.x + it * gridDim.x;
+            const int gt = 4 * mt + qd;
+            mbar_wait(BAR(B_MMA_DONE, s), u & 1);
+            tc_fence_after();
+            if (gt >= total_tiles) {
+                __syncwarp();
+                if (lane == 0) { mbar_arrive(BAR(B_A_FREE, s)); mbar_arrive(BAR(B_TMEM_FREE, s)); }
+                continue;
+            }
+            const int chunk = gt / pl.ntiles, t = gt % pl.ntiles;
+            const unsigned char *a_stage = sA + (size_t)s * nreg * TC_REGION_BYTES;
+            const int row = 32 * qd + lane;
+            const uint32_t trow = tmem_base + ((uint32_t)(32 * qd) << 16) + (uint32_t)(s * 256);
+
+            // ---- IQ-EMA block aggregate E -> tile-local block offsets cl[], tile aggregate
+            double2 excl = make_double2(0.0, 0.0);
+            if (IQ) {
+                uint32_t ce[16];
+                tmem_ld16(trow + 32 * NCOL, ce);
+                tmem_ld_wait();
+                const double er = tc_combine<NCOL>(ce, tc.scale24[32], tc.scale[32], tc.cst[32]);
+                const double ei = tc_combine<NCOL>(ce + NCOL, tc.scale24[33], tc.scale[33], tc.cst[33]);
+                double2 inc = make_double2(pl.Liq * er, pl.Liq * ei);
+#pragma unroll
+                for (int i = 0; i < 5; i++) {
+                    const double2 tt = shfl_up_c(inc, 1 << i);
+                    if (lane >= (1 << i)) { inc.x = fma(pl.lamq_pow[i], tt.x, inc.x); inc.y = fma(pl.lamq_pow[i], tt.y, inc.y); }
+                }
+                excl = shfl_up_c(inc, 1);
+                if (lane == 0) excl = make_double2(0.0, 0.0);
+                const double2 tagg = shfl_c(inc, 31);
+                if (lane == 0) sc.tile_agg[(size_t)chunk * pl.ntiles + t] = tagg;
+            }
+            cl[lane] = excl;
+            // ---- first sample of every block; tail window of the chunk's last block
+            x0s[lane] = tc_sample(a_stage, row, 0, pl, tc.xor_word);
+            if (t == pl.ntiles - 1) {
+                const double2 ex31 = shfl_c(excl, 31);
+                const int j0 = q - (pl.edge + 1);
+                const int jt = j0 + lane;
+                const int rowl = 32 * qd + 31;
+                double2 acc = make_double2(0.0, 0.0);
+                if (IQ) {
+                    for (int i = 0; i < q - 1; i++) {
+                        if (i < jt) {
+                            const double2 z = tc_sample(a_stage, rowl, i, pl, tc.xor_word);
+                            acc.x = fma(pl.lam, acc.x, z.x); acc.y = fma(pl.lam, acc.y, z.y);
+                        }
+                    }
+                }
+                if (lane <= pl.edge) {
+                    double2 z = tc_sample(a_stage, rowl, jt, pl, tc.xor_word);
+                    if (IQ) {
+                        z.x = fma(-pl.Liq, acc.x, z.x); z.y = fma(-pl.Liq, acc.y, z.y);
+                        const double lj = pl.lam_j[jt];
+                        z.x = fma(-lj, ex31.x, z.x); z.y = fma(-lj, ex31.y, z.y);
+                    }
+                    sc.tailwin[(size_t)chunk * (pl.edge + 1) + lane] = z;
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(BAR(B_A_FREE, s));
+
+            // ---- modal block sums: digit columns -> FP64, minus the tile-local offset response
+#pragma unroll 1
+            for (int og = 0; og < 8; og++) {
+                uint32_t c[32];
+                tmem_ld32(trow + 4 * NCOL * og, c);
+                tmem_ld_wait();
+#pragma unroll
+                for (int h = 0; h < 2; h++) {
+                    const int o = 4 * og + 2 * h;
+                    double vr = tc_combine<NCOL>(c + (2 * h) * NCOL, tc.scale24[o], tc.scale[o], tc.cst[o]);
+                    double vi = tc_combine<NCOL>(c + (2 * h + 1) * NCOL, tc.scale24[o + 1], tc.scale[o + 1], tc.cst[o + 1]);
+                    if (IQ) {
+                        const double2 ph = sPhi[o >> 1];
+                        vr -= fma(excl.x, ph.x, -excl.y * ph.y);
+                        vi -= fma(excl.x, ph.y, excl.y * ph.x);
+                    }
+                    xb[o * SDRB_XSTRIDE + lane] = vr;
+                    xb[(o + 1) * SDRB_XSTRIDE + lane] = vi;
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(BAR(B_TMEM_FREE, s));
+
+            // ---- tile-local scans in the rotating frame: lanes 0..7 forward poles, 8..15 backward
+            if (lane < 16) {
+                const bool fwd = lane < 8;
+                const double2 Pm = pl.Prot[(size_t)r * 16 + lane];
+                double2 st = make_double2(0.0, 0.0);
+                double *xr = xb + (2 * lane) * SDRB_XSTRIDE, *xi = xr + SDRB_XSTRIDE;
+                for (int step = 0; step < SDRB_TB; step++) {
+                    const int l = fwd ? step : SDRB_TB - 1 - step;
+                    const double2 v = make_double2(xr[l], xi[l]);
+                    const double2 nst = cfma(Pm, st, v);
+                    const double2 o = fwd ? st : nst;
+                    xr[l] = o.x; xi[l] = o.y;
+                    st = nst;
+                }
+                if (fwd) st = cmul(pl.T3[(size_t)r * (SDRB_TB + 1) + SDRB_TB - 1], st);
+                sc.agg[(((size_t)chunk * pl.R + r) * pl.ntiles + t) * 16 + lane] = st;
+            }
+            __syncwarp();
+            {
+                double2 sw = make_double2(0.0, 0.0), sT = make_double2(0.0, 0.0);
+#pragma unroll
+                for (int i = 0; i < 8; i++) {
+                    const double2 Wv = make_double2(xb[(2 * i) * SDRB_XSTRIDE + lane], xb[(2 * i + 1) * SDRB_XSTRIDE + lane]);
+                    const double2 Tv = make_double2(xb[(2 * (8 + i)) * SDRB_XSTRIDE + lane], xb[(2 * (8 + i) + 1) * SDRB_XSTRIDE + lane]);
+                    sw = cfma(pl.rho[i], Wv, sw);
+                    sT = cfma(pl.rho_p[i], Tv, sT);
+                }
+                const double2 epsb = cconj(pl.T3[(size_t)r * (SDRB_TB + 1) + 1]);
+                const double2 x0 = csub(x0s[lane], cl[lane]);
+                double2 ys = cfma(epsb, sw, sT);
+                ys.x = fma(pl.g0, x0.x, ys.x); ys.y = fma(pl.g0, x0.y, ys.y);
+                const double2 yp = cmul(pl.T3[(size_t)r * (SDRB_TB + 1) + lane], ys);
+                sc.ypart[((size_t)chunk * pl.R + r) * pl.Mf + (size_t)t * SDRB_TB + lane] = yp;
+            }
+            __syncwarp();
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
+    }
+}

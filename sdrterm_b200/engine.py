@@ -11,7 +11,7 @@ import ctypes as C
 import numpy as np
 
 from . import _native as nat
-from .plan import Plan
+from .plan import Plan, build_tc
 
 
 def _dp(a: np.ndarray):
@@ -19,7 +19,7 @@ def _dp(a: np.ndarray):
 
 
 class Engine:
-    def __init__(self, plan: Plan, max_chunks: int = 256, device: int = 0):
+    def __init__(self, plan: Plan, max_chunks: int = 256, device: int = 0, use_tc: bool = True):
         self.plan = plan
         self.max_chunks = int(max_chunks)
         self.device = int(device)
@@ -77,6 +77,18 @@ class Engine:
         tab.lam_tile[0], tab.lam_tile[1] = float(pl.lam_tile[0]), float(pl.lam_tile[1])
         if pl.fm_interp is not None:
             put('fm_interp', pl.fm_interp)
+        self.tc = build_tc(pl) if use_tc else None
+        if self.tc is not None:
+            tc = self.tc
+            tab.tc_enable, tab.tc_K, tab.tc_isz = 1, tc.K, tc.isz
+            tab.tc_ncol, tab.tc_nout, tab.tc_npad = tc.NCOL, tc.nout, tc.Npad
+            bq = np.ascontiguousarray(tc.Bq, dtype=np.int8)
+            self._keep.append(bq)
+            tab.tc_Bq = bq.ctypes.data_as(C.POINTER(C.c_int8))
+            put('tc_scale', tc.scale)
+            put('tc_cst', tc.cst)
+            for i in range(16):
+                tab.tc_xor[i] = int(tc.xor_mask[i])
         nat.check(L.sdrb_create(C.byref(cfg), C.byref(tab), C.byref(self._h)))
         self.M = int(L.sdrb_outputs_per_chunk(self._h))
         self.chunk_bytes = int(L.sdrb_chunk_bytes(self._h))

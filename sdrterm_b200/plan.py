@@ -358,3 +358,128 @@ def build_plan(fs: int, enc: str, dec: int, rows_hz, *, simo: bool = False, swap
                 lam_tile=lam_tile, demod=demod, out_sos=out_sos,
                 big_endian_out=bool(simo if big_endian_out is None else big_endian_out),
                 fm_interp=fm_interp, sos_Lseg=sos_Lseg, sos_AL=sos_AL, sos_CA=sos_CA)
+
+
+# ------------------------------------------------------------------------------------------------
+# Tensor-core block front end (k_tc): the per-block modal sums as ONE exact int8 GEMM over the raw
+# bytes.  Every quantity the block kernel needs from a block of q samples is a real-linear
+# functional of the block's integer samples -- decode, byte order, the block-local IQ correction
+# (a linear EMA), the NCO and the 16 modal sums F_i, G_i -- so it is a row of a coefficient matrix
+# applied to the block's bytes.  The coefficients are rounded once to ND*8-bit fixed point and cut
+# into balanced base-256 digits; with the data bytes as the other int8 operand every product and
+# every int32 column sum is exact, and the columns are recombined in int64/FP64.
+TC_ND = 6                 # coefficient digits (48-bit fixed point)
+TC_MODE_OUTPUTS = 32      # 8 poles x {F, G} x {re, im} per row
+
+
+@dataclass
+class TcTables:
+    K: int                 # bytes per block row = q * 2 * itemsize
+    isz: int               # bytes per I or Q item
+    ND: int
+    NCOL: int              # digit columns per output = ND + isz - 1
+    nout: int              # outputs = 32*R + 2 (the last two are the IQ-EMA block aggregate)
+    Npad: int              # GEMM N (multiple of 16)
+    xor_mask: np.ndarray   # (16,) uint8, XOR pattern of one 16-byte group of the raw stream
+    Bq: np.ndarray         # (Npad, K) int8 coefficient digits, column index NCOL*o + t
+    scale: np.ndarray      # (nout,) 2^-S_o
+    cst: np.ndarray        # (nout,) response to the constant the XOR removed
+
+
+def _balanced_digits(A: int, nd: int):
+    d = []
+    for _ in range(nd):
+        r = ((A + 128) % 256) - 128
+        d.append(r)
+        A = (A - r) // 256
+    if A != 0:
+        raise OverflowError('coefficient does not fit its digits')
+    return d[::-1]
+
+
+def tc_supported(pl: Plan) -> bool:
+    """Shapes the tensor-core front end handles; everything else takes the FP64 block kernel."""
+    if pl.enc not in ('b', 'B', 'h', 'H') or pl.norm is not None:
+        return False
+    K = pl.q * 2 * _ITEMSIZE[pl.enc]
+    return (K in (128, 256) and pl.rem == 0 and pl.Mf % TILE_BLOCKS == 0 and pl.R == 1
+            and pl.q >= pl.edge + 1)
+
+
+def build_tc(pl: Plan, nd: int = TC_ND) -> TcTables | None:
+    if not tc_supported(pl):
+        return None
+    mp.mp.dps = 50
+    q, R = pl.q, pl.R
+    isz = _ITEMSIZE[pl.enc]
+    sb = 2 * isz
+    K = q * sb
+    signed = pl.enc in ('b', 'h')
+    stored_le = not pl.swap
+    ncol = nd + isz - 1
+    nout = TC_MODE_OUTPUTS * R + 2
+    npad = -(-(nout * ncol) // 16) * 16
+    pm = pl.modes.mp_p
+    L = mp.mpf(pl.Liq)
+    lam = mp.mpf(1) - L
+
+    # byte bookkeeping of one sample: (component, significance, xored?) per byte
+    info = []
+    for bb in range(sb):
+        cpt, bi = divmod(bb, isz)
+        w = bi if stored_le else isz - 1 - bi
+        xored = not (signed and w == isz - 1)
+        info.append((cpt, w, xored))
+    xor_mask = np.array([0x80 if info[b % sb][2] else 0 for b in range(16)], dtype=np.uint8)
+    offs = sum(128 * 256 ** w for (cpt, w, x) in info if cpt == 0 and x)   # same for I and Q
+
+    def fold_iq(c):
+        """c'_j = c_j - L * sum_{j'>j} c_j' lam^(j'-1-j): the block-local EMA correction (zero
+        offset at the block start) moved from the samples onto the coefficients."""
+        out = [None] * q
+        s = mp.mpc(0)
+        for j in range(q - 1, -1, -1):
+            out[j] = c[j] - L * s
+            s = c[j] + lam * s
+        return out
+
+    rows = []   # per output: list over j of (coef on I_j, coef on Q_j), real mp numbers
+    for r in range(R):
+        T2 = [mp.mpc(complex(v)) for v in pl.T2[r]] if pl.use_nco[r] else [mp.mpc(1)] * q
+        for md in range(16):
+            i = md % 8
+            if md < 8:
+                c = [pm[i] ** (q - 1 - j) * T2[j] for j in range(q)]
+            else:
+                c = [pm[i] ** j * T2[j] for j in range(q)]
+            if pl.correct_iq:
+                c = fold_iq(c)
+            rows.append([(mp.re(v), -mp.im(v)) for v in c])    # Re(c*(I+jQ)) = cr I - ci Q
+            rows.append([(mp.im(v), mp.re(v)) for v in c])     # Im(c*(I+jQ)) = ci I + cr Q
+    e = [lam ** (q - 1 - j) for j in range(q)]
+    rows.append([(v, mp.mpf(0)) for v in e])
+    rows.append([(mp.mpf(0), v) for v in e])
+
+    Bq = np.zeros((npad, K), dtype=np.int8)
+    scale = np.zeros(nout)
+    cst = np.zeros(nout)
+    lim = 127 * 256 ** (nd - 1)
+    for o, row in enumerate(rows):
+        amax = max(max(abs(a), abs(b)) for a, b in row)
+        S = int(mp.floor(mp.log(lim / amax, 2)))
+        tot = 0
+        for j, ab in enumerate(row):
+            for cpt in (0, 1):
+                A = int(mp.nint(ab[cpt] * mp.mpf(2) ** S))
+                tot += A
+                dig = _balanced_digits(A, nd)
+                for bb, (c2_, w, _x) in enumerate(info):
+                    if c2_ != cpt:
+                        continue
+                    sh = isz - 1 - w
+                    for s_, dv in enumerate(dig):
+                        Bq[ncol * o + s_ + sh, j * sb + bb] = dv
+        scale[o] = float(mp.mpf(2) ** (-S))
+        cst[o] = float(mp.mpf(tot * offs) * mp.mpf(2) ** (-S))
+    return TcTables(K=K, isz=isz, ND=nd, NCOL=ncol, nout=nout, Npad=npad, xor_mask=xor_mask,
+                    Bq=Bq, scale=scale, cst=cst)

@@ -346,3 +346,104 @@ def emu_stream(pl: Plan, stream: bytes, off0: complex = 0j, stale_tail: bool = T
         ys.append(y)
         outs.append(emu_demod(pl, y))
     return np.concatenate(outs, axis=1), np.stack(ys), off
+
+
+# ------------------------------------------------------------------------------------------------
+# Tensor-core front end (k_tc): numpy twin.  The int8 GEMM is evaluated exactly in int64.
+def tc_block_values(pl: Plan, tc, raw: np.ndarray) -> np.ndarray:
+    """raw chunk bytes -> (Mf, nout) float64: the per-block linear functionals as k_tc's epilogue
+    reassembles them from the int32 digit columns."""
+    Mf, K, ncol, nout = pl.Mf, tc.K, tc.NCOL, tc.nout
+    by = np.frombuffer(raw, dtype=np.uint8)[:Mf * K].reshape(Mf, K)
+    sby = (by ^ np.tile(tc.xor_mask, K // 16)[None, :]).view(np.int8).astype(np.int64)
+    acc = sby @ tc.Bq.T.astype(np.int64)                        # exact column sums
+    assert np.max(np.abs(acc)) < 2 ** 31
+    cols = acc[:, :nout * ncol].reshape(Mf, nout, ncol)
+    nhi = ncol - 3
+    vhi = np.zeros((Mf, nout), dtype=np.int64)
+    vlo = np.zeros((Mf, nout), dtype=np.int64)
+    for t in range(nhi):
+        vhi = vhi * 256 + cols[:, :, t]
+    for t in range(nhi, ncol):
+        vlo = vlo * 256 + cols[:, :, t]
+    assert np.max(np.abs(vhi)) < 2 ** 51 and np.max(np.abs(vlo)) < 2 ** 51
+    # scale is a power of two: both products are exact, the sum rounds once (device: one FMA)
+    return (vhi.astype(np.float64) * (2.0 ** 24 * tc.scale)[None, :]
+            + vlo.astype(np.float64) * tc.scale[None, :]) + tc.cst[None, :]
+
+
+def emu_main_tc(pl: Plan, tc, raw: np.ndarray, z: np.ndarray):
+    """Same outputs as emu_main, with the block sums taken from the int8 GEMM (R == 1 rows only
+    for now).  z (decoded chunk) is used only for the first sample of each block and the tail
+    window, which the kernel decodes from the staged tile."""
+    q, Mf, nt = pl.q, pl.Mf, pl.ntiles
+    m = pl.modes
+    val = tc_block_values(pl, tc, raw)
+    zb = z[:q * Mf].reshape(Mf, q)
+    E = val[:, tc.nout - 2] + 1j * val[:, tc.nout - 1]
+    blk_agg = pl.Liq * E
+    off_loc = np.zeros(Mf, dtype=np.complex128)
+    tile_agg = np.zeros(nt, dtype=np.complex128)
+    for t in range(nt):
+        k0 = t * TILE_BLOCKS
+        o = 0j
+        for l in range(TILE_BLOCKS):
+            off_loc[k0 + l] = o
+            o = pl.lam_q * o + blk_agg[k0 + l]
+        tile_agg[t] = o
+    # tail window from the last block's samples: block-local EMA, then the tile-local offset
+    n0 = pl.N - 1 - pl.edge
+    tailwin = np.zeros(pl.edge + 1, dtype=np.complex128)
+    acc = np.zeros(Mf, dtype=np.complex128)
+    zp = np.empty_like(zb)
+    for j in range(q):
+        zp[:, j] = zb[:, j] - pl.Liq * acc
+        acc = pl.lam * acc + zb[:, j]
+    for n in range(n0, q * Mf):
+        k, j = divmod(n, q)
+        tailwin[n - n0] = zp[k, j] - pl.lam_j[j] * off_loc[k]
+
+    ypart = np.zeros((pl.R, Mf), dtype=np.complex128)
+    Wout = np.zeros((pl.R, nt, 8), dtype=np.complex128)
+    Tin = np.zeros((pl.R, nt, 8), dtype=np.complex128)
+    for r in range(pl.R):
+        v = val[:, 32 * r:32 * r + 32]
+        F = v[:, 0:16:2] + 1j * v[:, 1:16:2]
+        G = v[:, 16:32:2] + 1j * v[:, 17:32:2]
+        F = F - off_loc[:, None] * pl.PhiF[r][None, :]
+        G = G - off_loc[:, None] * pl.PhiG[r][None, :]
+        x0 = zb[:, 0] - off_loc
+        for t in range(nt):
+            k0 = t * TILE_BLOCKS
+            cnt = TILE_BLOCKS
+            rot = pl.T3[r][:cnt]
+            Fl = F[k0:k0 + cnt] * rot[:, None]
+            Gl = G[k0:k0 + cnt] * rot[:, None]
+            W = np.zeros((cnt + 1, 8), dtype=np.complex128)
+            for l in range(cnt):
+                W[l + 1] = pl.P * W[l] + Fl[l]
+            T = np.zeros((cnt + 1, 8), dtype=np.complex128)
+            for l in range(cnt - 1, -1, -1):
+                T[l] = pl.P * T[l + 1] + Gl[l]
+            ypart[r, k0:k0 + cnt] = (W[:cnt] @ m.rho + T[:cnt] @ m.rho_p
+                                      + m.g0 * x0[k0:k0 + cnt] * rot)
+            Wout[r, t] = W[cnt]
+            Tin[r, t] = T[0]
+    return dict(ypart=ypart, Wout=Wout, Tin=Tin, tile_agg=tile_agg, tailwin=tailwin)
+
+
+def emu_stream_tc(pl: Plan, tc, stream: bytes, off0: complex = 0j):
+    raw = np.frombuffer(stream, dtype=np.uint8)
+    cb = pl.chunk_bytes
+    buf = np.zeros(cb, dtype=np.uint8)
+    outs, ys = [], []
+    off = off0
+    for o in range(0, raw.size, cb):
+        part = raw[o:o + cb]
+        buf[:part.size] = part
+        z = decode(pl, buf)
+        mo = emu_main_tc(pl, tc, buf, z)
+        y, off = emu_fixup(pl, z, mo, off)
+        ys.append(y)
+        outs.append(emu_demod(pl, y))
+    return np.concatenate(outs, axis=1), np.stack(ys), off

@@ -29,11 +29,13 @@ def chunked(body: bytes, stale_tail: bool = True) -> np.ndarray:
     return out
 
 
-def run_case(name, max_chunks=8):
+def run_case(name, max_chunks=8, use_tc=True):
+    """use_tc=True takes the tensor-core block front end (k_tc) where the shape supports it;
+    False forces the FP64 block kernel (k_main)."""
     raw, body, kw = case_stream(name)
     pl = plan_for(kw)
     chunks = chunked(body)
-    with Engine(pl, max_chunks=max_chunks) as eng:
+    with Engine(pl, max_chunks=max_chunks, use_tc=use_tc) as eng:
         out = eng.process(chunks)
         y = eng.decimated(min(chunks.shape[0], max_chunks))
         off = eng.iq_state

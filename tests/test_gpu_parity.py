@@ -13,10 +13,22 @@ pytestmark = pytest.mark.gpu
 TOL = 1e-9
 
 
+def _tc_ok(name):
+    from gpu_util import plan_for
+    from sdrterm_b200.plan import tc_supported
+    from util import case_stream as cs
+    return tc_supported(plan_for(cs(name)[2]))
+
+
+@pytest.mark.parametrize('path', ['fp64', 'tc'])
 @pytest.mark.parametrize('name', sorted(CASES))
-def test_case_vs_oracle_and_golden(name):
+def test_case_vs_oracle_and_golden(name, path):
+    """Both block front ends: 'fp64' = k_main (FP64 tensor pipe, any shape), 'tc' = k_tc (tcgen05
+    int8 GEMM over the raw bytes, 8/16-bit integer encodings with 128- or 256-byte blocks)."""
     from gpu_util import run_case
-    kw, pl, chunks, out, y, off = run_case(name)
+    if path == 'tc' and not _tc_ok(name):
+        pytest.skip('shape not handled by the tensor-core front end (falls back to k_main)')
+    kw, pl, chunks, out, y, off = run_case(name, use_tc=(path == 'tc'))
     g = load_golden(name)
     ch = orc.Chain(**kw)
     zs = np.stack([ch.ingest(c.tobytes()).copy() for c in chunks])
@@ -57,3 +69,31 @@ def test_batch_split_and_state_carry():
     with Engine(pl, max_chunks=2) as e3:
         c = e3.process(chunks)            # internal batching path
     assert rel_err(b, a) < 1e-13 and rel_err(c, a) < 1e-13
+
+
+def test_tc_long_stream_matches_oracle_and_fp64_path():
+    """Many MMA tiles per CTA (persistent loop, both accumulator stages, barrier phases wrap):
+    300 chunks of the config-1 stream through k_tc vs the oracle and vs the FP64 block kernel."""
+    import signals
+    from gpu_util import plan_for
+    from sdrterm_b200.engine import Engine
+    nch = 300
+    base = signals.c1_bytes(20 * 32768, seed=7, header=False)
+    body = (base * (nch // 20))[:nch * 131072]
+    kw = dict(fs=1_024_000, enc='h', center=15000, dec=64, demod='fm', omega_out=5000, correct_iq=True,
+              vfos=None, simo=False, normalize=False, swap=False, big_endian=None)
+    pl = plan_for(kw)
+    with Engine(pl, max_chunks=nch, use_tc=True) as e1:
+        assert e1.tc is not None
+        a = e1.process(body)
+        ya = e1.decimated(nch)
+        offa = e1.iq_state
+    with Engine(pl, max_chunks=nch, use_tc=False) as e2:
+        b = e2.process(body)
+        yb = e2.decimated(nch)
+        offb = e2.iq_state
+    ref = orc.Chain(**kw, nthreads=orc.max_threads()).run_fast(body)
+    assert a.shape == b.shape == ref.shape
+    assert rel_err(ya, yb) < 1e-11
+    assert rel_err(a, ref) < TOL and rel_err(b, ref) < TOL
+    assert abs(offa - offb) <= 1e-9 * max(1.0, abs(offb))
