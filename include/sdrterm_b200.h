@@ -18,7 +18,7 @@
 extern "C" {
 #endif
 
-#define SDRB_ABI_VERSION 2
+#define SDRB_ABI_VERSION 3
 #define SDRB_TILE_BLOCKS 32
 #define SDRB_NPOLES 8
 #define SDRB_MAX_DECIMATION 256
@@ -96,16 +96,17 @@ typedef struct sdrb_tables {
     const double *sos_AL;    /* [ns][ns], ns = 2*n_out_sections: A^Lseg of the output cascade */
     const double *sos_CA;    /* [sos_Lseg][ns]: c A^i */
     /* tensor-core block front end (plan.py: build_tc); tc_enable == 0 selects the FP64 block
-     * kernel.  The raw stream is the int8 A operand of an exact GEMM against tc_Bq. */
+     * kernel.  The raw stream is the int8 A operand of an exact GEMM against one tc_Bq slice per
+     * row of the bank. */
     int32_t tc_enable;
     int32_t tc_K;            /* bytes per block row = q * 2 * itemsize (128 or 256) */
     int32_t tc_isz;          /* bytes per I or Q item */
-    int32_t tc_ncol;         /* digit columns per output */
-    int32_t tc_nout;         /* outputs = 32*R + 2 */
-    int32_t tc_npad;         /* GEMM N, multiple of 16, <= 256 */
-    const int8_t *tc_Bq;     /* [tc_npad][tc_K] coefficient digits, row NCOL*o + t */
-    const double *tc_scale;  /* [tc_nout] 2^-S_o */
-    const double *tc_cst;    /* [tc_nout] */
+    int32_t tc_ncol;         /* digit columns per fixed-point output */
+    int32_t tc_nout;         /* outputs per row = 36: 16 F, 16 G, 2 E, 2 x0 */
+    int32_t tc_npad;         /* GEMM N per row, multiple of 16, <= 256 */
+    int32_t tc_S;            /* fixed-point outputs are integers * 2^-tc_S */
+    const int8_t *tc_Bq;     /* [R][tc_npad][tc_K] coefficient digits */
+    const double *tc_cst;    /* [R][tc_nout] */
     uint8_t tc_xor[16];      /* XOR pattern of 16 consecutive stream bytes */
 } sdrb_tables;
 

@@ -16,7 +16,7 @@ LIB_PATH = os.path.join(_HERE, 'libsdrterm_b200.so')
 HEADER = os.path.join(ROOT, 'include', 'sdrterm_b200.h')
 SOURCES = [os.path.join(_HERE, 'csrc', f) for f in ('sdrb_api.cu', 'sdrb_kernels.cuh', 'sdrb_device.cuh', 'sdrb_tc.cuh')]
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 FM, AM, RE, IM = 0, 1, 2, 3
 DEMOD_CODE = {'fm': FM, 'am': AM, 're': RE, 'im': IM}
 
@@ -49,7 +49,7 @@ class Tables(C.Structure):
                 ('fm_interp', _DP), ('sos_Lseg', C.c_int32), ('sos_AL', _DP), ('sos_CA', _DP),
                 ('tc_enable', C.c_int32), ('tc_K', C.c_int32), ('tc_isz', C.c_int32),
                 ('tc_ncol', C.c_int32), ('tc_nout', C.c_int32), ('tc_npad', C.c_int32),
-                ('tc_Bq', C.POINTER(C.c_int8)), ('tc_scale', _DP), ('tc_cst', _DP),
+                ('tc_S', C.c_int32), ('tc_Bq', C.POINTER(C.c_int8)), ('tc_cst', _DP),
                 ('tc_xor', C.c_uint8 * 16)]
 
 

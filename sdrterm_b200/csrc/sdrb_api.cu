@@ -169,8 +169,10 @@ int make_byte_map(sdrb_handle *h, CUtensorMap *map, const void *base, uint64_t r
 template <bool IQ, int NCOL>
 int launch_tc_t(sdrb_handle *h, const CUtensorMap &map_a, size_t nch, int n_mtiles, cudaStream_t st)
 {
-    const int grid = std::min(h->num_sms, n_mtiles);
-    k_tc<IQ, NCOL><<<grid, TC_THREADS, h->tc_smem, st>>>(h->pl, h->tc, h->sc, map_a, h->map_b, (int)nch, n_mtiles);
+    // one row of the bank per CTA: the grid is a whole number of row groups
+    const int R = h->pl.R;
+    const int slots = std::max(1, std::min(h->num_sms / R, n_mtiles));
+    k_tc<IQ, NCOL><<<slots * R, TC_THREADS, h->tc_smem, st>>>(h->pl, h->tc, h->sc, map_a, h->map_b, (int)nch, n_mtiles);
     return 0;
 }
 
@@ -181,18 +183,34 @@ int launch_tc(sdrb_handle *h, const uint8_t *raw, size_t nch, cudaStream_t st, b
     int rc = make_byte_map(h, &map_a, raw, rows, (uint32_t)h->tc.K, 128);
     if (rc) return rc;
     const int n_mtiles = (int)((rows + 127) / 128);
-    if (h->tc.ncol == 7) return iq ? launch_tc_t<true, 7>(h, map_a, nch, n_mtiles, st) : launch_tc_t<false, 7>(h, map_a, nch, n_mtiles, st);
-    return iq ? launch_tc_t<true, 6>(h, map_a, nch, n_mtiles, st) : launch_tc_t<false, 6>(h, map_a, nch, n_mtiles, st);
+    switch (h->tc.ncol) {
+    case 5: return iq ? launch_tc_t<true, 5>(h, map_a, nch, n_mtiles, st) : launch_tc_t<false, 5>(h, map_a, nch, n_mtiles, st);
+    case 6: return iq ? launch_tc_t<true, 6>(h, map_a, nch, n_mtiles, st) : launch_tc_t<false, 6>(h, map_a, nch, n_mtiles, st);
+    case 7: return iq ? launch_tc_t<true, 7>(h, map_a, nch, n_mtiles, st) : launch_tc_t<false, 7>(h, map_a, nch, n_mtiles, st);
+    }
+    return fail(h, SDRB_ERR_ARG, "unsupported digit column count %d", h->tc.ncol);
 }
 
-int setup_tc(sdrb_handle *h, const sdrb_tables *tab)
+template <bool IQ, int NCOL>
+int tc_attr(sdrb_handle *h)
+{
+    CK(h, cudaFuncSetAttribute(k_tc<IQ, NCOL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->tc_smem));
+    return 0;
+}
+
+int setup_tc(sdrb_handle *h, const sdrb_tables *tab, const std::vector<double2> &prot)
 {
     if (!tab->tc_enable || env_int("SDRB_NO_TC", 0)) return 0;
-    if (h->pl.R != 1 || (tab->tc_K != 128 && tab->tc_K != 256) || tab->tc_nout != TC_MAX_OUT ||
-        (tab->tc_ncol != 6 && tab->tc_ncol != 7) || tab->tc_npad > 256 || tab->tc_npad % 16 ||
-        tab->tc_npad < tab->tc_nout * tab->tc_ncol || tab->tc_K != h->pl.q * h->pl.sb || h->pl.rem != 0 ||
-        h->pl.cnt_last != SDRB_TB || h->pl.q < h->pl.edge + 1 || h->pl.normalize || !tab->tc_Bq || !tab->tc_scale || !tab->tc_cst)
+    const int R = h->pl.R;
+    if ((tab->tc_K != 128 && tab->tc_K != 256) || tab->tc_nout != TC_NOUT || tab->tc_ncol < 5 || tab->tc_ncol > 7 ||
+        tab->tc_isz < 1 || tab->tc_isz > 2 || tab->tc_npad > 256 || tab->tc_npad % 16 ||
+        tab->tc_npad < 34 * tab->tc_ncol + 2 * tab->tc_isz || tab->tc_K != h->pl.q * h->pl.sb || h->pl.rem != 0 ||
+        h->pl.cnt_last != SDRB_TB || h->pl.q < h->pl.edge + 1 || h->pl.normalize || !tab->tc_Bq || !tab->tc_cst)
         return fail(h, SDRB_ERR_ARG, "tensor-core tables do not match the configuration");
+    cudaDeviceProp prop;
+    CK(h, cudaGetDeviceProperties(&prop, h->cfg.device));
+    h->num_sms = prop.multiProcessorCount;
+    if (R > h->num_sms) return 0;            // more rows than SMs: FP64 block kernel
     TcDev &tc = h->tc;
     tc.K = tab->tc_K; tc.isz = tab->tc_isz; tc.ncol = tab->tc_ncol; tc.nout = tab->tc_nout; tc.npad = tab->tc_npad;
     tc.nregion = tc.K / 128;
@@ -200,25 +218,33 @@ int setup_tc(sdrb_handle *h, const sdrb_tables *tab)
     for (int i = 0; i < 16; i++)
         if (tab->tc_xor[i] != tab->tc_xor[i & 3]) return fail(h, SDRB_ERR_ARG, "XOR pattern is not 4-periodic");
     tc.idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(tc.npad >> 3) << 17) | ((128u >> 4) << 24);
-    for (int o = 0; o < tc.nout; o++) {
-        tc.scale[o] = tab->tc_scale[o];
-        tc.scale24[o] = tab->tc_scale[o] * 16777216.0;
-        tc.cst[o] = tab->tc_cst[o];
+    tc.scale = ldexp(1.0, -tab->tc_S);
+    tc.scale24 = ldexp(1.0, 24 - tab->tc_S);
+    // powers 0..8 of the rotating-frame block multipliers (segment carries of the tile scans)
+    std::vector<double2> ppow((size_t)R * 16 * 9);
+    for (int i = 0; i < R * 16; i++) {
+        long double ar = 1.0L, ai = 0.0L;
+        const long double br = prot[i].x, bi = prot[i].y;
+        for (int k = 0; k <= 8; k++) {
+            ppow[(size_t)i * 9 + k] = make_double2((double)ar, (double)ai);
+            const long double nr = ar * br - ai * bi, ni = ar * bi + ai * br;
+            ar = nr; ai = ni;
+        }
     }
-    const int8_t *d_bq = nullptr;
-    int rc = upload(h, tab->tc_Bq, (size_t)tc.npad * tc.K, &d_bq);
+    int rc = upload(h, ppow.data(), ppow.size(), &tc.prot_pow);
     if (rc) return rc;
-    rc = make_byte_map(h, &h->map_b, d_bq, (uint64_t)tc.npad, (uint32_t)tc.K, (uint32_t)tc.npad);
+    rc = upload(h, tab->tc_cst, (size_t)R * TC_NOUT, &tc.cst);
+    if (rc) return rc;
+    const int8_t *d_bq = nullptr;
+    rc = upload(h, tab->tc_Bq, (size_t)R * tc.npad * tc.K, &d_bq);
+    if (rc) return rc;
+    rc = make_byte_map(h, &h->map_b, d_bq, (uint64_t)R * tc.npad, (uint32_t)tc.K, (uint32_t)tc.npad);
     if (rc) return rc;
     h->tc_smem = tc_smem_bytes(tc.npad, tc.nregion);
     if (h->tc_smem > 227 * 1024) return fail(h, SDRB_ERR_ARG, "k_tc needs %zu bytes of shared memory", h->tc_smem);
-    cudaDeviceProp prop;
-    CK(h, cudaGetDeviceProperties(&prop, h->cfg.device));
-    h->num_sms = prop.multiProcessorCount;
-    CK(h, cudaFuncSetAttribute(k_tc<true, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->tc_smem));
-    CK(h, cudaFuncSetAttribute(k_tc<false, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->tc_smem));
-    CK(h, cudaFuncSetAttribute(k_tc<true, 7>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->tc_smem));
-    CK(h, cudaFuncSetAttribute(k_tc<false, 7>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->tc_smem));
+    if ((rc = tc_attr<true, 5>(h)) || (rc = tc_attr<false, 5>(h)) || (rc = tc_attr<true, 6>(h)) ||
+        (rc = tc_attr<false, 6>(h)) || (rc = tc_attr<true, 7>(h)) || (rc = tc_attr<false, 7>(h)))
+        return rc;
     h->tc_on = true;
     return 0;
 }
@@ -458,7 +484,6 @@ int sdrb_create(const sdrb_config *cfg, const sdrb_tables *tab, sdrb_handle **ou
     UP(dalloc(h, nch * R * pl.Mf, &sc.ypart));
     UP(dalloc(h, nch * R * nt * 16, &sc.agg));
     UP(dalloc(h, nch * nt, &sc.tile_agg));
-    UP(dalloc(h, nch * (pl.edge + 1), &sc.tailwin));
     UP(dalloc(h, nch * (nt + 1), &sc.off_tile));
     UP(dalloc(h, nch * R * (nt + 1) * 16, &sc.carry));
     UP(dalloc(h, nch * R * M, &sc.y));
@@ -469,7 +494,7 @@ int sdrb_create(const sdrb_config *cfg, const sdrb_tables *tab, sdrb_handle **ou
         UP(dalloc(h, nch * R * 2 * M, &sc.fftbuf));
         UP(dalloc(h, nch * R * M, &sc.zrow));
     }
-    UP(setup_tc(h, tab));
+    UP(setup_tc(h, tab, prot));
 #undef UP
     for (int s = 0; s < 2; s++) {
         if (cudaStreamCreateWithFlags(&h->slot[s].stream, cudaStreamNonBlocking) != cudaSuccess ||

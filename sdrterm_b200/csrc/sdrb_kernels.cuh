@@ -20,7 +20,6 @@ struct Scratch {
     double2 *ypart;     // [nch][R][Mf]
     double2 *agg;       // [nch][R][ntiles][16]   0..7 Wout, 8..15 Tin
     double2 *tile_agg;  // [nch][ntiles]
-    double2 *tailwin;   // [nch][edge+1]
     double2 *off_tile;  // [nch][ntiles+1]
     double2 *carry;     // [nch][R][ntiles+1][16] 0..7 Win[t], 8..15 Tn[t]
     double2 *y;         // [nch][R][M]
@@ -147,24 +146,6 @@ k_main(const __grid_constant__ DevPlan pl, Scratch sc, const uint8_t *__restrict
             if (lane == 0) sc.tile_agg[(size_t)chunk * pl.ntiles + t] = tagg;
         }
         cl[lane] = excl;
-        // tail window: tile-local-corrected samples n in [N-1-edge, q*Mf), lane <-> block
-        const long n0 = pl.N - 1 - pl.edge;
-        const long base_n = ((long)t * SDRB_TB + lane) * q;
-        if (lane < cnt && base_n + q > n0) {
-            const unsigned char *rowp = tb + (size_t)lane * rowb;
-            double2 acc = make_double2(0.0, 0.0);
-            for (int j = 0; j < q; j++) {
-                const double2 z = decode_sample<ENC>(pl, rowp, j);
-                double2 zp = z;
-                if (IQ) {
-                    zp.x = fma(-pl.Liq, acc.x, z.x); zp.y = fma(-pl.Liq, acc.y, z.y);
-                    acc.x = fma(pl.lam, acc.x, z.x); acc.y = fma(pl.lam, acc.y, z.y);
-                    const double lj = pl.lam_j[j];
-                    zp.x = fma(-lj, excl.x, zp.x); zp.y = fma(-lj, excl.y, zp.y);
-                }
-                if (base_n + j >= n0) sc.tailwin[(size_t)chunk * (pl.edge + 1) + (base_n + j - n0)] = zp;
-            }
-        }
     }
     __syncthreads();
 
@@ -436,29 +417,14 @@ k_fixup(const __grid_constant__ DevPlan pl, Scratch sc, const uint8_t *__restric
 
     if (threadIdx.x < 32) {
         const int lane = threadIdx.x;
-        // fetch: raw head samples, and the end window (tile-local-corrected inside full blocks,
-        // raw in the partial block); every load is independent
-        const long n0 = pl.N - 1 - edge;
+        // fetch: raw head samples and the raw end window; every load is independent
         for (int n = lane; n <= edge; n += 32) s_h[n] = decode_sample<ENC>(pl, rawc, n);
-        for (int i = lane; i < pl.nend; i += 32) {
-            const long n = pl.ws + i;
-            double2 x;
-            if (n < (long)q * pl.Mf) {
-                x = sc.tailwin[(size_t)chunk * (edge + 1) + (n - n0)];
-                if (iq) {
-                    const int t = (int)((n / q) / SDRB_TB);
-                    const double lp = pow(pl.lam, (double)(n - (long)t * SDRB_TB * q));
-                    const double2 ot = offt[t];
-                    x.x = fma(-lp, ot.x, x.x); x.y = fma(-lp, ot.y, x.y);
-                }
-            } else {
-                x = decode_sample<ENC>(pl, rawc, n);
-            }
-            s_e[i] = x;
-        }
+        for (int i = lane; i < pl.nend; i += 32) s_e[i] = decode_sample<ENC>(pl, rawc, (long)pl.ws + i);
         __syncwarp();
-        // serial IQ recurrences over the few raw samples (head from the chunk-start offset,
-        // partial block from the offset at q*Mf), then the NCO phases
+        // serial IQ recurrences over these few samples (read_file.py:72-77): the head runs forward
+        // from the chunk-start offset, the partial block forward from the offset at q*Mf, and the
+        // window samples inside full blocks BACKWARD from the offset at q*Mf
+        // (off[n] = (off[n+1] - L z[n]) / lam), then the NCO phases
         if (iq) {
             if (lane == 0) {
                 double2 o = offt[0];
@@ -473,6 +439,13 @@ k_fixup(const __grid_constant__ DevPlan pl, Scratch sc, const uint8_t *__restric
                     const double2 x = csub(s_e[i], o);
                     o.x = fma(x.x, pl.Liq, o.x); o.y = fma(x.y, pl.Liq, o.y);
                     s_e[i] = x;
+                }
+            } else if (lane == 2) {
+                double2 o = offt[nt];
+                for (int i = pl.nend - pl.rem - 1; i >= 0; i--) {
+                    const double2 z = s_e[i];
+                    o.x = fma(-pl.Liq, z.x, o.x) * pl.lam_inv; o.y = fma(-pl.Liq, z.y, o.y) * pl.lam_inv;
+                    s_e[i] = csub(z, o);
                 }
             }
             __syncwarp();

@@ -15,13 +15,18 @@
 // rounding) and continue exactly like k_main: tile-local IQ offsets, modal scans in the rotating
 // frame, partial outputs and tile aggregates for k_fixup.
 //
-// Warp roles (384 threads, one CTA per SM, persistent over MMA tiles of 128 blocks = 4 tiles):
+// Warp roles (640 threads, one CTA per SM, persistent over MMA tiles of 128 blocks = 4 tiles; a
+// CTA serves one row r of the VFO bank, blockIdx.x % R):
 //   warp 0      TMA producer (one lane)
-//   warp 1      TMEM allocation; tcgen05.mma issue (one lane)
+//   warp 1      TMEM allocation; tcgen05.mma issue (one lane); the MMA's own completion frees the
+//               A stage (tcgen05.commit), nothing in the epilogue touches the staged bytes
 //   warps 2-3   sign fix-up: XOR 0x80 into the bytes that are not the signed top byte, so that
 //               every byte is a valid two's-complement int8 operand (the constant this removes is
 //               added back as cst[o])
-//   warps 4-7   epilogue of accumulator stage 0, warps 8-11 of stage 1 (warp%4 = TMEM lane quarter)
+//   warps 4-19  epilogue: warp = 4 + 8*stage + 4*half + quarter.  `quarter` (= warp%4) is the TMEM
+//               lane quarter = one tile of 32 blocks (lane <-> block); half 0 takes the eight
+//               forward modal sums F_i (and x0), half 1 the eight backward sums G_i of the same
+//               tile; the two meet once per tile on a named barrier to form the partial output
 //
 // Reference behaviour reproduced: src/misc/read_file.py:100-103, src/dsp/demodulation.py:71-79,
 // the block form of scipy.signal.decimate (src/dsp/dsp_processor.py:147).  tests/emulator.py
@@ -30,8 +35,10 @@
 #include <cuda.h>
 #include "sdrb_kernels.cuh"
 
-#define TC_MAX_OUT 34
-#define TC_THREADS 384
+#define TC_NOUT 36                     // outputs per row: 16 F, 16 G, 2 E, 2 x0
+#define TC_THREADS 640
+#define TC_EPI_WARPS 16
+#define TC_XS 33                       // exchange-buffer row stride in double2
 #define TC_STAGES 2
 #define TC_REGION_BYTES 16384          // 128 rows x 128 bytes, one SWIZZLE_128B operand slab
 
@@ -39,21 +46,25 @@ struct TcDev {
     int K, isz, ncol, nout, npad, nregion;
     uint32_t xor_word;                 // XOR pattern of 4 consecutive stream bytes
     uint32_t idesc;                    // tcgen05 instruction descriptor (i8 x i8 -> s32, M=128, N=npad)
-    double scale[TC_MAX_OUT];          // 2^-S_o
-    double scale24[TC_MAX_OUT];        // 2^(24-S_o)
-    double cst[TC_MAX_OUT];
+    double scale;                      // 2^-S, common to every fixed-point output
+    double scale24;                    // 2^(24-S)
+    const double *cst;                 // [R][TC_NOUT] response to the constant the XOR removed
+    const double2 *prot_pow;           // [R][16][9] powers 0..8 of the rotating-frame block multipliers
 };
 
 __host__ __device__ inline size_t tc_warp_bytes()
 {
-    return main_warp_bytes() + SDRB_TB * sizeof(double2);      // xb + x0s + cl
+    return (size_t)8 * TC_XS * sizeof(double2);                // xs[8 modes][33]
 }
 __host__ __device__ inline size_t tc_smem_bytes(int npad, int nregion)
 {
     size_t b = (size_t)nregion * npad * 128;                   // B slabs
     b += (size_t)TC_STAGES * nregion * TC_REGION_BYTES;        // A stages
-    b += 8 * tc_warp_bytes();
-    b += 32 * sizeof(double2);                                 // PhiF, PhiG
+    b += TC_EPI_WARPS * tc_warp_bytes();                       // xs
+    b += 2 * 8 * 32 * sizeof(double2);                         // F/G pair exchange, double-buffered
+    b += 16 * sizeof(double2);                                 // PhiF, PhiG
+    b += 16 * 9 * sizeof(double2);                             // prot_pow of this row
+    b += TC_NOUT * sizeof(double);                             // cst of this row
     b += 16 * sizeof(unsigned long long);                      // mbarriers
     return b + 1024;                                           // alignment slack
 }
@@ -154,28 +165,8 @@ __device__ __forceinline__ double tc_combine(const uint32_t *c, double s24, doub
     long long vlo = (int)c[NHI];
 #pragma unroll
     for (int t = NHI + 1; t < NCOL; t++) vlo = vlo * 256 + (int)c[t];
-    return fma(i64_to_double(vhi), s24, i64_to_double(vlo) * s) + cst;
+    return fma(i64_to_double(vhi), s24, fma(i64_to_double(vlo), s, cst));
 }
-
-// One complex sample j of tile row `row`, read back from the staged (sign-fixed, swizzled) A tile.
-__device__ __forceinline__ double2 tc_sample(const unsigned char *a_stage, int row, int j, const DevPlan &pl,
-                                             uint32_t xor_word)
-{
-    const int kb = j * pl.sb;
-    const int region = kb >> 7, kin = kb & 127;
-    const unsigned char *p = a_stage + (size_t)region * TC_REGION_BYTES + row * 128 +
-                             ((((kin >> 4) ^ (row & 7)) << 4) | (kin & 15));
-    if (pl.sb == 4) {
-        uint32_t v = *reinterpret_cast<const uint32_t *>(p) ^ xor_word;
-        if (pl.swap) v = __byte_perm(v, 0, 0x2301);
-        if (pl.enc == ENC_h) return make_double2((double)(int16_t)(v & 0xffff), (double)(int16_t)(v >> 16));
-        return make_double2((double)(v & 0xffff), (double)(v >> 16));
-    }
-    const uint32_t v = (uint32_t)(*reinterpret_cast<const uint16_t *>(p)) ^ (xor_word & 0xffffu);
-    if (pl.enc == ENC_b) return make_double2((double)(int8_t)(v & 0xff), (double)(int8_t)(v >> 8));
-    return make_double2((double)(v & 0xff), (double)(v >> 8));
-}
-
 // ------------------------------------------------------------------------------------- k_tc
 template <bool IQ, int NCOL>
 __global__ void __launch_bounds__(TC_THREADS, 1)
@@ -189,31 +180,36 @@ k_tc(const __grid_constant__ DevPlan pl, const __grid_constant__ TcDev tc, Scrat
     const int nreg = tc.nregion, npad = tc.npad;
     unsigned char *sB = smem;
     unsigned char *sA = sB + (size_t)nreg * npad * 128;
-    unsigned char *sW = sA + (size_t)TC_STAGES * nreg * TC_REGION_BYTES;
-    double2 *sPhi = reinterpret_cast<double2 *>(sW + 8 * tc_warp_bytes());
-    unsigned long long *bars = reinterpret_cast<unsigned long long *>(sPhi + 32);
+    double2 *sXS = reinterpret_cast<double2 *>(sA + (size_t)TC_STAGES * nreg * TC_REGION_BYTES);
+    double2 *sPB = sXS + (size_t)TC_EPI_WARPS * 8 * TC_XS;
+    double2 *sPhi = sPB + 2 * 8 * 32;
+    double2 *sPow = sPhi + 16;
+    double *sCst = reinterpret_cast<double *>(sPow + 16 * 9);
+    unsigned long long *bars = reinterpret_cast<unsigned long long *>(sCst + TC_NOUT);
     __shared__ uint32_t tmem_base_s;
-    // barrier indices
     const uint32_t bar0 = smem_u32(bars);
     auto BAR = [&](int kind, int s) { return bar0 + 8u * (uint32_t)(kind * TC_STAGES + s); };
     enum { B_FULL_A = 0, B_XORED = 1, B_MMA_DONE = 2, B_A_FREE = 3, B_TMEM_FREE = 4, B_BFULL = 5 };
+
+    // one row of the bank per CTA; the CTAs of a row share its MMA tiles round-robin
+    const int r = (int)blockIdx.x % pl.R;
+    const int slot = (int)blockIdx.x / pl.R, nslots = (int)gridDim.x / pl.R;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < TC_STAGES; s++) {
             mbar_init(BAR(B_FULL_A, s), 1);
             mbar_init(BAR(B_XORED, s), 2);
             mbar_init(BAR(B_MMA_DONE, s), 1);
-            mbar_init(BAR(B_A_FREE, s), 4);
-            mbar_init(BAR(B_TMEM_FREE, s), 4);
+            mbar_init(BAR(B_A_FREE, s), 1);
+            mbar_init(BAR(B_TMEM_FREE, s), 8);
         }
         mbar_init(BAR(B_BFULL, 0), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (threadIdx.x < 32) {
-        if (threadIdx.x < 16) {
-            sPhi[threadIdx.x] = threadIdx.x < 8 ? pl.PhiF[threadIdx.x] : pl.PhiG[threadIdx.x - 8];
-        }
-    }
+    if (threadIdx.x < 16)
+        sPhi[threadIdx.x] = threadIdx.x < 8 ? pl.PhiF[(size_t)r * 8 + threadIdx.x] : pl.PhiG[(size_t)r * 8 + threadIdx.x - 8];
+    for (int i = threadIdx.x; i < 16 * 9; i += blockDim.x) sPow[i] = tc.prot_pow[(size_t)r * 16 * 9 + i];
+    if (threadIdx.x >= 64 && threadIdx.x < 64 + TC_NOUT) sCst[threadIdx.x - 64] = tc.cst[(size_t)r * TC_NOUT + threadIdx.x - 64];
     if (warp == 1) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(&tmem_base_s)) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -222,18 +218,18 @@ k_tc(const __grid_constant__ DevPlan pl, const __grid_constant__ TcDev tc, Scrat
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = tmem_base_s;
-    const int my_iters = (n_mtiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+    const int my_iters = slot < nslots ? (n_mtiles - slot + nslots - 1) / nslots : 0;
     const int total_tiles = nchunks * pl.ntiles;
 
     if (warp == 0) {
         // ===================================================================== TMA producer
-        if (lane == 0) {
+        if (lane == 0 && my_iters > 0) {
             mbar_expect_tx(BAR(B_BFULL, 0), (uint32_t)(nreg * npad * 128));
             for (int rg = 0; rg < nreg; rg++)
-                tma_load_2d(smem_u32(sB + (size_t)rg * npad * 128), &map_b, rg * 128, 0, BAR(B_BFULL, 0));
+                tma_load_2d(smem_u32(sB + (size_t)rg * npad * 128), &map_b, rg * 128, r * npad, BAR(B_BFULL, 0));
             for (int it = 0; it < my_iters; it++) {
                 const int s = it & 1, u = it >> 1;
-                const int mt = blockIdx.x + it * gridDim.x;
+                const int mt = slot + it * nslots;
                 mbar_wait(BAR(B_A_FREE, s), (u & 1) ^ 1);
                 mbar_expect_tx(BAR(B_FULL_A, s), (uint32_t)(nreg * TC_REGION_BYTES));
                 for (int rg = 0; rg < nreg; rg++)
@@ -243,7 +239,7 @@ k_tc(const __grid_constant__ DevPlan pl, const __grid_constant__ TcDev tc, Scrat
         }
     } else if (warp == 1) {
         // ===================================================================== MMA issuer
-        if (lane == 0) {
+        if (lane == 0 && my_iters > 0) {
             mbar_wait(BAR(B_BFULL, 0), 0);
             for (int it = 0; it < my_iters; it++) {
                 const int s = it & 1, u = it >> 1;
@@ -258,6 +254,7 @@ k_tc(const __grid_constant__ DevPlan pl, const __grid_constant__ TcDev tc, Scrat
                     const uint64_t db = umma_desc(smem_u32(sB + (size_t)rg * npad * 128) + kin);
                     umma_i8(d, da, db, tc.idesc, ks > 0 ? 1u : 0u);
                 }
+                umma_commit(BAR(B_A_FREE, s));       // the staged bytes are dead once the MMAs retire
                 umma_commit(BAR(B_MMA_DONE, s));
             }
         }
@@ -282,135 +279,137 @@ k_tc(const __grid_constant__ DevPlan pl, const __grid_constant__ TcDev tc, Scrat
         }
     } else {
         // ===================================================================== epilogue
-        const int g = (warp - 4) >> 2, qd = warp & 3;
-        unsigned char *wbase = sW + (size_t)(warp - 4) * tc_warp_bytes();
-        double *xb = reinterpret_cast<double *>(wbase);
-        double2 *x0s = reinterpret_cast<double2 *>(xb + 32 * SDRB_XSTRIDE);
-        double2 *cl = x0s + SDRB_TB;
-        const int q = pl.q;
-        const int r = 0;
+        const int e = warp - 4, qd = e & 3, half = (e >> 2) & 1, g = e >> 3;
+        double2 *xs = sXS + (size_t)e * 8 * TC_XS;
+        const int pole = lane & 7, seg = lane >> 3;
+        const double2 *pw = sPow + (half * 8 + pole) * 9;
+        const double2 Pm = pw[1], Pm8 = pw[8];
+        const double2 rot = pl.T3[(size_t)r * (SDRB_TB + 1) + lane];
+        const double2 rot31 = pl.T3[(size_t)r * (SDRB_TB + 1) + SDRB_TB - 1];
+        const double2 epsb = cconj(pl.T3[(size_t)r * (SDRB_TB + 1) + 1]);
+        const uint32_t pair_bar = 1u + (uint32_t)(g * 4 + qd);
+        const double s24 = tc.scale24, s1 = tc.scale;
         for (int it = g; it < my_iters; it += 2) {
-            const int s = it & 1, u = it >> 1;
-            const int mt = blockIdx.x + it * gridDim.x;
+            const int s = g, u = it >> 1;
+            const int mt = slot + it * nslots;
             const int gt = 4 * mt + qd;
             mbar_wait(BAR(B_MMA_DONE, s), u & 1);
             tc_fence_after();
             if (gt >= total_tiles) {
                 __syncwarp();
-                if (lane == 0) { mbar_arrive(BAR(B_A_FREE, s)); mbar_arrive(BAR(B_TMEM_FREE, s)); }
+                if (lane == 0) mbar_arrive(BAR(B_TMEM_FREE, s));
                 continue;
             }
             const int chunk = gt / pl.ntiles, t = gt % pl.ntiles;
-            const unsigned char *a_stage = sA + (size_t)s * nreg * TC_REGION_BYTES;
-            const int row = 32 * qd + lane;
             const uint32_t trow = tmem_base + ((uint32_t)(32 * qd) << 16) + (uint32_t)(s * 256);
+            uint32_t c[32];
 
-            // ---- IQ-EMA block aggregate E -> tile-local block offsets cl[], tile aggregate
-            double2 excl = make_double2(0.0, 0.0);
-            if (IQ) {
-                uint32_t ce[16];
-                tmem_ld16(trow + 32 * NCOL, ce);
+            // ---- IQ-EMA block aggregate E -> tile-local block offsets, tile aggregate; x0
+            double2 excl = make_double2(0.0, 0.0), x0 = make_double2(0.0, 0.0);
+            if (IQ || half == 0) {
+                tmem_ld32(trow + 32 * NCOL, c);
                 tmem_ld_wait();
-                const double er = tc_combine<NCOL>(ce, tc.scale24[32], tc.scale[32], tc.cst[32]);
-                const double ei = tc_combine<NCOL>(ce + NCOL, tc.scale24[33], tc.scale[33], tc.cst[33]);
-                double2 inc = make_double2(pl.Liq * er, pl.Liq * ei);
-#pragma unroll
-                for (int i = 0; i < 5; i++) {
-                    const double2 tt = shfl_up_c(inc, 1 << i);
-                    if (lane >= (1 << i)) { inc.x = fma(pl.lamq_pow[i], tt.x, inc.x); inc.y = fma(pl.lamq_pow[i], tt.y, inc.y); }
+                if (half == 0) {                  // x0: isz exact columns per component
+                    int xr, xi;
+                    if (tc.isz == 2) {
+                        xr = (int)c[2 * NCOL] * 256 + (int)c[2 * NCOL + 1];
+                        xi = (int)c[2 * NCOL + 2] * 256 + (int)c[2 * NCOL + 3];
+                    } else {
+                        xr = (int)c[2 * NCOL]; xi = (int)c[2 * NCOL + 1];
+                    }
+                    x0 = make_double2((double)xr + sCst[34], (double)xi + sCst[35]);
                 }
-                excl = shfl_up_c(inc, 1);
-                if (lane == 0) excl = make_double2(0.0, 0.0);
-                const double2 tagg = shfl_c(inc, 31);
-                if (lane == 0) sc.tile_agg[(size_t)chunk * pl.ntiles + t] = tagg;
-            }
-            cl[lane] = excl;
-            // ---- first sample of every block; tail window of the chunk's last block
-            x0s[lane] = tc_sample(a_stage, row, 0, pl, tc.xor_word);
-            if (t == pl.ntiles - 1) {
-                const double2 ex31 = shfl_c(excl, 31);
-                const int j0 = q - (pl.edge + 1);
-                const int jt = j0 + lane;
-                const int rowl = 32 * qd + 31;
-                double2 acc = make_double2(0.0, 0.0);
                 if (IQ) {
-                    for (int i = 0; i < q - 1; i++) {
-                        if (i < jt) {
-                            const double2 z = tc_sample(a_stage, rowl, i, pl, tc.xor_word);
-                            acc.x = fma(pl.lam, acc.x, z.x); acc.y = fma(pl.lam, acc.y, z.y);
-                        }
+                    const double er = tc_combine<NCOL>(c, s24, s1, sCst[32]);
+                    const double ei = tc_combine<NCOL>(c + NCOL, s24, s1, sCst[33]);
+                    double2 inc = make_double2(pl.Liq * er, pl.Liq * ei);
+#pragma unroll
+                    for (int i = 0; i < 5; i++) {
+                        const double2 tt = shfl_up_c(inc, 1 << i);
+                        if (lane >= (1 << i)) { inc.x = fma(pl.lamq_pow[i], tt.x, inc.x); inc.y = fma(pl.lamq_pow[i], tt.y, inc.y); }
                     }
-                }
-                if (lane <= pl.edge) {
-                    double2 z = tc_sample(a_stage, rowl, jt, pl, tc.xor_word);
-                    if (IQ) {
-                        z.x = fma(-pl.Liq, acc.x, z.x); z.y = fma(-pl.Liq, acc.y, z.y);
-                        const double lj = pl.lam_j[jt];
-                        z.x = fma(-lj, ex31.x, z.x); z.y = fma(-lj, ex31.y, z.y);
-                    }
-                    sc.tailwin[(size_t)chunk * (pl.edge + 1) + lane] = z;
+                    excl = shfl_up_c(inc, 1);
+                    if (lane == 0) excl = make_double2(0.0, 0.0);
+                    if (half == 0 && lane == 31 && r == 0) sc.tile_agg[(size_t)chunk * pl.ntiles + t] = inc;
                 }
             }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(BAR(B_A_FREE, s));
-
-            // ---- modal block sums: digit columns -> FP64, minus the tile-local offset response
-#pragma unroll 1
-            for (int og = 0; og < 8; og++) {
-                uint32_t c[32];
-                tmem_ld32(trow + 4 * NCOL * og, c);
+            // ---- this half's eight modal block sums: digit columns -> FP64, minus the response
+            //      to the tile-local offset; lane <-> block, parked mode-major for the scans
+#pragma unroll
+            for (int og = 0; og < 4; og++) {
+                tmem_ld32(trow + 4 * NCOL * (4 * half + og), c);
                 tmem_ld_wait();
 #pragma unroll
                 for (int h = 0; h < 2; h++) {
-                    const int o = 4 * og + 2 * h;
-                    double vr = tc_combine<NCOL>(c + (2 * h) * NCOL, tc.scale24[o], tc.scale[o], tc.cst[o]);
-                    double vi = tc_combine<NCOL>(c + (2 * h + 1) * NCOL, tc.scale24[o + 1], tc.scale[o + 1], tc.cst[o + 1]);
+                    const int md = 2 * og + h;                     // mode within this half
+                    const int o = 16 * half + 2 * md;              // output index of its real part
+                    double vr = tc_combine<NCOL>(c + (2 * h) * NCOL, s24, s1, sCst[o]);
+                    double vi = tc_combine<NCOL>(c + (2 * h + 1) * NCOL, s24, s1, sCst[o + 1]);
                     if (IQ) {
-                        const double2 ph = sPhi[o >> 1];
+                        const double2 ph = sPhi[8 * half + md];
                         vr -= fma(excl.x, ph.x, -excl.y * ph.y);
                         vi -= fma(excl.x, ph.y, excl.y * ph.x);
                     }
-                    xb[o * SDRB_XSTRIDE + lane] = vr;
-                    xb[(o + 1) * SDRB_XSTRIDE + lane] = vi;
+                    xs[md * TC_XS + lane] = make_double2(vr, vi);
                 }
             }
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(BAR(B_TMEM_FREE, s));
 
-            // ---- tile-local scans in the rotating frame: lanes 0..7 forward poles, 8..15 backward
-            if (lane < 16) {
-                const bool fwd = lane < 8;
-                const double2 Pm = pl.Prot[(size_t)r * 16 + lane];
-                double2 st = make_double2(0.0, 0.0);
-                double *xr = xb + (2 * lane) * SDRB_XSTRIDE, *xi = xr + SDRB_XSTRIDE;
-                for (int step = 0; step < SDRB_TB; step++) {
-                    const int l = fwd ? step : SDRB_TB - 1 - step;
-                    const double2 v = make_double2(xr[l], xi[l]);
-                    const double2 nst = cfma(Pm, st, v);
-                    const double2 o = fwd ? st : nst;
-                    xr[l] = o.x; xi[l] = o.y;
-                    st = nst;
+            // ---- tile-local scans in the rotating frame, lane = (segment of 8 blocks, mode):
+            //      A. each segment from a zero state, B. carries across the 4 segments,
+            //      C. carry applied with the multiplier powers
+            double2 loc[8];
+            double2 st = make_double2(0.0, 0.0);
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                const int l = seg * 8 + (half ? 7 - j : j);
+                const double2 v = xs[pole * TC_XS + l];
+                const double2 nst = cfma(Pm, st, v);
+                loc[j] = half ? nst : st;
+                st = nst;
+            }
+            double2 cin = make_double2(0.0, 0.0);
+            if (half == 0) {
+#pragma unroll
+                for (int j = 0; j < 3; j++) {
+                    const double2 ej = shfl_c(st, j * 8 + pole);
+                    if (j < seg) cin = cfma(Pm8, cin, ej);
                 }
-                if (fwd) st = cmul(pl.T3[(size_t)r * (SDRB_TB + 1) + SDRB_TB - 1], st);
-                sc.agg[(((size_t)chunk * pl.R + r) * pl.ntiles + t) * 16 + lane] = st;
+            } else {
+#pragma unroll
+                for (int j = 3; j > 0; j--) {
+                    const double2 ej = shfl_c(st, j * 8 + pole);
+                    if (j > seg) cin = cfma(Pm8, cin, ej);
+                }
+            }
+            {
+                const double2 tot = cfma(Pm8, cin, st);
+                double2 *ag = sc.agg + (((size_t)chunk * pl.R + r) * pl.ntiles + t) * 16;
+                if (half == 0 && seg == 3) ag[pole] = cmul(rot31, tot);
+                if (half == 1 && seg == 0) ag[8 + pole] = tot;
+            }
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                const int l = seg * 8 + (half ? 7 - j : j);
+                xs[pole * TC_XS + l] = cfma(pw[half ? j + 1 : j], cin, loc[j]);
             }
             __syncwarp();
-            {
-                double2 sw = make_double2(0.0, 0.0), sT = make_double2(0.0, 0.0);
+            // ---- partial output of each block (lane <-> block): half 0 sums rho_i W_i, half 1
+            //      rho_i/p_i T_i; half 0 finishes
+            double2 acc = make_double2(0.0, 0.0);
 #pragma unroll
-                for (int i = 0; i < 8; i++) {
-                    const double2 Wv = make_double2(xb[(2 * i) * SDRB_XSTRIDE + lane], xb[(2 * i + 1) * SDRB_XSTRIDE + lane]);
-                    const double2 Tv = make_double2(xb[(2 * (8 + i)) * SDRB_XSTRIDE + lane], xb[(2 * (8 + i) + 1) * SDRB_XSTRIDE + lane]);
-                    sw = cfma(pl.rho[i], Wv, sw);
-                    sT = cfma(pl.rho_p[i], Tv, sT);
-                }
-                const double2 epsb = cconj(pl.T3[(size_t)r * (SDRB_TB + 1) + 1]);
-                const double2 x0 = csub(x0s[lane], cl[lane]);
-                double2 ys = cfma(epsb, sw, sT);
-                ys.x = fma(pl.g0, x0.x, ys.x); ys.y = fma(pl.g0, x0.y, ys.y);
-                const double2 yp = cmul(pl.T3[(size_t)r * (SDRB_TB + 1) + lane], ys);
-                sc.ypart[((size_t)chunk * pl.R + r) * pl.Mf + (size_t)t * SDRB_TB + lane] = yp;
+            for (int i = 0; i < 8; i++) acc = cfma(half ? pl.rho_p[i] : pl.rho[i], xs[i * TC_XS + lane], acc);
+            double2 *pb = sPB + ((size_t)(u & 1) * 8 + (g * 4 + qd)) * 32;
+            if (half) pb[lane] = acc;
+            asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
+            if (half == 0) {
+                const double2 sT = pb[lane];
+                const double2 xc = csub(x0, excl);
+                double2 ys = cfma(epsb, acc, sT);
+                ys.x = fma(pl.g0, xc.x, ys.x); ys.y = fma(pl.g0, xc.y, ys.y);
+                sc.ypart[((size_t)chunk * pl.R + r) * pl.Mf + (size_t)t * SDRB_TB + lane] = cmul(rot, ys);
             }
             __syncwarp();
         }
@@ -418,6 +417,6 @@ k_tc(const __grid_constant__ DevPlan pl, const __grid_constant__ TcDev tc, Scrat
     tc_fence_before();
     __syncthreads();
     if (warp == 1) {
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base));
     }
 }

@@ -81,11 +81,10 @@ class Engine:
         if self.tc is not None:
             tc = self.tc
             tab.tc_enable, tab.tc_K, tab.tc_isz = 1, tc.K, tc.isz
-            tab.tc_ncol, tab.tc_nout, tab.tc_npad = tc.NCOL, tc.nout, tc.Npad
+            tab.tc_ncol, tab.tc_nout, tab.tc_npad, tab.tc_S = tc.NCOL, tc.nout, tc.Npad, tc.S
             bq = np.ascontiguousarray(tc.Bq, dtype=np.int8)
             self._keep.append(bq)
             tab.tc_Bq = bq.ctypes.data_as(C.POINTER(C.c_int8))
-            put('tc_scale', tc.scale)
             put('tc_cst', tc.cst)
             for i in range(16):
                 tab.tc_xor[i] = int(tc.xor_mask[i])

@@ -127,13 +127,6 @@ def emu_main(pl: Plan, z: np.ndarray):
             off_loc[k0 + l] = o
             o = pl.lam_q * o + blk_agg[k0 + l]
         tile_agg[t] = o
-    # tail window: tile-local-corrected samples n in [N-1-edge, q*Mf)
-    n0 = pl.N - 1 - pl.edge
-    tailwin = np.zeros(pl.edge + 1, dtype=np.complex128)
-    for n in range(n0, q * Mf):
-        k, j = divmod(n, q)
-        tailwin[n - n0] = zp[k, j] - pl.lam_j[j] * off_loc[k]
-
     ypart = np.zeros((pl.R, Mf), dtype=np.complex128)
     Wout = np.zeros((pl.R, nt, 8), dtype=np.complex128)
     Tin = np.zeros((pl.R, nt, 8), dtype=np.complex128)
@@ -179,7 +172,7 @@ def emu_main(pl: Plan, z: np.ndarray):
                                       + m.g0 * x0[k0:k0 + cnt] * rot)
             Wout[r, t] = W[cnt]
             Tin[r, t] = T[0]
-    return dict(ypart=ypart, Wout=Wout, Tin=Tin, tile_agg=tile_agg, tailwin=tailwin)
+    return dict(ypart=ypart, Wout=Wout, Tin=Tin, tile_agg=tile_agg)
 
 
 def emu_iq_scan(pl: Plan, tile_aggs: np.ndarray, off0: complex):
@@ -210,19 +203,17 @@ def emu_fixup(pl: Plan, z: np.ndarray, mo: dict, off_chunk: complex):
     for n in range(edge + 1):
         xh[n] = z[n] - o
         o = o + xh[n] * pl.Liq
-    # corrected end-window samples ws..N-1
-    n0 = N - 1 - edge
+    # corrected end-window samples ws..N-1: inside full blocks BACKWARD from the offset at q*Mf
+    # (off[n] = (off[n+1] - L z[n]) / lam), in the partial block forward from it
     xe = np.empty(pl.nend, dtype=np.complex128)
+    o = off_tile[nt]
+    for n in range(q * Mf - 1, pl.ws - 1, -1):
+        o = (o - pl.Liq * z[n]) * pl.lam_inv
+        xe[n - pl.ws] = z[n] - o
     o = off_tile[nt]                       # offset at sample q*Mf
-    for i in range(pl.nend):
-        n = pl.ws + i
-        if n < q * Mf:
-            t = (n // q) // TILE_BLOCKS
-            nt0 = t * TILE_BLOCKS * q
-            xe[i] = mo['tailwin'][n - n0] - off_tile[t] * pl.lam ** (n - nt0)
-        else:
-            xe[i] = z[n] - o
-            o = o + xe[i] * pl.Liq
+    for n in range(q * Mf, N):
+        xe[n - pl.ws] = z[n] - o
+        o = o + xe[n - pl.ws] * pl.Liq
     off_after = o
     if pl.rem == 0:
         off_after = off_tile[nt]
@@ -350,26 +341,36 @@ def emu_stream(pl: Plan, stream: bytes, off0: complex = 0j, stale_tail: bool = T
 
 # ------------------------------------------------------------------------------------------------
 # Tensor-core front end (k_tc): numpy twin.  The int8 GEMM is evaluated exactly in int64.
-def tc_block_values(pl: Plan, tc, raw: np.ndarray) -> np.ndarray:
-    """raw chunk bytes -> (Mf, nout) float64: the per-block linear functionals as k_tc's epilogue
-    reassembles them from the int32 digit columns."""
+def tc_block_values(pl: Plan, tc, raw: np.ndarray, r: int = 0) -> np.ndarray:
+    """raw chunk bytes -> (Mf, nout) float64: the per-block linear functionals of row r as k_tc's
+    epilogue reassembles them from the int32 digit columns."""
     Mf, K, ncol, nout = pl.Mf, tc.K, tc.NCOL, tc.nout
     by = np.frombuffer(raw, dtype=np.uint8)[:Mf * K].reshape(Mf, K)
     sby = (by ^ np.tile(tc.xor_mask, K // 16)[None, :]).view(np.int8).astype(np.int64)
-    acc = sby @ tc.Bq.T.astype(np.int64)                        # exact column sums
+    acc = sby @ tc.Bq[r].T.astype(np.int64)                     # exact column sums
     assert np.max(np.abs(acc)) < 2 ** 31
-    cols = acc[:, :nout * ncol].reshape(Mf, nout, ncol)
+    val = np.zeros((Mf, nout))
+    scale = 2.0 ** -tc.S
     nhi = ncol - 3
-    vhi = np.zeros((Mf, nout), dtype=np.int64)
-    vlo = np.zeros((Mf, nout), dtype=np.int64)
-    for t in range(nhi):
-        vhi = vhi * 256 + cols[:, :, t]
-    for t in range(nhi, ncol):
-        vlo = vlo * 256 + cols[:, :, t]
-    assert np.max(np.abs(vhi)) < 2 ** 51 and np.max(np.abs(vlo)) < 2 ** 51
-    # scale is a power of two: both products are exact, the sum rounds once (device: one FMA)
-    return (vhi.astype(np.float64) * (2.0 ** 24 * tc.scale)[None, :]
-            + vlo.astype(np.float64) * tc.scale[None, :]) + tc.cst[None, :]
+    for o in range(nout):
+        cols = acc[:, tc.col0[o]:tc.col0[o] + tc.ncols[o]]
+        if tc.ncols[o] != ncol:                                 # x0: exact small integer
+            v = np.zeros(Mf, dtype=np.int64)
+            for t in range(cols.shape[1]):
+                v = v * 256 + cols[:, t]
+            val[:, o] = v.astype(np.float64) + tc.cst[r, o]
+            continue
+        vhi = np.zeros(Mf, dtype=np.int64)
+        vlo = np.zeros(Mf, dtype=np.int64)
+        for t in range(nhi):
+            vhi = vhi * 256 + cols[:, t]
+        for t in range(nhi, ncol):
+            vlo = vlo * 256 + cols[:, t]
+        assert np.max(np.abs(vhi)) < 2 ** 51 and np.max(np.abs(vlo)) < 2 ** 51
+        # scale is a power of two: both products are exact, the sums round (device: two FMAs)
+        val[:, o] = vhi.astype(np.float64) * (2.0 ** 24 * scale) + (vlo.astype(np.float64) * scale
+                                                                     + tc.cst[r, o])
+    return val
 
 
 def emu_main_tc(pl: Plan, tc, raw: np.ndarray, z: np.ndarray):
@@ -378,9 +379,10 @@ def emu_main_tc(pl: Plan, tc, raw: np.ndarray, z: np.ndarray):
     window, which the kernel decodes from the staged tile."""
     q, Mf, nt = pl.q, pl.Mf, pl.ntiles
     m = pl.modes
-    val = tc_block_values(pl, tc, raw)
+    val = tc_block_values(pl, tc, raw, 0)
     zb = z[:q * Mf].reshape(Mf, q)
-    E = val[:, tc.nout - 2] + 1j * val[:, tc.nout - 1]
+    E = val[:, 32] + 1j * val[:, 33]
+    assert np.array_equal(val[:, 34] + 1j * val[:, 35], zb[:, 0])   # x0 comes out of the GEMM exactly
     blk_agg = pl.Liq * E
     off_loc = np.zeros(Mf, dtype=np.complex128)
     tile_agg = np.zeros(nt, dtype=np.complex128)
@@ -391,23 +393,11 @@ def emu_main_tc(pl: Plan, tc, raw: np.ndarray, z: np.ndarray):
             off_loc[k0 + l] = o
             o = pl.lam_q * o + blk_agg[k0 + l]
         tile_agg[t] = o
-    # tail window from the last block's samples: block-local EMA, then the tile-local offset
-    n0 = pl.N - 1 - pl.edge
-    tailwin = np.zeros(pl.edge + 1, dtype=np.complex128)
-    acc = np.zeros(Mf, dtype=np.complex128)
-    zp = np.empty_like(zb)
-    for j in range(q):
-        zp[:, j] = zb[:, j] - pl.Liq * acc
-        acc = pl.lam * acc + zb[:, j]
-    for n in range(n0, q * Mf):
-        k, j = divmod(n, q)
-        tailwin[n - n0] = zp[k, j] - pl.lam_j[j] * off_loc[k]
-
     ypart = np.zeros((pl.R, Mf), dtype=np.complex128)
     Wout = np.zeros((pl.R, nt, 8), dtype=np.complex128)
     Tin = np.zeros((pl.R, nt, 8), dtype=np.complex128)
     for r in range(pl.R):
-        v = val[:, 32 * r:32 * r + 32]
+        v = tc_block_values(pl, tc, raw, r)
         F = v[:, 0:16:2] + 1j * v[:, 1:16:2]
         G = v[:, 16:32:2] + 1j * v[:, 17:32:2]
         F = F - off_loc[:, None] * pl.PhiF[r][None, :]
@@ -429,7 +419,7 @@ def emu_main_tc(pl: Plan, tc, raw: np.ndarray, z: np.ndarray):
                                       + m.g0 * x0[k0:k0 + cnt] * rot)
             Wout[r, t] = W[cnt]
             Tin[r, t] = T[0]
-    return dict(ypart=ypart, Wout=Wout, Tin=Tin, tile_agg=tile_agg, tailwin=tailwin)
+    return dict(ypart=ypart, Wout=Wout, Tin=Tin, tile_agg=tile_agg)
 
 
 def emu_stream_tc(pl: Plan, tc, stream: bytes, off0: complex = 0j):
