@@ -95,6 +95,7 @@ typedef struct sdrb_tables {
     int32_t sos_Lseg;        /* output SOS evaluated in 32 segments of this many samples */
     const double *sos_AL;    /* [ns][ns], ns = 2*n_out_sections: A^Lseg of the output cascade */
     const double *sos_CA;    /* [sos_Lseg][ns]: c A^i */
+    const double *sos_AP;    /* [5][ns][ns]: (A^Lseg)^(2^lv), lv = 0..4 */
     /* tensor-core block front end (plan.py: build_tc); tc_enable == 0 selects the FP64 block
      * kernel.  The raw stream is the int8 A operand of an exact GEMM against one tc_Bq slice per
      * row of the bank. */

@@ -12,6 +12,7 @@
 #include "../../include/sdrterm_b200.h"
 #include "sdrb_kernels.cuh"
 #include "sdrb_tc.cuh"
+#include "sdrb_finish.cuh"
 
 namespace {
 
@@ -39,6 +40,9 @@ struct sdrb_handle {
     int enc_code = 0;
     int tpc = 1, warps = 4;
     size_t main_smem = 0, demod_smem = 0;
+    bool finish_on = false;         // fused k_finish instead of k_fixup + k_demod
+    size_t finish_smem = 0;
+    int keep_y = 1;
     long long launches = 0;
     size_t last_nchunks = 0;
     bool profiling = false;
@@ -186,7 +190,6 @@ int launch_tc(sdrb_handle *h, const uint8_t *raw, size_t nch, cudaStream_t st, b
     switch (h->tc.ncol) {
     case 5: return iq ? launch_tc_t<true, 5>(h, map_a, nch, n_mtiles, st) : launch_tc_t<false, 5>(h, map_a, nch, n_mtiles, st);
     case 6: return iq ? launch_tc_t<true, 6>(h, map_a, nch, n_mtiles, st) : launch_tc_t<false, 6>(h, map_a, nch, n_mtiles, st);
-    case 7: return iq ? launch_tc_t<true, 7>(h, map_a, nch, n_mtiles, st) : launch_tc_t<false, 7>(h, map_a, nch, n_mtiles, st);
     }
     return fail(h, SDRB_ERR_ARG, "unsupported digit column count %d", h->tc.ncol);
 }
@@ -202,7 +205,7 @@ int setup_tc(sdrb_handle *h, const sdrb_tables *tab, const std::vector<double2> 
 {
     if (!tab->tc_enable || env_int("SDRB_NO_TC", 0)) return 0;
     const int R = h->pl.R;
-    if ((tab->tc_K != 128 && tab->tc_K != 256) || tab->tc_nout != TC_NOUT || tab->tc_ncol < 5 || tab->tc_ncol > 7 ||
+    if ((tab->tc_K != 128 && tab->tc_K != 256) || tab->tc_nout != TC_NOUT || tab->tc_ncol < 5 || tab->tc_ncol > 6 ||
         tab->tc_isz < 1 || tab->tc_isz > 2 || tab->tc_npad > 256 || tab->tc_npad % 16 ||
         tab->tc_npad < 34 * tab->tc_ncol + 2 * tab->tc_isz || tab->tc_K != h->pl.q * h->pl.sb || h->pl.rem != 0 ||
         h->pl.cnt_last != SDRB_TB || h->pl.q < h->pl.edge + 1 || h->pl.normalize || !tab->tc_Bq || !tab->tc_cst)
@@ -219,7 +222,7 @@ int setup_tc(sdrb_handle *h, const sdrb_tables *tab, const std::vector<double2> 
         if (tab->tc_xor[i] != tab->tc_xor[i & 3]) return fail(h, SDRB_ERR_ARG, "XOR pattern is not 4-periodic");
     tc.idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(tc.npad >> 3) << 17) | ((128u >> 4) << 24);
     tc.scale = ldexp(1.0, -tab->tc_S);
-    tc.scale24 = ldexp(1.0, 24 - tab->tc_S);
+    tc.scale16 = ldexp(1.0, 16 - tab->tc_S);
     // powers 0..8 of the rotating-frame block multipliers (segment carries of the tile scans)
     std::vector<double2> ppow((size_t)R * 16 * 9);
     for (int i = 0; i < R * 16; i++) {
@@ -243,7 +246,7 @@ int setup_tc(sdrb_handle *h, const sdrb_tables *tab, const std::vector<double2> 
     h->tc_smem = tc_smem_bytes(tc.npad, tc.nregion);
     if (h->tc_smem > 227 * 1024) return fail(h, SDRB_ERR_ARG, "k_tc needs %zu bytes of shared memory", h->tc_smem);
     if ((rc = tc_attr<true, 5>(h)) || (rc = tc_attr<false, 5>(h)) || (rc = tc_attr<true, 6>(h)) ||
-        (rc = tc_attr<false, 6>(h)) || (rc = tc_attr<true, 7>(h)) || (rc = tc_attr<false, 7>(h)))
+        (rc = tc_attr<false, 6>(h)))
         return rc;
     h->tc_on = true;
     return 0;
@@ -280,7 +283,14 @@ int launch_chain_t(sdrb_handle *h, const uint8_t *raw, size_t nch, double *out, 
         h->launches += 3;
     }
     mark(2);
-    if (phases & PH_FINISH) {
+    if ((phases & PH_FINISH) && h->finish_on) {
+        const size_t items = nch * (size_t)pl.R;
+        const unsigned grid = (unsigned)std::min<size_t>((items + FIN_WARPS - 1) / FIN_WARPS, (size_t)h->num_sms * 2);
+        k_finish<ENC><<<grid, 32 * FIN_WARPS, h->finish_smem, st>>>(pl, h->sc, raw, out, (int)nch, h->keep_y);
+        h->launches++;
+        mark(3);
+        mark(4);
+    } else if (phases & PH_FINISH) {
         k_fixup<ENC><<<(unsigned)(nch * pl.R), 128, 0, st>>>(pl, h->sc, raw, (int)nch);
         h->launches++;
         mark(3);
@@ -313,6 +323,8 @@ template <int ENC, bool IQ>
 int set_smem_attr_t(sdrb_handle *h)
 {
     CK(h, cudaFuncSetAttribute(k_main<ENC, IQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->main_smem));
+    if (h->finish_on)
+        CK(h, cudaFuncSetAttribute(k_finish<ENC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->finish_smem));
     return 0;
 }
 int set_smem_attr(sdrb_handle *h)
@@ -381,6 +393,8 @@ int sdrb_create(const sdrb_config *cfg, const sdrb_tables *tab, sdrb_handle **ou
         if (!tab->sos_AL || !tab->sos_CA || tab->sos_Lseg * 32 < pl.M)
             return bail(fail(h, SDRB_ERR_ARG, "output SOS segment tables missing or too short"));
         for (int i = 0; i < pl.sos_ns * pl.sos_ns; i++) pl.sos_AL[i] = tab->sos_AL[i];
+        if (pl.sos_ns == 4 && tab->sos_AP)
+            for (int i = 0; i < 80; i++) pl.sos_AP[i] = tab->sos_AP[i];
     }
     pl.ws = std::min(pl.q * pl.Mf, pl.N - 1 - pl.edge); pl.nend = pl.N - pl.ws;
     pl.k_bnd = tab->k_bnd; pl.nsec_out = cfg->n_out_sections;
@@ -470,6 +484,16 @@ int sdrb_create(const sdrb_config *cfg, const sdrb_tables *tab, sdrb_handle **ou
     while (h->warps > 1 && smem_for(h->tpc, h->warps) > 220 * 1024) h->warps--;
     h->main_smem = smem_for(h->tpc, h->warps);
     if (h->main_smem > 227 * 1024) return bail(fail(h, SDRB_ERR_ARG, "decimation %d needs too much shared memory", q));
+    {
+        cudaDeviceProp prop;
+        if (cudaGetDeviceProperties(&prop, cfg->device) == cudaSuccess) h->num_sms = prop.multiProcessorCount;
+        const bool pow2 = is_pow2(M);
+        h->finish_on = !env_int("SDRB_NO_FINISH", 0) && pl.rem == 0 && pl.cnt_last == SDRB_TB && q >= pl.edge + 1 &&
+                       pow2 && M >= 64 && M <= 1024 && pl.edge + 1 <= 32 &&
+                       (cfg->n_out_sections == 0 || (cfg->n_out_sections == 2 && tab->sos_AP));
+        h->finish_smem = h->finish_on ? finish_smem_bytes(M) : 0;
+        if (h->finish_smem > 227 * 1024) h->finish_on = false;
+    }
     UP(set_smem_attr(h));
     const size_t dsm = (size_t)M * (2 * sizeof(double2) + sizeof(double));
     pl.demod_in_smem = dsm <= 96 * 1024 ? 1 : 0;

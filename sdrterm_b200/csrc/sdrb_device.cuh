@@ -23,6 +23,7 @@ struct DevPlan {
     double Liq, lam, lam_q, lam_N, lam_inv, g0, d, norm_xmin, norm_k;
     double lam_run[8];     // lam^run_len
     double sos_AL[64];     // [ns][ns] A^Lseg of the output cascade
+    double sos_AP[80];     // [5][4][4] (A^Lseg)^(2^lv), two-section cascades (k_finish's lane scan)
     double lamq_pow[5];    // lam_q^(1,2,4,8,16)
     double lam_tile[2];
     double2 p[SDRB_NP], P[SDRB_NP], rho[SDRB_NP], rho_p[SDRB_NP], c[SDRB_NP], zhat[SDRB_NP];

@@ -47,7 +47,7 @@ struct TcDev {
     uint32_t xor_word;                 // XOR pattern of 4 consecutive stream bytes
     uint32_t idesc;                    // tcgen05 instruction descriptor (i8 x i8 -> s32, M=128, N=npad)
     double scale;                      // 2^-S, common to every fixed-point output
-    double scale24;                    // 2^(24-S)
+    double scale16;                    // 2^(16-S): weight of the columns above the low pair
     const double *cst;                 // [R][TC_NOUT] response to the constant the XOR removed
     const double2 *prot_pow;           // [R][16][9] powers 0..8 of the rotating-frame block multipliers
 };
@@ -90,13 +90,23 @@ __device__ __forceinline__ bool mbar_try(uint32_t a, uint32_t parity)
                  : "=r"(ok) : "r"(a), "r"(parity) : "memory");
     return ok != 0;
 }
-// Bounded wait: a protocol error traps (and surfaces as a CUDA error) instead of hanging the GPU.
+// Bounded waits: a protocol error traps (and surfaces as a CUDA error) instead of hanging the GPU.
+// try_wait itself suspends the warp for a hardware-defined interval, so the loop body is kept to
+// the bare minimum; `mbar_wait_sleep` additionally backs off (used by the producer-side warps
+// whose waits are long and whose wake-up latency does not matter).
 __device__ __forceinline__ void mbar_wait(uint32_t a, uint32_t parity)
 {
-    if (mbar_try(a, parity)) return;
-    const long long t0 = clock64();
+    uint32_t n = 0;
     while (!mbar_try(a, parity))
-        if (clock64() - t0 > 4000000000LL) __trap();
+        if (++n > (1u << 28)) __trap();
+}
+__device__ __forceinline__ void mbar_wait_sleep(uint32_t a, uint32_t parity)
+{
+    uint32_t n = 0;
+    while (!mbar_try(a, parity)) {
+        __nanosleep(64);
+        if (++n > (1u << 26)) __trap();
+    }
 }
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map, int x, int y, uint32_t bar)
 {
@@ -153,41 +163,212 @@ __device__ __forceinline__ double i64_to_double(long long v)
 {
     return __longlong_as_double(v + 0x4338000000000000LL) - 6755399441055744.0;
 }
-
-// Digit columns c[0..NCOL) (most significant first, weight 256 per step) -> value * scale + cst.
-template <int NCOL>
-__device__ __forceinline__ double tc_combine(const uint32_t *c, double s24, double s, double cst)
+// int32 -> 2^52 + 2^31 + v as a double (exact); the caller folds the bias into its constant.
+__device__ __forceinline__ double i32_biased(int v)
 {
-    constexpr int NHI = NCOL - 3;
-    long long vhi = (int)c[0];
-#pragma unroll
-    for (int t = 1; t < NHI; t++) vhi = vhi * 256 + (int)c[t];
-    long long vlo = (int)c[NHI];
-#pragma unroll
-    for (int t = NHI + 1; t < NCOL; t++) vlo = vlo * 256 + (int)c[t];
-    return fma(i64_to_double(vhi), s24, fma(i64_to_double(vlo), s, cst));
+    return __hiloint2double(0x43300000, v ^ 0x80000000);
 }
+#define TC_BIAS32 4503601774854144.0      // 2^52 + 2^31
+
+// Digit columns c[0..NCOL) (most significant first, weight 256 per step) -> value * 2^-S + cst.
+// Columns are summed in adjacent pairs in 32 bits (|column| < 2^22), the high pairs are joined by
+// one wide multiply-add and converted through the 2^52 bias; the low pair rides on the bias of a
+// single FMA whose constant `cstb` = cst - (2^52 + 2^31) * 2^-S already removes it.
+template <int NCOL>
+__device__ __forceinline__ double tc_combine(const uint32_t *c, double s16, double s1, double cstb)
+{
+    static_assert(NCOL >= 5 && NCOL <= 7, "digit columns");
+    constexpr int NH = NCOL - 2;                       // columns above the low pair
+    const int lo = (int)c[NCOL - 2] * 256 + (int)c[NCOL - 1];
+    long long hi;
+    if (NH == 3) {
+        hi = (long long)(int)c[0] * 65536 + (long long)((int)c[1] * 256 + (int)c[2]);
+    } else if (NH == 4) {
+        hi = (long long)((int)c[0] * 256 + (int)c[1]) * 65536 + (long long)((int)c[2] * 256 + (int)c[3]);
+    } else {
+        hi = ((long long)((int)c[0] * 256 + (int)c[1]) * 65536 + (long long)((int)c[2] * 256 + (int)c[3])) * 256 +
+             (long long)(int)c[4];
+    }
+    return fma(i64_to_double(hi), s16, fma(i32_biased(lo), s1, cstb));
+}
+
 // ------------------------------------------------------------------------------------- k_tc
+struct TcShared {
+    unsigned char *sB, *sA;
+    double2 *sXS, *sPB, *sPhi, *sPow;
+    double *sCst;
+    uint32_t bar0;
+};
+
+// Epilogue of one warp: HALF 0 = forward modal sums F_i (+ x0, tile aggregate of the IQ offsets),
+// HALF 1 = backward sums G_i.  See the file header for the stages.
+template <bool IQ, int NCOL, int HALF>
+__device__ __forceinline__ void tc_epilogue(const DevPlan &pl, const TcDev &tc, const Scratch &sc, const TcShared &sh,
+                                            uint32_t tmem_base, int e, int lane, int r, int slot, int nslots,
+                                            int my_iters, int total_tiles)
+{
+    enum { B_MMA_DONE = 2, B_TMEM_FREE = 4 };
+    const int qd = e & 3, g = e >> 3;
+    double2 *xs = sh.sXS + (size_t)e * 8 * TC_XS;
+    const int pole = lane & 7, seg = lane >> 3;
+    const double2 *pw = sh.sPow + (HALF * 8 + pole) * 9;
+    const double2 Pm = pw[1], Pm8 = pw[8];
+    const double2 rot = pl.T3[(size_t)r * (SDRB_TB + 1) + lane];
+    const double2 rot31 = pl.T3[(size_t)r * (SDRB_TB + 1) + SDRB_TB - 1];
+    const double2 epsb = cconj(pl.T3[(size_t)r * (SDRB_TB + 1) + 1]);
+    const uint32_t pair_bar = 1u + (uint32_t)(g * 4 + qd);
+    const double s16 = tc.scale16, s1 = tc.scale;
+    const uint32_t bar_done = sh.bar0 + 8u * (uint32_t)(B_MMA_DONE * TC_STAGES + g);
+    const uint32_t bar_free = sh.bar0 + 8u * (uint32_t)(B_TMEM_FREE * TC_STAGES + g);
+    const uint32_t trow = tmem_base + ((uint32_t)(32 * qd) << 16) + (uint32_t)(g * 256);
+    double2 *xsl = xs + lane;                      // lane <-> block view
+    double2 *xsp = xs + pole * TC_XS + seg * 8;    // (segment, mode) view
+
+    for (int it = g; it < my_iters; it += 2) {
+        const int u = it >> 1;
+        const int mt = slot + it * nslots;
+        const int gt = 4 * mt + qd;
+        mbar_wait(bar_done, u & 1);
+        tc_fence_after();
+        if (gt >= total_tiles) {
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_free);
+            continue;
+        }
+        const int chunk = gt / pl.ntiles, t = gt - chunk * pl.ntiles;
+        uint32_t c[32];
+
+        // ---- IQ-EMA block aggregate E -> tile-local block offsets, tile aggregate; x0
+        double2 excl = make_double2(0.0, 0.0), x0 = make_double2(0.0, 0.0);
+        if (IQ || HALF == 0) {
+            tmem_ld32(trow + 32 * NCOL, c);
+            tmem_ld_wait();
+            if (HALF == 0) {                      // x0: isz exact columns per component
+                int xr, xi;
+                if (tc.isz == 2) {
+                    xr = (int)c[2 * NCOL] * 256 + (int)c[2 * NCOL + 1];
+                    xi = (int)c[2 * NCOL + 2] * 256 + (int)c[2 * NCOL + 3];
+                } else {
+                    xr = (int)c[2 * NCOL]; xi = (int)c[2 * NCOL + 1];
+                }
+                x0 = make_double2(i32_biased(xr) + sh.sCst[34], i32_biased(xi) + sh.sCst[35]);
+            }
+            if (IQ) {
+                const double er = tc_combine<NCOL>(c, s16, s1, sh.sCst[32]);
+                const double ei = tc_combine<NCOL>(c + NCOL, s16, s1, sh.sCst[33]);
+                double2 inc = make_double2(pl.Liq * er, pl.Liq * ei);
+#pragma unroll
+                for (int i = 0; i < 5; i++) {
+                    const double2 tt = shfl_up_c(inc, 1 << i);
+                    if (lane >= (1 << i)) { inc.x = fma(pl.lamq_pow[i], tt.x, inc.x); inc.y = fma(pl.lamq_pow[i], tt.y, inc.y); }
+                }
+                excl = shfl_up_c(inc, 1);
+                if (lane == 0) excl = make_double2(0.0, 0.0);
+                if (HALF == 0 && lane == 31 && r == 0) sc.tile_agg[(size_t)chunk * pl.ntiles + t] = inc;
+            }
+        }
+        // ---- this half's eight modal block sums: digit columns -> FP64, minus the response to
+        //      the tile-local offset; lane <-> block, parked mode-major for the scans
+#pragma unroll
+        for (int og = 0; og < 4; og++) {
+            tmem_ld32(trow + 4 * NCOL * (4 * HALF + og), c);
+            tmem_ld_wait();
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                const int md = 2 * og + h;                     // mode within this half
+                const int o = 16 * HALF + 2 * md;              // output index of its real part
+                double vr = tc_combine<NCOL>(c + (2 * h) * NCOL, s16, s1, sh.sCst[o]);
+                double vi = tc_combine<NCOL>(c + (2 * h + 1) * NCOL, s16, s1, sh.sCst[o + 1]);
+                if (IQ) {
+                    const double2 ph = sh.sPhi[8 * HALF + md];
+                    vr -= fma(excl.x, ph.x, -excl.y * ph.y);
+                    vi -= fma(excl.x, ph.y, excl.y * ph.x);
+                }
+                xsl[md * TC_XS] = make_double2(vr, vi);
+            }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_free);
+
+        // ---- tile-local scans in the rotating frame, lane = (segment of 8 blocks, mode):
+        //      A. each segment from a zero state, B. carries across the 4 segments,
+        //      C. carry applied with the multiplier powers
+        double2 loc[8];
+        double2 st = make_double2(0.0, 0.0);
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            const double2 v = xsp[HALF ? 7 - j : j];
+            const double2 nst = cfma(Pm, st, v);
+            loc[j] = HALF ? nst : st;
+            st = nst;
+        }
+        double2 cin = make_double2(0.0, 0.0);
+        if (HALF == 0) {
+#pragma unroll
+            for (int j = 0; j < 3; j++) {
+                const double2 ej = shfl_c(st, j * 8 + pole);
+                if (j < seg) cin = cfma(Pm8, cin, ej);
+            }
+        } else {
+#pragma unroll
+            for (int j = 3; j > 0; j--) {
+                const double2 ej = shfl_c(st, j * 8 + pole);
+                if (j > seg) cin = cfma(Pm8, cin, ej);
+            }
+        }
+        if (seg == (HALF ? 0 : 3)) {
+            const double2 tot = cfma(Pm8, cin, st);
+            double2 *ag = sc.agg + (((size_t)chunk * pl.R + r) * pl.ntiles + t) * 16;
+            if (HALF == 0) ag[pole] = cmul(rot31, tot);
+            else ag[8 + pole] = tot;
+        }
+#pragma unroll
+        for (int j = 0; j < 8; j++) xsp[HALF ? 7 - j : j] = cfma(pw[HALF ? j + 1 : j], cin, loc[j]);
+        __syncwarp();
+        // ---- partial output of each block (lane <-> block): half 0 sums rho_i W_i, half 1
+        //      rho_i/p_i T_i; half 0 finishes
+        double2 acc = make_double2(0.0, 0.0);
+#pragma unroll
+        for (int i = 0; i < 8; i++) acc = cfma(HALF ? pl.rho_p[i] : pl.rho[i], xsl[i * TC_XS], acc);
+        double2 *pb = sh.sPB + ((size_t)(u & 1) * 8 + (g * 4 + qd)) * 32;
+        if (HALF) pb[lane] = acc;
+        asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
+        if (HALF == 0) {
+            const double2 sT = pb[lane];
+            const double2 xc = csub(x0, excl);
+            double2 ys = cfma(epsb, acc, sT);
+            ys.x = fma(pl.g0, xc.x, ys.x); ys.y = fma(pl.g0, xc.y, ys.y);
+            sc.ypart[((size_t)chunk * pl.R + r) * pl.Mf + (size_t)t * SDRB_TB + lane] = cmul(rot, ys);
+        }
+        __syncwarp();
+    }
+}
+
 template <bool IQ, int NCOL>
 __global__ void __launch_bounds__(TC_THREADS, 1)
-k_tc(const __grid_constant__ DevPlan pl, const __grid_constant__ TcDev tc, Scratch sc,
+k_tc(const __grid_constant__ DevPlan pl, const __grid_constant__ TcDev tc, const __grid_constant__ Scratch sc,
      const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
      int nchunks, int n_mtiles)
 {
     extern __shared__ unsigned char smem_dyn[];
-    unsigned char *smem = reinterpret_cast<unsigned char *>(((uintptr_t)smem_dyn + 1023) & ~(uintptr_t)1023);
+    // keep the shared address space visible to the compiler: offset the array, do not re-cast
+    unsigned char *smem = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nreg = tc.nregion, npad = tc.npad;
-    unsigned char *sB = smem;
-    unsigned char *sA = sB + (size_t)nreg * npad * 128;
-    double2 *sXS = reinterpret_cast<double2 *>(sA + (size_t)TC_STAGES * nreg * TC_REGION_BYTES);
-    double2 *sPB = sXS + (size_t)TC_EPI_WARPS * 8 * TC_XS;
-    double2 *sPhi = sPB + 2 * 8 * 32;
-    double2 *sPow = sPhi + 16;
-    double *sCst = reinterpret_cast<double *>(sPow + 16 * 9);
-    unsigned long long *bars = reinterpret_cast<unsigned long long *>(sCst + TC_NOUT);
+    TcShared sh;
+    sh.sB = smem;
+    sh.sA = sh.sB + (size_t)nreg * npad * 128;
+    sh.sXS = reinterpret_cast<double2 *>(sh.sA + (size_t)TC_STAGES * nreg * TC_REGION_BYTES);
+    sh.sPB = sh.sXS + (size_t)TC_EPI_WARPS * 8 * TC_XS;
+    sh.sPhi = sh.sPB + 2 * 8 * 32;
+    sh.sPow = sh.sPhi + 16;
+    sh.sCst = reinterpret_cast<double *>(sh.sPow + 16 * 9);
+    unsigned long long *bars = reinterpret_cast<unsigned long long *>(sh.sCst + TC_NOUT);
     __shared__ uint32_t tmem_base_s;
     const uint32_t bar0 = smem_u32(bars);
+    sh.bar0 = bar0;
+    unsigned char *sA = sh.sA, *sB = sh.sB;
     auto BAR = [&](int kind, int s) { return bar0 + 8u * (uint32_t)(kind * TC_STAGES + s); };
     enum { B_FULL_A = 0, B_XORED = 1, B_MMA_DONE = 2, B_A_FREE = 3, B_TMEM_FREE = 4, B_BFULL = 5 };
 
@@ -207,9 +388,13 @@ k_tc(const __grid_constant__ DevPlan pl, const __grid_constant__ TcDev tc, Scrat
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (threadIdx.x < 16)
-        sPhi[threadIdx.x] = threadIdx.x < 8 ? pl.PhiF[(size_t)r * 8 + threadIdx.x] : pl.PhiG[(size_t)r * 8 + threadIdx.x - 8];
-    for (int i = threadIdx.x; i < 16 * 9; i += blockDim.x) sPow[i] = tc.prot_pow[(size_t)r * 16 * 9 + i];
-    if (threadIdx.x >= 64 && threadIdx.x < 64 + TC_NOUT) sCst[threadIdx.x - 64] = tc.cst[(size_t)r * TC_NOUT + threadIdx.x - 64];
+        sh.sPhi[threadIdx.x] = threadIdx.x < 8 ? pl.PhiF[(size_t)r * 8 + threadIdx.x] : pl.PhiG[(size_t)r * 8 + threadIdx.x - 8];
+    for (int i = threadIdx.x; i < 16 * 9; i += blockDim.x) sh.sPow[i] = tc.prot_pow[(size_t)r * 16 * 9 + i];
+    if (threadIdx.x >= 64 && threadIdx.x < 64 + TC_NOUT) {
+        // fixed-point outputs carry the 2^52 + 2^31 bias of their low column pair, x0 its own
+        const int o = threadIdx.x - 64;
+        sh.sCst[o] = tc.cst[(size_t)r * TC_NOUT + o] - TC_BIAS32 * (o < 34 ? tc.scale : 1.0);
+    }
     if (warp == 1) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(&tmem_base_s)) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -230,7 +415,7 @@ k_tc(const __grid_constant__ DevPlan pl, const __grid_constant__ TcDev tc, Scrat
             for (int it = 0; it < my_iters; it++) {
                 const int s = it & 1, u = it >> 1;
                 const int mt = slot + it * nslots;
-                mbar_wait(BAR(B_A_FREE, s), (u & 1) ^ 1);
+                mbar_wait_sleep(BAR(B_A_FREE, s), (u & 1) ^ 1);
                 mbar_expect_tx(BAR(B_FULL_A, s), (uint32_t)(nreg * TC_REGION_BYTES));
                 for (int rg = 0; rg < nreg; rg++)
                     tma_load_2d(smem_u32(sA + ((size_t)s * nreg + rg) * TC_REGION_BYTES), &map_a, rg * 128, mt * 128,
@@ -240,10 +425,10 @@ k_tc(const __grid_constant__ DevPlan pl, const __grid_constant__ TcDev tc, Scrat
     } else if (warp == 1) {
         // ===================================================================== MMA issuer
         if (lane == 0 && my_iters > 0) {
-            mbar_wait(BAR(B_BFULL, 0), 0);
+            mbar_wait_sleep(BAR(B_BFULL, 0), 0);
             for (int it = 0; it < my_iters; it++) {
                 const int s = it & 1, u = it >> 1;
-                mbar_wait(BAR(B_XORED, s), u & 1);
+                mbar_wait_sleep(BAR(B_XORED, s), u & 1);
                 mbar_wait(BAR(B_TMEM_FREE, s), (u & 1) ^ 1);
                 tc_fence_after();
                 const uint32_t d = tmem_base + (uint32_t)(s * 256);
@@ -264,7 +449,7 @@ k_tc(const __grid_constant__ DevPlan pl, const __grid_constant__ TcDev tc, Scrat
         const uint32_t m = tc.xor_word;
         for (int it = 0; it < my_iters; it++) {
             const int s = it & 1, u = it >> 1;
-            mbar_wait(BAR(B_FULL_A, s), u & 1);
+            mbar_wait_sleep(BAR(B_FULL_A, s), u & 1);
             uint4 *base = reinterpret_cast<uint4 *>(sA + (size_t)s * nreg * TC_REGION_BYTES);
             const int n16 = nreg * (TC_REGION_BYTES / 16);
 #pragma unroll 8
@@ -279,140 +464,9 @@ k_tc(const __grid_constant__ DevPlan pl, const __grid_constant__ TcDev tc, Scrat
         }
     } else {
         // ===================================================================== epilogue
-        const int e = warp - 4, qd = e & 3, half = (e >> 2) & 1, g = e >> 3;
-        double2 *xs = sXS + (size_t)e * 8 * TC_XS;
-        const int pole = lane & 7, seg = lane >> 3;
-        const double2 *pw = sPow + (half * 8 + pole) * 9;
-        const double2 Pm = pw[1], Pm8 = pw[8];
-        const double2 rot = pl.T3[(size_t)r * (SDRB_TB + 1) + lane];
-        const double2 rot31 = pl.T3[(size_t)r * (SDRB_TB + 1) + SDRB_TB - 1];
-        const double2 epsb = cconj(pl.T3[(size_t)r * (SDRB_TB + 1) + 1]);
-        const uint32_t pair_bar = 1u + (uint32_t)(g * 4 + qd);
-        const double s24 = tc.scale24, s1 = tc.scale;
-        for (int it = g; it < my_iters; it += 2) {
-            const int s = g, u = it >> 1;
-            const int mt = slot + it * nslots;
-            const int gt = 4 * mt + qd;
-            mbar_wait(BAR(B_MMA_DONE, s), u & 1);
-            tc_fence_after();
-            if (gt >= total_tiles) {
-                __syncwarp();
-                if (lane == 0) mbar_arrive(BAR(B_TMEM_FREE, s));
-                continue;
-            }
-            const int chunk = gt / pl.ntiles, t = gt % pl.ntiles;
-            const uint32_t trow = tmem_base + ((uint32_t)(32 * qd) << 16) + (uint32_t)(s * 256);
-            uint32_t c[32];
-
-            // ---- IQ-EMA block aggregate E -> tile-local block offsets, tile aggregate; x0
-            double2 excl = make_double2(0.0, 0.0), x0 = make_double2(0.0, 0.0);
-            if (IQ || half == 0) {
-                tmem_ld32(trow + 32 * NCOL, c);
-                tmem_ld_wait();
-                if (half == 0) {                  // x0: isz exact columns per component
-                    int xr, xi;
-                    if (tc.isz == 2) {
-                        xr = (int)c[2 * NCOL] * 256 + (int)c[2 * NCOL + 1];
-                        xi = (int)c[2 * NCOL + 2] * 256 + (int)c[2 * NCOL + 3];
-                    } else {
-                        xr = (int)c[2 * NCOL]; xi = (int)c[2 * NCOL + 1];
-                    }
-                    x0 = make_double2((double)xr + sCst[34], (double)xi + sCst[35]);
-                }
-                if (IQ) {
-                    const double er = tc_combine<NCOL>(c, s24, s1, sCst[32]);
-                    const double ei = tc_combine<NCOL>(c + NCOL, s24, s1, sCst[33]);
-                    double2 inc = make_double2(pl.Liq * er, pl.Liq * ei);
-#pragma unroll
-                    for (int i = 0; i < 5; i++) {
-                        const double2 tt = shfl_up_c(inc, 1 << i);
-                        if (lane >= (1 << i)) { inc.x = fma(pl.lamq_pow[i], tt.x, inc.x); inc.y = fma(pl.lamq_pow[i], tt.y, inc.y); }
-                    }
-                    excl = shfl_up_c(inc, 1);
-                    if (lane == 0) excl = make_double2(0.0, 0.0);
-                    if (half == 0 && lane == 31 && r == 0) sc.tile_agg[(size_t)chunk * pl.ntiles + t] = inc;
-                }
-            }
-            // ---- this half's eight modal block sums: digit columns -> FP64, minus the response
-            //      to the tile-local offset; lane <-> block, parked mode-major for the scans
-#pragma unroll
-            for (int og = 0; og < 4; og++) {
-                tmem_ld32(trow + 4 * NCOL * (4 * half + og), c);
-                tmem_ld_wait();
-#pragma unroll
-                for (int h = 0; h < 2; h++) {
-                    const int md = 2 * og + h;                     // mode within this half
-                    const int o = 16 * half + 2 * md;              // output index of its real part
-                    double vr = tc_combine<NCOL>(c + (2 * h) * NCOL, s24, s1, sCst[o]);
-                    double vi = tc_combine<NCOL>(c + (2 * h + 1) * NCOL, s24, s1, sCst[o + 1]);
-                    if (IQ) {
-                        const double2 ph = sPhi[8 * half + md];
-                        vr -= fma(excl.x, ph.x, -excl.y * ph.y);
-                        vi -= fma(excl.x, ph.y, excl.y * ph.x);
-                    }
-                    xs[md * TC_XS + lane] = make_double2(vr, vi);
-                }
-            }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(BAR(B_TMEM_FREE, s));
-
-            // ---- tile-local scans in the rotating frame, lane = (segment of 8 blocks, mode):
-            //      A. each segment from a zero state, B. carries across the 4 segments,
-            //      C. carry applied with the multiplier powers
-            double2 loc[8];
-            double2 st = make_double2(0.0, 0.0);
-#pragma unroll
-            for (int j = 0; j < 8; j++) {
-                const int l = seg * 8 + (half ? 7 - j : j);
-                const double2 v = xs[pole * TC_XS + l];
-                const double2 nst = cfma(Pm, st, v);
-                loc[j] = half ? nst : st;
-                st = nst;
-            }
-            double2 cin = make_double2(0.0, 0.0);
-            if (half == 0) {
-#pragma unroll
-                for (int j = 0; j < 3; j++) {
-                    const double2 ej = shfl_c(st, j * 8 + pole);
-                    if (j < seg) cin = cfma(Pm8, cin, ej);
-                }
-            } else {
-#pragma unroll
-                for (int j = 3; j > 0; j--) {
-                    const double2 ej = shfl_c(st, j * 8 + pole);
-                    if (j > seg) cin = cfma(Pm8, cin, ej);
-                }
-            }
-            {
-                const double2 tot = cfma(Pm8, cin, st);
-                double2 *ag = sc.agg + (((size_t)chunk * pl.R + r) * pl.ntiles + t) * 16;
-                if (half == 0 && seg == 3) ag[pole] = cmul(rot31, tot);
-                if (half == 1 && seg == 0) ag[8 + pole] = tot;
-            }
-#pragma unroll
-            for (int j = 0; j < 8; j++) {
-                const int l = seg * 8 + (half ? 7 - j : j);
-                xs[pole * TC_XS + l] = cfma(pw[half ? j + 1 : j], cin, loc[j]);
-            }
-            __syncwarp();
-            // ---- partial output of each block (lane <-> block): half 0 sums rho_i W_i, half 1
-            //      rho_i/p_i T_i; half 0 finishes
-            double2 acc = make_double2(0.0, 0.0);
-#pragma unroll
-            for (int i = 0; i < 8; i++) acc = cfma(half ? pl.rho_p[i] : pl.rho[i], xs[i * TC_XS + lane], acc);
-            double2 *pb = sPB + ((size_t)(u & 1) * 8 + (g * 4 + qd)) * 32;
-            if (half) pb[lane] = acc;
-            asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
-            if (half == 0) {
-                const double2 sT = pb[lane];
-                const double2 xc = csub(x0, excl);
-                double2 ys = cfma(epsb, acc, sT);
-                ys.x = fma(pl.g0, xc.x, ys.x); ys.y = fma(pl.g0, xc.y, ys.y);
-                sc.ypart[((size_t)chunk * pl.R + r) * pl.Mf + (size_t)t * SDRB_TB + lane] = cmul(rot, ys);
-            }
-            __syncwarp();
-        }
+        const int e = warp - 4;
+        if ((e >> 2) & 1) tc_epilogue<IQ, NCOL, 1>(pl, tc, sc, sh, tmem_base, e, lane, r, slot, nslots, my_iters, total_tiles);
+        else tc_epilogue<IQ, NCOL, 0>(pl, tc, sc, sh, tmem_base, e, lane, r, slot, nslots, my_iters, total_tiles);
     }
     tc_fence_before();
     __syncthreads();

@@ -73,6 +73,7 @@ class Engine:
         if pl.sos_AL is not None:
             put('sos_AL', pl.sos_AL)
             put('sos_CA', pl.sos_CA)
+            put('sos_AP', pl.sos_AP)
         tab.lam_N = float(pl.lam_N)
         tab.lam_tile[0], tab.lam_tile[1] = float(pl.lam_tile[0]), float(pl.lam_tile[1])
         if pl.fm_interp is not None:

@@ -191,6 +191,7 @@ class Plan:
     sos_Lseg: int = 0                     # output SOS evaluated in 32 segments of this length
     sos_AL: np.ndarray | None = None      # (ns, ns) A^Lseg of the output cascade (ns = 2*sections)
     sos_CA: np.ndarray | None = None      # (Lseg, ns) c A^i
+    sos_AP: np.ndarray | None = None      # (5, ns, ns) (A^Lseg)^(2^lv)
 
     @property
     def chunk_bytes(self) -> int:
@@ -331,7 +332,7 @@ def build_plan(fs: int, enc: str, dec: int, rows_hz, *, simo: bool = False, swap
                        fs=fs // q), dtype=np.float64)
     elif demod not in ('re', 'im'):
         raise ValueError(f'Invalid demod type {demod}')
-    sos_Lseg, sos_AL, sos_CA = 0, None, None
+    sos_Lseg, sos_AL, sos_CA, sos_AP = 0, None, None, None
     if out_sos is not None:
         sos_Lseg = -(-M // 32)
         mp.mp.dps = 40
@@ -344,6 +345,11 @@ def build_plan(fs: int, enc: str, dec: int, rows_hz, *, simo: bool = False, swap
         for i in range(sos_Lseg):
             sos_CA[i] = [float(cur[0, j]) for j in range(ns)]
             cur = cur * A_
+        sos_AP = np.zeros((5, ns, ns))
+        Apw = AL
+        for lv in range(5):
+            sos_AP[lv] = [[float(Apw[i, j]) for j in range(ns)] for i in range(ns)]
+            Apw = Apw * Apw
     fm_interp = None
     h = M >> 1
     if demod == 'fm' and not (M == 2 * h and h & (h - 1) == 0):
@@ -357,7 +363,7 @@ def build_plan(fs: int, enc: str, dec: int, rows_hz, *, simo: bool = False, swap
                 ws=ws, nend=nend, PhiF=PhiF, PhiG=PhiG, PsiW=PsiW, PsiT=PsiT, psiY=psiY,
                 lam_tile=lam_tile, demod=demod, out_sos=out_sos,
                 big_endian_out=bool(simo if big_endian_out is None else big_endian_out),
-                fm_interp=fm_interp, sos_Lseg=sos_Lseg, sos_AL=sos_AL, sos_CA=sos_CA)
+                fm_interp=fm_interp, sos_Lseg=sos_Lseg, sos_AL=sos_AL, sos_CA=sos_CA, sos_AP=sos_AP)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -433,8 +439,8 @@ def build_tc(pl: Plan, nd: int = TC_ND) -> TcTables | None:
     ncols = np.array([ncol] * 34 + [isz, isz])
     col0 = np.concatenate([[0], np.cumsum(ncols)[:-1]])
     npad = -(-int(ncols.sum()) // 16) * 16
-    if npad > 256:
-        raise ValueError(f'{nd} digits need {npad} GEMM columns (> 256)')
+    if not 5 <= ncol <= 6:
+        raise ValueError(f'{nd} digits of {isz}-byte items need {ncol} columns per output; k_tc takes 5 or 6')
     pm = pl.modes.mp_p
     L = mp.mpf(pl.Liq)
     lam = mp.mpf(1) - L

@@ -55,6 +55,21 @@ def test_stage_parity_vs_emulator(name):
     assert rel_err(np.asarray(out, dtype=np.float64), eo) < 1e-11
 
 
+@pytest.mark.parametrize('name', ['c1_fm_wav_int16', 'c2_am_u8_d64', 'c3_simo16_int16be', 'enc_H_swap_im'])
+def test_general_finish_kernels_match_fused(name, monkeypatch):
+    """k_fixup + k_demod (the general path, forced with SDRB_NO_FINISH=1) against the fused
+    k_finish on shapes both handle, and against the oracle."""
+    from gpu_util import run_case
+    kw, pl, chunks, out_f, y_f, off_f = run_case(name)
+    monkeypatch.setenv('SDRB_NO_FINISH', '1')
+    kw, pl, chunks, out_g, y_g, off_g = run_case(name)
+    ch = orc.Chain(**kw)
+    oo = ch.run(chunks.tobytes())
+    assert rel_err(y_g, y_f) < 1e-12
+    assert rel_err(np.asarray(out_g, dtype=np.float64), np.asarray(out_f, dtype=np.float64)) < 1e-11
+    assert rel_err(np.asarray(out_g, dtype=np.float64), oo) < TOL
+
+
 def test_batch_split_and_state_carry():
     """Feeding chunk by chunk (max_chunks=1) equals one batch: the IQ state chains."""
     from gpu_util import chunked, plan_for
