@@ -18,7 +18,7 @@
 extern "C" {
 #endif
 
-#define SDRB_ABI_VERSION 3
+#define SDRB_ABI_VERSION 5
 #define SDRB_TILE_BLOCKS 32
 #define SDRB_NPOLES 8
 #define SDRB_MAX_DECIMATION 256
@@ -70,11 +70,16 @@ typedef struct sdrb_tables {
     double g0, d;
     const double *Ec, *Oc;   /* [4][Hq] complex, Hq = ceil(q/2) */
     const double *Ppow;      /* [TILE_BLOCKS+1][8] complex */
+    const double *pk;        /* [edge+1][8] complex: p_i^k */
+    const double *Pt;        /* [ntiles][8] complex: p_i^(q*TILE_BLOCKS*m) */
+    const double *bx;        /* [8] complex: p_i^edge / kappa_i */
     const double *bnd;       /* [M][8] complex */
     int32_t k_bnd;
     /* IQ corrector */
     double lam, lam_q, lam_N, lam_inv;
     const double *lam_j;     /* [q+1] */
+    const double *lam_k;     /* [33] lam^k */
+    const double *mu_k;      /* [33] lam^-k */
     double lam_tile[2];
     int32_t RL;              /* pairs per DMMA k-lane = ceil(Hq/4) */
     int32_t run_len[8];      /* samples per run of a block, sample order */

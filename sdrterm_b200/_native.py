@@ -16,7 +16,7 @@ LIB_PATH = os.path.join(_HERE, 'libsdrterm_b200.so')
 HEADER = os.path.join(ROOT, 'include', 'sdrterm_b200.h')
 SOURCES = [os.path.join(_HERE, 'csrc', f) for f in ('sdrb_api.cu', 'sdrb_kernels.cuh', 'sdrb_device.cuh', 'sdrb_tc.cuh', 'sdrb_finish.cuh')]
 
-ABI_VERSION = 3
+ABI_VERSION = 5
 FM, AM, RE, IM = 0, 1, 2, 3
 DEMOD_CODE = {'fm': FM, 'am': AM, 're': RE, 'im': IM}
 
@@ -40,9 +40,9 @@ _DP = C.POINTER(C.c_double)
 class Tables(C.Structure):
     _fields_ = [('p', _DP), ('P', _DP), ('rho', _DP), ('rho_p', _DP), ('c', _DP), ('zhat', _DP),
                 ('xi', _DP), ('g0', C.c_double), ('d', C.c_double), ('Ec', _DP), ('Oc', _DP),
-                ('Ppow', _DP), ('bnd', _DP), ('k_bnd', C.c_int32), ('lam', C.c_double),
+                ('Ppow', _DP), ('pk', _DP), ('Pt', _DP), ('bx', _DP), ('bnd', _DP), ('k_bnd', C.c_int32), ('lam', C.c_double),
                 ('lam_q', C.c_double), ('lam_N', C.c_double), ('lam_inv', C.c_double),
-                ('lam_j', _DP), ('lam_tile', C.c_double * 2), ('RL', C.c_int32),
+                ('lam_j', _DP), ('lam_k', _DP), ('mu_k', _DP), ('lam_tile', C.c_double * 2), ('RL', C.c_int32),
                 ('run_len', C.c_int32 * 8), ('lam_run', C.c_double * 8), ('T2', _DP), ('T3', _DP), ('T1', _DP),
                 ('Ehead', _DP), ('Eend', _DP), ('PhiF', _DP), ('PhiG', _DP), ('PsiW', _DP),
                 ('PsiT', _DP), ('psiY', _DP), ('use_nco', C.POINTER(C.c_uint8)), ('out_sos', _DP),

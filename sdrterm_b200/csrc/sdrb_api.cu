@@ -285,7 +285,7 @@ int launch_chain_t(sdrb_handle *h, const uint8_t *raw, size_t nch, double *out, 
     mark(2);
     if ((phases & PH_FINISH) && h->finish_on) {
         const size_t items = nch * (size_t)pl.R;
-        const unsigned grid = (unsigned)std::min<size_t>((items + FIN_WARPS - 1) / FIN_WARPS, (size_t)h->num_sms * 2);
+        const unsigned grid = (unsigned)std::min<size_t>((items + FIN_WARPS - 1) / FIN_WARPS, (size_t)h->num_sms * 3);
         k_finish<ENC><<<grid, 32 * FIN_WARPS, h->finish_smem, st>>>(pl, h->sc, raw, out, (int)nch, h->keep_y);
         h->launches++;
         mark(3);
@@ -449,6 +449,11 @@ int sdrb_create(const sdrb_config *cfg, const sdrb_tables *tab, sdrb_handle **ou
     UP(upload(h, afrag.data(), afrag.size(), &pl.Afrag));
     UP(upload(h, tab->lam_j, (size_t)q + 1, &pl.lam_j));
     UP(upload(h, reinterpret_cast<const double2 *>(tab->Ppow), (size_t)(SDRB_TB + 1) * 8, &pl.Ppow));
+    if (!tab->pk || !tab->lam_k || !tab->mu_k || !tab->Pt || !tab->bx) return bail(fail(h, SDRB_ERR_ARG, "pole / IQ power tables missing"));
+    UP(upload(h, reinterpret_cast<const double2 *>(tab->pk), (size_t)(pl.edge + 1) * 8, &pl.pk));
+    for (int i = 0; i < 33; i++) { pl.lam_pw[i] = tab->lam_k[i]; pl.mu_pw[i] = tab->mu_k[i]; }
+    UP(upload(h, reinterpret_cast<const double2 *>(tab->Pt), (size_t)nt * 8, &pl.Pt));
+    for (int i = 0; i < SDRB_NP; i++) pl.bx[i] = c2(tab->bx, i);
     UP(upload(h, rw.data(), rw.size(), &pl.RW));
     UP(upload(h, rt.data(), rt.size(), &pl.RT));
     UP(upload(h, reinterpret_cast<const double2 *>(tab->bnd), (size_t)M * 8, &pl.bnd));
@@ -491,7 +496,7 @@ int sdrb_create(const sdrb_config *cfg, const sdrb_tables *tab, sdrb_handle **ou
         h->finish_on = !env_int("SDRB_NO_FINISH", 0) && pl.rem == 0 && pl.cnt_last == SDRB_TB && q >= pl.edge + 1 &&
                        pow2 && M >= 64 && M <= 1024 && pl.edge + 1 <= 32 &&
                        (cfg->n_out_sections == 0 || (cfg->n_out_sections == 2 && tab->sos_AP));
-        h->finish_smem = h->finish_on ? finish_smem_bytes(M) : 0;
+        h->finish_smem = h->finish_on ? finish_smem_bytes(M, pl.edge) : 0;
         if (h->finish_smem > 227 * 1024) h->finish_on = false;
     }
     UP(set_smem_attr(h));

@@ -25,13 +25,18 @@ struct DevPlan {
     double sos_AL[64];     // [ns][ns] A^Lseg of the output cascade
     double sos_AP[80];     // [5][4][4] (A^Lseg)^(2^lv), two-section cascades (k_finish's lane scan)
     double lamq_pow[5];    // lam_q^(1,2,4,8,16)
+    double lam_pw[33];     // lam^k, k = 0..32 (k_finish's IQ scans)
+    double mu_pw[33];      // lam^-k
     double lam_tile[2];
     double2 p[SDRB_NP], P[SDRB_NP], rho[SDRB_NP], rho_p[SDRB_NP], c[SDRB_NP], zhat[SDRB_NP];
     double2 xi[SDRB_NP * SDRB_NP];
+    double2 bx[SDRB_NP];   // p_i^edge / kappa_i: boundary vector -> anticausal carry (k_finish)
     double out_sos[4 * 6];
     const double *Afrag;   // [KS][2][32]  DMMA A fragments: even-part (Ec) and odd-part (Oc)
     const double *lam_j;   // [q+1]
     const double2 *Ppow;   // [TB+1][8]
+    const double2 *pk;     // [edge+1][8]  p_i^k (closed forms of the head / tail recurrences)
+    const double2 *Pt;     // [ntiles][8]  P_i^(32 m): a carry moved m whole tiles
     const double2 *RW;     // [TB+1][8]  rho_i   * P_i^l
     const double2 *RT;     // [TB+1][8]  rho_p_i * P_i^l
     const double2 *bnd;    // [M][8]

@@ -22,43 +22,57 @@
 
 #define FIN_WARPS 4
 
-// Per-warp shared memory (bytes) and per-CTA twiddle table.
+// Per-warp shared memory (bytes); per CTA: twiddles exp(-2 pi i k / M) (k < M/2) and the pole
+// powers p_i^k (k <= edge).
 __host__ __device__ inline size_t finish_warp_bytes(int M)
 {
     const int nt = M / SDRB_TB;
     size_t b = (size_t)(nt + 1) * 16 * sizeof(double2);      // carry
-    b += (size_t)M * sizeof(double2);                        // ybuf (addv aliases its head)
-    b += 4 * 32 * sizeof(double2);                           // sh, se, seqA, seqB
-    b += 8 * sizeof(double2);                                // zeta
-    b += 2 * (size_t)(M / 4) * sizeof(double2);              // fa, fb
+    b += 2 * (size_t)(M / 4) * sizeof(double2);              // fa, fb (addv aliases them)
+    b += 2 * 32 * sizeof(double2);                           // seqA, seqB
     b += (size_t)(M + 32) * sizeof(double);                  // zrow, one pad per segment
     return b;
 }
-__host__ __device__ inline size_t finish_smem_bytes(int M)
+__host__ __device__ inline size_t finish_smem_bytes(int M, int edge)
 {
-    return (size_t)(M / 2) * sizeof(double2) + FIN_WARPS * finish_warp_bytes(M);
+    return (size_t)(M / 2) * sizeof(double2) + (size_t)(edge + 1) * 8 * sizeof(double2) + FIN_WARPS * finish_warp_bytes(M);
 }
 
-// Stockham radix-2 pass over n points by one warp; twiddle exp(-+2 pi i k / (2 Ns)) = tw[k * tstride].
+// Stockham radix-2 pass over n points by one warp (two butterflies in flight per lane); twiddle
+// exp(-+2 pi i k / (2 Ns)) = tw[k * tstride].
 __device__ __forceinline__ void fin_fft_pass(const double2 *in, double2 *out, int n, int Ns, int tstride,
                                              bool inverse, const double2 *tw, int lane)
 {
     const int half = n >> 1;
-    for (int j = lane; j < half; j += 32) {
-        const int k = j & (Ns - 1);
-        double2 w = tw[k * tstride];
-        if (inverse) w.y = -w.y;
-        const double2 a = in[j], b = cmul(w, in[j + half]);
-        const int j0 = ((j - k) << 1) + k;
-        out[j0] = cadd(a, b);
-        out[j0 + Ns] = csub(a, b);
+    for (int j = lane; j < half; j += 64) {
+        const int jb = j + 32;
+        const bool two = jb < half;
+        const int ka = j & (Ns - 1), kb = jb & (Ns - 1);
+        double2 wa = tw[ka * tstride], wb = tw[kb * tstride];
+        if (inverse) { wa.y = -wa.y; wb.y = -wb.y; }
+        const double2 a0 = in[j], a1 = in[j + half];
+        const double2 b0 = two ? in[jb] : a0, b1 = two ? in[jb + half] : a1;
+        const double2 ta = cmul(wa, a1), tb = cmul(wb, b1);
+        const int ja = ((j - ka) << 1) + ka, jc = ((jb - kb) << 1) + kb;
+        out[ja] = cadd(a0, ta);
+        out[ja + Ns] = csub(a0, ta);
+        if (two) {
+            out[jc] = cadd(b0, tb);
+            out[jc + Ns] = csub(b0, tb);
+        }
     }
 }
 
+__device__ __forceinline__ double fin_demod_scalar(double2 a, int demod)
+{
+    if (demod == 1) return hypot(fma(a.x, a.x, -a.y * a.y), 2.0 * a.x * a.y);   // abs(square(z))
+    return demod == 2 ? a.x : a.y;
+}
+
 template <int ENC>
-__global__ void __launch_bounds__(32 * FIN_WARPS, 2)
-k_finish(const __grid_constant__ DevPlan pl, Scratch sc, const uint8_t *__restrict__ raw, double *__restrict__ out,
-         int nchunks, int keep_y)
+__global__ void __launch_bounds__(32 * FIN_WARPS, 3)
+k_finish(const __grid_constant__ DevPlan pl, const __grid_constant__ Scratch sc, const uint8_t *__restrict__ raw,
+         double *__restrict__ out, int nchunks, int keep_y)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -66,15 +80,15 @@ k_finish(const __grid_constant__ DevPlan pl, Scratch sc, const uint8_t *__restri
     const bool iq = pl.correct_iq != 0;
 
     double2 *tw = reinterpret_cast<double2 *>(smem_raw);                 // exp(-2 pi i k / M), k < M/2
+    double2 *pk = tw + h;                                                // p_i^k, [edge+1][8]
     for (int k = threadIdx.x; k < h; k += blockDim.x) tw[k] = pl.tw[k];
-    unsigned char *wb = smem_raw + (size_t)h * sizeof(double2) + (size_t)warp * finish_warp_bytes(M);
+    for (int k = threadIdx.x; k < (edge + 1) * 8; k += blockDim.x) pk[k] = pl.pk[k];
+    unsigned char *wb = smem_raw + (size_t)(h + (edge + 1) * 8) * sizeof(double2) + (size_t)warp * finish_warp_bytes(M);
     double2 *carry = reinterpret_cast<double2 *>(wb);
-    double2 *ybuf = carry + (size_t)(nt + 1) * 16;
-    double2 *addv = ybuf;                                                // dead before ybuf is written
-    double2 *s_h = ybuf + M, *s_e = s_h + 32, *seqA = s_e + 32, *seqB = seqA + 32;
-    double2 *s_zeta = seqB + 32;
-    double2 *fa = s_zeta + 8, *fb = fa + n2;
-    double *zrow = reinterpret_cast<double *>(fb + n2);
+    double2 *fa = carry + (size_t)(nt + 1) * 16, *fb = fa + n2;
+    double2 *addv = fa;                                                  // dead before the FFT buffers are written
+    double2 *seqA = fb + n2, *seqB = seqA + 32;
+    double *zrow = reinterpret_cast<double *>(seqB + 32);
     __syncthreads();
 
     // lane-invariant tables: this lane's block position l = lane inside every tile
@@ -84,9 +98,11 @@ k_finish(const __grid_constant__ DevPlan pl, Scratch sc, const uint8_t *__restri
         rw[i] = pl.RW[(size_t)lane * 8 + i];
         rt[i] = pl.RT[(size_t)(SDRB_TB - lane) * 8 + i];
     }
-    const int i8 = lane & 7, grp = (lane >> 3) & 1;
+    const int i8 = lane & 7, grp = (lane >> 3) & 1, sub = lane >> 3;
     const double2 p_i = pl.p[i8], P32 = pl.Ppow[(size_t)SDRB_TB * 8 + i8];
-    const int Ls = pl.sos_Lseg;
+    const int Ls = pl.sos_Lseg, lsh = 31 - __clz(Ls);
+    const int dchunk = (edge + 3) >> 2;                                  // dot-product terms per lane group
+    const double lamn = pl.lam_pw[lane], mun = pl.mu_pw[min(32, max(0, edge + 1 - lane))];
 
     const int gw = blockIdx.x * FIN_WARPS + warp, nw = gridDim.x * FIN_WARPS;
     for (int item = gw; item < nchunks * R; item += nw) {
@@ -95,69 +111,113 @@ k_finish(const __grid_constant__ DevPlan pl, Scratch sc, const uint8_t *__restri
         const double2 *offt = sc.off_tile + (size_t)chunk * (nt + 1);
         const double2 *aggr = sc.agg + ((size_t)chunk * R + r) * nt * 16;
         const double2 *T1r = pl.T1 + (size_t)r * nt;
+        const double2 *ypr = sc.ypart + ((size_t)chunk * R + r) * pl.Mf;
 
         // ---------------------------------------------------------------- 1a. loads
+        double2 xh = make_double2(0.0, 0.0), xe = make_double2(0.0, 0.0);
         if (lane <= edge) {
-            s_h[lane] = decode_sample<ENC>(pl, rawc, lane);
-            s_e[lane] = decode_sample<ENC>(pl, rawc, (long)pl.ws + lane);
+            xh = decode_sample<ENC>(pl, rawc, lane);
+            xe = decode_sample<ENC>(pl, rawc, (long)pl.ws + lane);
         }
-        for (int idx = lane; idx < nt * 16; idx += 32) {
-            const int t = idx >> 4, m = idx & 15;
-            double2 a = aggr[idx];
-            if (iq) {
-                const int kind = (t == nt - 1) ? 1 : 0;
-                const double2 o = offt[t];
-                const double2 psi = m < 8 ? pl.PsiW[((size_t)kind * R + r) * 8 + m]
-                                          : pl.PsiT[((size_t)kind * R + r) * 8 + m - 8];
-                a = cfma(make_double2(-o.x, -o.y), psi, a);
-            }
-            addv[idx] = cmul(T1r[t], a);
+        // offsets at the tile starts: lane t keeps offt[t] (shuffled out where needed)
+        double2 offr = make_double2(0.0, 0.0), oE = offr;
+        if (iq) {
+            if (lane < nt) offr = offt[lane];
+            oE = offt[nt];
         }
-        __syncwarp();
-        // ---------------------------------------------------------------- 1b. IQ recurrences
-        // lane 0: head forward from the chunk-start offset (x = z - o; o += L x); lane 1: end
-        // window backward from the offset at q*Mf (o = (o - L z) / lam; x = z - o)
-        if (iq && lane < 2) {
-            const bool fwd = lane == 0;
-            double2 *buf = fwd ? s_h : s_e;
-            double2 o = fwd ? offt[0] : offt[nt];
-            for (int step = 0; step <= edge; step++) {
-                const int idx = fwd ? step : edge - step;
-                const double2 z = buf[idx];
-                double2 x;
-                if (fwd) {
-                    x = csub(z, o);
-                    o.x = fma(x.x, pl.Liq, o.x); o.y = fma(x.y, pl.Liq, o.y);
-                } else {
-                    o.x = fma(-pl.Liq, z.x, o.x) * pl.lam_inv; o.y = fma(-pl.Liq, z.y, o.y) * pl.lam_inv;
-                    x = csub(z, o);
+        {   // the next item's inputs start their way into L2 now
+            const int nitem = item + nw;
+            if (nitem < nchunks * R) {
+                const int nchunk = nitem / R, nr = nitem - nchunk * R;
+                const char *py = reinterpret_cast<const char *>(sc.ypart + ((size_t)nchunk * R + nr) * pl.Mf);
+                const char *pa = reinterpret_cast<const char *>(sc.agg + ((size_t)nchunk * R + nr) * nt * 16);
+                for (int o = lane * 128; o < M * 16; o += 32 * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(py + o));
+                for (int o = lane * 128; o < nt * 256; o += 32 * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(pa + o));
+                if (lane < 2) {
+                    const uint8_t *pr = raw + (size_t)nchunk * pl.N * pl.sb + (lane ? (size_t)pl.ws * pl.sb : 0);
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(pr));
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(pr + 128));
                 }
-                buf[idx] = x;
             }
         }
-        __syncwarp();
-        // ---------------------------------------------------------------- 1c. NCO, extensions
-        if (lane <= edge) {
-            s_h[lane] = cmul(s_h[lane], pl.Ehead[(size_t)r * (edge + 1) + lane]);
-            s_e[lane] = cmul(s_e[lane], pl.Eend[(size_t)r * pl.nend + lane]);
+        for (int i0 = 0; i0 < nt * 16; i0 += 8 * 32) {
+            double2 av[8];
+#pragma unroll
+            for (int u = 0; u < 8; u++)
+                av[u] = (i0 + u * 32 + lane < nt * 16) ? aggr[i0 + u * 32 + lane] : make_double2(0.0, 0.0);
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+                const int idx = i0 + u * 32 + lane, t = min(idx >> 4, nt - 1), m = idx & 15;
+                double2 a = av[u];
+                if (iq) {
+                    const int kind = (t == nt - 1) ? 1 : 0;
+                    const double2 o = shfl_c(offr, t);
+                    const double2 psi = m < 8 ? pl.PsiW[((size_t)kind * R + r) * 8 + m]
+                                              : pl.PsiT[((size_t)kind * R + r) * 8 + m - 8];
+                    a = cfma(make_double2(-o.x, -o.y), psi, a);
+                }
+                if (idx < nt * 16) addv[idx] = cmul(T1r[min(t, nt - 1)], a);
+            }
         }
-        __syncwarp();
-        const double2 x0 = s_h[0], xN1 = s_e[edge];
-        if (lane < edge) {
-            seqA[lane] = csub(cscale(2.0, x0), s_h[edge - lane]);           // odd extension, head
-            seqB[lane] = csub(cscale(2.0, xN1), s_e[edge - 1 - lane]);      // odd extension, tail
+        // ---------------------------------------------------------------- 1b. IQ correction
+        // read_file.py:72-77 is the linear recurrence off' = lam off + L z; lane <-> sample.  Head:
+        // off_n = lam^n off_0 + L sum_{i<n} lam^(n-1-i) z_i (scan upwards).  End window, from the
+        // offset at q*Mf backwards: off_n = mu^m off_E - L mu sum_{i>=n} mu^(i-n) z_i, mu = 1/lam.
+        if (iq) {
+            const double2 o0 = shfl_c(offr, 0);
+            double2 S = xh, B = xe;
+#pragma unroll
+            for (int lv = 0; lv < 5; lv++) {
+                const double2 tu = shfl_up_c(S, 1 << lv);
+                const double2 td = make_double2(__shfl_down_sync(0xffffffffu, B.x, 1 << lv), __shfl_down_sync(0xffffffffu, B.y, 1 << lv));
+                if (lane >= (1 << lv)) { S.x = fma(pl.lam_pw[1 << lv], tu.x, S.x); S.y = fma(pl.lam_pw[1 << lv], tu.y, S.y); }
+                if (lane + (1 << lv) < 32) { B.x = fma(pl.mu_pw[1 << lv], td.x, B.x); B.y = fma(pl.mu_pw[1 << lv], td.y, B.y); }
+            }
+            double2 Sx = shfl_up_c(S, 1);
+            if (lane == 0) Sx = make_double2(0.0, 0.0);
+            xh.x -= fma(lamn, o0.x, pl.Liq * Sx.x); xh.y -= fma(lamn, o0.y, pl.Liq * Sx.y);
+            const double lm = pl.Liq * pl.mu_pw[1];
+            xe.x -= fma(mun, oE.x, -lm * B.x); xe.y -= fma(mun, oE.y, -lm * B.y);
+        }
+        // ---------------------------------------------------------------- 1c. NCO, odd extensions
+        if (lane <= edge) {
+            xh = cmul(xh, pl.Ehead[(size_t)r * (edge + 1) + lane]);
+            xe = cmul(xe, pl.Eend[(size_t)r * pl.nend + lane]);
+        }
+        {
+            const double2 x0 = shfl_c(xh, 0), xN1 = shfl_c(xe, edge);
+            const double2 ha = shfl_c(xh, max(0, edge - lane)), eb = shfl_c(xe, max(0, edge - 1 - lane));
+            if (lane < edge) {
+                seqA[lane] = make_double2(fma(2.0, x0.x, -ha.x), fma(2.0, x0.y, -ha.y));       // head extension
+                seqB[lane] = make_double2(fma(2.0, xN1.x, -eb.x), fma(2.0, xN1.y, -eb.y));     // tail extension
+            }
         }
         __syncwarp();
         // ---------------------------------------------------------------- 1d. head / tail states
-        // lanes 0..7: forward modal state at n = edge (zi start-up, then the head extension);
-        // lanes 8..15: anticausal state at n = edge + q*Mf from the tail extension
-        double2 st = grp ? make_double2(0.0, 0.0) : cmul(pl.zhat[i8], seqA[0]);
-        for (int j = 0; j < edge; j++) {
-            const double2 v = grp ? seqB[edge - 1 - j] : seqA[j];
-            st = cfma(p_i, st, v);
+        // closed forms of the serial recurrences: w(edge) = p^edge zhat ext0 + sum_j p^(edge-1-j) ext_j,
+        // T(end) = sum_k p^k tail_k, and the tail-driven part of w(L-2); lane = (pole, quarter of j)
+        double2 accA = make_double2(0.0, 0.0), accB = accA, accC = accA;
+        {
+            const int j0 = sub * dchunk, j1 = min(edge, j0 + dchunk);
+            for (int j = j0; j < j1; j++) {
+                const double2 a = seqA[j], b = seqB[j];
+                accA = cfma(pk[(edge - 1 - j) * 8 + i8], a, accA);
+                accB = cfma(pk[j * 8 + i8], b, accB);
+                if (j <= edge - 2) accC = cfma(pk[(edge - 2 - j) * 8 + i8], b, accC);
+            }
+#pragma unroll
+            for (int sft = 8; sft < 32; sft <<= 1) {
+                accA = cadd(accA, shfl_xor_c(accA, sft));
+                accB = cadd(accB, shfl_xor_c(accB, sft));
+                accC = cadd(accC, shfl_xor_c(accC, sft));
+            }
+            accA = cfma(pk[edge * 8 + i8], cmul(pl.zhat[i8], seqA[0]), accA);
         }
         // ---------------------------------------------------------------- 1e. carries across tiles
-        if (lane < 16 && grp) carry[(size_t)nt * 16 + 8 + i8] = st;
+        // lanes 0..7: forward modal states (Win[t] = state entering tile t); lanes 8..15: anticausal
+        // states (Tn[t] = state entering tile t from above)
+        double2 st = grp ? accB : accA;
+        if (lane >= 8 && lane < 16) carry[(size_t)nt * 16 + 8 + i8] = st;
         for (int tt = 0; tt < nt; tt++) {
             const int t = grp ? nt - 1 - tt : tt;
             if (lane < 8) carry[(size_t)t * 16 + i8] = st;
@@ -165,71 +225,96 @@ k_finish(const __grid_constant__ DevPlan pl, Scratch sc, const uint8_t *__restri
             if (lane >= 8 && lane < 16) carry[(size_t)t * 16 + 8 + i8] = st;
         }
         if (lane < 8) carry[(size_t)nt * 16 + i8] = st;
-        __syncwarp();
-        // ---------------------------------------------------------------- 1f. end, boundary vector
+        // ---------------------------------------------------------------- 1f. boundary vector zeta
         {
-            double2 w = carry[(size_t)nt * 16 + i8], wL1 = w, last = make_double2(0.0, 0.0);
-            for (int k = 0; k < edge; k++) {
-                const double2 v = seqB[k];
-                if (k == edge - 1) { wL1 = w; last = v; }
-                w = cfma(p_i, w, v);
-            }
+            const double2 Wn = shfl_c(st, i8);                              // forward state at n = edge + q*Mf
+            const double2 last = seqB[edge - 1];
+            const double2 wL1 = cfma(pk[(edge - 1) * 8 + i8], Wn, accC);
+            const double2 wL = cfma(p_i, wL1, last);
             double2 part = cmul(pl.c[i8], wL1);
             for (int sft = 1; sft < 8; sft <<= 1) part = cadd(part, shfl_xor_c(part, sft));
             const double2 yfL1 = make_double2(fma(pl.d, last.x, part.x), fma(pl.d, last.y, part.y));
-            double2 zeta = cmul(pl.zhat[i8], yfL1);
+            double2 za = cmul(pl.zhat[i8], yfL1), zb = make_double2(0.0, 0.0);
 #pragma unroll
-            for (int l = 0; l < 8; l++) {
-                const double2 wl = shfl_c(w, l);
-                zeta = csub(zeta, cmul(pl.xi[i8 * 8 + l], wl));
+            for (int l = 0; l < 8; l += 2) {
+                za = csub(za, cmul(pl.xi[i8 * 8 + l], shfl_c(wL, l)));
+                zb = csub(zb, cmul(pl.xi[i8 * 8 + l + 1], shfl_c(wL, l + 1)));
             }
-            if (lane < 8) s_zeta[i8] = zeta;
+            // sosfiltfilt's boundary term c_i p_i^(L-1-n) zeta_i is an anticausal modal response:
+            // it rides on the backward carries as X_i = p_i^edge / kappa_i zeta_i at n = edge + q*Mf
+            const double2 X = cmul(pl.bx[i8], cadd(za, zb));
+            __syncwarp();
+            for (int t = sub; t < nt; t += 4) {
+                double2 *Tn = carry + (size_t)(t + 1) * 16 + 8 + i8;
+                *Tn = cfma(pl.Pt[(size_t)(nt - 1 - t) * 8 + i8], X, *Tn);
+            }
         }
         __syncwarp();
-        // ---------------------------------------------------------------- 2. outputs, lane <-> block
+        // ---------------------------------------------------------------- 2+3a. outputs, lane <-> block
+        // y[k] = T1 (ypart - off psi) + sum_i rho_i P_i^l Win_i + rho_i/p_i P_i^(32-l) Tn_i (+ boundary),
+        // two tiles per round; fm forms the pair phases in registers (even lanes take tile t0's
+        // pairs, odd lanes tile t1's), the other modes go straight to the output row
         {
-            const double2 *ypr = sc.ypart + ((size_t)chunk * R + r) * pl.Mf;
             double2 *yg = sc.y + ((size_t)chunk * R + r) * M;
             const double2 psi0 = pl.psiY[((size_t)0 * R + r) * SDRB_TB + lane];
             const double2 psi1 = pl.psiY[((size_t)1 * R + r) * SDRB_TB + lane];
-            for (int t = 0; t < nt; t++) {
-                const int k = t * SDRB_TB + lane;
-                double2 v = ypr[k];
-                if (iq) {
-                    const double2 o = offt[t];
-                    v = cfma(make_double2(-o.x, -o.y), (t == nt - 1) ? psi1 : psi0, v);
-                }
-                v = cmul(T1r[t], v);
-                const double2 *Win = carry + (size_t)t * 16, *Tn = carry + (size_t)(t + 1) * 16 + 8;
+            double *ph = reinterpret_cast<double *>(fa);
+            // ypart is fetched two rounds (four tiles) ahead of its use
+            double2 yq[4];
 #pragma unroll
-                for (int i = 0; i < 8; i++) {
-                    v = cfma(rw[i], Win[i], v);
-                    v = cfma(rt[i], Tn[i], v);
-                }
-                if (k >= pl.k_bnd) {
+            for (int u = 0; u < 4; u++) yq[u] = u < nt ? ypr[u * SDRB_TB + lane] : make_double2(0.0, 0.0);
+            for (int t0 = 0; t0 < nt; t0 += 2) {
+                double2 yv[2];
+                const double2 yin0 = yq[0], yin1 = yq[1];
+                yq[0] = yq[2]; yq[1] = yq[3];
+                if (t0 + 4 < nt) { yq[2] = ypr[(t0 + 4) * SDRB_TB + lane]; yq[3] = ypr[(t0 + 5) * SDRB_TB + lane]; }
 #pragma unroll
-                    for (int i = 0; i < 8; i++) v = cfma(pl.bnd[(size_t)k * 8 + i], s_zeta[i], v);
+                for (int u = 0; u < 2; u++) {
+                    const int t = t0 + u, k = t * SDRB_TB + lane;
+                    double2 v = u ? yin1 : yin0;
+                    if (iq) {
+                        const double2 o = shfl_c(offr, t);
+                        v = cfma(make_double2(-o.x, -o.y), (t == nt - 1) ? psi1 : psi0, v);
+                    }
+                    v = cmul(T1r[t], v);
+                    const double2 *Win = carry + (size_t)t * 16, *Tn = carry + (size_t)(t + 1) * 16 + 8;
+                    double2 a0 = make_double2(0.0, 0.0), a1 = a0, a2 = a0;
+#pragma unroll
+                    for (int i = 0; i < 4; i++) {
+                        v = cfma(rw[i], Win[i], v);
+                        a0 = cfma(rw[i + 4], Win[i + 4], a0);
+                        a1 = cfma(rt[i], Tn[i], a1);
+                        a2 = cfma(rt[i + 4], Tn[i + 4], a2);
+                    }
+                    v = cadd(cadd(v, a0), cadd(a1, a2));
+                    if (keep_y) yg[k] = v;
+                    yv[u] = v;
                 }
-                ybuf[k] = v;
-                if (keep_y) yg[k] = v;
+                if (pl.demod == 0) {
+                    const bool odd = lane & 1;
+                    const double2 snd = odd ? yv[0] : yv[1];
+                    const double2 rcv = shfl_xor_c(snd, 1);
+                    const double2 a = odd ? rcv : yv[0], b = odd ? yv[1] : rcv;
+                    const double re = fma(a.x, b.x, a.y * b.y), im = fma(a.y, b.x, -a.x * b.y);   // a conj(b)
+                    const double v = atan2(im, re);
+                    const int i = 16 * (t0 + (odd ? 1 : 0)) + (lane >> 1);
+                    ph[i] = v;
+                    zrow[2 * i + ((2 * i) >> lsh)] = v;
+                } else {
+#pragma unroll
+                    for (int u = 0; u < 2; u++) {
+                        const int k = (t0 + u) * SDRB_TB + lane;
+                        zrow[k + (k >> lsh)] = fin_demod_scalar(yv[u], pl.demod);
+                    }
+                }
             }
         }
         __syncwarp();
-        // ---------------------------------------------------------------- 3. demodulation
+        // ---------------------------------------------------------------- 3b. fm: 2x interpolation
         if (pl.demod == 0) {
-            // pair phases (demodulation.py:25-32); even outputs of the 2x interpolation are the
-            // phases themselves, the odd ones come from the half-sample-shifted spectrum
-            double *ph = reinterpret_cast<double *>(fa);
-            for (int i = lane; i < h; i += 32) {
-                const double2 a = ybuf[2 * i], b = ybuf[2 * i + 1];
-                const double re = fma(a.x, b.x, a.y * b.y), im = fma(a.y, b.x, -a.x * b.y);
-                const double v = atan2(im, re);
-                ph[i] = v;
-                const int ko = 2 * i;
-                zrow[ko + ko / Ls] = v;
-            }
-            __syncwarp();
-            // forward FFT of z[m] = ph[2m] + i ph[2m+1], n2 = h/2 points
+            // even outputs of scipy.signal.resample(ph, 2h) are the phases themselves (already in
+            // zrow), the odd ones come from the half-sample-shifted spectrum.  Forward FFT of
+            // z[m] = ph[2m] + i ph[2m+1], n2 = h/2 points
             double2 *src = fa, *dst = fb;
             for (int Ns = 1; Ns < n2; Ns <<= 1) {
                 fin_fft_pass(src, dst, n2, Ns, M / (2 * Ns), false, tw, lane);
@@ -272,41 +357,26 @@ k_finish(const __grid_constant__ DevPlan pl, Scratch sc, const uint8_t *__restri
             for (int m = lane; m < n2; m += 32) {
                 const double2 v = src[m];
                 const int k1 = 4 * m + 1, k3 = 4 * m + 3;
-                zrow[k1 + k1 / Ls] = v.x * sc1;
-                zrow[k3 + k3 / Ls] = v.y * sc1;
+                zrow[k1 + (k1 >> lsh)] = v.x * sc1;
+                zrow[k3 + (k3 >> lsh)] = v.y * sc1;
             }
-        } else {
-            for (int k = lane; k < M; k += 32) {
-                const double2 a = ybuf[k];
-                double v;
-                if (pl.demod == 1) v = hypot(fma(a.x, a.x, -a.y * a.y), 2.0 * a.x * a.y);   // abs(square(z))
-                else v = pl.demod == 2 ? a.x : a.y;
-                zrow[k + k / Ls] = v;
-            }
+            __syncwarp();
         }
-        __syncwarp();
         // ---------------------------------------------------------------- 4. output low-pass
         if (pl.nsec_out > 0) {
-            const int nsec = pl.nsec_out;
             double *zs = zrow + (size_t)lane * (Ls + 1);
+            const double *c0 = pl.out_sos, *c1 = pl.out_sos + 6;
             double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
+#pragma unroll 4
             for (int k = 0; k < Ls; k++) {
-                double xc = zs[k];
-                {
-                    const double *cf = pl.out_sos;
-                    const double xn = __dadd_rn(__dmul_rn(cf[0], xc), s0);
-                    s0 = __dadd_rn(__dadd_rn(__dmul_rn(cf[1], xc), -__dmul_rn(cf[4], xn)), s1);
-                    s1 = __dadd_rn(__dmul_rn(cf[2], xc), -__dmul_rn(cf[5], xn));
-                    xc = xn;
-                }
-                if (nsec > 1) {
-                    const double *cf = pl.out_sos + 6;
-                    const double xn = __dadd_rn(__dmul_rn(cf[0], xc), s2);
-                    s2 = __dadd_rn(__dadd_rn(__dmul_rn(cf[1], xc), -__dmul_rn(cf[4], xn)), s3);
-                    s3 = __dadd_rn(__dmul_rn(cf[2], xc), -__dmul_rn(cf[5], xn));
-                    xc = xn;
-                }
-                zs[k] = xc;
+                const double xc = zs[k];
+                const double xn = __dadd_rn(__dmul_rn(c0[0], xc), s0);
+                s0 = __dadd_rn(__dadd_rn(__dmul_rn(c0[1], xc), -__dmul_rn(c0[4], xn)), s1);
+                s1 = __dadd_rn(__dmul_rn(c0[2], xc), -__dmul_rn(c0[5], xn));
+                const double xm = __dadd_rn(__dmul_rn(c1[0], xn), s2);
+                s2 = __dadd_rn(__dadd_rn(__dmul_rn(c1[1], xn), -__dmul_rn(c1[4], xm)), s3);
+                s3 = __dadd_rn(__dmul_rn(c1[2], xn), -__dmul_rn(c1[5], xm));
+                zs[k] = xm;
             }
             // inclusive Kogge-Stone scan of the segment maps s -> A^Ls s + b_lane
 #pragma unroll
@@ -324,16 +394,17 @@ k_finish(const __grid_constant__ DevPlan pl, Scratch sc, const uint8_t *__restri
             double i0 = __shfl_up_sync(0xffffffffu, s0, 1), i1 = __shfl_up_sync(0xffffffffu, s1, 1);
             double i2 = __shfl_up_sync(0xffffffffu, s2, 1), i3 = __shfl_up_sync(0xffffffffu, s3, 1);
             if (lane == 0) { i0 = 0; i1 = 0; i2 = 0; i3 = 0; }
+#pragma unroll 4
             for (int k = 0; k < Ls; k++) {
                 const double *ca = pl.sos_CA + (size_t)k * 4;
                 zs[k] = fma(ca[0], i0, fma(ca[1], i1, fma(ca[2], i2, fma(ca[3], i3, zs[k]))));
             }
+            __syncwarp();
         }
-        __syncwarp();
         // ---------------------------------------------------------------- 5. framing
         double *o = out + ((size_t)r * nchunks + chunk) * M;
         for (int k = lane; k < M; k += 32) {
-            const double v = zrow[k + k / Ls];
+            const double v = zrow[k + (k >> lsh)];
             o[k] = pl.be_out ? bswap_double(v) : v;
         }
         __syncwarp();

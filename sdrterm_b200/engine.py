@@ -54,7 +54,8 @@ class Engine:
         m = pl.modes
         for name, arr in (('p', m.p), ('P', pl.P), ('rho', m.rho), ('rho_p', m.rho_p), ('c', m.c),
                           ('zhat', m.zhat), ('xi', m.xi), ('Ec', pl.Ec), ('Oc', pl.Oc),
-                          ('Ppow', pl.Ppow), ('bnd', pl.bnd), ('lam_j', pl.lam_j), ('T2', pl.T2),
+                          ('Ppow', pl.Ppow), ('pk', pl.Pk), ('Pt', pl.Pt), ('bx', pl.bx), ('bnd', pl.bnd), ('lam_j', pl.lam_j),
+                          ('lam_k', pl.lam_k), ('mu_k', pl.mu_k), ('T2', pl.T2),
                           ('T3', pl.T3), ('T1', pl.T1), ('Ehead', pl.Ehead), ('Eend', pl.Eend),
                           ('PhiF', pl.PhiF), ('PhiG', pl.PhiG), ('PsiW', pl.PsiW),
                           ('PsiT', pl.PsiT), ('psiY', pl.psiY)):

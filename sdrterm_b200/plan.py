@@ -152,6 +152,9 @@ class Plan:
     Ec: np.ndarray         # (4, Hq) complex: even-part coefficients, upper poles
     Oc: np.ndarray         # (4, Hq) complex: odd-part coefficients
     Ppow: np.ndarray       # (TILE_BLOCKS+1, 8) P^l
+    Pk: np.ndarray         # (edge+1, 8) p^k
+    Pt: np.ndarray         # (ntiles, 8) p^(q*TILE_BLOCKS*m)
+    bx: np.ndarray         # (8,) p^edge / kappa
     bnd: np.ndarray        # (M, 8) c_i p_i^(L-1-n_k)
     k_bnd: int             # first k whose boundary term is not negligible
     # IQ corrector
@@ -162,6 +165,8 @@ class Plan:
     lam_q: float
     lam_N: float
     lam_inv: float         # 1/lam (backward EMA over the descending half of a block)
+    lam_k: np.ndarray      # (33,) lam^k
+    mu_k: np.ndarray       # (33,) lam^-k
     RL: int                # pairs per DMMA k-lane = ceil(Hq/4): lane k owns pairs [k*RL, (k+1)*RL)
     run_len: np.ndarray    # (8,) samples per run, in sample order (4 ascending + 4 descending runs)
     lam_run: np.ndarray    # (8,) lam^run_len
@@ -242,6 +247,9 @@ def build_plan(fs: int, enc: str, dec: int, rows_hz, *, simo: bool = False, swap
                 Ec[m, j] = _c((pm[m] ** (q - 1 - j) + pm[m] ** j) / 2)
                 Oc[m, j] = _c((pm[m] ** (q - 1 - j) - pm[m] ** j) / 2)
     Ppow = np.array([[_c(pm[i] ** (q * l)) for i in range(n8)] for l in range(TILE_BLOCKS + 1)])
+    Pk = np.array([[_c(pm[i] ** k) for i in range(n8)] for k in range(edge + 1)])
+    Pt = np.array([[_c(pm[i] ** (q * TILE_BLOCKS * m_)) for i in range(n8)] for m_ in range(ntiles)])
+    bx = np.array([_c(pm[i] ** edge / mp.mpc(modes.kappa[i])) for i in range(n8)])
     # boundary weights c_i p_i^(L-1-n_k), n_k = edge + q k
     bnd = np.zeros((M, n8), dtype=np.complex128)
     rmax = max(abs(v) for v in pm)
@@ -261,6 +269,8 @@ def build_plan(fs: int, enc: str, dec: int, rows_hz, *, simo: bool = False, swap
     lam_q = float(mlam ** q)
     lam_N = float(mlam ** N)
     lam_inv = float(1 / mlam)
+    lam_k = np.array([float(mlam ** k) for k in range(33)])
+    mu_k = np.array([float(mlam ** -k) for k in range(33)])
     RL = -(-Hq // 4)
     run_len = np.zeros(8, dtype=np.int64)
     for k in range(4):
@@ -357,7 +367,7 @@ def build_plan(fs: int, enc: str, dec: int, rows_hz, *, simo: bool = False, swap
         fm_interp = np.ascontiguousarray(_sig.resample(np.eye(h), M, axis=0))
     return Plan(enc=enc, swap=bool(swap), fs=fs, q=q, N=N, edge=edge, L=L, Mf=Mf, rem=rem, M=M,
                 ntiles=ntiles, cnt_last=cnt_last, Hq=Hq, rows_hz=rows_hz, R=R, sos=sos, zi=zi,
-                modes=modes, P=P, Ec=Ec, Oc=Oc, Ppow=Ppow, bnd=bnd, k_bnd=k_bnd,
+                modes=modes, P=P, Ec=Ec, Oc=Oc, Ppow=Ppow, Pk=Pk, Pt=Pt, bx=bx, lam_k=lam_k, mu_k=mu_k, bnd=bnd, k_bnd=k_bnd,
                 correct_iq=bool(correct_iq), Liq=Liq, lam=lam, lam_j=lam_j, lam_q=lam_q, lam_N=lam_N, lam_inv=lam_inv, RL=RL, run_len=run_len, lam_run=lam_run,
                 norm=norm, w=w, use_nco=use_nco, T2=T2, T3=T3, T1=T1, Ehead=Ehead, Eend=Eend,
                 ws=ws, nend=nend, PhiF=PhiF, PhiG=PhiG, PsiW=PsiW, PsiT=PsiT, psiY=psiY,
