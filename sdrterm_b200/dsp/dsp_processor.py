@@ -1,0 +1,232 @@
+"""``DspProcessor``: the reference's consumer object (src/dsp/dsp_processor.py:48-236) with the
+same constructor, properties, selectors and ``processData`` contract, whose hot loop
+(``_processChunk`` :140-149 + framing :162) runs on the GPU through one ``Engine`` handle.
+
+Differences that matter to a caller:
+  * chunks taken from the queue may be the reference's payload (1-D complex128 arrays, already
+    decoded / normalised / IQ-corrected by the producer, read_file.py:100-112) **or** raw chunk
+    bytes (``bytes`` / uint8 arrays), in which case decode, ``-X``, ``--normalize-input`` and
+    ``--correct-iq`` also run on the device (keyword arguments ``enc``, ``swapEndianness``,
+    ``normalize``, ``correctIq`` as misc/io_args.py passes them);
+  * an empty chunk is a clean end of stream, ``-d`` values that do not divide the
+    chunk produce ceil(N/q) outputs per chunk (8-Q1), ``re``/``im`` produce output (8-Q2);
+  * no CUDA state exists before ``processData`` runs, so the object pickles into a spawned child
+    exactly like the reference's (io_args.py:93).
+"""
+from __future__ import annotations
+
+import queue as _queue
+from sys import stdout
+from typing import Any, Callable
+
+import numpy as np
+
+from .data_processor import DataProcessor
+from .demodulation import amDemod, fmDemod, imagOutput, realOutput
+
+_DEMOD_NAME = {fmDemod: 'fm', amDemod: 'am', realOutput: 're', imagOutput: 'im'}
+
+
+def generateEllipFilter(fs: int, deg: int, Wn, btype: str):
+    """Output low-pass design, SciPy's as in the reference (dsp_processor.py:39-45); design is
+    setup, not hot path, and keeps the coefficients identical to the reference's."""
+    from scipy.signal import ellip
+    return ellip(deg, 1, 30, Wn, btype=btype, analog=False, output='sos', fs=fs)
+
+
+class DspProcessor(DataProcessor):
+    _FILTER_DEGREE = 3
+    MAX_BATCH = 64          # chunks drained from the queue per device call
+
+    def __init__(self, fs: int, center: int = 0, omegaOut: int = 0, tuned: int = 0, dec: int = 2,
+                 smooth: bool = False, fileInfo: dict | None = None, **kwargs):
+        self._demod = None
+        self._shift = None
+        self.bandwidth = None
+        self.__fs = None
+        self.__decimatedFs = None
+        self._isDead = False
+        self._outputFilters = []
+        self._nFreq = 1
+        self._decimationFactor = dec
+        self.fs = fs
+        self.centerFreq = center
+        self.tunedFreq = tuned
+        self.omegaOut = omegaOut
+        self.smooth = smooth
+        self.__fileInfo = fileInfo
+        # ingest switches for raw-byte chunks (read_file.py:31-44 keyword names)
+        self._enc = kwargs.get('enc')
+        self._swap = bool(kwargs.get('swapEndianness', False))
+        self._correctIq = bool(kwargs.get('correctIq', False))
+        self._normalize = bool(kwargs.get('normalize', False))
+        self._device = int(kwargs.get('device', 0))
+        self._engine = None
+
+    # ---------------------------------------------------------------- properties (:78-103)
+    @property
+    def fs(self) -> int:
+        return self.__fs
+
+    @fs.setter
+    def fs(self, fs: int) -> None:
+        self.__fs = fs
+        self.__decimatedFs = fs // self._decimationFactor
+
+    @property
+    def decimation(self) -> int:
+        return self._decimationFactor
+
+    @decimation.setter
+    def decimation(self, decimation: int) -> None:
+        if decimation < 2:
+            raise ValueError('Decimation must be at least 2.')
+        self._decimationFactor = decimation
+        self.fs = self.__fs
+
+    @property
+    def decimatedFs(self) -> int:
+        return self.__decimatedFs
+
+    # ---------------------------------------------------------------- demodulation choice (:105-138)
+    def demod(self, *_, **__):
+        pass
+
+    def _setDemod(self, fun: Callable[[np.ndarray, np.ndarray], None], *filters) -> Callable[..., Any]:
+        if fun is not None:
+            self._outputFilters.clear()
+            if len(filters):
+                self._outputFilters.extend(*filters)
+            setattr(self, 'demod', fun)
+            return self.demod
+        raise ValueError('Demodulation function, or filters not defined')
+
+    def selectOutputFm(self):
+        self.bandwidth = 12500
+        self._setDemod(fmDemod, generateEllipFilter(self.__decimatedFs, self._FILTER_DEGREE,
+                                                    self.omegaOut, 'lowpass'))
+
+    def selectOutputAm(self):
+        self.bandwidth = 10000
+        self._setDemod(amDemod, generateEllipFilter(self.__decimatedFs, self._FILTER_DEGREE,
+                                                    self.omegaOut, 'lowpass'))
+
+    def selectOutputReal(self):
+        self.bandwidth = self.decimatedFs
+        self._setDemod(realOutput)
+
+    def selectOutputImag(self):
+        self.bandwidth = self.decimatedFs
+        self._setDemod(imagOutput)
+
+    # ---------------------------------------------------------------- NCO table (:185-187)
+    def _generateShift(self, c: int) -> None:
+        """Kept for API parity (tests read ``_shift``); the device path builds its own phasor
+        tables from the same expression (plan.py: reference_w)."""
+        if self.centerFreq:
+            self._shift = np.array([np.exp(-2j * np.pi * (self.centerFreq / self.__fs) * np.arange(c))])
+
+    # ---------------------------------------------------------------- device engine
+    def _rowsHz(self) -> list[int]:
+        return [int(self.centerFreq)]
+
+    def _simo(self) -> bool:
+        return False
+
+    def _demodName(self) -> str:
+        name = _DEMOD_NAME.get(getattr(self, 'demod', None))
+        if name is None:
+            raise ValueError('no demodulation selected (call selectOutputFm/Am/Real/Imag first)')
+        return name
+
+    def _makeEngine(self, first):
+        from ..engine import Engine
+        from ..plan import build_plan
+        if isinstance(first, np.ndarray) and np.iscomplexobj(first):
+            enc, swap, ciq, norm = 'Z', False, False, False       # producer already did these
+            chunk_bytes = first.size * 16
+        else:
+            enc = self._enc
+            if enc is None and self.__fileInfo is not None:
+                enc = np.dtype(self.__fileInfo['bitsPerSample']).char
+                self._swap ^= np.dtype(self.__fileInfo['bitsPerSample']).byteorder == '>'
+            if enc is None:
+                raise ValueError('raw chunks need the sample encoding (enc=... or fileInfo)')
+            swap, ciq, norm = self._swap, self._correctIq, self._normalize
+            chunk_bytes = len(first) if not isinstance(first, np.ndarray) else first.nbytes
+        plan = build_plan(self.__fs, enc, self._decimationFactor, self._rowsHz(), simo=self._simo(),
+                          swap=swap, correct_iq=ciq, normalize=norm, demod=self._demodName(),
+                          omega_out=self.omegaOut, chunk_bytes=chunk_bytes)
+        self._chunkBytes = chunk_bytes
+        return Engine(plan, max_chunks=self.MAX_BATCH, device=self._device)
+
+    @staticmethod
+    def _asBytes(chunk) -> np.ndarray:
+        if isinstance(chunk, np.ndarray):
+            if np.iscomplexobj(chunk):
+                chunk = np.ascontiguousarray(chunk, dtype=np.complex128)
+            return np.ascontiguousarray(chunk).view(np.uint8).reshape(-1)
+        return np.frombuffer(chunk, dtype=np.uint8)
+
+    def _emit(self, out: np.ndarray, nchunks: int, file) -> None:
+        """Standard mode: one stream, native doubles, chunk after chunk (:162)."""
+        file.write(out[0].tobytes())
+
+    def _processData(self, isDead, buffer, file=None) -> None:
+        eof = False
+        while not (self._isDead or isDead.value or eof):
+            batch = [buffer.get()]
+            while len(batch) < self.MAX_BATCH:
+                try:
+                    batch.append(buffer.get_nowait())
+                except _queue.Empty:
+                    break
+            chunks = []
+            for c in batch:
+                if c is None or len(c) == 0:          # end-of-stream marker (read_file.py:169-171)
+                    eof = True
+                    break
+                chunks.append(self._asBytes(c))
+            if not chunks:
+                break
+            if self._engine is None:
+                self._engine = self._makeEngine(batch[0])
+            if any(c.size != self._chunkBytes for c in chunks):
+                raise ValueError('chunks must all have the size of the first one')
+            raw = np.concatenate(chunks) if len(chunks) > 1 else chunks[0]
+            out = self._engine.process(raw)
+            self._emit(out, len(chunks), file)
+
+    def processData(self, isDead, buffer, f: str | None, *args, **kwargs) -> None:
+        with open(f, 'wb') if f is not None else open(stdout.fileno(), 'wb', closefd=False) as file:
+            try:
+                self._processData(isDead, buffer, file)
+                file.flush()
+            except KeyboardInterrupt:
+                pass
+            finally:
+                if self._engine is not None:
+                    self._engine.close()
+                    self._engine = None
+                for m in ('close', 'join_thread'):
+                    if hasattr(buffer, m):
+                        getattr(buffer, m)()
+
+    # ---------------------------------------------------------------- pickling / repr
+    def __getstate__(self):
+        d = dict(self.__dict__)
+        d['_engine'] = None
+        return d
+
+    def __repr__(self):
+        from json import dumps
+        d = {k: v for k, v in self.__dict__.items()
+             if not (v is None or k.startswith('_') or callable(v) or isinstance(v, np.ndarray))}
+        if self.__fileInfo is not None:
+            d['encoding'] = str(self.__fileInfo.get('bitsPerSample'))
+        d['fs'] = self.__fs
+        d['decimatedFs'] = self.__decimatedFs
+        return dumps(d, indent=2, default=str)
+
+    def __str__(self):
+        return self.__class__.__name__

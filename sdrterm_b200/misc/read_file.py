@@ -1,0 +1,78 @@
+"""Producer: fixed 131072-byte reads from a file, stdin or a ``host:port`` socket, handed to the
+consumer queues as raw bytes (reference: src/misc/read_file.py:31-171).
+
+What the reference does per chunk on the CPU (view as ``[('re',T),('im',T)]``, ``re + 1j*im``,
+normalise, IQ-correct, pickle 16 bytes per sample through a pipe) is not done here at all: the
+bytes go to the device as they are.  Kept from the reference because they decide WHICH bytes form
+a chunk: the seek to ``dataOffset``, the reused read buffer whose stale tail is processed after a
+short final read, the empty end-of-stream marker, and the socket retry loop."""
+from __future__ import annotations
+
+import socket
+import sys
+
+import numpy as np
+
+READ_SIZE = 131072          # read_file.py:38
+
+
+def generateDomain(dataType: str):
+    """(xmin, 1/(xmax - xmin)) of ``--normalize-input`` (read_file.py:177-196)."""
+    dom = {'B': (0, 255), 'h': (-32768, 32767), 'b': (-128, 127), 'i': (-2147483648, 2147483647),
+           'H': (0, 65536), 'I': (0, 4294967295), 'L': (0, 18446744073709551615),
+           'l': (-9223372036854775808, 9223372036854775807)}.get(dataType)
+    if dom is None:
+        return None
+    return dom[0], 1 / (-dom[0] + dom[1])
+
+
+def chunks(reader, readSize: int = READ_SIZE, isDead=None):
+    """Yield whole chunks exactly as the reference's reader presents them: ``readinto`` a reused
+    buffer; a short read leaves the previous chunk's tail in place and the whole buffer counts."""
+    buf = np.zeros(readSize, dtype=np.uint8)
+    view = memoryview(buf)
+    while isDead is None or not isDead.value:
+        if not reader.readinto(view):
+            return
+        yield buf.copy()
+
+
+def readFile(bitsPerSample=None, dataOffset: int = 0, fs: int | None = None, buffers=None,
+             processes=None, isDead=None, inFile: str | None = None, readSize: int = READ_SIZE,
+             isSocket: bool = False, **_) -> None:
+    """Feed every queue in ``buffers`` with raw chunks until EOF or ``isDead``; then the empty
+    end-of-stream marker (read_file.py:169-171)."""
+    if fs is None:
+        raise ValueError('fs is not specified')
+    clients = list(buffers or [])
+
+    def feed(reader):
+        for c in chunks(reader, readSize, isDead):
+            for q in clients:
+                q.put(c)
+
+    if isSocket:
+        host, port = inFile.split(':')
+        retries, MAX_RETRIES = 0, 5
+        while retries < MAX_RETRIES and not (isDead is not None and isDead.value):
+            try:
+                with socket.create_connection((host, int(port)), timeout=5) as sock:
+                    sock.setsockopt(socket.SOL_SOCKET, socket.SO_KEEPALIVE, 1)
+                    retries = 0
+                    with sock.makefile('rb') as reader:
+                        feed(reader)
+                    break
+            except (TimeoutError, ConnectionError, socket.gaierror) as e:
+                retries += 1
+                print(f'Connection failed: {e}. Retrying {retries} of {MAX_RETRIES} times', file=sys.stderr)
+    else:
+        isFile = inFile is not None
+        with open(inFile if isFile else sys.stdin.fileno(), 'rb', closefd=isFile) as fh:
+            if dataOffset and fh.seekable():
+                fh.seek(dataOffset)
+            feed(fh)                      # open(..., 'rb') is already a BufferedReader
+    for q in clients:
+        try:
+            q.put(b'')
+        except Exception:
+            pass

@@ -30,7 +30,7 @@ from scipy import signal as _sig
 
 TILE_BLOCKS = 32          # one warp: lane <-> block
 CHUNK_BYTES = 131072      # src/misc/read_file.py:38
-_ITEMSIZE = {'b': 1, 'B': 1, 'h': 2, 'H': 2, 'i': 4, 'I': 4, 'f': 4, 'd': 8, 'Z': 16}
+_ITEMSIZE = {'b': 1, 'B': 1, 'h': 2, 'H': 2, 'i': 4, 'I': 4, 'f': 4, 'd': 8, 'Z': 8}
 
 
 def _c(x) -> complex:

@@ -1,0 +1,89 @@
+"""``python -m sdrterm`` drop-in: same options as the reference's CLI (src/sdrterm.py:54-107) for
+the demodulation path.  Plots and the smoothing filter are not part of this build.
+
+A reader thread feeds raw chunks to the GPU consumer in this process; the reference's two-process
+layout exists to overlap CPU work that no longer happens on the CPU."""
+from __future__ import annotations
+
+import argparse
+import queue
+import sys
+import threading
+
+from .misc.file_util import ENCODINGS, checkWavHeader, parseIntString
+from .misc.read_file import readFile
+
+
+class _Flag:
+    """multiprocessing.Value-like stop flag."""
+
+    def __init__(self):
+        self.value = 0
+
+
+def buildParser() -> argparse.ArgumentParser:
+    ap = argparse.ArgumentParser(prog='sdrterm', description='B200 demodulation chain behind the sdrterm CLI')
+    ap.add_argument('--fs', '-r', type=parseIntString, default=None, help='Sampling frequency in k/M/Samples per sec')
+    ap.add_argument('--center-frequency', '-c', dest='center', type=parseIntString, default=0)
+    ap.add_argument('--input', '-i', dest='inFile', default=None, help='file, host:port, or stdin')
+    ap.add_argument('--output', '-o', dest='outFile', default=None, help='file or stdout')
+    ap.add_argument('--plot', default=None, help='accepted and ignored (plots are out of scope)')
+    ap.add_argument('--demodulation', '-m', dest='demod', type=str.lower, default='fm',
+                    choices=['fm', 'nfm', 'am', 're', 'im'])
+    ap.add_argument('--tuned-frequency', '-t', dest='tuned', type=parseIntString, default=0)
+    ap.add_argument('--vfos', default=None, help='CSV of integer offsets from the tuned frequency')
+    ap.add_argument('--decimation', '-d', dest='dec', type=int, default=2)
+    ap.add_argument('--encoding', '-e', dest='enc', choices=list(ENCODINGS), default=None)
+    ap.add_argument('--omega-out', '-w', dest='omegaOut', type=parseIntString, default=12500)
+    ap.add_argument('--correct-iq', dest='correct_iq', action='store_true')
+    ap.add_argument('--no-correct-iq', dest='correct_iq', action='store_false')
+    ap.add_argument('--simo', action='store_true')
+    ap.add_argument('--no-simo', dest='simo', action='store_false')
+    ap.add_argument('--verbose', '-v', action='count', default=0)
+    ap.add_argument('--smooth-output', dest='smooth_output', type=int, default=0)
+    ap.add_argument('--vfo-host', dest='vfo_host', default='localhost')
+    ap.add_argument('--swap-input-endianness', '-X', dest='swap', action='store_true')
+    ap.add_argument('--normalize-input', dest='normalize', action='store_true')
+    ap.add_argument('--no-normalize-input', dest='normalize', action='store_false')
+    return ap
+
+
+def makeProcessor(a, fileInfo):
+    """What IOArgs._initializeOutputHandlers does (src/misc/io_args.py:97-141)."""
+    from .dsp.dsp_processor import DspProcessor
+    from .dsp.vfo_processor import VfoProcessor
+    if a.dec < 2:
+        raise ValueError('Decimation must be at least 2.')
+    if a.smooth_output:
+        raise ValueError('--smooth-output is not part of this build')
+    kw = dict(center=a.center, omegaOut=a.omegaOut, tuned=a.tuned, dec=a.dec, smooth=False,
+              fileInfo=fileInfo, swapEndianness=a.swap, correctIq=a.correct_iq, normalize=a.normalize)
+    fs = fileInfo['sampRate']
+    proc = VfoProcessor(fs, vfoHost=a.vfo_host, vfos=a.vfos, **kw) if a.simo else DspProcessor(fs, **kw)
+    {'fm': proc.selectOutputFm, 'nfm': proc.selectOutputFm, 'am': proc.selectOutputAm,
+     're': proc.selectOutputReal, 'im': proc.selectOutputImag}[a.demod]()
+    return proc
+
+
+def main(argv=None) -> int:
+    a = buildParser().parse_args(argv)
+    fileInfo = checkWavHeader(a.inFile, a.fs, a.enc)           # a WAV header overrides -r / -e
+    proc = makeProcessor(a, fileInfo)
+    if a.verbose:
+        print(repr(proc), file=sys.stderr)
+    isDead = _Flag()
+    buf = queue.Queue(maxsize=256)
+    reader = threading.Thread(target=readFile, daemon=True,
+                              kwargs=dict(buffers=[buf], isDead=isDead, inFile=a.inFile,
+                                          fs=fileInfo['sampRate'], dataOffset=fileInfo['dataOffset'],
+                                          isSocket=fileInfo['isSocket']))
+    reader.start()
+    try:
+        proc.processData(isDead, buf, a.outFile)
+    finally:
+        isDead.value = 1
+    return 0
+
+
+if __name__ == '__main__':
+    sys.exit(main())

@@ -1,0 +1,187 @@
+"""Host-side mirror of the reference's processor / ingest API (no GPU needed): the cases of the
+reference's own test/dsp/dsp_processor_test.py:21-75, test/misc/read_file_test.py and
+test/misc/file_util_test.py that concern this path, against sdrterm_b200.dsp / .misc and the
+``src/`` import shims."""
+import io
+import math
+import os
+import pickle
+import struct
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+import sdrterm_b200.dsp.demodulation as dem
+import sdrterm_b200.dsp.dsp_processor as dsp
+from sdrterm_b200.dsp.data_processor import DataProcessor
+from sdrterm_b200.dsp.vfo_processor import VfoProcessor
+from sdrterm_b200.misc import file_util, read_file
+
+FS, CENTER, NSHIFT, DEC = 48000, -1000, 8, 3
+
+
+def test_processor_surface_like_reference():
+    p = dsp.DspProcessor(FS, omegaOut=250)
+    assert p.fs == FS and p.decimation == 2 and p.decimatedFs == FS >> 1
+    p.selectOutputFm()
+    assert p.demod == dem.fmDemod and p.bandwidth == 12500 and len(p._outputFilters) == 2
+    p.selectOutputAm()
+    assert p.demod == dem.amDemod and p.bandwidth == 10000
+    p.selectOutputReal()
+    assert p.demod == dem.realOutput and p._outputFilters == [] and p.bandwidth == p.decimatedFs
+    p.selectOutputImag()
+    assert p.demod == dem.imagOutput
+    with pytest.raises(ValueError):
+        p.decimation = 1
+    with pytest.raises(AttributeError):
+        p.decimatedFs = 1
+    with pytest.raises(ValueError):
+        p._setDemod(None, ())
+    with pytest.raises(TypeError):
+        p._setDemod('asdf', None)
+    p.decimation = DEC
+    assert p.decimation == DEC and p.decimatedFs == FS / DEC
+    p._generateShift(NSHIFT)
+    assert p._shift is None                       # centre 0: no shift (dsp_processor.py:185-187)
+    p.centerFreq = CENTER
+    p._generateShift(NSHIFT)
+    assert p._shift.size == NSHIFT
+    for k in range(NSHIFT):
+        assert p._shift[0][k] == np.pow(math.e, -2j * math.pi * (CENTER / FS) * k)
+    with pytest.raises(FileNotFoundError):
+        p.processData(None, None, '')
+    with pytest.raises(AttributeError):
+        p.processData(None, None, None)
+    with pytest.raises(TypeError):
+        DataProcessor()
+    DataProcessor.processData(None)
+
+
+def test_processor_pickles_without_cuda_state():
+    p = dsp.DspProcessor(1_024_000, center=15000, omegaOut=5000, dec=64, enc='h', correctIq=True)
+    p.selectOutputFm()
+    q = pickle.loads(pickle.dumps(p))
+    assert q.fs == p.fs and q.decimation == 64 and q.demod == dem.fmDemod and q._engine is None
+    assert 'decimatedFs' in repr(q)
+
+
+def test_vfo_processor_rows_and_errors():
+    with pytest.raises(ValueError):
+        VfoProcessor(2_400_000, vfos=None)
+    with pytest.raises(ValueError):
+        VfoProcessor(2_400_000, vfos='')
+    v = VfoProcessor(2_400_000, vfoHost='127.0.0.1:0', vfos='-100000,200000', center=5000, dec=64)
+    assert list(v.vfos) == [-95000, 205000, 5000] and v._nFreq == 3     # centre appended (8-Q9)
+    assert v.host == '127.0.0.1' and v.port == 0 and v.vfosStr == '-100000,200000,0'
+    v._generateShift(4)
+    w = -2j * np.pi * (v.vfos / v.fs)
+    assert np.array_equal(v._shift, np.exp(w[:, None] * np.arange(4)[None, :]))
+    v2 = VfoProcessor(2_400_000, vfoHost='127.0.0.1', vfos='1')
+    assert v2.port > 0
+
+
+def test_generate_domain_table():
+    """test/misc/read_file_test.py:12-19."""
+    assert read_file.generateDomain('B') == (0, 1 / 255)
+    assert read_file.generateDomain('b') == (-128, 1 / 255)
+    assert read_file.generateDomain('h') == (-32768, 1 / 65535)
+    assert read_file.generateDomain('H') == (0, 1 / 65536)
+    assert read_file.generateDomain('i') == (-2147483648, 1 / 4294967295)
+    assert read_file.generateDomain('I') == (0, 1 / 4294967295)
+    assert read_file.generateDomain('f') is None and read_file.generateDomain('d') is None
+
+
+def _wav(tmp_path, tag=b'RIFF', fmt=1, bits=16, rate=1_024_000, payload=b'\x01\x02' * 64):
+    e = '<' if tag == b'RIFF' else '>'
+    hdr = tag + struct.pack(e + 'I', 36 + len(payload)) + b'WAVEfmt ' + \
+        struct.pack(e + 'IHHIIHH', 16, fmt, 2, rate, rate * 2 * bits // 8, 2 * bits // 8, bits) + \
+        b'data' + struct.pack(e + 'I', len(payload)) + payload
+    f = tmp_path / 'x.wav'
+    f.write_bytes(hdr)
+    return str(f)
+
+
+def test_wav_header_and_offset_quirk(tmp_path):
+    info = file_util.checkWavHeader(_wav(tmp_path), None, None)
+    assert info['sampRate'] == 1_024_000 and info['bitsPerSample'] == np.dtype('<i2')
+    assert info['dataOffset'] == 40 and not info['isSocket']        # 4 bytes short of 44 (8-Q4)
+    info = file_util.checkWavHeader(_wav(tmp_path, tag=b'RIFX'), None, None)
+    assert info['bitsPerSample'] == np.dtype('>i2')
+    info = file_util.checkWavHeader(_wav(tmp_path, fmt=3, bits=32), None, None)
+    assert info['bitsPerSample'] == np.dtype('<f4')
+    info = file_util.checkWavHeader(_wav(tmp_path, bits=8), None, None)
+    assert info['bitsPerSample'] == np.dtype('u1')
+    with pytest.raises(ValueError):
+        file_util.checkWavHeader(_wav(tmp_path, fmt=7), None, None)
+
+
+def test_raw_type_rules(tmp_path):
+    raw = tmp_path / 'x.raw'
+    raw.write_bytes(b'\0' * 64)
+    info = file_util.checkWavHeader(str(raw), 2_400_000, 'B')
+    assert info['bitsPerSample'] == np.dtype('u1') and info['dataOffset'] == 0
+    with pytest.raises(ValueError):
+        file_util.checkWavHeader(str(raw), None, 'B')
+    with pytest.raises(ValueError):
+        file_util.parseRawType(None, 1000, None)
+    assert file_util.parseRawType('host:1234', 1000, 'h', True)['bitsPerSample'] == np.dtype('>i2')
+    assert file_util.parseIntString('15k') == 15000 and file_util.parseIntString('2.4M') == 2_400_000
+    assert file_util.parseIntString('64') == 64 and file_util.parseIntString(7) == 7
+
+
+def test_chunk_reader_reuses_its_buffer_like_the_reference():
+    """A short final read leaves the previous chunk's tail in the buffer and the whole buffer is
+    processed."""
+    data = bytes(range(256)) * 4 + b'\xff' * 100
+    got = list(read_file.chunks(io.BytesIO(data), readSize=512))
+    assert len(got) == 3
+    assert got[0].tobytes() == data[:512] and got[1].tobytes() == data[512:1024]
+    assert got[2].tobytes() == b'\xff' * 100 + data[512 + 100:1024]
+
+
+def test_read_file_feeds_queues_and_marks_eof(tmp_path):
+    import queue
+    f = tmp_path / 'in.raw'
+    f.write_bytes(b'\x07' * (131072 + 10))
+    q = queue.Queue()
+    read_file.readFile(fs=1000, buffers=[q], inFile=str(f), dataOffset=4)
+    items = []
+    while not q.empty():
+        items.append(q.get())
+    assert [len(i) for i in items] == [131072, 131072, 0]
+    with pytest.raises(ValueError):
+        read_file.readFile(fs=None, buffers=[q])
+
+
+def test_cli_parser_matches_reference_options():
+    from sdrterm_b200.sdrterm import buildParser, makeProcessor
+    a = buildParser().parse_args(['-r', '1024k', '-c', '15k', '-w', '5k', '-d', '64', '--correct-iq',
+                                  '-e', 'h', '-m', 'FM', '-X', '-i', 'x', '-o', 'y'])
+    assert (a.fs, a.center, a.omegaOut, a.dec, a.correct_iq, a.enc, a.demod, a.swap) == \
+        (1_024_000, 15000, 5000, 64, True, 'h', 'fm', True)
+    info = file_util.parseRawType(None, a.fs, a.enc)
+    p = makeProcessor(a, info)
+    assert isinstance(p, dsp.DspProcessor) and p.demod == dem.fmDemod and p.decimatedFs == 16000
+    b = buildParser().parse_args(['-r', '2400k', '-e', 'h', '--simo', '--vfos', '100000,-200000', '-d', '64',
+                                  '--vfo-host', '127.0.0.1:0'])
+    v = makeProcessor(b, file_util.parseRawType(None, b.fs, b.enc))
+    assert isinstance(v, VfoProcessor) and v._nFreq == 3
+    with pytest.raises(ValueError):
+        makeProcessor(buildParser().parse_args(['-r', '1k', '-e', 'h', '-d', '1']), info)
+
+
+def test_reference_import_names_resolve_to_this_build():
+    sys.path.insert(0, os.path.join(ROOT, 'src'))
+    try:
+        import dsp.demodulation as d2
+        import dsp.dsp_processor as p2
+        import misc.read_file as r2
+        import sdrterm as cli
+        assert d2 is dem and p2 is dsp and r2 is read_file and callable(cli.main)
+    finally:
+        sys.path.remove(os.path.join(ROOT, 'src'))
+        for k in [k for k in sys.modules if k in ('dsp', 'misc', 'sdrterm') or k.startswith(('dsp.', 'misc.'))]:
+            del sys.modules[k]
