@@ -236,6 +236,7 @@ def run_cuda_arm(args):
     import torch.distributed as dist
     from sdrterm_b200.engine import Engine
     from sdrterm_b200.plan import build_plan
+    from sdrterm_b200 import sharding
 
     world = int(os.environ.get('WORLD_SIZE', '1'))
     rank = int(os.environ.get('RANK', '0'))
@@ -268,7 +269,6 @@ def run_cuda_arm(args):
     raw = synth_c1_device(torch, nsamp, seed=5 + rank, device=dev)
     out = torch.empty((1, nch * pl.M), dtype=torch.float64, device=dev)
     stream = torch.cuda.current_stream().cuda_stream
-    decay_seg = pl.lam ** nsamp            # IQ-offset decay over one rank's segment
 
     def step_device():
         if world == 1:
@@ -277,15 +277,7 @@ def run_cuda_arm(args):
         # time-segment sharding: block kernel + offset gain from zero, exchange, finish
         eng.iq_state = 0j
         eng.process_device_phases(raw.data_ptr(), nch, 0, 1 | 2, stream)
-        g = eng.iq_state
-        mine = torch.tensor([g.real, g.imag], dtype=torch.float64, device=dev)
-        allg = torch.empty((world, 2), dtype=torch.float64, device=dev)
-        dist.all_gather_into_tensor(allg, mine)
-        gains = allg.cpu().numpy()
-        off = 0j
-        for i in range(rank):
-            off = decay_seg * off + complex(gains[i, 0], gains[i, 1])
-        eng.iq_state = off
+        eng.iq_state = sharding.exchange_iq_gain(dist, torch, eng.iq_state, nsamp, pl.lam, device=dev)
         eng.process_device_phases(raw.data_ptr(), nch, out.data_ptr(), 2 | 4, stream)
 
     clocks = Clocks(local)
@@ -335,8 +327,8 @@ def run_cuda_arm(args):
         import signals
         offs = signals.vfo_grid(16, 100_000)
         rows_all = [o for o in offs] + [0]
-        per = -(-len(rows_all) // world)
-        mine = rows_all[rank * per:(rank + 1) * per]
+        lo, hi = sharding.row_shard(len(rows_all), world, rank)
+        mine = rows_all[lo:hi]
         sch = args.simo_chunks
         if mine:
             pls = build_plan(2_400_000, 'h', 64, mine, simo=True, swap=True, demod='fm', omega_out=5000)
@@ -347,7 +339,7 @@ def run_cuda_arm(args):
 
         def step_simo():
             if world > 1:
-                dist.broadcast(raws, src=0)
+                sharding.broadcast_raw(dist, torch, raws, src=0)
             if mine:
                 engs.process_device(raws.data_ptr(), sch, outs.data_ptr(), stream)
 
@@ -389,14 +381,18 @@ def run_cuda_arm(args):
         tpath = os.path.join(ROOT, 'profiles', 'traffic.json')
         if os.path.exists(tpath):
             try:
-                traffic = json.load(open(tpath)).get('k_main_dram_bytes_per_launch')
+                per_chunk = json.load(open(tpath)).get('k_tc_dram_bytes_per_chunk')
+                traffic = per_chunk * nch if (per_chunk and eng.tc is not None) else None
             except Exception:
                 traffic = None
         kname = 'k_tc' if eng.tc is not None else 'k_main'
         roof = {'bound': 'hbm', 'kernel': kname, 'achieved': ach, 'peak': peak, 'unit': 'GB/s',
                 'frac': ach / peak, 'traffic': traffic, 'peak_source': peak_src,
                 'algorithmic_bytes_per_sample': bytes_per_sample,
-                'kernel_ms': {kname: kavg[0], 'k_iqscan': kavg[1], 'k_fixup': kavg[2], 'k_demod': kavg[3]},
+                'kernel_ms': {kname: kavg[0], 'k_iqgain+k_iqscan+k_iqtiles': kavg[1],
+                              'k_finish (or k_fixup)': kavg[2], 'k_demod (general path only)': kavg[3]},
+                'algorithmic_bytes_per_launch': bytes_per_sample * nsamp,
+                'traffic_source': 'profiles/traffic.json: ncu dram bytes per chunk x chunks per launch',
                 'note': 'dominant kernel = block front end; k_tc = tcgen05 int8 GEMM over the raw bytes + FP64 epilogue (DESIGN.md 3.4)'}
         if simo is not None:
             simo['frac_hbm'] = simo['input_msps'] * 1e6 * simo['bytes_per_sample'] / 1e9 / peak

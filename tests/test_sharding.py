@@ -1,0 +1,130 @@
+"""Multi-process (world size 2, gloo, CPU) coverage of the N>1 paths: time-segment sharding with
+the IQ-offset hand-off, and VFO-row sharding with the raw-chunk broadcast.  The compute engine in
+these CPU tests is the oracle (the checker); what is under test is sdrterm_b200/sharding.py."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from sdrterm_b200 import sharding
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CB = 131072
+
+
+def test_partitions_cover_everything_once():
+    for n in (1, 2, 7, 17, 257):
+        for w in (1, 2, 3, 4, 8):
+            rows = [sharding.row_shard(n, w, r) for r in range(w)]
+            assert rows[0][0] == 0 and rows[-1][1] == n
+            assert all(rows[i][1] == rows[i + 1][0] or rows[i + 1][0] == n for i in range(w - 1))
+            segs = [sharding.segment_shard(n, w, r) for r in range(w)]
+            assert sum(c for _, c in segs) == n
+            assert all(segs[i][0] + segs[i][1] == segs[i + 1][0] for i in range(w - 1))
+            assert max(c for _, c in segs) - min(c for _, c in segs) <= 1
+
+
+def test_iq_prefix_equals_serial_recurrence():
+    rng = np.random.default_rng(0)
+    lam, L = 1 - 50 / 1_024_000, 50 / 1_024_000
+    z = rng.normal(size=3000) + 1j * rng.normal(size=3000) + (3 - 2j)
+    cuts = [0, 700, 1500, 1501, 3000]
+    offs, off = [], 0j
+    for n in range(3000):
+        if n in cuts:
+            offs.append(off)
+        off = off + (z[n] - off) * L
+    gains, lens = [], []
+    for a, b in zip(cuts[:-1], cuts[1:]):
+        g = 0j
+        for n in range(a, b):
+            g = g + (z[n] - g) * L
+        gains.append(g)
+        lens.append(b - a)
+    for r in range(4):
+        assert abs(sharding.iq_start_offset(gains, lens, lam, r) - offs[r]) < 1e-13
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(('127.0.0.1', 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, q):
+    for p in (ROOT, os.path.join(ROOT, 'tests')):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    import signals
+    from oracle import oracle as orc
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        # ---------------- time segments (config 5 shape, 5 chunks over 2 ranks)
+        kw = dict(fs=1_024_000, enc='h', center=15000, dec=64, demod='fm', omega_out=5000, correct_iq=True)
+        body = signals.c1_bytes(5 * 32768, seed=5, header=False)
+        start, cnt = sharding.segment_shard(5, world, rank)
+        seg = body[start * CB:(start + cnt) * CB]
+        ch = orc.Chain(**kw)
+        ch.run(seg)                                           # pass 1: gain from a zero offset
+        off0 = sharding.exchange_iq_gain(dist, torch, complex(ch._off[0]), cnt * 32768,
+                                         1 - 50 / kw['fs'])
+        ch2 = orc.Chain(**kw)
+        ch2._off[0] = off0
+        out = ch2.run(seg)                                    # pass 2 from the true start offset
+        # ---------------- VFO rows (config 3 shape, 5 rows over 2 ranks), raw broadcast
+        raw3, vf = signals.c3_bytes(2 * 32768, seed=3, k=4)
+        t = torch.from_numpy(np.frombuffer(raw3, dtype=np.uint8).copy()) if rank == 0 else \
+            torch.empty(len(raw3), dtype=torch.uint8)
+        sharding.broadcast_raw(dist, torch, t, src=0)
+        kw3 = dict(fs=2_400_000, enc='h', swap=True, center=0, dec=64, demod='fm', omega_out=5000,
+                   simo=True, vfos=vf)
+        full = orc.Chain(**kw3)
+        lo, hi = sharding.row_shard(full.R, world, rank)
+        mine = orc.Chain(**kw3)
+        mine.rows = full.rows[lo:hi]
+        mine.R = hi - lo
+        mine.shift = orc.nco_table(mine.rows, mine.fs, mine.n, True)
+        rows = mine.run(t.numpy().tobytes())
+        q.put((rank, start, cnt, out, lo, hi, rows))
+        dist.barrier()
+    except BaseException as e:                                # surface the failure, do not hang the parent
+        q.put((rank, repr(e)))
+        raise
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+def test_two_rank_gloo_matches_single_process():
+    import signals
+    from oracle import oracle as orc
+    world, port = 2, _free_port()
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=240) for _ in range(world)]
+    assert all(len(r) == 7 for r in res), res
+    res.sort(key=lambda x: x[0])
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    kw = dict(fs=1_024_000, enc='h', center=15000, dec=64, demod='fm', omega_out=5000, correct_iq=True)
+    body = signals.c1_bytes(5 * 32768, seed=5, header=False)
+    serial = orc.Chain(**kw).run(body)
+    got = np.concatenate([r[3] for r in res], axis=1)
+    assert got.shape == serial.shape
+    assert np.max(np.abs(got - serial)) / np.max(np.abs(serial)) < 1e-12
+    raw3, vf = signals.c3_bytes(2 * 32768, seed=3, k=4)
+    kw3 = dict(fs=2_400_000, enc='h', swap=True, center=0, dec=64, demod='fm', omega_out=5000,
+               simo=True, vfos=vf)
+    serial3 = orc.Chain(**kw3).run(raw3)
+    got3 = sharding.concat_rows([r[6] for r in res])
+    assert got3.shape == serial3.shape and np.array_equal(got3, serial3)
