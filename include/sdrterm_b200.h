@@ -170,6 +170,9 @@ int sdrb_set_iq_state(sdrb_handle *h, const double off[2]);
 /* Test/diagnostic access: complex decimator output of the last batch, [chunk][row][M]
  * interleaved doubles (what `y` holds after dsp_processor.py:147). */
 int sdrb_read_decimated(sdrb_handle *h, size_t nchunks, double *y_host);
+/* The fused finish kernel keeps y on chip; it is written out only when this is switched on
+ * (off by default; the general k_fixup/k_demod path always writes it). */
+int sdrb_keep_decimated(sdrb_handle *h, int on);
 
 /* Kernel launches issued by this handle since creation (bench.py's gpu_launches). */
 long long sdrb_launch_count(const sdrb_handle *h);

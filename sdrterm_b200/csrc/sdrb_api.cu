@@ -42,7 +42,7 @@ struct sdrb_handle {
     size_t main_smem = 0, demod_smem = 0;
     bool finish_on = false;         // fused k_finish instead of k_fixup + k_demod
     size_t finish_smem = 0;
-    int keep_y = 1;
+    int keep_y = 0;
     long long launches = 0;
     size_t last_nchunks = 0;
     bool profiling = false;
@@ -681,9 +681,17 @@ int sdrb_set_iq_state(sdrb_handle *h, const double off[2])
     return SDRB_OK;
 }
 
+int sdrb_keep_decimated(sdrb_handle *h, int on)
+{
+    if (!h) return fail(h, SDRB_ERR_ARG, "null argument");
+    h->keep_y = on != 0;
+    return SDRB_OK;
+}
+
 int sdrb_read_decimated(sdrb_handle *h, size_t nchunks, double *y_host)
 {
     if (!h || !y_host) return fail(h, SDRB_ERR_ARG, "null argument");
+    if (h->finish_on && !h->keep_y) return fail(h, SDRB_ERR_STATE, "decimator output not kept: call sdrb_keep_decimated(h, 1) first");
     if (nchunks > h->last_nchunks) return fail(h, SDRB_ERR_STATE, "only %zu chunks in the last batch", h->last_nchunks);
     CK(h, cudaSetDevice(h->cfg.device));
     CK(h, cudaDeviceSynchronize());

@@ -83,30 +83,27 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t a, uint32_t bytes)
 {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(a), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ bool mbar_try(uint32_t a, uint32_t parity)
+// try_wait with a suspend-time hint: the hardware parks the thread until the phase completes or
+// the hint (ns) expires, instead of the warp burning issue slots in a spin loop.
+__device__ __forceinline__ bool mbar_try(uint32_t a, uint32_t parity, uint32_t hint_ns)
 {
     uint32_t ok;
-    asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
-                 : "=r"(ok) : "r"(a), "r"(parity) : "memory");
+    asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\nselp.u32 %0, 1, 0, p;\n}"
+                 : "=r"(ok) : "r"(a), "r"(parity), "r"(hint_ns) : "memory");
     return ok != 0;
 }
 // Bounded waits: a protocol error traps (and surfaces as a CUDA error) instead of hanging the GPU.
-// try_wait itself suspends the warp for a hardware-defined interval, so the loop body is kept to
-// the bare minimum; `mbar_wait_sleep` additionally backs off (used by the producer-side warps
-// whose waits are long and whose wake-up latency does not matter).
 __device__ __forceinline__ void mbar_wait(uint32_t a, uint32_t parity)
 {
     uint32_t n = 0;
-    while (!mbar_try(a, parity))
-        if (++n > (1u << 28)) __trap();
+    while (!mbar_try(a, parity, 20000u))
+        if (++n > (1u << 22)) __trap();
 }
 __device__ __forceinline__ void mbar_wait_sleep(uint32_t a, uint32_t parity)
 {
     uint32_t n = 0;
-    while (!mbar_try(a, parity)) {
-        __nanosleep(64);
-        if (++n > (1u << 26)) __trap();
-    }
+    while (!mbar_try(a, parity, 100000u))
+        if (++n > (1u << 20)) __trap();
 }
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map, int x, int y, uint32_t bar)
 {
@@ -281,8 +278,8 @@ __device__ __forceinline__ void tc_epilogue(const DevPlan &pl, const TcDev &tc, 
                 double vi = tc_combine<NCOL>(c + (2 * h + 1) * NCOL, s16, s1, sh.sCst[o + 1]);
                 if (IQ) {
                     const double2 ph = sh.sPhi[8 * HALF + md];
-                    vr -= fma(excl.x, ph.x, -excl.y * ph.y);
-                    vi -= fma(excl.x, ph.y, excl.y * ph.x);
+                    vr = fma(-excl.x, ph.x, fma(excl.y, ph.y, vr));
+                    vi = fma(-excl.x, ph.y, fma(-excl.y, ph.x, vi));
                 }
                 xsl[md * TC_XS] = make_double2(vr, vi);
             }

@@ -19,7 +19,8 @@ def _dp(a: np.ndarray):
 
 
 class Engine:
-    def __init__(self, plan: Plan, max_chunks: int = 256, device: int = 0, use_tc: bool = True):
+    def __init__(self, plan: Plan, max_chunks: int = 256, device: int = 0, use_tc: bool = True,
+                 keep_decimated: bool = False):
         self.plan = plan
         self.max_chunks = int(max_chunks)
         self.device = int(device)
@@ -92,6 +93,8 @@ class Engine:
                 tab.tc_xor[i] = int(tc.xor_mask[i])
         nat.check(L.sdrb_create(C.byref(cfg), C.byref(tab), C.byref(self._h)))
         self.M = int(L.sdrb_outputs_per_chunk(self._h))
+        if keep_decimated:
+            nat.check(L.sdrb_keep_decimated(self._h, 1), self._h)
         self.chunk_bytes = int(L.sdrb_chunk_bytes(self._h))
         self.R = pl.R
 

@@ -35,7 +35,7 @@ def run_case(name, max_chunks=8, use_tc=True):
     raw, body, kw = case_stream(name)
     pl = plan_for(kw)
     chunks = chunked(body)
-    with Engine(pl, max_chunks=max_chunks, use_tc=use_tc) as eng:
+    with Engine(pl, max_chunks=max_chunks, use_tc=use_tc, keep_decimated=True) as eng:
         out = eng.process(chunks)
         y = eng.decimated(min(chunks.shape[0], max_chunks))
         off = eng.iq_state

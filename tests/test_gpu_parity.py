@@ -98,12 +98,12 @@ def test_tc_long_stream_matches_oracle_and_fp64_path():
     kw = dict(fs=1_024_000, enc='h', center=15000, dec=64, demod='fm', omega_out=5000, correct_iq=True,
               vfos=None, simo=False, normalize=False, swap=False, big_endian=None)
     pl = plan_for(kw)
-    with Engine(pl, max_chunks=nch, use_tc=True) as e1:
+    with Engine(pl, max_chunks=nch, use_tc=True, keep_decimated=True) as e1:
         assert e1.tc is not None
         a = e1.process(body)
         ya = e1.decimated(nch)
         offa = e1.iq_state
-    with Engine(pl, max_chunks=nch, use_tc=False) as e2:
+    with Engine(pl, max_chunks=nch, use_tc=False, keep_decimated=True) as e2:
         b = e2.process(body)
         yb = e2.decimated(nch)
         offb = e2.iq_state
