@@ -1,0 +1,31 @@
+"""k_tc pipeline timeline of CTA 0 (diagnostic): SDRB_TC_DEBUG=1 python microbench/tc_timeline.py"""
+import os, sys
+os.environ['SDRB_TC_DEBUG'] = '1'
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path[:0] = [ROOT, os.path.join(ROOT, 'tests')]
+import numpy as np, torch
+import signals
+from sdrterm_b200 import _native as nat
+from sdrterm_b200.engine import Engine
+from sdrterm_b200.plan import build_plan
+nch = 2048
+pl = build_plan(1_024_000, 'h', 64, [15000], correct_iq=True, demod='fm', omega_out=5000)
+eng = Engine(pl, max_chunks=nch)
+base = np.frombuffer(signals.c1_bytes(16 * 32768, seed=0, header=False), dtype=np.uint8)
+raw = torch.from_numpy(np.tile(base, nch // 16)).cuda()
+out = torch.empty((1, nch * pl.M), dtype=torch.float64, device='cuda')
+for _ in range(3):
+    eng.process_device(raw.data_ptr(), nch, out.data_ptr(), 0)
+torch.cuda.synchronize()
+buf = np.zeros(512, dtype=np.uint64)
+nat.check(nat.lib().sdrb_read_debug(eng._h, buf.ctypes.data), eng._h)
+t = buf.reshape(64, 8).astype(np.int64)
+t0 = t[0, 0]
+names = ['tma_issue', 'xor_start', 'xor_done', 'mma_start', 'mma_issued', 'epi_start', 'tmem_free', 'epi_end']
+print('tile ' + ' '.join(f'{n:>10s}' for n in names))
+for it in range(2, 40):
+    print(f'{it:4d} ' + ' '.join(f'{(t[it, e] - t0):10d}' for e in range(8)))
+d = np.diff(t[8:56, 0])
+print('cycles per tile (tma_issue to tma_issue):', d.mean())
+for a, b in ((0, 1), (1, 2), (2, 3), (3, 4), (4, 5), (5, 6), (6, 7), (0, 7)):
+    print(f'{names[a]:>10s} -> {names[b]:<10s}: mean {np.mean(t[8:56, b] - t[8:56, a]):8.0f}')

@@ -58,7 +58,7 @@ EXPORTS = ['sdrb_create', 'sdrb_destroy', 'sdrb_last_error', 'sdrb_outputs_per_c
            'sdrb_get_iq_state', 'sdrb_set_iq_state', 'sdrb_read_decimated', 'sdrb_launch_count',
            'sdrb_fm_demod', 'sdrb_am_demod', 'sdrb_real_output', 'sdrb_imag_output',
            'sdrb_shift_freq', 'sdrb_global_error', 'sdrb_process_device_phases',
-           'sdrb_set_profiling', 'sdrb_kernel_times', 'sdrb_keep_decimated']
+           'sdrb_set_profiling', 'sdrb_kernel_times', 'sdrb_keep_decimated', 'sdrb_read_debug']
 
 
 def nvcc_command(out: str = LIB_PATH) -> list[str]:
@@ -109,6 +109,7 @@ def lib():
         L.sdrb_set_iq_state.argtypes = [vp, _DP]
         L.sdrb_read_decimated.argtypes = [vp, sz, vp]
         L.sdrb_keep_decimated.argtypes = [vp, C.c_int]
+        L.sdrb_read_debug.argtypes = [vp, vp]
         L.sdrb_launch_count.argtypes = [vp]
         L.sdrb_launch_count.restype = C.c_longlong
         for name in ('sdrb_fm_demod', 'sdrb_am_demod', 'sdrb_real_output', 'sdrb_imag_output'):

@@ -518,7 +518,11 @@ int sdrb_create(const sdrb_config *cfg, const sdrb_tables *tab, sdrb_handle **ou
     UP(dalloc(h, nch * R * M, &sc.y));
     UP(dalloc(h, (size_t)1, &sc.iq_state));
     if (cudaMemset(sc.iq_state, 0, sizeof(double2)) != cudaSuccess) return bail(fail(h, SDRB_ERR_CUDA, "memset failed"));
-    sc.fftbuf = nullptr; sc.zrow = nullptr;
+    sc.fftbuf = nullptr; sc.zrow = nullptr; sc.dbg = nullptr;
+    if (env_int("SDRB_TC_DEBUG", 0)) {
+        UP(dalloc(h, (size_t)64 * 8, &sc.dbg));
+        cudaMemset(sc.dbg, 0, 64 * 8 * sizeof(unsigned long long));
+    }
     if (!pl.demod_in_smem) {
         UP(dalloc(h, nch * R * 2 * M, &sc.fftbuf));
         UP(dalloc(h, nch * R * M, &sc.zrow));
@@ -678,6 +682,15 @@ int sdrb_set_iq_state(sdrb_handle *h, const double off[2])
     CK(h, cudaSetDevice(h->cfg.device));
     CK(h, cudaDeviceSynchronize());
     CK(h, cudaMemcpy(h->sc.iq_state, off, sizeof(double2), cudaMemcpyHostToDevice));
+    return SDRB_OK;
+}
+
+/* diagnostic: k_tc pipeline timeline of CTA 0 (clock64 per event), needs SDRB_TC_DEBUG=1 at create */
+int sdrb_read_debug(sdrb_handle *h, unsigned long long *out512)
+{
+    if (!h || !out512 || !h->sc.dbg) return fail(h, SDRB_ERR_STATE, "no debug buffer");
+    CK(h, cudaDeviceSynchronize());
+    CK(h, cudaMemcpy(out512, h->sc.dbg, 64 * 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
     return SDRB_OK;
 }
 

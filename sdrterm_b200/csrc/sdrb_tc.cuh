@@ -39,7 +39,8 @@
 #define TC_THREADS 640
 #define TC_EPI_WARPS 16
 #define TC_XS 33                       // exchange-buffer row stride in double2
-#define TC_STAGES 2
+#define TC_STAGES 2                    // TMEM accumulator stages
+#define TC_ASTAGES 3                   // shared-memory A stages (TMA -> sign fix-up -> MMA ring)
 #define TC_REGION_BYTES 16384          // 128 rows x 128 bytes, one SWIZZLE_128B operand slab
 
 struct TcDev {
@@ -59,13 +60,13 @@ __host__ __device__ inline size_t tc_warp_bytes()
 __host__ __device__ inline size_t tc_smem_bytes(int npad, int nregion)
 {
     size_t b = (size_t)nregion * npad * 128;                   // B slabs
-    b += (size_t)TC_STAGES * nregion * TC_REGION_BYTES;        // A stages
+    b += (size_t)TC_ASTAGES * nregion * TC_REGION_BYTES;       // A stages
     b += TC_EPI_WARPS * tc_warp_bytes();                       // xs
     b += 2 * 8 * 32 * sizeof(double2);                         // F/G pair exchange, double-buffered
     b += 16 * sizeof(double2);                                 // PhiF, PhiG
     b += 16 * 9 * sizeof(double2);                             // prot_pow of this row
     b += TC_NOUT * sizeof(double);                             // cst of this row
-    b += 16 * sizeof(unsigned long long);                      // mbarriers
+    b += 24 * sizeof(unsigned long long);                      // mbarriers
     return b + 1024;                                           // alignment slack
 }
 
@@ -189,6 +190,8 @@ __device__ __forceinline__ double tc_combine(const uint32_t *c, double s16, doub
     return fma(i64_to_double(hi), s16, fma(i32_biased(lo), s1, cstb));
 }
 
+#define TC_DBG(sc, it, ev) do { if ((sc).dbg && blockIdx.x == 0 && (it) < 64) (sc).dbg[(it) * 8 + (ev)] = clock64(); } while (0)
+
 // ------------------------------------------------------------------------------------- k_tc
 struct TcShared {
     unsigned char *sB, *sA;
@@ -215,8 +218,8 @@ __device__ __forceinline__ void tc_epilogue(const DevPlan &pl, const TcDev &tc, 
     const double2 epsb = cconj(pl.T3[(size_t)r * (SDRB_TB + 1) + 1]);
     const uint32_t pair_bar = 1u + (uint32_t)(g * 4 + qd);
     const double s16 = tc.scale16, s1 = tc.scale;
-    const uint32_t bar_done = sh.bar0 + 8u * (uint32_t)(B_MMA_DONE * TC_STAGES + g);
-    const uint32_t bar_free = sh.bar0 + 8u * (uint32_t)(B_TMEM_FREE * TC_STAGES + g);
+    const uint32_t bar_done = sh.bar0 + 8u * (uint32_t)(B_MMA_DONE * TC_ASTAGES + g);
+    const uint32_t bar_free = sh.bar0 + 8u * (uint32_t)(B_TMEM_FREE * TC_ASTAGES + g);
     const uint32_t trow = tmem_base + ((uint32_t)(32 * qd) << 16) + (uint32_t)(g * 256);
     double2 *xsl = xs + lane;                      // lane <-> block view
     double2 *xsp = xs + pole * TC_XS + seg * 8;    // (segment, mode) view
@@ -227,6 +230,7 @@ __device__ __forceinline__ void tc_epilogue(const DevPlan &pl, const TcDev &tc, 
         const int gt = 4 * mt + qd;
         mbar_wait(bar_done, u & 1);
         tc_fence_after();
+        if (HALF == 0 && qd == 0 && lane == 0) TC_DBG(sc, it, 5);
         if (gt >= total_tiles) {
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_free);
@@ -287,6 +291,7 @@ __device__ __forceinline__ void tc_epilogue(const DevPlan &pl, const TcDev &tc, 
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_free);
+        if (HALF == 0 && qd == 0 && lane == 0) TC_DBG(sc, it, 6);
 
         // ---- tile-local scans in the rotating frame, lane = (segment of 8 blocks, mode):
         //      A. each segment from a zero state, B. carries across the 4 segments,
@@ -339,6 +344,7 @@ __device__ __forceinline__ void tc_epilogue(const DevPlan &pl, const TcDev &tc, 
             sc.ypart[((size_t)chunk * pl.R + r) * pl.Mf + (size_t)t * SDRB_TB + lane] = cmul(rot, ys);
         }
         __syncwarp();
+        if (HALF == 0 && qd == 0 && lane == 0) TC_DBG(sc, it, 7);
     }
 }
 
@@ -356,7 +362,7 @@ k_tc(const __grid_constant__ DevPlan pl, const __grid_constant__ TcDev tc, const
     TcShared sh;
     sh.sB = smem;
     sh.sA = sh.sB + (size_t)nreg * npad * 128;
-    sh.sXS = reinterpret_cast<double2 *>(sh.sA + (size_t)TC_STAGES * nreg * TC_REGION_BYTES);
+    sh.sXS = reinterpret_cast<double2 *>(sh.sA + (size_t)TC_ASTAGES * nreg * TC_REGION_BYTES);
     sh.sPB = sh.sXS + (size_t)TC_EPI_WARPS * 8 * TC_XS;
     sh.sPhi = sh.sPB + 2 * 8 * 32;
     sh.sPow = sh.sPhi + 16;
@@ -366,7 +372,7 @@ k_tc(const __grid_constant__ DevPlan pl, const __grid_constant__ TcDev tc, const
     const uint32_t bar0 = smem_u32(bars);
     sh.bar0 = bar0;
     unsigned char *sA = sh.sA, *sB = sh.sB;
-    auto BAR = [&](int kind, int s) { return bar0 + 8u * (uint32_t)(kind * TC_STAGES + s); };
+    auto BAR = [&](int kind, int s) { return bar0 + 8u * (uint32_t)(kind * TC_ASTAGES + s); };
     enum { B_FULL_A = 0, B_XORED = 1, B_MMA_DONE = 2, B_A_FREE = 3, B_TMEM_FREE = 4, B_BFULL = 5 };
 
     // one row of the bank per CTA; the CTAs of a row share its MMA tiles round-robin
@@ -374,11 +380,13 @@ k_tc(const __grid_constant__ DevPlan pl, const __grid_constant__ TcDev tc, const
     const int slot = (int)blockIdx.x / pl.R, nslots = (int)gridDim.x / pl.R;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < TC_STAGES; s++) {
+        for (int s = 0; s < TC_ASTAGES; s++) {
             mbar_init(BAR(B_FULL_A, s), 1);
             mbar_init(BAR(B_XORED, s), 2);
-            mbar_init(BAR(B_MMA_DONE, s), 1);
             mbar_init(BAR(B_A_FREE, s), 1);
+        }
+        for (int s = 0; s < TC_STAGES; s++) {
+            mbar_init(BAR(B_MMA_DONE, s), 1);
             mbar_init(BAR(B_TMEM_FREE, s), 8);
         }
         mbar_init(BAR(B_BFULL, 0), 1);
@@ -410,9 +418,10 @@ k_tc(const __grid_constant__ DevPlan pl, const __grid_constant__ TcDev tc, const
             for (int rg = 0; rg < nreg; rg++)
                 tma_load_2d(smem_u32(sB + (size_t)rg * npad * 128), &map_b, rg * 128, r * npad, BAR(B_BFULL, 0));
             for (int it = 0; it < my_iters; it++) {
-                const int s = it & 1, u = it >> 1;
+                const int s = it % TC_ASTAGES, u = it / TC_ASTAGES;
                 const int mt = slot + it * nslots;
                 mbar_wait_sleep(BAR(B_A_FREE, s), (u & 1) ^ 1);
+                TC_DBG(sc, it, 0);
                 mbar_expect_tx(BAR(B_FULL_A, s), (uint32_t)(nreg * TC_REGION_BYTES));
                 for (int rg = 0; rg < nreg; rg++)
                     tma_load_2d(smem_u32(sA + ((size_t)s * nreg + rg) * TC_REGION_BYTES), &map_a, rg * 128, mt * 128,
@@ -424,11 +433,13 @@ k_tc(const __grid_constant__ DevPlan pl, const __grid_constant__ TcDev tc, const
         if (lane == 0 && my_iters > 0) {
             mbar_wait_sleep(BAR(B_BFULL, 0), 0);
             for (int it = 0; it < my_iters; it++) {
-                const int s = it & 1, u = it >> 1;
-                mbar_wait_sleep(BAR(B_XORED, s), u & 1);
-                mbar_wait(BAR(B_TMEM_FREE, s), (u & 1) ^ 1);
+                const int s = it % TC_ASTAGES, ua = it / TC_ASTAGES;     // A stage
+                const int ts = it & 1, u = it >> 1;                      // TMEM stage
+                mbar_wait_sleep(BAR(B_XORED, s), ua & 1);
+                mbar_wait(BAR(B_TMEM_FREE, ts), (u & 1) ^ 1);
                 tc_fence_after();
-                const uint32_t d = tmem_base + (uint32_t)(s * 256);
+                TC_DBG(sc, it, 3);
+                const uint32_t d = tmem_base + (uint32_t)(ts * 256);
                 const int ksteps = tc.K >> 5;
                 for (int ks = 0; ks < ksteps; ks++) {
                     const int rg = ks >> 2, kin = (ks & 3) * 32;
@@ -437,7 +448,8 @@ k_tc(const __grid_constant__ DevPlan pl, const __grid_constant__ TcDev tc, const
                     umma_i8(d, da, db, tc.idesc, ks > 0 ? 1u : 0u);
                 }
                 umma_commit(BAR(B_A_FREE, s));       // the staged bytes are dead once the MMAs retire
-                umma_commit(BAR(B_MMA_DONE, s));
+                umma_commit(BAR(B_MMA_DONE, ts));
+                TC_DBG(sc, it, 4);
             }
         }
     } else if (warp < 4) {
@@ -445,8 +457,9 @@ k_tc(const __grid_constant__ DevPlan pl, const __grid_constant__ TcDev tc, const
         const int tx = threadIdx.x - 64;
         const uint32_t m = tc.xor_word;
         for (int it = 0; it < my_iters; it++) {
-            const int s = it & 1, u = it >> 1;
+            const int s = it % TC_ASTAGES, u = it / TC_ASTAGES;
             mbar_wait_sleep(BAR(B_FULL_A, s), u & 1);
+            if (threadIdx.x == 64) TC_DBG(sc, it, 1);
             uint4 *base = reinterpret_cast<uint4 *>(sA + (size_t)s * nreg * TC_REGION_BYTES);
             const int n16 = nreg * (TC_REGION_BYTES / 16);
 #pragma unroll 8
@@ -458,6 +471,7 @@ k_tc(const __grid_constant__ DevPlan pl, const __grid_constant__ TcDev tc, const
             fence_proxy_async();
             __syncwarp();
             if (lane == 0) mbar_arrive(BAR(B_XORED, s));
+            if (threadIdx.x == 64) TC_DBG(sc, it, 2);
         }
     } else {
         // ===================================================================== epilogue
