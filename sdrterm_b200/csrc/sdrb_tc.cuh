@@ -212,7 +212,7 @@ __device__ __forceinline__ void tc_epilogue(const DevPlan &pl, const TcDev &tc, 
     double2 *xs = sh.sXS + (size_t)e * 8 * TC_XS;
     const int pole = lane & 7, seg = lane >> 3;
     const double2 *pw = sh.sPow + (HALF * 8 + pole) * 9;
-    const double2 Pm = pw[1], Pm8 = pw[8];
+    const double2 Pm = pw[1], Pm8 = pw[8], Pm16 = cmul(pw[8], pw[8]);
     const double2 rot = pl.T3[(size_t)r * (SDRB_TB + 1) + lane];
     const double2 rot31 = pl.T3[(size_t)r * (SDRB_TB + 1) + SDRB_TB - 1];
     const double2 epsb = cconj(pl.T3[(size_t)r * (SDRB_TB + 1) + 1]);
@@ -237,26 +237,33 @@ __device__ __forceinline__ void tc_epilogue(const DevPlan &pl, const TcDev &tc, 
             continue;
         }
         const int chunk = gt / pl.ntiles, t = gt - chunk * pl.ntiles;
-        uint32_t c[32];
 
+        // ---- TMEM reads are double-buffered: the load of the next 16 columns is in flight while
+        //      the current ones are recombined (tcgen05.wait::ld waits for all earlier loads, so
+        //      every wait is followed at once by the issue of the next load)
+        uint32_t ce[16], ca[16], cb[16];
+        constexpr int MODE_COLS = 2 * NCOL;                    // one complex mode = re, im digit columns
+        const uint32_t tmode = trow + MODE_COLS * (8 * HALF);
+        if (IQ || HALF == 0) tmem_ld16(trow + 32 * NCOL, ce);
+        tmem_ld16(tmode, ca);
+        tmem_ld_wait();
+        tmem_ld16(tmode + MODE_COLS, cb);
         // ---- IQ-EMA block aggregate E -> tile-local block offsets, tile aggregate; x0
         double2 excl = make_double2(0.0, 0.0), x0 = make_double2(0.0, 0.0);
         if (IQ || HALF == 0) {
-            tmem_ld32(trow + 32 * NCOL, c);
-            tmem_ld_wait();
             if (HALF == 0) {                      // x0: isz exact columns per component
                 int xr, xi;
                 if (tc.isz == 2) {
-                    xr = (int)c[2 * NCOL] * 256 + (int)c[2 * NCOL + 1];
-                    xi = (int)c[2 * NCOL + 2] * 256 + (int)c[2 * NCOL + 3];
+                    xr = (int)ce[2 * NCOL] * 256 + (int)ce[2 * NCOL + 1];
+                    xi = (int)ce[2 * NCOL + 2] * 256 + (int)ce[2 * NCOL + 3];
                 } else {
-                    xr = (int)c[2 * NCOL]; xi = (int)c[2 * NCOL + 1];
+                    xr = (int)ce[2 * NCOL]; xi = (int)ce[2 * NCOL + 1];
                 }
                 x0 = make_double2(i32_biased(xr) + sh.sCst[34], i32_biased(xi) + sh.sCst[35]);
             }
             if (IQ) {
-                const double er = tc_combine<NCOL>(c, s16, s1, sh.sCst[32]);
-                const double ei = tc_combine<NCOL>(c + NCOL, s16, s1, sh.sCst[33]);
+                const double er = tc_combine<NCOL>(ce, s16, s1, sh.sCst[32]);
+                const double ei = tc_combine<NCOL>(ce + NCOL, s16, s1, sh.sCst[33]);
                 double2 inc = make_double2(pl.Liq * er, pl.Liq * ei);
 #pragma unroll
                 for (int i = 0; i < 5; i++) {
@@ -271,22 +278,21 @@ __device__ __forceinline__ void tc_epilogue(const DevPlan &pl, const TcDev &tc, 
         // ---- this half's eight modal block sums: digit columns -> FP64, minus the response to
         //      the tile-local offset; lane <-> block, parked mode-major for the scans
 #pragma unroll
-        for (int og = 0; og < 4; og++) {
-            tmem_ld32(trow + 4 * NCOL * (4 * HALF + og), c);
-            tmem_ld_wait();
-#pragma unroll
-            for (int h = 0; h < 2; h++) {
-                const int md = 2 * og + h;                     // mode within this half
-                const int o = 16 * HALF + 2 * md;              // output index of its real part
-                double vr = tc_combine<NCOL>(c + (2 * h) * NCOL, s16, s1, sh.sCst[o]);
-                double vi = tc_combine<NCOL>(c + (2 * h + 1) * NCOL, s16, s1, sh.sCst[o + 1]);
-                if (IQ) {
-                    const double2 ph = sh.sPhi[8 * HALF + md];
-                    vr = fma(-excl.x, ph.x, fma(excl.y, ph.y, vr));
-                    vi = fma(-excl.x, ph.y, fma(-excl.y, ph.x, vi));
-                }
-                xsl[md * TC_XS] = make_double2(vr, vi);
+        for (int md = 0; md < 8; md++) {
+            const uint32_t *c = (md & 1) ? cb : ca;
+            const int o = 16 * HALF + 2 * md;                  // output index of the real part
+            double vr = tc_combine<NCOL>(c, s16, s1, sh.sCst[o]);
+            double vi = tc_combine<NCOL>(c + NCOL, s16, s1, sh.sCst[o + 1]);
+            if (md < 7) {
+                tmem_ld_wait();                                // mode md + 1 has landed ...
+                if (md < 6) tmem_ld16(tmode + MODE_COLS * (md + 2), (md & 1) ? cb : ca);   // ... fetch md + 2
             }
+            if (IQ) {
+                const double2 ph = sh.sPhi[8 * HALF + md];
+                vr = fma(-excl.x, ph.x, fma(excl.y, ph.y, vr));
+                vi = fma(-excl.x, ph.y, fma(-excl.y, ph.x, vi));
+            }
+            xsl[md * TC_XS] = make_double2(vr, vi);
         }
         tc_fence_before();
         __syncwarp();
@@ -305,19 +311,18 @@ __device__ __forceinline__ void tc_epilogue(const DevPlan &pl, const TcDev &tc, 
             loc[j] = HALF ? nst : st;
             st = nst;
         }
-        double2 cin = make_double2(0.0, 0.0);
-        if (HALF == 0) {
-#pragma unroll
-            for (int j = 0; j < 3; j++) {
-                const double2 ej = shfl_c(st, j * 8 + pole);
-                if (j < seg) cin = cfma(Pm8, cin, ej);
-            }
-        } else {
-#pragma unroll
-            for (int j = 3; j > 0; j--) {
-                const double2 ej = shfl_c(st, j * 8 + pole);
-                if (j > seg) cin = cfma(Pm8, cin, ej);
-            }
+        // carry into this segment from the ones before (after) it: Pm8^2 e_a2 + Pm8 e_a1 + e_a0,
+        // two dependent complex FMAs instead of a three-step chain
+        double2 cin;
+        {
+            const int dist = HALF ? 3 - seg : seg;                         // segments feeding this one
+            const int dir = HALF ? 1 : -1;
+            const double2 n1 = shfl_c(st, ((seg + dir) & 3) * 8 + pole);   // nearest
+            const double2 n2 = shfl_c(st, ((seg + 2 * dir) & 3) * 8 + pole);
+            const double2 n3 = shfl_c(st, ((seg + 3 * dir) & 3) * 8 + pole);
+            const double2 z = make_double2(0.0, 0.0);
+            const double2 t1 = cfma(Pm8, dist >= 2 ? n2 : z, dist >= 1 ? n1 : z);
+            cin = dist >= 3 ? cfma(Pm16, n3, t1) : t1;
         }
         if (seg == (HALF ? 0 : 3)) {
             const double2 tot = cfma(Pm8, cin, st);
@@ -330,9 +335,15 @@ __device__ __forceinline__ void tc_epilogue(const DevPlan &pl, const TcDev &tc, 
         __syncwarp();
         // ---- partial output of each block (lane <-> block): half 0 sums rho_i W_i, half 1
         //      rho_i/p_i T_i; half 0 finishes
-        double2 acc = make_double2(0.0, 0.0);
-#pragma unroll
-        for (int i = 0; i < 8; i++) acc = cfma(HALF ? pl.rho_p[i] : pl.rho[i], xsl[i * TC_XS], acc);
+        double2 acc;
+        {
+            const double2 *rh = HALF ? pl.rho_p : pl.rho;
+            const double2 q0 = cfma(rh[4], xsl[4 * TC_XS], cmul(rh[0], xsl[0]));
+            const double2 q1 = cfma(rh[5], xsl[5 * TC_XS], cmul(rh[1], xsl[1 * TC_XS]));
+            const double2 q2 = cfma(rh[6], xsl[6 * TC_XS], cmul(rh[2], xsl[2 * TC_XS]));
+            const double2 q3 = cfma(rh[7], xsl[7 * TC_XS], cmul(rh[3], xsl[3 * TC_XS]));
+            acc = cadd(cadd(q0, q1), cadd(q2, q3));
+        }
         double2 *pb = sh.sPB + ((size_t)(u & 1) * 8 + (g * 4 + qd)) * 32;
         if (HALF) pb[lane] = acc;
         asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
