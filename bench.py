@@ -120,7 +120,7 @@ class Clocks:
         try:
             self.proc = subprocess.Popen(
                 ['nvidia-smi', f'--id={self.index}', f'--query-gpu={self.Q}',
-                 '--format=csv,noheader,nounits', '-lms', '100'],
+                 '--format=csv,noheader,nounits', '-lms', '20'],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
@@ -152,7 +152,8 @@ class Clocks:
                 pass
         sm.sort()
         return {'sm_mhz': sm[len(sm) // 2] if sm else None, 'sm_max_mhz': mx or None,
-                'reasons': sorted(reasons), 'samples': len(sm)}
+                'reasons': sorted(reasons), 'samples': len(sm),
+                'window': 'nvidia-smi -lms 20 over warm-up, the timed steps and the identical profiled steps that follow'}
 
 
 # ------------------------------------------------------------------------------ synthetic input
@@ -246,7 +247,10 @@ def run_cuda_arm(args):
     torch.cuda.set_device(local)
     dev = torch.device('cuda', local)
     if world > 1:
-        dist.init_process_group('nccl', device_id=dev)
+        import datetime
+        # keep stdout to the one JSON line (NCCL prints its version banner there at VERSION level)
+        os.environ['NCCL_DEBUG'] = os.environ.get('SDRB_NCCL_DEBUG', 'WARN')
+        dist.init_process_group('nccl', device_id=dev, timeout=datetime.timedelta(seconds=180))
     if world != args.gpus and rank == 0:
         print(f'# note: --gpus {args.gpus} but WORLD_SIZE {world}', file=sys.stderr)
 
@@ -269,24 +273,42 @@ def run_cuda_arm(args):
     raw = synth_c1_device(torch, nsamp, seed=5 + rank, device=dev)
     out = torch.empty((1, nch * pl.M), dtype=torch.float64, device=dev)
     stream = torch.cuda.current_stream().cuda_stream
+    gain_mine = torch.zeros(3, dtype=torch.float64, device=dev)
+    gain_all = torch.zeros(3 * world, dtype=torch.float64, device=dev)
 
     def step_device():
         if world == 1:
             eng.process_device(raw.data_ptr(), nch, out.data_ptr(), stream)
             return
         # time-segment sharding: block kernel + offset gain from zero, exchange, finish
-        eng.iq_state = 0j
-        eng.process_device_phases(raw.data_ptr(), nch, 0, 1 | 2, stream)
-        eng.iq_state = sharding.exchange_iq_gain(dist, torch, eng.iq_state, nsamp, pl.lam, device=dev)
+        # (no host round trip: gain export, NCCL all-gather and prefix all run on the stream)
+        eng.process_device_phases(raw.data_ptr(), nch, 0, 1 | 2 | 8, stream)
+        eng.iq_export_device(gain_mine.data_ptr(), nsamp, stream)
+        dist.all_gather_into_tensor(gain_all, gain_mine)
+        eng.iq_prefix_device(gain_all.data_ptr(), rank, stream)
         eng.process_device_phases(raw.data_ptr(), nch, out.data_ptr(), 2 | 4, stream)
 
     clocks = Clocks(local)
     eng.set_profiling(world == 1)
-    for _ in range(args.warmup):
-        step_device()
-    barrier()
     if rank == 0:
-        clocks.start()
+        clocks.start()                      # nvidia-smi needs ~0.1 s to produce its first row
+    # the same step, untimed, for >= 0.3 s: brings the clocks under load before the timed region
+    # (every rank runs the SAME number of steps: with N > 1 a step contains a collective)
+    torch.cuda.synchronize()
+    t_pre = time.perf_counter()
+    step_device()
+    torch.cuda.synchronize()
+    t_one = max(time.perf_counter() - t_pre, 1e-4)
+    extra = int(min(2000, 0.3 / t_one))
+    if world > 1:
+        tt = torch.tensor([extra], dtype=torch.int64, device=dev)
+        dist.broadcast(tt, src=0)
+        extra = int(tt.item())
+    for i in range(args.warmup + extra):
+        step_device()
+        if i % 16 == 15:
+            torch.cuda.synchronize()
+    barrier()
     l0 = eng.launches
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ktimes = []
@@ -310,6 +332,13 @@ def run_cuda_arm(args):
             torch.cuda.synchronize()
             acc += np.array(eng.kernel_times())
         kavg = (acc / reps).tolist()
+    # keep the identical step running so that the sampler sees it for ~0.3 s more (same count on
+    # every rank)
+    for i in range(extra):
+        step_device()
+        if i % 16 == 15:
+            torch.cuda.synchronize()
+    torch.cuda.synchronize()
     if rank == 0:
         clocks.stop()
     ms_step = ms_total / args.steps

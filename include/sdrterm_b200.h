@@ -148,8 +148,15 @@ int sdrb_process_device(sdrb_handle *h, const void *raw_dev, size_t nchunks, dou
 #define SDRB_PHASE_MAIN 1
 #define SDRB_PHASE_IQSCAN 2
 #define SDRB_PHASE_FINISH 4
+#define SDRB_PHASE_ZERO_IQ 8   /* clear the IQ state (on the stream) before anything else */
 int sdrb_process_device_phases(sdrb_handle *h, const void *raw_dev, size_t nchunks, double *out_dev,
                                void *stream, int phases);
+
+/* The exchange between the two passes without a host round trip: export this segment's gained
+ * offset and length as 3 doubles (re, im, nsamples) into a device buffer the caller all-gathers,
+ * then fold the gains of ranks 0..rank-1 ([world][3] doubles) into this handle's IQ state. */
+int sdrb_iq_export_device(sdrb_handle *h, double *dst3_dev, double nsamples, void *stream);
+int sdrb_iq_prefix_device(sdrb_handle *h, const double *gains3_dev, int rank, void *stream);
 
 /* CUDA-event timing of the four kernels of the last full sdrb_process_device call
  * (ms[0..3] = block kernel, IQ scan, fix-up, demodulation), for bench.py's roofline. */

@@ -58,7 +58,8 @@ EXPORTS = ['sdrb_create', 'sdrb_destroy', 'sdrb_last_error', 'sdrb_outputs_per_c
            'sdrb_get_iq_state', 'sdrb_set_iq_state', 'sdrb_read_decimated', 'sdrb_launch_count',
            'sdrb_fm_demod', 'sdrb_am_demod', 'sdrb_real_output', 'sdrb_imag_output',
            'sdrb_shift_freq', 'sdrb_global_error', 'sdrb_process_device_phases',
-           'sdrb_set_profiling', 'sdrb_kernel_times', 'sdrb_keep_decimated', 'sdrb_read_debug']
+           'sdrb_set_profiling', 'sdrb_kernel_times', 'sdrb_keep_decimated', 'sdrb_read_debug', 'sdrb_iq_export_device',
+           'sdrb_iq_prefix_device']
 
 
 def nvcc_command(out: str = LIB_PATH) -> list[str]:
@@ -110,6 +111,8 @@ def lib():
         L.sdrb_read_decimated.argtypes = [vp, sz, vp]
         L.sdrb_keep_decimated.argtypes = [vp, C.c_int]
         L.sdrb_read_debug.argtypes = [vp, vp]
+        L.sdrb_iq_export_device.argtypes = [vp, vp, C.c_double, vp]
+        L.sdrb_iq_prefix_device.argtypes = [vp, vp, C.c_int, vp]
         L.sdrb_launch_count.argtypes = [vp]
         L.sdrb_launch_count.restype = C.c_longlong
         for name in ('sdrb_fm_demod', 'sdrb_am_demod', 'sdrb_real_output', 'sdrb_imag_output'):

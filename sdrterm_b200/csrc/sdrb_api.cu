@@ -646,7 +646,29 @@ int sdrb_process_device_phases(sdrb_handle *h, const void *raw_dev, size_t nchun
     if (nchunks > h->max_chunks) return fail(h, SDRB_ERR_ARG, "nchunks %zu > max_chunks %zu", nchunks, h->max_chunks);
     CK(h, cudaSetDevice(h->cfg.device));
     h->last_nchunks = nchunks;
-    return launch_chain(h, static_cast<const uint8_t *>(raw_dev), nchunks, out_dev, static_cast<cudaStream_t>(stream), phases);
+    if (phases & SDRB_PHASE_ZERO_IQ)
+        CK(h, cudaMemsetAsync(h->sc.iq_state, 0, sizeof(double2), static_cast<cudaStream_t>(stream)));
+    return launch_chain(h, static_cast<const uint8_t *>(raw_dev), nchunks, out_dev, static_cast<cudaStream_t>(stream), phases & 7);
+}
+
+int sdrb_iq_export_device(sdrb_handle *h, double *dst3_dev, double nsamples, void *stream)
+{
+    if (!h || !dst3_dev) return fail(h, SDRB_ERR_ARG, "null argument");
+    CK(h, cudaSetDevice(h->cfg.device));
+    k_iq_export<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(h->sc, dst3_dev, nsamples);
+    h->launches++;
+    CK(h, cudaGetLastError());
+    return SDRB_OK;
+}
+
+int sdrb_iq_prefix_device(sdrb_handle *h, const double *gains3_dev, int rank, void *stream)
+{
+    if (!h || !gains3_dev || rank < 0) return fail(h, SDRB_ERR_ARG, "bad argument");
+    CK(h, cudaSetDevice(h->cfg.device));
+    k_iq_prefix<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(h->sc, gains3_dev, rank, h->pl.lam);
+    h->launches++;
+    CK(h, cudaGetLastError());
+    return SDRB_OK;
 }
 
 int sdrb_set_profiling(sdrb_handle *h, int on)

@@ -394,6 +394,28 @@ k_iqtiles(const __grid_constant__ DevPlan pl, Scratch sc, int nchunks)
     ot[nt] = o;      // offset at sample q*Mf
 }
 
+// Time-segment sharding: the IQ offset a segment gained from a zero start, and the
+// fold of the gains of the segments before this rank's into its start offset -- on the device, so
+// that the exchange between the two passes needs no host round trip.
+__global__ void k_iq_export(Scratch sc, double *dst3, double nsamples)
+{
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        const double2 g = sc.iq_state[0];
+        dst3[0] = g.x; dst3[1] = g.y; dst3[2] = nsamples;
+    }
+}
+__global__ void k_iq_prefix(Scratch sc, const double *gains3, int rank, double lam)
+{
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        double2 off = make_double2(0.0, 0.0);
+        for (int i = 0; i < rank; i++) {
+            const double d = pow(lam, gains3[3 * i + 2]);
+            off.x = fma(d, off.x, gains3[3 * i]); off.y = fma(d, off.y, gains3[3 * i + 1]);
+        }
+        sc.iq_state[0] = off;
+    }
+}
+
 // ----------------------------------------------------------------------------------- k_fixup
 // One CTA per (chunk, row).  Warp 0: raw head / end-window samples are fetched by all lanes at
 // once, then lanes 0..7 <-> poles run the head, the cross-tile carries, the end segment and the

@@ -152,6 +152,14 @@ class Engine:
         nat.check(nat.lib().sdrb_process_device_phases(self._h, raw_ptr, nchunks, out_ptr, stream,
                                                        phases), self._h)
 
+    def iq_export_device(self, dst_ptr: int, nsamples: int, stream: int = 0) -> None:
+        """(gain.re, gain.im, nsamples) of the pass just run from a zero offset -> 3 device doubles."""
+        nat.check(nat.lib().sdrb_iq_export_device(self._h, dst_ptr, float(nsamples), stream), self._h)
+
+    def iq_prefix_device(self, gains_ptr: int, rank: int, stream: int = 0) -> None:
+        """Fold the all-gathered [world][3] gains of the ranks before ``rank`` into the IQ state."""
+        nat.check(nat.lib().sdrb_iq_prefix_device(self._h, gains_ptr, rank, stream), self._h)
+
     def set_profiling(self, on: bool) -> None:
         nat.check(nat.lib().sdrb_set_profiling(self._h, int(on)), self._h)
 

@@ -112,3 +112,38 @@ def test_tc_long_stream_matches_oracle_and_fp64_path():
     assert rel_err(ya, yb) < 1e-11
     assert rel_err(a, ref) < TOL and rel_err(b, ref) < TOL
     assert abs(offa - offb) <= 1e-9 * max(1.0, abs(offb))
+
+
+def test_time_segment_phases_with_device_side_iq_exchange():
+    """Two 'ranks' on one GPU: each runs MAIN|IQSCAN from a zero offset, exports its gain, the gains
+    are folded on the device (sdrb_iq_prefix_device) and IQSCAN|FINISH completes; the concatenation
+    equals one pass over the whole stream."""
+    import torch
+    import signals
+    from gpu_util import plan_for
+    from sdrterm_b200.engine import Engine
+    kw = dict(fs=1_024_000, enc='h', center=15000, dec=64, demod='fm', omega_out=5000, correct_iq=True,
+              vfos=None, simo=False, normalize=False, swap=False, big_endian=None)
+    pl = plan_for(kw)
+    body = np.frombuffer(signals.c1_bytes(12 * 32768, seed=9, header=False), dtype=np.uint8)
+    segs = [(0, 7), (7, 5)]
+    with Engine(pl, max_chunks=12) as e0:
+        whole = e0.process(body)
+    raw = torch.from_numpy(body.copy()).cuda()
+    gains = torch.zeros(6, dtype=torch.float64, device='cuda')
+    outs, engs = [], []
+    for r, (s, n) in enumerate(segs):
+        e = Engine(pl, max_chunks=n)
+        engs.append(e)
+        e.process_device_phases(raw.data_ptr() + s * 131072, n, 0, 1 | 2 | 8)
+        e.iq_export_device(gains.data_ptr() + 24 * r, n * 32768)
+    for r, (s, n) in enumerate(segs):
+        o = torch.empty((1, n * pl.M), dtype=torch.float64, device='cuda')
+        engs[r].iq_prefix_device(gains.data_ptr(), r)
+        engs[r].process_device_phases(raw.data_ptr() + s * 131072, n, o.data_ptr(), 2 | 4)
+        outs.append(o)
+    torch.cuda.synchronize()
+    got = torch.cat(outs, dim=1).cpu().numpy()
+    for e in engs:
+        e.close()
+    assert got.shape == whole.shape and rel_err(got, whole) < 1e-12
