@@ -180,7 +180,7 @@ int sdrb_read_decimated(sdrb_handle *h, size_t nchunks, double *y_host);
 /* The fused finish kernel keeps y on chip; it is written out only when this is switched on
  * (off by default; the general k_fixup/k_demod path always writes it). */
 int sdrb_keep_decimated(sdrb_handle *h, int on);
-/* Diagnostic: clock64 timeline of k_tc's pipeline on CTA 0, [64 tiles][8 events]; needs the
+/* Diagnostic: clock64 timeline of k_tc's pipeline on CTA 0, [64 tiles][16 events] (1024 values); needs the
  * environment variable SDRB_TC_DEBUG=1 when the handle is created. */
 int sdrb_read_debug(sdrb_handle *h, unsigned long long *out512);
 

@@ -17,15 +17,16 @@ out = torch.empty((1, nch * pl.M), dtype=torch.float64, device='cuda')
 for _ in range(3):
     eng.process_device(raw.data_ptr(), nch, out.data_ptr(), 0)
 torch.cuda.synchronize()
-buf = np.zeros(512, dtype=np.uint64)
+buf = np.zeros(1024, dtype=np.uint64)
 nat.check(nat.lib().sdrb_read_debug(eng._h, buf.ctypes.data), eng._h)
-t = buf.reshape(64, 8).astype(np.int64)
+t = buf.reshape(64, 16).astype(np.int64)
 t0 = t[0, 0]
-names = ['tma_issue', 'xor_start', 'xor_done', 'mma_start', 'mma_issued', 'epi_start', 'tmem_free', 'epi_end']
+names = ['tma_issue', 'xor_start', 'xor_done', 'mma_start', 'mma_issued', 'epi_start', 'tmem_free', 'epi_end',
+         'excl', 'scanA', 'scanBC', 'dot', 'pair']
 print('tile ' + ' '.join(f'{n:>10s}' for n in names))
 for it in range(2, 40):
     print(f'{it:4d} ' + ' '.join(f'{(t[it, e] - t0):10d}' for e in range(8)))
 d = np.diff(t[8:56, 0])
 print('cycles per tile (tma_issue to tma_issue):', d.mean())
-for a, b in ((0, 1), (1, 2), (2, 3), (3, 4), (4, 5), (5, 6), (6, 7), (0, 7)):
+for a, b in ((0, 1), (1, 2), (2, 3), (3, 4), (4, 5), (5, 8), (8, 6), (6, 9), (9, 10), (10, 11), (11, 12), (12, 7), (5, 7), (0, 7)):
     print(f'{names[a]:>10s} -> {names[b]:<10s}: mean {np.mean(t[8:56, b] - t[8:56, a]):8.0f}')

@@ -213,7 +213,7 @@ int setup_tc(sdrb_handle *h, const sdrb_tables *tab, const std::vector<double2> 
     cudaDeviceProp prop;
     CK(h, cudaGetDeviceProperties(&prop, h->cfg.device));
     h->num_sms = prop.multiProcessorCount;
-    if (R > h->num_sms) return 0;            // more rows than SMs: FP64 block kernel
+    if (R > TC_MAX_R) return 0;              // wider banks take the FP64 block kernel
     TcDev &tc = h->tc;
     tc.K = tab->tc_K; tc.isz = tab->tc_isz; tc.ncol = tab->tc_ncol; tc.nout = tab->tc_nout; tc.npad = tab->tc_npad;
     tc.nregion = tc.K / 128;
@@ -236,8 +236,14 @@ int setup_tc(sdrb_handle *h, const sdrb_tables *tab, const std::vector<double2> 
     }
     int rc = upload(h, ppow.data(), ppow.size(), &tc.prot_pow);
     if (rc) return rc;
-    rc = upload(h, tab->tc_cst, (size_t)R * TC_NOUT, &tc.cst);
-    if (rc) return rc;
+    for (int r = 0; r < R; r++) {
+        for (int o = 0; o < TC_NOUT; o++)
+            tc.cstb[r][o] = tab->tc_cst[(size_t)r * TC_NOUT + o] - TC_BIAS32 * (o < 34 ? tc.scale : 1.0);
+        for (int i = 0; i < 8; i++) {
+            tc.phi[r][i] = c2(tab->PhiF, (size_t)r * 8 + i);
+            tc.phi[r][8 + i] = c2(tab->PhiG, (size_t)r * 8 + i);
+        }
+    }
     const int8_t *d_bq = nullptr;
     rc = upload(h, tab->tc_Bq, (size_t)R * tc.npad * tc.K, &d_bq);
     if (rc) return rc;
@@ -520,8 +526,8 @@ int sdrb_create(const sdrb_config *cfg, const sdrb_tables *tab, sdrb_handle **ou
     if (cudaMemset(sc.iq_state, 0, sizeof(double2)) != cudaSuccess) return bail(fail(h, SDRB_ERR_CUDA, "memset failed"));
     sc.fftbuf = nullptr; sc.zrow = nullptr; sc.dbg = nullptr;
     if (env_int("SDRB_TC_DEBUG", 0)) {
-        UP(dalloc(h, (size_t)64 * 8, &sc.dbg));
-        cudaMemset(sc.dbg, 0, 64 * 8 * sizeof(unsigned long long));
+        UP(dalloc(h, (size_t)64 * 16, &sc.dbg));
+        cudaMemset(sc.dbg, 0, 64 * 16 * sizeof(unsigned long long));
     }
     if (!pl.demod_in_smem) {
         UP(dalloc(h, nch * R * 2 * M, &sc.fftbuf));
@@ -712,7 +718,7 @@ int sdrb_read_debug(sdrb_handle *h, unsigned long long *out512)
 {
     if (!h || !out512 || !h->sc.dbg) return fail(h, SDRB_ERR_STATE, "no debug buffer");
     CK(h, cudaDeviceSynchronize());
-    CK(h, cudaMemcpy(out512, h->sc.dbg, 64 * 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    CK(h, cudaMemcpy(out512, h->sc.dbg, 64 * 16 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
     return SDRB_OK;
 }
 

@@ -26,7 +26,7 @@ struct Scratch {
     double2 *iq_state;  // [1] offset before the batch (in) / after it (out)
     double2 *fftbuf;    // [nch*R][2][M] when the demod buffers do not fit shared memory
     double *zrow;       // [nch*R][M]     "
-    unsigned long long *dbg;  // optional k_tc timeline (SDRB_TC_DEBUG): [64 tiles][8 events] clock64 of CTA 0
+    unsigned long long *dbg;  // optional k_tc timeline (SDRB_TC_DEBUG): [64 tiles][16 events] clock64 of CTA 0
 };
 
 // Shared-memory carve-up of k_main (host mirrors this in sdrb_api.cu: main_smem_bytes()).

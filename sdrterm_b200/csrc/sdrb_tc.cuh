@@ -36,6 +36,7 @@
 #include "sdrb_kernels.cuh"
 
 #define TC_NOUT 36                     // outputs per row: 16 F, 16 G, 2 E, 2 x0
+#define TC_MAX_R 32                    // rows of the VFO bank this kernel takes
 #define TC_THREADS 640
 #define TC_EPI_WARPS 16
 #define TC_XS 33                       // exchange-buffer row stride in double2
@@ -49,8 +50,11 @@ struct TcDev {
     uint32_t idesc;                    // tcgen05 instruction descriptor (i8 x i8 -> s32, M=128, N=npad)
     double scale;                      // 2^-S, common to every fixed-point output
     double scale16;                    // 2^(16-S): weight of the columns above the low pair
-    const double *cst;                 // [R][TC_NOUT] response to the constant the XOR removed
     const double2 *prot_pow;           // [R][16][9] powers 0..8 of the rotating-frame block multipliers
+    // per row, read through the constant cache (shared-memory bandwidth is this kernel's limit):
+    double cstb[TC_MAX_R][TC_NOUT];    // response to the constant the XOR removed, minus the 2^52 + 2^31
+                                       // bias of the low digit pair (x0: minus the bias itself)
+    double2 phi[TC_MAX_R][16];         // PhiF (0..7), PhiG (8..15)
 };
 
 __host__ __device__ inline size_t tc_warp_bytes()
@@ -63,9 +67,7 @@ __host__ __device__ inline size_t tc_smem_bytes(int npad, int nregion)
     b += (size_t)TC_ASTAGES * nregion * TC_REGION_BYTES;       // A stages
     b += TC_EPI_WARPS * tc_warp_bytes();                       // xs
     b += 2 * 8 * 32 * sizeof(double2);                         // F/G pair exchange, double-buffered
-    b += 16 * sizeof(double2);                                 // PhiF, PhiG
     b += 16 * 9 * sizeof(double2);                             // prot_pow of this row
-    b += TC_NOUT * sizeof(double);                             // cst of this row
     b += 24 * sizeof(unsigned long long);                      // mbarriers
     return b + 1024;                                           // alignment slack
 }
@@ -190,13 +192,12 @@ __device__ __forceinline__ double tc_combine(const uint32_t *c, double s16, doub
     return fma(i64_to_double(hi), s16, fma(i32_biased(lo), s1, cstb));
 }
 
-#define TC_DBG(sc, it, ev) do { if ((sc).dbg && blockIdx.x == 0 && (it) < 64) (sc).dbg[(it) * 8 + (ev)] = clock64(); } while (0)
+#define TC_DBG(sc, it, ev) do { if ((sc).dbg && blockIdx.x == 0 && (it) < 64) (sc).dbg[(it) * 16 + (ev)] = clock64(); } while (0)
 
 // ------------------------------------------------------------------------------------- k_tc
 struct TcShared {
     unsigned char *sB, *sA;
-    double2 *sXS, *sPB, *sPhi, *sPow;
-    double *sCst;
+    double2 *sXS, *sPB, *sPow;
     uint32_t bar0;
 };
 
@@ -212,7 +213,7 @@ __device__ __forceinline__ void tc_epilogue(const DevPlan &pl, const TcDev &tc, 
     double2 *xs = sh.sXS + (size_t)e * 8 * TC_XS;
     const int pole = lane & 7, seg = lane >> 3;
     const double2 *pw = sh.sPow + (HALF * 8 + pole) * 9;
-    const double2 Pm = pw[1], Pm8 = pw[8], Pm16 = cmul(pw[8], pw[8]);
+    const double2 Pm = pw[1], Pm2 = pw[2], Pm8 = pw[8], Pm16 = cmul(pw[8], pw[8]);
     const double2 rot = pl.T3[(size_t)r * (SDRB_TB + 1) + lane];
     const double2 rot31 = pl.T3[(size_t)r * (SDRB_TB + 1) + SDRB_TB - 1];
     const double2 epsb = cconj(pl.T3[(size_t)r * (SDRB_TB + 1) + 1]);
@@ -222,13 +223,17 @@ __device__ __forceinline__ void tc_epilogue(const DevPlan &pl, const TcDev &tc, 
     const uint32_t bar_free = sh.bar0 + 8u * (uint32_t)(B_TMEM_FREE * TC_ASTAGES + g);
     const uint32_t trow = tmem_base + ((uint32_t)(32 * qd) << 16) + (uint32_t)(g * 256);
     double2 *xsl = xs + lane;                      // lane <-> block view
+    const int nt_shift = (pl.ntiles & (pl.ntiles - 1)) == 0 ? 31 - __clz(pl.ntiles) : -1;
     double2 *xsp = xs + pole * TC_XS + seg * 8;    // (segment, mode) view
 
     for (int it = g; it < my_iters; it += 2) {
         const int u = it >> 1;
         const int mt = slot + it * nslots;
         const int gt = 4 * mt + qd;
-        mbar_wait(bar_done, u & 1);
+        // one warp of the stage polls the mbarrier; the other seven sleep on a named barrier
+        // (bar.sync blocks in hardware, a try_wait loop spends issue slots)
+        if (HALF == 0 && qd == 0) mbar_wait(bar_done, u & 1);
+        asm volatile("bar.sync %0, 256;" ::"r"(9u + (uint32_t)g) : "memory");
         tc_fence_after();
         if (HALF == 0 && qd == 0 && lane == 0) TC_DBG(sc, it, 5);
         if (gt >= total_tiles) {
@@ -236,7 +241,7 @@ __device__ __forceinline__ void tc_epilogue(const DevPlan &pl, const TcDev &tc, 
             if (lane == 0) mbar_arrive(bar_free);
             continue;
         }
-        const int chunk = gt / pl.ntiles, t = gt - chunk * pl.ntiles;
+        const int chunk = nt_shift >= 0 ? (gt >> nt_shift) : gt / pl.ntiles, t = gt - chunk * pl.ntiles;
 
         // ---- TMEM reads are double-buffered: the load of the next 16 columns is in flight while
         //      the current ones are recombined (tcgen05.wait::ld waits for all earlier loads, so
@@ -259,11 +264,11 @@ __device__ __forceinline__ void tc_epilogue(const DevPlan &pl, const TcDev &tc, 
                 } else {
                     xr = (int)ce[2 * NCOL]; xi = (int)ce[2 * NCOL + 1];
                 }
-                x0 = make_double2(i32_biased(xr) + sh.sCst[34], i32_biased(xi) + sh.sCst[35]);
+                x0 = make_double2(i32_biased(xr) + tc.cstb[r][34], i32_biased(xi) + tc.cstb[r][35]);
             }
             if (IQ) {
-                const double er = tc_combine<NCOL>(ce, s16, s1, sh.sCst[32]);
-                const double ei = tc_combine<NCOL>(ce + NCOL, s16, s1, sh.sCst[33]);
+                const double er = tc_combine<NCOL>(ce, s16, s1, tc.cstb[r][32]);
+                const double ei = tc_combine<NCOL>(ce + NCOL, s16, s1, tc.cstb[r][33]);
                 double2 inc = make_double2(pl.Liq * er, pl.Liq * ei);
 #pragma unroll
                 for (int i = 0; i < 5; i++) {
@@ -275,20 +280,21 @@ __device__ __forceinline__ void tc_epilogue(const DevPlan &pl, const TcDev &tc, 
                 if (HALF == 0 && lane == 31 && r == 0) sc.tile_agg[(size_t)chunk * pl.ntiles + t] = inc;
             }
         }
+        if (HALF == 0 && qd == 0 && lane == 0) TC_DBG(sc, it, 8);       // excl known
         // ---- this half's eight modal block sums: digit columns -> FP64, minus the response to
         //      the tile-local offset; lane <-> block, parked mode-major for the scans
 #pragma unroll
         for (int md = 0; md < 8; md++) {
             const uint32_t *c = (md & 1) ? cb : ca;
             const int o = 16 * HALF + 2 * md;                  // output index of the real part
-            double vr = tc_combine<NCOL>(c, s16, s1, sh.sCst[o]);
-            double vi = tc_combine<NCOL>(c + NCOL, s16, s1, sh.sCst[o + 1]);
+            double vr = tc_combine<NCOL>(c, s16, s1, tc.cstb[r][o]);
+            double vi = tc_combine<NCOL>(c + NCOL, s16, s1, tc.cstb[r][o + 1]);
             if (md < 7) {
                 tmem_ld_wait();                                // mode md + 1 has landed ...
                 if (md < 6) tmem_ld16(tmode + MODE_COLS * (md + 2), (md & 1) ? cb : ca);   // ... fetch md + 2
             }
             if (IQ) {
-                const double2 ph = sh.sPhi[8 * HALF + md];
+                const double2 ph = tc.phi[r][8 * HALF + md];
                 vr = fma(-excl.x, ph.x, fma(excl.y, ph.y, vr));
                 vi = fma(-excl.x, ph.y, fma(-excl.y, ph.x, vi));
             }
@@ -302,15 +308,19 @@ __device__ __forceinline__ void tc_epilogue(const DevPlan &pl, const TcDev &tc, 
         // ---- tile-local scans in the rotating frame, lane = (segment of 8 blocks, mode):
         //      A. each segment from a zero state, B. carries across the 4 segments,
         //      C. carry applied with the multiplier powers
+        // (shared-memory bandwidth is the scarce resource of this kernel -- MMA operand reads, the
+        // TMA writes, the sign fix-up and these transposes all share 128 B/clk -- so the scans
+        // touch xs exactly once per direction: read for A, write after C)
         double2 loc[8];
         double2 st = make_double2(0.0, 0.0);
 #pragma unroll
         for (int j = 0; j < 8; j++) {
             const double2 v = xsp[HALF ? 7 - j : j];
             const double2 nst = cfma(Pm, st, v);
-            loc[j] = HALF ? nst : st;
+            loc[j] = HALF ? nst : st;                              // local (segment-relative) prefix
             st = nst;
         }
+        if (HALF == 0 && qd == 0 && lane == 0) TC_DBG(sc, it, 9);       // phase A done
         // carry into this segment from the ones before (after) it: Pm8^2 e_a2 + Pm8 e_a1 + e_a0,
         // two dependent complex FMAs instead of a three-step chain
         double2 cin;
@@ -330,23 +340,52 @@ __device__ __forceinline__ void tc_epilogue(const DevPlan &pl, const TcDev &tc, 
             if (HALF == 0) ag[pole] = cmul(rot31, tot);
             else ag[8 + pole] = tot;
         }
+        // ---- C. carry times Pm^j (forward: j = 0..7, backward: 1..8) as two running products, in
+        //      registers; res[k] = rho * state of this lane's mode at block 8 seg + k
+        double2 res[8];
+        {
+            const double2 rho_l = HALF ? pl.rho_p[pole] : pl.rho[pole];
+            double2 ce = HALF ? cmul(Pm, cin) : cin;
+            double2 co = cmul(Pm, ce);
 #pragma unroll
-        for (int j = 0; j < 8; j++) xsp[HALF ? 7 - j : j] = cfma(pw[HALF ? j + 1 : j], cin, loc[j]);
-        __syncwarp();
-        // ---- partial output of each block (lane <-> block): half 0 sums rho_i W_i, half 1
-        //      rho_i/p_i T_i; half 0 finishes
+            for (int j = 0; j < 8; j += 2) {
+                res[HALF ? 7 - j : j] = cmul(rho_l, cadd(loc[j], ce));
+                res[HALF ? 6 - j : j + 1] = cmul(rho_l, cadd(loc[j + 1], co));
+                if (j < 6) { ce = cmul(Pm2, ce); co = cmul(Pm2, co); }
+            }
+        }
+        if (HALF == 0 && qd == 0 && lane == 0) TC_DBG(sc, it, 10);      // phases B, C done
+        // ---- partial output of each block: sum over the 8 modes = over the 8 lanes of a segment
+        //      group, by a transpose-reduce butterfly (3 exchanges of 4, 2, 1 values) that leaves
+        //      block 8 seg + (lane & 7) = lane in each lane -- shuffles instead of a second pass
+        //      through shared memory
         double2 acc;
         {
-            const double2 *rh = HALF ? pl.rho_p : pl.rho;
-            const double2 q0 = cfma(rh[4], xsl[4 * TC_XS], cmul(rh[0], xsl[0]));
-            const double2 q1 = cfma(rh[5], xsl[5 * TC_XS], cmul(rh[1], xsl[1 * TC_XS]));
-            const double2 q2 = cfma(rh[6], xsl[6 * TC_XS], cmul(rh[2], xsl[2 * TC_XS]));
-            const double2 q3 = cfma(rh[7], xsl[7 * TC_XS], cmul(rh[3], xsl[3 * TC_XS]));
-            acc = cadd(cadd(q0, q1), cadd(q2, q3));
+            double2 v4[4], v2[2];
+            const bool b2 = lane & 4, b1 = lane & 2, b0 = lane & 1;
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const double2 snd = b2 ? res[k] : res[k + 4];
+                const double2 kp = b2 ? res[k + 4] : res[k];
+                v4[k] = cadd(kp, shfl_xor_c(snd, 4));
+            }
+#pragma unroll
+            for (int k = 0; k < 2; k++) {
+                const double2 snd = b1 ? v4[k] : v4[k + 2];
+                const double2 kp = b1 ? v4[k + 2] : v4[k];
+                v2[k] = cadd(kp, shfl_xor_c(snd, 2));
+            }
+            {
+                const double2 snd = b0 ? v2[0] : v2[1];
+                const double2 kp = b0 ? v2[1] : v2[0];
+                acc = cadd(kp, shfl_xor_c(snd, 1));
+            }
         }
         double2 *pb = sh.sPB + ((size_t)(u & 1) * 8 + (g * 4 + qd)) * 32;
         if (HALF) pb[lane] = acc;
+        if (HALF == 0 && qd == 0 && lane == 0) TC_DBG(sc, it, 11);      // dot done
         asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
+        if (HALF == 0 && qd == 0 && lane == 0) TC_DBG(sc, it, 12);      // partner arrived
         if (HALF == 0) {
             const double2 sT = pb[lane];
             const double2 xc = csub(x0, excl);
@@ -375,10 +414,8 @@ k_tc(const __grid_constant__ DevPlan pl, const __grid_constant__ TcDev tc, const
     sh.sA = sh.sB + (size_t)nreg * npad * 128;
     sh.sXS = reinterpret_cast<double2 *>(sh.sA + (size_t)TC_ASTAGES * nreg * TC_REGION_BYTES);
     sh.sPB = sh.sXS + (size_t)TC_EPI_WARPS * 8 * TC_XS;
-    sh.sPhi = sh.sPB + 2 * 8 * 32;
-    sh.sPow = sh.sPhi + 16;
-    sh.sCst = reinterpret_cast<double *>(sh.sPow + 16 * 9);
-    unsigned long long *bars = reinterpret_cast<unsigned long long *>(sh.sCst + TC_NOUT);
+    sh.sPow = sh.sPB + 2 * 8 * 32;
+    unsigned long long *bars = reinterpret_cast<unsigned long long *>(sh.sPow + 16 * 9);
     __shared__ uint32_t tmem_base_s;
     const uint32_t bar0 = smem_u32(bars);
     sh.bar0 = bar0;
@@ -403,14 +440,7 @@ k_tc(const __grid_constant__ DevPlan pl, const __grid_constant__ TcDev tc, const
         mbar_init(BAR(B_BFULL, 0), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (threadIdx.x < 16)
-        sh.sPhi[threadIdx.x] = threadIdx.x < 8 ? pl.PhiF[(size_t)r * 8 + threadIdx.x] : pl.PhiG[(size_t)r * 8 + threadIdx.x - 8];
     for (int i = threadIdx.x; i < 16 * 9; i += blockDim.x) sh.sPow[i] = tc.prot_pow[(size_t)r * 16 * 9 + i];
-    if (threadIdx.x >= 64 && threadIdx.x < 64 + TC_NOUT) {
-        // fixed-point outputs carry the 2^52 + 2^31 bias of their low column pair, x0 its own
-        const int o = threadIdx.x - 64;
-        sh.sCst[o] = tc.cst[(size_t)r * TC_NOUT + o] - TC_BIAS32 * (o < 34 ? tc.scale : 1.0);
-    }
     if (warp == 1) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(&tmem_base_s)) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");

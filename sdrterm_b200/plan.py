@@ -430,7 +430,7 @@ def tc_supported(pl: Plan) -> bool:
     if pl.enc not in ('b', 'B', 'h', 'H') or pl.norm is not None:
         return False
     K = pl.q * 2 * _ITEMSIZE[pl.enc]
-    return (K in (128, 256) and pl.rem == 0 and pl.Mf % TILE_BLOCKS == 0 and 1 <= pl.R <= 64
+    return (K in (128, 256) and pl.rem == 0 and pl.Mf % TILE_BLOCKS == 0 and 1 <= pl.R <= 32
             and pl.q >= pl.edge + 1)
 
 
