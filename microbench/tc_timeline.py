@@ -30,3 +30,10 @@ d = np.diff(t[8:56, 0])
 print('cycles per tile (tma_issue to tma_issue):', d.mean())
 for a, b in ((0, 1), (1, 2), (2, 3), (3, 4), (4, 5), (5, 8), (8, 6), (6, 9), (9, 10), (10, 11), (11, 12), (12, 7), (5, 7), (0, 7)):
     print(f'{names[a]:>10s} -> {names[b]:<10s}: mean {np.mean(t[8:56, b] - t[8:56, a]):8.0f}')
+
+f = t[32:48, :11]          # k_finish events of warp 0 / CTA 0 live in the second half of the buffer
+fn = ['start', '1a loads', '1b iq', '1c nco', '1d dots', '1e tiles', '1f zeta', '2 outputs+phase', '3b fft', '4 sos', '5 store']
+print('k_finish phases (cycles, mean over items 1..12):')
+for e in range(10):
+    print(f'  {fn[e + 1]:>16s}: {np.mean(f[1:13, e + 1] - f[1:13, e]):8.0f}')
+print(f'  {"item":>16s}: {np.mean(f[1:13, 10] - f[1:13, 0]):8.0f}')

@@ -280,13 +280,21 @@ int launch_chain_t(sdrb_handle *h, const uint8_t *raw, size_t nch, double *out, 
     }
     mark(1);
     if ((phases & PH_IQSCAN) && IQ) {
-        const unsigned gb = (unsigned)((nch + 127) / 128);
-        k_iqgain<ENC><<<gb, 128, 0, st>>>(pl, h->sc, raw, (int)nch);
         int nth = 1024;
         while (nth > 32 && (size_t)nth / 2 >= nch) nth /= 2;
-        k_iqscan<<<1, nth, 0, st>>>(pl, h->sc, (int)nch);
-        k_iqtiles<<<gb, 128, 0, st>>>(pl, h->sc, (int)nch);
-        h->launches += 3;
+        if (h->finish_on && pl.ntiles <= 32) {
+            // whole-tile chunks: warp-parallel gains, the chunk scan; k_finish derives the offsets
+            // at the tile starts itself
+            k_iqgain_w<<<(unsigned)((nch + 7) / 8), 256, 0, st>>>(pl, h->sc, (int)nch);
+            k_iqscan_c<<<1, 1024, 0, st>>>(pl, h->sc, (int)nch);
+            h->launches += 2;
+        } else {
+            const unsigned gb = (unsigned)((nch + 127) / 128);
+            k_iqgain<ENC><<<gb, 128, 0, st>>>(pl, h->sc, raw, (int)nch);
+            k_iqscan<<<1, nth, 0, st>>>(pl, h->sc, (int)nch);
+            k_iqtiles<<<gb, 128, 0, st>>>(pl, h->sc, (int)nch);
+            h->launches += 3;
+        }
     }
     mark(2);
     if ((phases & PH_FINISH) && h->finish_on) {
@@ -500,7 +508,7 @@ int sdrb_create(const sdrb_config *cfg, const sdrb_tables *tab, sdrb_handle **ou
         if (cudaGetDeviceProperties(&prop, cfg->device) == cudaSuccess) h->num_sms = prop.multiProcessorCount;
         const bool pow2 = is_pow2(M);
         h->finish_on = !env_int("SDRB_NO_FINISH", 0) && pl.rem == 0 && pl.cnt_last == SDRB_TB && q >= pl.edge + 1 &&
-                       pow2 && M >= 64 && M <= 1024 && pl.edge + 1 <= 32 &&
+                       pow2 && M >= 64 && M <= 1024 && pl.edge + 1 <= 32 && pl.ntiles <= 32 &&
                        (cfg->n_out_sections == 0 || (cfg->n_out_sections == 2 && tab->sos_AP));
         h->finish_smem = h->finish_on ? finish_smem_bytes(M, pl.edge) : 0;
         if (h->finish_smem > 227 * 1024) h->finish_on = false;
@@ -520,6 +528,8 @@ int sdrb_create(const sdrb_config *cfg, const sdrb_tables *tab, sdrb_handle **ou
     UP(dalloc(h, nch * R * nt * 16, &sc.agg));
     UP(dalloc(h, nch * nt, &sc.tile_agg));
     UP(dalloc(h, nch * (nt + 1), &sc.off_tile));
+    UP(dalloc(h, nch, &sc.gain));
+    UP(dalloc(h, nch, &sc.start));
     UP(dalloc(h, nch * R * (nt + 1) * 16, &sc.carry));
     UP(dalloc(h, nch * R * M, &sc.y));
     UP(dalloc(h, (size_t)1, &sc.iq_state));

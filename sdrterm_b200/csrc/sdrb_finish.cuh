@@ -21,6 +21,7 @@
 #include "sdrb_kernels.cuh"
 
 #define FIN_WARPS 4
+#define FIN_DBG(ev) do { if (sc.dbg && blockIdx.x == 0 && warp == 0 && lane == 0 && nit < 16) sc.dbg[512 + nit * 16 + (ev)] = clock64(); } while (0)
 
 // Per-warp shared memory (bytes); per CTA: twiddles exp(-2 pi i k / M) (k < M/2) and the pole
 // powers p_i^k (k <= edge).
@@ -29,8 +30,7 @@ __host__ __device__ inline size_t finish_warp_bytes(int M)
     const int nt = M / SDRB_TB;
     size_t b = (size_t)(nt + 1) * 16 * sizeof(double2);      // carry
     b += 2 * (size_t)(M / 4) * sizeof(double2);              // fa, fb (addv aliases them)
-    b += 2 * 32 * sizeof(double2);                           // seqA, seqB
-    b += (size_t)(M + 32) * sizeof(double);                  // zrow, one pad per segment
+    b += (size_t)(M + 32) * sizeof(double);                  // zrow, one pad per segment (seqA, seqB alias its head)
     return b;
 }
 __host__ __device__ inline size_t finish_smem_bytes(int M, int edge)
@@ -87,8 +87,8 @@ k_finish(const __grid_constant__ DevPlan pl, const __grid_constant__ Scratch sc,
     double2 *carry = reinterpret_cast<double2 *>(wb);
     double2 *fa = carry + (size_t)(nt + 1) * 16, *fb = fa + n2;
     double2 *addv = fa;                                                  // dead before the FFT buffers are written
-    double2 *seqA = fb + n2, *seqB = seqA + 32;
-    double *zrow = reinterpret_cast<double *>(seqB + 32);
+    double2 *seqA = fb + n2, *seqB = seqA + 32;                          // dead before zrow is written
+    double *zrow = reinterpret_cast<double *>(fb + n2);
     __syncthreads();
 
     // lane-invariant tables: this lane's block position l = lane inside every tile
@@ -105,10 +105,12 @@ k_finish(const __grid_constant__ DevPlan pl, const __grid_constant__ Scratch sc,
     const double lamn = pl.lam_pw[lane], mun = pl.mu_pw[min(32, max(0, edge + 1 - lane))];
 
     const int gw = blockIdx.x * FIN_WARPS + warp, nw = gridDim.x * FIN_WARPS;
+    int nit = -1;
     for (int item = gw; item < nchunks * R; item += nw) {
+        nit++;
+        FIN_DBG(0);
         const int chunk = item / R, r = item - chunk * R;
         const uint8_t *rawc = raw + (size_t)chunk * pl.N * pl.sb;
-        const double2 *offt = sc.off_tile + (size_t)chunk * (nt + 1);
         const double2 *aggr = sc.agg + ((size_t)chunk * R + r) * nt * 16;
         const double2 *T1r = pl.T1 + (size_t)r * nt;
         const double2 *ypr = sc.ypart + ((size_t)chunk * R + r) * pl.Mf;
@@ -119,11 +121,25 @@ k_finish(const __grid_constant__ DevPlan pl, const __grid_constant__ Scratch sc,
             xh = decode_sample<ENC>(pl, rawc, lane);
             xe = decode_sample<ENC>(pl, rawc, (long)pl.ws + lane);
         }
-        // offsets at the tile starts: lane t keeps offt[t] (shuffled out where needed)
+        // offsets at the tile starts from the chunk-start offset and the tile aggregates of the
+        // front end: lane t scans the maps o -> lam_tile o + agg[t] and keeps the offset entering
+        // tile t (shuffled out where needed); oE = the offset at the end of the chunk
         double2 offr = make_double2(0.0, 0.0), oE = offr;
         if (iq) {
-            if (lane < nt) offr = offt[lane];
-            oE = offt[nt];
+            double m = 1.0;
+            double2 a = make_double2(0.0, 0.0);
+            if (lane < nt) { m = pl.lam_tile[lane == nt - 1 ? 1 : 0]; a = sc.tile_agg[(size_t)chunk * nt + lane]; }
+            const double2 o0 = sc.start[chunk];
+#pragma unroll
+            for (int lv = 0; lv < 5; lv++) {
+                const double pm = __shfl_up_sync(0xffffffffu, m, 1 << lv);
+                const double2 pa = shfl_up_c(a, 1 << lv);
+                if (lane >= (1 << lv)) { a.x = fma(m, pa.x, a.x); a.y = fma(m, pa.y, a.y); m *= pm; }
+            }
+            const double2 incl = make_double2(fma(m, o0.x, a.x), fma(m, o0.y, a.y));   // offset leaving tile `lane`
+            offr = shfl_up_c(incl, 1);
+            if (lane == 0) offr = o0;
+            oE = shfl_c(incl, nt - 1);
         }
         {   // the next item's inputs start their way into L2 now
             const int nitem = item + nw;
@@ -159,6 +175,7 @@ k_finish(const __grid_constant__ DevPlan pl, const __grid_constant__ Scratch sc,
                 if (idx < nt * 16) addv[idx] = cmul(T1r[min(t, nt - 1)], a);
             }
         }
+        FIN_DBG(1);
         // ---------------------------------------------------------------- 1b. IQ correction
         // read_file.py:72-77 is the linear recurrence off' = lam off + L z; lane <-> sample.  Head:
         // off_n = lam^n off_0 + L sum_{i<n} lam^(n-1-i) z_i (scan upwards).  End window, from the
@@ -179,6 +196,7 @@ k_finish(const __grid_constant__ DevPlan pl, const __grid_constant__ Scratch sc,
             const double lm = pl.Liq * pl.mu_pw[1];
             xe.x -= fma(mun, oE.x, -lm * B.x); xe.y -= fma(mun, oE.y, -lm * B.y);
         }
+        FIN_DBG(2);
         // ---------------------------------------------------------------- 1c. NCO, odd extensions
         if (lane <= edge) {
             xh = cmul(xh, pl.Ehead[(size_t)r * (edge + 1) + lane]);
@@ -193,6 +211,7 @@ k_finish(const __grid_constant__ DevPlan pl, const __grid_constant__ Scratch sc,
             }
         }
         __syncwarp();
+        FIN_DBG(3);
         // ---------------------------------------------------------------- 1d. head / tail states
         // closed forms of the serial recurrences: w(edge) = p^edge zhat ext0 + sum_j p^(edge-1-j) ext_j,
         // T(end) = sum_k p^k tail_k, and the tail-driven part of w(L-2); lane = (pole, quarter of j)
@@ -213,6 +232,7 @@ k_finish(const __grid_constant__ DevPlan pl, const __grid_constant__ Scratch sc,
             }
             accA = cfma(pk[edge * 8 + i8], cmul(pl.zhat[i8], seqA[0]), accA);
         }
+        FIN_DBG(4);
         // ---------------------------------------------------------------- 1e. carries across tiles
         // lanes 0..7: forward modal states (Win[t] = state entering tile t); lanes 8..15: anticausal
         // states (Tn[t] = state entering tile t from above)
@@ -225,6 +245,7 @@ k_finish(const __grid_constant__ DevPlan pl, const __grid_constant__ Scratch sc,
             if (lane >= 8 && lane < 16) carry[(size_t)t * 16 + 8 + i8] = st;
         }
         if (lane < 8) carry[(size_t)nt * 16 + i8] = st;
+        FIN_DBG(5);
         // ---------------------------------------------------------------- 1f. boundary vector zeta
         {
             const double2 Wn = shfl_c(st, i8);                              // forward state at n = edge + q*Mf
@@ -250,6 +271,7 @@ k_finish(const __grid_constant__ DevPlan pl, const __grid_constant__ Scratch sc,
             }
         }
         __syncwarp();
+        FIN_DBG(6);
         // ---------------------------------------------------------------- 2+3a. outputs, lane <-> block
         // y[k] = T1 (ypart - off psi) + sum_i rho_i P_i^l Win_i + rho_i/p_i P_i^(32-l) Tn_i (+ boundary),
         // two tiles per round; fm forms the pair phases in registers (even lanes take tile t0's
@@ -310,6 +332,7 @@ k_finish(const __grid_constant__ DevPlan pl, const __grid_constant__ Scratch sc,
             }
         }
         __syncwarp();
+        FIN_DBG(7);
         // ---------------------------------------------------------------- 3b. fm: 2x interpolation
         if (pl.demod == 0) {
             // even outputs of scipy.signal.resample(ph, 2h) are the phases themselves (already in
@@ -362,6 +385,7 @@ k_finish(const __grid_constant__ DevPlan pl, const __grid_constant__ Scratch sc,
             }
             __syncwarp();
         }
+        FIN_DBG(8);
         // ---------------------------------------------------------------- 4. output low-pass
         if (pl.nsec_out > 0) {
             double *zs = zrow + (size_t)lane * (Ls + 1);
@@ -401,6 +425,7 @@ k_finish(const __grid_constant__ DevPlan pl, const __grid_constant__ Scratch sc,
             }
             __syncwarp();
         }
+        FIN_DBG(9);
         // ---------------------------------------------------------------- 5. framing
         double *o = out + ((size_t)r * nchunks + chunk) * M;
         for (int k = lane; k < M; k += 32) {
@@ -408,5 +433,6 @@ k_finish(const __grid_constant__ DevPlan pl, const __grid_constant__ Scratch sc,
             o[k] = pl.be_out ? bswap_double(v) : v;
         }
         __syncwarp();
+        FIN_DBG(10);
     }
 }

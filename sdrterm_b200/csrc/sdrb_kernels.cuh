@@ -21,6 +21,8 @@ struct Scratch {
     double2 *agg;       // [nch][R][ntiles][16]   0..7 Wout, 8..15 Tin
     double2 *tile_agg;  // [nch][ntiles]
     double2 *off_tile;  // [nch][ntiles+1]
+    double2 *gain;      // [nch] offset gained over a chunk from zero (whole-tile fast path)
+    double2 *start;     // [nch] offset at the chunk start            "
     double2 *carry;     // [nch][R][ntiles+1][16] 0..7 Win[t], 8..15 Tn[t]
     double2 *y;         // [nch][R][M]
     double2 *iq_state;  // [1] offset before the batch (in) / after it (out)
@@ -310,6 +312,96 @@ k_iqgain(const __grid_constant__ DevPlan pl, Scratch sc, const uint8_t *__restri
         o.x = fma(lr, o.x, pl.Liq * acc.x); o.y = fma(lr, o.y, pl.Liq * acc.y);
     }
     sc.off_tile[(size_t)c * (nt + 1) + nt] = o;
+}
+
+// k_iqgain_w: warp <-> chunk, lane <-> tile (whole-tile chunks, ntiles <= 32): the same gain as
+// k_iqgain by a warp scan of the tile maps o -> lam_tile o + agg[t]; coalesced, no serial loop.
+__global__ void __launch_bounds__(256)
+k_iqgain_w(const __grid_constant__ DevPlan pl, Scratch sc, int nchunks)
+{
+    const int lane = threadIdx.x & 31;
+    const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (c >= nchunks) return;
+    const int nt = pl.ntiles;
+    double m = 1.0;
+    double2 a = make_double2(0.0, 0.0);
+    if (lane < nt) { m = pl.lam_tile[lane == nt - 1 ? 1 : 0]; a = sc.tile_agg[(size_t)c * nt + lane]; }
+#pragma unroll
+    for (int lv = 0; lv < 5; lv++) {
+        const double pm = __shfl_up_sync(0xffffffffu, m, 1 << lv);
+        const double2 pa = shfl_up_c(a, 1 << lv);
+        if (lane >= (1 << lv)) { a.x = fma(m, pa.x, a.x); a.y = fma(m, pa.y, a.y); m *= pm; }
+    }
+    if (lane == nt - 1) sc.gain[c] = a;
+}
+
+// k_iqscan_c: one CTA of 1024 threads; exclusive scan of the per-chunk maps o -> lam_N o + gain[c]
+// from the handle's IQ state -> start[c] and the new state.  8 chunks per thread and round (their
+// gains are loaded together), warp-shuffle scans, one shared-memory hop across the 32 warps.
+__global__ void __launch_bounds__(1024)
+k_iqscan_c(const __grid_constant__ DevPlan pl, Scratch sc, int nchunks)
+{
+    __shared__ double2 s_a[32];
+    __shared__ double s_m[32];
+    __shared__ double2 s_state;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const double2 *__restrict__ gain = sc.gain;
+    double2 *__restrict__ start = sc.start;
+    if (tid == 0) s_state = sc.iq_state[0];
+    __syncthreads();
+    for (int base = 0; base < nchunks; base += 1024 * 8) {
+        const int c0 = base + tid * 8;
+        double2 g[8];
+#pragma unroll
+        for (int i = 0; i < 8; i++) g[i] = (c0 + i < nchunks) ? gain[c0 + i] : make_double2(0.0, 0.0);
+        double m = 1.0;
+        double2 a = make_double2(0.0, 0.0);
+#pragma unroll
+        for (int i = 0; i < 8; i++)
+            if (c0 + i < nchunks) { a.x = fma(pl.lam_N, a.x, g[i].x); a.y = fma(pl.lam_N, a.y, g[i].y); m *= pl.lam_N; }
+        // inclusive scan of the thread maps inside the warp
+#pragma unroll
+        for (int lv = 0; lv < 5; lv++) {
+            const double pm = __shfl_up_sync(0xffffffffu, m, 1 << lv);
+            const double2 pa = shfl_up_c(a, 1 << lv);
+            if (lane >= (1 << lv)) { a.x = fma(m, pa.x, a.x); a.y = fma(m, pa.y, a.y); m *= pm; }
+        }
+        if (lane == 31) { s_a[warp] = a; s_m[warp] = m; }
+        __syncthreads();
+        if (warp == 0) {
+            double wm = s_m[lane];
+            double2 wa = s_a[lane];
+#pragma unroll
+            for (int lv = 0; lv < 5; lv++) {
+                const double pm = __shfl_up_sync(0xffffffffu, wm, 1 << lv);
+                const double2 pa = shfl_up_c(wa, 1 << lv);
+                if (lane >= (1 << lv)) { wa.x = fma(wm, pa.x, wa.x); wa.y = fma(wm, pa.y, wa.y); wm *= pm; }
+            }
+            s_a[lane] = wa; s_m[lane] = wm;
+        }
+        __syncthreads();
+        // exclusive map of this thread = (warps before) then (lanes before in this warp)
+        double em = __shfl_up_sync(0xffffffffu, m, 1);
+        double2 ea = shfl_up_c(a, 1);
+        if (lane == 0) { em = 1.0; ea = make_double2(0.0, 0.0); }
+        if (warp > 0) {
+            const double wm = s_m[warp - 1];
+            const double2 wa = s_a[warp - 1];
+            ea.x = fma(em, wa.x, ea.x); ea.y = fma(em, wa.y, ea.y); em *= wm;
+        }
+        const double2 st0 = s_state;
+        double2 o = make_double2(fma(em, st0.x, ea.x), fma(em, st0.y, ea.y));
+#pragma unroll
+        for (int i = 0; i < 8; i++)
+            if (c0 + i < nchunks) {
+                start[c0 + i] = o;
+                o.x = fma(pl.lam_N, o.x, g[i].x); o.y = fma(pl.lam_N, o.y, g[i].y);
+            }
+        __syncthreads();
+        if (tid == 1023) s_state = make_double2(fma(s_m[31], st0.x, s_a[31].x), fma(s_m[31], st0.y, s_a[31].y));
+        __syncthreads();
+    }
+    if (tid == 0) sc.iq_state[0] = s_state;
 }
 
 // k_iqscan: one CTA; exclusive scan of the per-chunk affine maps o -> lam_N*o + gain, starting from
