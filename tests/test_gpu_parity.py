@@ -147,3 +147,64 @@ def test_time_segment_phases_with_device_side_iq_exchange():
     for e in engs:
         e.close()
     assert got.shape == whole.shape and rel_err(got, whole) < 1e-12
+
+
+def test_empty_and_single_chunk_batches():
+    """Edge sizes: no chunks at all, and one chunk (fewer MMA tiles than SMs) on the tensor-core path."""
+    from gpu_util import plan_for
+    from sdrterm_b200.engine import Engine
+    raw, body, kw = case_stream('c1_fm_wav_int16')
+    pl = plan_for(kw)
+    with Engine(pl, max_chunks=4) as e:
+        out0 = e.process(b'')
+        assert out0.shape == (1, 0)
+        one = e.process(body[:131072])
+        with pytest.raises(ValueError):
+            e.process(body[:131072 + 5])              # not a whole number of chunks
+    ref = orc.Chain(**kw).run(body[:131072])
+    assert one.shape == ref.shape and rel_err(one, ref) < TOL
+
+
+def test_full_size_linearity_and_batch_invariance():
+    """BASELINE-size batch (8192 chunks = 2^28 samples, 1 GiB of int16 IQ) through size-independent
+    properties: the chain up to the decimator is linear (re output, IQ correction on), so
+    out(a) + out(b) == out(a + b); and one 8192-chunk call equals eight 1024-chunk calls (the IQ
+    state chains).  Device-resident buffers, C ABI entry point sdrb_process_device."""
+    import torch
+    from sdrterm_b200.engine import Engine
+    from sdrterm_b200.plan import build_plan
+    nch = 8192
+    pl = build_plan(1_024_000, 'h', 64, [15000], correct_iq=True, demod='re', omega_out=5000)
+    g = torch.Generator(device='cuda')
+    g.manual_seed(11)
+    n = nch * 32768 * 2
+    a = torch.randint(-12000, 12000, (n,), generator=g, device='cuda', dtype=torch.int16)
+    b = torch.randint(-12000, 12000, (n,), generator=g, device='cuda', dtype=torch.int16)
+    c = a + b
+    outs = []
+    with Engine(pl, max_chunks=nch) as e:
+        assert e.tc is not None
+        for x in (a, b, c):
+            o = torch.empty((1, nch * pl.M), dtype=torch.float64, device='cuda')
+            e.iq_state = 0j
+            e.process_device(x.data_ptr(), nch, o.data_ptr())
+            torch.cuda.synchronize()
+            outs.append(o)
+        ssum = outs[0] + outs[1]
+        err = float((ssum - outs[2]).abs().max() / outs[2].abs().max())
+        assert err < 1e-11, err
+        # eight batches of 1024 chunks with the state carried == one batch
+        o8 = torch.empty_like(outs[2])
+        e.iq_state = 0j
+        for k in range(8):
+            tmp = torch.empty((1, 1024 * pl.M), dtype=torch.float64, device='cuda')
+            e.process_device(c.data_ptr() + k * 1024 * 131072, 1024, tmp.data_ptr())
+            torch.cuda.synchronize()
+            o8[0, k * 1024 * pl.M:(k + 1) * 1024 * pl.M] = tmp[0]
+        err8 = float((o8 - outs[2]).abs().max() / outs[2].abs().max())
+        assert err8 < 1e-12, err8
+    # spot check of the first and last chunk against the oracle
+    kw = dict(fs=1_024_000, enc='h', center=15000, dec=64, demod='re', omega_out=5000, correct_iq=True)
+    host = c[:32768 * 2].cpu().numpy().tobytes()
+    ref0 = orc.Chain(**kw).run(host)
+    assert rel_err(outs[2][0, :pl.M].cpu().numpy()[None], ref0) < TOL
