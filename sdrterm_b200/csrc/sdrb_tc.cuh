@@ -340,46 +340,28 @@ __device__ __forceinline__ void tc_epilogue(const DevPlan &pl, const TcDev &tc, 
             if (HALF == 0) ag[pole] = cmul(rot31, tot);
             else ag[8 + pole] = tot;
         }
-        // ---- C. carry times Pm^j (forward: j = 0..7, backward: 1..8) as two running products, in
-        //      registers; res[k] = rho * state of this lane's mode at block 8 seg + k
-        double2 res[8];
-        {
-            const double2 rho_l = HALF ? pl.rho_p[pole] : pl.rho[pole];
-            double2 ce = HALF ? cmul(Pm, cin) : cin;
-            double2 co = cmul(Pm, ce);
+        // ---- C. carry applied with the multiplier powers (table in shared memory, fetched four at a
+        //      time so that the loads are in flight together), parked back for the per-block sums
 #pragma unroll
-            for (int j = 0; j < 8; j += 2) {
-                res[HALF ? 7 - j : j] = cmul(rho_l, cadd(loc[j], ce));
-                res[HALF ? 6 - j : j + 1] = cmul(rho_l, cadd(loc[j + 1], co));
-                if (j < 6) { ce = cmul(Pm2, ce); co = cmul(Pm2, co); }
-            }
+        for (int j0 = 0; j0 < 8; j0 += 4) {
+            double2 pp[4];
+#pragma unroll
+            for (int u4 = 0; u4 < 4; u4++) pp[u4] = pw[HALF ? j0 + u4 + 1 : j0 + u4];
+#pragma unroll
+            for (int u4 = 0; u4 < 4; u4++) xsp[HALF ? 7 - (j0 + u4) : j0 + u4] = cfma(pp[u4], cin, loc[j0 + u4]);
         }
+        __syncwarp();
         if (HALF == 0 && qd == 0 && lane == 0) TC_DBG(sc, it, 10);      // phases B, C done
-        // ---- partial output of each block: sum over the 8 modes = over the 8 lanes of a segment
-        //      group, by a transpose-reduce butterfly (3 exchanges of 4, 2, 1 values) that leaves
-        //      block 8 seg + (lane & 7) = lane in each lane -- shuffles instead of a second pass
-        //      through shared memory
+        // ---- partial output of each block (lane <-> block): half 0 sums rho_i W_i, half 1
+        //      rho_i/p_i T_i, four independent partial sums
         double2 acc;
         {
-            double2 v4[4], v2[2];
-            const bool b2 = lane & 4, b1 = lane & 2, b0 = lane & 1;
-#pragma unroll
-            for (int k = 0; k < 4; k++) {
-                const double2 snd = b2 ? res[k] : res[k + 4];
-                const double2 kp = b2 ? res[k + 4] : res[k];
-                v4[k] = cadd(kp, shfl_xor_c(snd, 4));
-            }
-#pragma unroll
-            for (int k = 0; k < 2; k++) {
-                const double2 snd = b1 ? v4[k] : v4[k + 2];
-                const double2 kp = b1 ? v4[k + 2] : v4[k];
-                v2[k] = cadd(kp, shfl_xor_c(snd, 2));
-            }
-            {
-                const double2 snd = b0 ? v2[0] : v2[1];
-                const double2 kp = b0 ? v2[1] : v2[0];
-                acc = cadd(kp, shfl_xor_c(snd, 1));
-            }
+            const double2 *rh = HALF ? pl.rho_p : pl.rho;
+            const double2 q0 = cfma(rh[4], xsl[4 * TC_XS], cmul(rh[0], xsl[0]));
+            const double2 q1 = cfma(rh[5], xsl[5 * TC_XS], cmul(rh[1], xsl[1 * TC_XS]));
+            const double2 q2 = cfma(rh[6], xsl[6 * TC_XS], cmul(rh[2], xsl[2 * TC_XS]));
+            const double2 q3 = cfma(rh[7], xsl[7 * TC_XS], cmul(rh[3], xsl[3 * TC_XS]));
+            acc = cadd(cadd(q0, q1), cadd(q2, q3));
         }
         double2 *pb = sh.sPB + ((size_t)(u & 1) * 8 + (g * 4 + qd)) * 32;
         if (HALF) pb[lane] = acc;
