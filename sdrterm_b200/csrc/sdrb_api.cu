@@ -223,6 +223,7 @@ int setup_tc(sdrb_handle *h, const sdrb_tables *tab, const std::vector<double2> 
     tc.idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(tc.npad >> 3) << 17) | ((128u >> 4) << 24);
     tc.scale = ldexp(1.0, -tab->tc_S);
     tc.scale16 = ldexp(1.0, 16 - tab->tc_S);
+    tc.stagger_ns = (uint32_t)env_int("SDRB_TC_STAGGER_NS", 0);
     // powers 0..8 of the rotating-frame block multipliers (segment carries of the tile scans)
     std::vector<double2> ppow((size_t)R * 16 * 9);
     for (int i = 0; i < R * 16; i++) {

@@ -50,6 +50,7 @@ struct TcDev {
     uint32_t idesc;                    // tcgen05 instruction descriptor (i8 x i8 -> s32, M=128, N=npad)
     double scale;                      // 2^-S, common to every fixed-point output
     double scale16;                    // 2^(16-S): weight of the columns above the low pair
+    uint32_t stagger_ns;               // one-off delay of accumulator stage 1's first epilogue
     const double2 *prot_pow;           // [R][16][9] powers 0..8 of the rotating-frame block multipliers
     // per row, read through the constant cache (shared-memory bandwidth is this kernel's limit):
     double cstb[TC_MAX_R][TC_NOUT];    // response to the constant the XOR removed, minus the 2^52 + 2^31
@@ -232,7 +233,12 @@ __device__ __forceinline__ void tc_epilogue(const DevPlan &pl, const TcDev &tc, 
         const int gt = 4 * mt + qd;
         // one warp of the stage polls the mbarrier; the other seven sleep on a named barrier
         // (bar.sync blocks in hardware, a try_wait loop spends issue slots)
-        if (HALF == 0 && qd == 0) mbar_wait(bar_done, u & 1);
+        if (HALF == 0 && qd == 0) {
+            mbar_wait(bar_done, u & 1);
+            // stagger the two accumulator stages by half an item once: left alone they fall into
+            // lockstep (both in their integer-heavy TMEM phase, then both in their FP64 scans)
+            if (g == 1 && it == 1 && tc.stagger_ns) __nanosleep(tc.stagger_ns);
+        }
         asm volatile("bar.sync %0, 256;" ::"r"(9u + (uint32_t)g) : "memory");
         tc_fence_after();
         if (HALF == 0 && qd == 0 && lane == 0) TC_DBG(sc, it, 5);
