@@ -35,7 +35,9 @@ __host__ __device__ inline size_t finish_warp_bytes(int M)
 }
 __host__ __device__ inline size_t finish_smem_bytes(int M, int edge)
 {
-    return (size_t)(M / 2) * sizeof(double2) + (size_t)(edge + 1) * 8 * sizeof(double2) + FIN_WARPS * finish_warp_bytes(M);
+    const int nt = M / SDRB_TB;
+    const size_t tables = (size_t)(nt + 32 + nt * 8 + 32 + 32 + 64) * sizeof(double2);   // single-row tables
+    return (size_t)(M / 2) * sizeof(double2) + (size_t)(edge + 1) * 8 * sizeof(double2) + tables + FIN_WARPS * finish_warp_bytes(M);
 }
 
 // Stockham radix-2 pass over n points by one warp (two butterflies in flight per lane); twiddle
@@ -83,7 +85,20 @@ k_finish(const __grid_constant__ DevPlan pl, const __grid_constant__ Scratch sc,
     double2 *pk = tw + h;                                                // p_i^k, [edge+1][8]
     for (int k = threadIdx.x; k < h; k += blockDim.x) tw[k] = pl.tw[k];
     for (int k = threadIdx.x; k < (edge + 1) * 8; k += blockDim.x) pk[k] = pl.pk[k];
-    unsigned char *wb = smem_raw + (size_t)(h + (edge + 1) * 8) * sizeof(double2) + (size_t)warp * finish_warp_bytes(M);
+    // row tables: resident in shared memory when the bank has one row (the L1 copies are evicted
+    // by the streaming ypart / agg reads), read from global memory per item otherwise
+    double2 *tbT1 = pk + (edge + 1) * 8, *tbPsi = tbT1 + nt, *tbPt = tbPsi + 32, *tbEh = tbPt + nt * 8,
+            *tbEe = tbEh + 32, *tbPy = tbEe + 32;
+    if (R == 1) {
+        for (int k = threadIdx.x; k < nt; k += blockDim.x) tbT1[k] = pl.T1[k];
+        for (int k = threadIdx.x; k < 32; k += blockDim.x)
+            tbPsi[k] = (k & 15) < 8 ? pl.PsiW[(size_t)(k >> 4) * 8 + (k & 15)] : pl.PsiT[(size_t)(k >> 4) * 8 + (k & 15) - 8];
+        for (int k = threadIdx.x; k < nt * 8; k += blockDim.x) tbPt[k] = pl.Pt[k];
+        for (int k = threadIdx.x; k <= edge; k += blockDim.x) { tbEh[k] = pl.Ehead[k]; tbEe[k] = pl.Eend[k]; }
+        for (int k = threadIdx.x; k < 64; k += blockDim.x) tbPy[k] = pl.psiY[k];
+    }
+    unsigned char *wb = smem_raw + (size_t)(h + (edge + 1) * 8 + nt + 32 + nt * 8 + 32 + 32 + 64) * sizeof(double2) +
+                        (size_t)warp * finish_warp_bytes(M);
     double2 *carry = reinterpret_cast<double2 *>(wb);
     double2 *fa = carry + (size_t)(nt + 1) * 16, *fb = fa + n2;
     double2 *addv = fa;                                                  // dead before the FFT buffers are written
@@ -112,7 +127,7 @@ k_finish(const __grid_constant__ DevPlan pl, const __grid_constant__ Scratch sc,
         const int chunk = item / R, r = item - chunk * R;
         const uint8_t *rawc = raw + (size_t)chunk * pl.N * pl.sb;
         const double2 *aggr = sc.agg + ((size_t)chunk * R + r) * nt * 16;
-        const double2 *T1r = pl.T1 + (size_t)r * nt;
+        const double2 *T1r = R == 1 ? tbT1 : pl.T1 + (size_t)r * nt;
         const double2 *ypr = sc.ypart + ((size_t)chunk * R + r) * pl.Mf;
 
         // ---------------------------------------------------------------- 1a. loads
@@ -168,8 +183,9 @@ k_finish(const __grid_constant__ DevPlan pl, const __grid_constant__ Scratch sc,
                 if (iq) {
                     const int kind = (t == nt - 1) ? 1 : 0;
                     const double2 o = shfl_c(offr, t);
-                    const double2 psi = m < 8 ? pl.PsiW[((size_t)kind * R + r) * 8 + m]
-                                              : pl.PsiT[((size_t)kind * R + r) * 8 + m - 8];
+                    const double2 psi = R == 1 ? tbPsi[kind * 16 + m]
+                                      : (m < 8 ? pl.PsiW[((size_t)kind * R + r) * 8 + m]
+                                               : pl.PsiT[((size_t)kind * R + r) * 8 + m - 8]);
                     a = cfma(make_double2(-o.x, -o.y), psi, a);
                 }
                 if (idx < nt * 16) addv[idx] = cmul(T1r[min(t, nt - 1)], a);
@@ -199,8 +215,8 @@ k_finish(const __grid_constant__ DevPlan pl, const __grid_constant__ Scratch sc,
         FIN_DBG(2);
         // ---------------------------------------------------------------- 1c. NCO, odd extensions
         if (lane <= edge) {
-            xh = cmul(xh, pl.Ehead[(size_t)r * (edge + 1) + lane]);
-            xe = cmul(xe, pl.Eend[(size_t)r * pl.nend + lane]);
+            xh = cmul(xh, R == 1 ? tbEh[lane] : pl.Ehead[(size_t)r * (edge + 1) + lane]);
+            xe = cmul(xe, R == 1 ? tbEe[lane] : pl.Eend[(size_t)r * pl.nend + lane]);
         }
         {
             const double2 x0 = shfl_c(xh, 0), xN1 = shfl_c(xe, edge);
@@ -267,7 +283,7 @@ k_finish(const __grid_constant__ DevPlan pl, const __grid_constant__ Scratch sc,
             __syncwarp();
             for (int t = sub; t < nt; t += 4) {
                 double2 *Tn = carry + (size_t)(t + 1) * 16 + 8 + i8;
-                *Tn = cfma(pl.Pt[(size_t)(nt - 1 - t) * 8 + i8], X, *Tn);
+                *Tn = cfma((R == 1 ? tbPt : pl.Pt)[(size_t)(nt - 1 - t) * 8 + i8], X, *Tn);
             }
         }
         __syncwarp();
@@ -278,8 +294,8 @@ k_finish(const __grid_constant__ DevPlan pl, const __grid_constant__ Scratch sc,
         // pairs, odd lanes tile t1's), the other modes go straight to the output row
         {
             double2 *yg = sc.y + ((size_t)chunk * R + r) * M;
-            const double2 psi0 = pl.psiY[((size_t)0 * R + r) * SDRB_TB + lane];
-            const double2 psi1 = pl.psiY[((size_t)1 * R + r) * SDRB_TB + lane];
+            const double2 psi0 = R == 1 ? tbPy[lane] : pl.psiY[((size_t)0 * R + r) * SDRB_TB + lane];
+            const double2 psi1 = R == 1 ? tbPy[32 + lane] : pl.psiY[((size_t)1 * R + r) * SDRB_TB + lane];
             double *ph = reinterpret_cast<double *>(fa);
             // ypart is fetched two rounds (four tiles) ahead of its use
             double2 yq[4];
