@@ -143,8 +143,9 @@ int sdrb_process_device(sdrb_handle *h, const void *raw_dev, size_t nchunks, dou
 
 /* The same chain split for time-segment sharding across GPUs: phase bits
  * 1 = block kernel, 2 = IQ-offset scan from the handle's IQ state, 4 = fix-up + demodulation.
- * A rank runs (1|2) from a zero state, reads its segment's offset gain with sdrb_get_iq_state,
- * exchanges gains, sets its true initial state and runs (2|4); the raw data is read once. */
+ * A rank runs (1|2|8) from a zero state, exports its segment's offset gain, the ranks exchange
+ * gains, each folds the ones before it into its initial state and runs (2|4); the raw data is
+ * read once. */
 #define SDRB_PHASE_MAIN 1
 #define SDRB_PHASE_IQSCAN 2
 #define SDRB_PHASE_FINISH 4
@@ -158,8 +159,9 @@ int sdrb_process_device_phases(sdrb_handle *h, const void *raw_dev, size_t nchun
 int sdrb_iq_export_device(sdrb_handle *h, double *dst3_dev, double nsamples, void *stream);
 int sdrb_iq_prefix_device(sdrb_handle *h, const double *gains3_dev, int rank, void *stream);
 
-/* CUDA-event timing of the four kernels of the last full sdrb_process_device call
- * (ms[0..3] = block kernel, IQ scan, fix-up, demodulation), for bench.py's roofline. */
+/* CUDA-event timing of the kernel groups of the last full sdrb_process_device call: ms[0] = block
+ * front end (k_tc / k_main), ms[1] = IQ-offset kernels, ms[2] = k_finish (or k_fixup), ms[3] =
+ * k_demod (general path only, 0 otherwise); for bench.py's roofline. */
 int sdrb_set_profiling(sdrb_handle *h, int on);
 int sdrb_kernel_times(sdrb_handle *h, float ms[4]);
 
@@ -180,9 +182,10 @@ int sdrb_read_decimated(sdrb_handle *h, size_t nchunks, double *y_host);
 /* The fused finish kernel keeps y on chip; it is written out only when this is switched on
  * (off by default; the general k_fixup/k_demod path always writes it). */
 int sdrb_keep_decimated(sdrb_handle *h, int on);
-/* Diagnostic: clock64 timeline of k_tc's pipeline on CTA 0, [64 tiles][16 events] (1024 values); needs the
- * environment variable SDRB_TC_DEBUG=1 when the handle is created. */
-int sdrb_read_debug(sdrb_handle *h, unsigned long long *out512);
+/* Diagnostic: clock64 timelines of CTA 0 -- k_tc's pipeline [32 tiles][16 events] in the first 512
+ * values, k_finish's phases [16 items][16 events] in the second 512 (microbench/tc_timeline.py);
+ * needs the environment variable SDRB_TC_DEBUG=1 when the handle is created. */
+int sdrb_read_debug(sdrb_handle *h, unsigned long long *out1024);
 
 /* Kernel launches issued by this handle since creation (bench.py's gpu_launches). */
 long long sdrb_launch_count(const sdrb_handle *h);

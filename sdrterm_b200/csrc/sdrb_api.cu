@@ -725,11 +725,11 @@ int sdrb_set_iq_state(sdrb_handle *h, const double off[2])
 }
 
 /* diagnostic: k_tc pipeline timeline of CTA 0 (clock64 per event), needs SDRB_TC_DEBUG=1 at create */
-int sdrb_read_debug(sdrb_handle *h, unsigned long long *out512)
+int sdrb_read_debug(sdrb_handle *h, unsigned long long *out1024)
 {
-    if (!h || !out512 || !h->sc.dbg) return fail(h, SDRB_ERR_STATE, "no debug buffer");
+    if (!h || !out1024 || !h->sc.dbg) return fail(h, SDRB_ERR_STATE, "no debug buffer");
     CK(h, cudaDeviceSynchronize());
-    CK(h, cudaMemcpy(out512, h->sc.dbg, 64 * 16 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    CK(h, cudaMemcpy(out1024, h->sc.dbg, 64 * 16 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
     return SDRB_OK;
 }
 

@@ -193,7 +193,7 @@ __device__ __forceinline__ double tc_combine(const uint32_t *c, double s16, doub
     return fma(i64_to_double(hi), s16, fma(i32_biased(lo), s1, cstb));
 }
 
-#define TC_DBG(sc, it, ev) do { if ((sc).dbg && blockIdx.x == 0 && (it) < 64) (sc).dbg[(it) * 16 + (ev)] = clock64(); } while (0)
+#define TC_DBG(sc, it, ev) do { if ((sc).dbg && blockIdx.x == 0 && (it) < 32) (sc).dbg[(it) * 16 + (ev)] = clock64(); } while (0)
 
 // ------------------------------------------------------------------------------------- k_tc
 struct TcShared {
