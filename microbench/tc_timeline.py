@@ -24,12 +24,12 @@ t0 = t[0, 0]
 names = ['tma_issue', 'xor_start', 'xor_done', 'mma_start', 'mma_issued', 'epi_start', 'tmem_free', 'epi_end',
          'excl', 'scanA', 'scanBC', 'dot', 'pair']
 print('tile ' + ' '.join(f'{n:>10s}' for n in names))
-for it in range(2, 40):
+for it in range(2, 32):
     print(f'{it:4d} ' + ' '.join(f'{(t[it, e] - t0):10d}' for e in range(8)))
-d = np.diff(t[8:56, 0])
+d = np.diff(t[8:31, 0])
 print('cycles per tile (tma_issue to tma_issue):', d.mean())
 for a, b in ((0, 1), (1, 2), (2, 3), (3, 4), (4, 5), (5, 8), (8, 6), (6, 9), (9, 10), (10, 11), (11, 12), (12, 7), (5, 7), (0, 7)):
-    print(f'{names[a]:>10s} -> {names[b]:<10s}: mean {np.mean(t[8:56, b] - t[8:56, a]):8.0f}')
+    print(f'{names[a]:>10s} -> {names[b]:<10s}: mean {np.mean(t[8:31, b] - t[8:31, a]):8.0f}')
 
 f = t[32:48, :11]          # k_finish events of warp 0 / CTA 0 live in the second half of the buffer
 fn = ['start', '1a loads', '1b iq', '1c nco', '1d dots', '1e tiles', '1f zeta', '2 outputs+phase', '3b fft', '4 sos', '5 store']
