@@ -8,7 +8,7 @@ import signals
 from sdrterm_b200 import _native as nat
 from sdrterm_b200.engine import Engine
 from sdrterm_b200.plan import build_plan
-nch = 2048
+nch = 8192
 pl = build_plan(1_024_000, 'h', 64, [15000], correct_iq=True, demod='fm', omega_out=5000)
 eng = Engine(pl, max_chunks=nch)
 base = np.frombuffer(signals.c1_bytes(16 * 32768, seed=0, header=False), dtype=np.uint8)
@@ -33,7 +33,7 @@ for a, b in ((0, 1), (1, 2), (2, 3), (3, 4), (4, 5), (5, 8), (8, 6), (6, 9), (9,
 
 f = t[32:48, :11]          # k_finish events of warp 0 / CTA 0 live in the second half of the buffer
 fn = ['start', '1a loads', '1b iq', '1c nco', '1d dots', '1e tiles', '1f zeta', '2 outputs+phase', '3b fft', '4 sos', '5 store']
-print('k_finish phases (cycles, mean over items 1..12):')
+print('k_finish phases of warp 0 / CTA 0 (cycles, mean over its items 1..3):')
 for e in range(10):
-    print(f'  {fn[e + 1]:>16s}: {np.mean(f[1:13, e + 1] - f[1:13, e]):8.0f}')
-print(f'  {"item":>16s}: {np.mean(f[1:13, 10] - f[1:13, 0]):8.0f}')
+    print(f'  {fn[e + 1]:>16s}: {np.mean(f[1:4, e + 1] - f[1:4, e]):8.0f}')
+print(f'  {"item":>16s}: {np.mean(f[1:4, 10] - f[1:4, 0]):8.0f}')
