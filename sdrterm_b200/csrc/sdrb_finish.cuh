@@ -107,11 +107,14 @@ k_finish(const __grid_constant__ DevPlan pl, const __grid_constant__ Scratch sc,
     __syncthreads();
 
     // lane-invariant tables: this lane's block position l = lane inside every tile
-    double2 rw[8], rt[8];
+    // (the filter is real: poles 4..7 are the conjugates of 0..3 and so are their weights, hence
+    // sum_i c_i w_i = 2 Re(c_i Wr_i) + 2j Re(c_i Wi_i) over i < 4 with the modal states of the real and
+    // imaginary input streams Wr = (w_i + conj w_{i+4}) / 2, Wi = (w_i - conj w_{i+4}) / 2j: half the FMAs)
+    double2 rw[4], rt[4];
 #pragma unroll
-    for (int i = 0; i < 8; i++) {
-        rw[i] = pl.RW[(size_t)lane * 8 + i];
-        rt[i] = pl.RT[(size_t)(SDRB_TB - lane) * 8 + i];
+    for (int i = 0; i < 4; i++) {
+        rw[i] = cscale(2.0, pl.RW[(size_t)lane * 8 + i]);
+        rt[i] = cscale(2.0, pl.RT[(size_t)(SDRB_TB - lane) * 8 + i]);
     }
     const int i8 = lane & 7, grp = (lane >> 3) & 1, sub = lane >> 3;
     const double2 p_i = pl.p[i8], P32 = pl.Ppow[(size_t)SDRB_TB * 8 + i8];
@@ -287,6 +290,14 @@ k_finish(const __grid_constant__ DevPlan pl, const __grid_constant__ Scratch sc,
             }
         }
         __syncwarp();
+        // carries -> states of the real / imaginary input streams (slots i and i + 4 of each group)
+        for (int idx = lane; idx < (nt + 1) * 8; idx += 32) {
+            double2 *c = carry + (size_t)(idx >> 2) * 8 + (idx & 3);       // group = (tile, direction)
+            const double2 a = c[0], b = cconj(c[4]);
+            c[0] = make_double2(0.5 * (a.x + b.x), 0.5 * (a.y + b.y));
+            c[4] = make_double2(0.5 * (a.y - b.y), -0.5 * (a.x - b.x));
+        }
+        __syncwarp();
         FIN_DBG(6);
         // ---------------------------------------------------------------- 2+3a. outputs, lane <-> block
         // y[k] = T1 (ypart - off psi) + sum_i rho_i P_i^l Win_i + rho_i/p_i P_i^(32-l) Tn_i (+ boundary),
@@ -316,15 +327,15 @@ k_finish(const __grid_constant__ DevPlan pl, const __grid_constant__ Scratch sc,
                     }
                     v = cmul(T1r[t], v);
                     const double2 *Win = carry + (size_t)t * 16, *Tn = carry + (size_t)(t + 1) * 16 + 8;
-                    double2 a0 = make_double2(0.0, 0.0), a1 = a0, a2 = a0;
+                    double2 a1 = make_double2(0.0, 0.0);
 #pragma unroll
                     for (int i = 0; i < 4; i++) {
-                        v = cfma(rw[i], Win[i], v);
-                        a0 = cfma(rw[i + 4], Win[i + 4], a0);
-                        a1 = cfma(rt[i], Tn[i], a1);
-                        a2 = cfma(rt[i + 4], Tn[i + 4], a2);
+                        v.x = fma(rw[i].x, Win[i].x, fma(-rw[i].y, Win[i].y, v.x));
+                        v.y = fma(rw[i].x, Win[i + 4].x, fma(-rw[i].y, Win[i + 4].y, v.y));
+                        a1.x = fma(rt[i].x, Tn[i].x, fma(-rt[i].y, Tn[i].y, a1.x));
+                        a1.y = fma(rt[i].x, Tn[i + 4].x, fma(-rt[i].y, Tn[i + 4].y, a1.y));
                     }
-                    v = cadd(cadd(v, a0), cadd(a1, a2));
+                    v = cadd(v, a1);
                     if (keep_y) yg[k] = v;
                     yv[u] = v;
                 }
