@@ -35,6 +35,9 @@
 #include <cuda.h>
 #include "sdrb_kernels.cuh"
 
+#ifndef TC_ABL
+#define TC_ABL 0                       // timing experiments only (wrong results): see microbench/ablate.sh
+#endif
 #define TC_NOUT 36                     // outputs per row: 16 F, 16 G, 2 E, 2 x0
 #define TC_MAX_R 32                    // rows of the VFO bank this kernel takes
 #define TC_THREADS 640
@@ -304,7 +307,7 @@ __device__ __forceinline__ void tc_epilogue(const DevPlan &pl, const TcDev &tc, 
                 vr = fma(-excl.x, ph.x, fma(excl.y, ph.y, vr));
                 vi = fma(-excl.x, ph.y, fma(-excl.y, ph.x, vi));
             }
-            xsl[md * TC_XS] = make_double2(vr, vi);
+            if (!(TC_ABL & 16) || md == 0) xsl[md * TC_XS] = make_double2(vr, vi);
         }
         tc_fence_before();
         __syncwarp();
@@ -321,7 +324,7 @@ __device__ __forceinline__ void tc_epilogue(const DevPlan &pl, const TcDev &tc, 
         double2 st = make_double2(0.0, 0.0);
 #pragma unroll
         for (int j = 0; j < 8; j++) {
-            const double2 v = xsp[HALF ? 7 - j : j];
+            const double2 v = (TC_ABL & 16) ? make_double2((double)j, excl.x) : xsp[HALF ? 7 - j : j];
             const double2 nst = cfma(Pm, st, v);
             loc[j] = HALF ? nst : st;                              // local (segment-relative) prefix
             st = nst;
@@ -340,7 +343,7 @@ __device__ __forceinline__ void tc_epilogue(const DevPlan &pl, const TcDev &tc, 
             const double2 t1 = cfma(Pm8, dist >= 2 ? n2 : z, dist >= 1 ? n1 : z);
             cin = dist >= 3 ? cfma(Pm16, n3, t1) : t1;
         }
-        if (seg == (HALF ? 0 : 3)) {
+        if (seg == (HALF ? 0 : 3) && !(TC_ABL & 1)) {
             const double2 tot = cfma(Pm8, cin, st);
             double2 *ag = sc.agg + (((size_t)chunk * pl.R + r) * pl.ntiles + t) * 16;
             if (HALF == 0) ag[pole] = cmul(rot31, tot);
@@ -354,7 +357,10 @@ __device__ __forceinline__ void tc_epilogue(const DevPlan &pl, const TcDev &tc, 
 #pragma unroll
             for (int u4 = 0; u4 < 4; u4++) pp[u4] = pw[HALF ? j0 + u4 + 1 : j0 + u4];
 #pragma unroll
-            for (int u4 = 0; u4 < 4; u4++) xsp[HALF ? 7 - (j0 + u4) : j0 + u4] = cfma(pp[u4], cin, loc[j0 + u4]);
+            for (int u4 = 0; u4 < 4; u4++) {
+                const double2 w = cfma(pp[u4], cin, loc[j0 + u4]);
+                if (TC_ABL & 8) loc[j0 + u4] = w; else xsp[HALF ? 7 - (j0 + u4) : j0 + u4] = w;
+            }
         }
         __syncwarp();
         if (HALF == 0 && qd == 0 && lane == 0) TC_DBG(sc, it, 10);      // phases B, C done
@@ -363,23 +369,24 @@ __device__ __forceinline__ void tc_epilogue(const DevPlan &pl, const TcDev &tc, 
         double2 acc;
         {
             const double2 *rh = HALF ? pl.rho_p : pl.rho;
-            const double2 q0 = cfma(rh[4], xsl[4 * TC_XS], cmul(rh[0], xsl[0]));
-            const double2 q1 = cfma(rh[5], xsl[5 * TC_XS], cmul(rh[1], xsl[1 * TC_XS]));
-            const double2 q2 = cfma(rh[6], xsl[6 * TC_XS], cmul(rh[2], xsl[2 * TC_XS]));
-            const double2 q3 = cfma(rh[7], xsl[7 * TC_XS], cmul(rh[3], xsl[3 * TC_XS]));
+            const double2 q0 = (TC_ABL & 8) ? cfma(rh[4], loc[4], cmul(rh[0], loc[0])) : cfma(rh[4], xsl[4 * TC_XS], cmul(rh[0], xsl[0]));
+            const double2 q1 = (TC_ABL & 8) ? cfma(rh[5], loc[5], cmul(rh[1], loc[1])) : cfma(rh[5], xsl[5 * TC_XS], cmul(rh[1], xsl[1 * TC_XS]));
+            const double2 q2 = (TC_ABL & 8) ? cfma(rh[6], loc[6], cmul(rh[2], loc[2])) : cfma(rh[6], xsl[6 * TC_XS], cmul(rh[2], xsl[2 * TC_XS]));
+            const double2 q3 = (TC_ABL & 8) ? cfma(rh[7], loc[7], cmul(rh[3], loc[3])) : cfma(rh[7], xsl[7 * TC_XS], cmul(rh[3], xsl[3 * TC_XS]));
             acc = cadd(cadd(q0, q1), cadd(q2, q3));
         }
         double2 *pb = sh.sPB + ((size_t)(u & 1) * 8 + (g * 4 + qd)) * 32;
-        if (HALF) pb[lane] = acc;
+        if (HALF && !(TC_ABL & 2)) pb[lane] = acc;
         if (HALF == 0 && qd == 0 && lane == 0) TC_DBG(sc, it, 11);      // dot done
-        asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
+        if (!(TC_ABL & 2)) asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
         if (HALF == 0 && qd == 0 && lane == 0) TC_DBG(sc, it, 12);      // partner arrived
         if (HALF == 0) {
-            const double2 sT = pb[lane];
+            const double2 sT = (TC_ABL & 2) ? acc : pb[lane];
             const double2 xc = csub(x0, excl);
             double2 ys = cfma(epsb, acc, sT);
             ys.x = fma(pl.g0, xc.x, ys.x); ys.y = fma(pl.g0, xc.y, ys.y);
-            sc.ypart[((size_t)chunk * pl.R + r) * pl.Mf + (size_t)t * SDRB_TB + lane] = cmul(rot, ys);
+            { const double2 yo = cmul(rot, ys);
+              if (!(TC_ABL & 4) || yo.x != yo.x) sc.ypart[((size_t)chunk * pl.R + r) * pl.Mf + (size_t)t * SDRB_TB + lane] = yo; }
         }
         __syncwarp();
         if (HALF == 0 && qd == 0 && lane == 0) TC_DBG(sc, it, 7);
