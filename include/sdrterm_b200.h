@@ -200,6 +200,25 @@ int sdrb_am_demod(int device, const double *y, int R, int M, double *out);
 int sdrb_real_output(int device, const double *y, int R, int M, double *out);
 int sdrb_imag_output(int device, const double *y, int R, int M, double *out);
 int sdrb_shift_freq(int device, const double *y, const double *shift, int R, int N, double *res);
+/* sdrb_fm_demod takes any even row length: 2*2^k rows run the FFT interpolation, other lengths a
+ * dense scipy.signal.resample matrix built on the host in extended precision. */
+
+/* The decode step of feedBuffers on its own (src/misc/read_file.py:100-101): the structured view
+ * [('re',T),('im',T)] of `raw` -> interleaved complex128, bit-exact for every encoding; `swap` =
+ * stored byte order differs from little-endian.  nsamples complex samples in, 2*nsamples doubles out. */
+int sdrb_decode_iq(int device, const void *raw, size_t nsamples, char enc, int swap, double *z_out);
+
+/* The reference's compiled-plugin seam, dsp.fast.iq_correction.IQCorrection.correctIq(data, off)
+ * (extra/src/iq_correction.pyx:37-70, picked up by src/misc/read_file.py:58-63): in place on
+ * nsamples interleaved complex128 values, `off_inout` is the corrector's carried complex offset,
+ * L = impedance / fs. */
+int sdrb_correct_iq(int device, double *z_inout, size_t nsamples, double off_inout[2], double L);
+
+/* Test access to the tensor-core front end's integer decode: when switched on, the kernel also
+ * stores the first raw sample of every block (two unit-coefficient outputs of the int8 GEMM,
+ * exact integers) as [chunk][row][N/q] interleaved complex128. */
+int sdrb_keep_x0(sdrb_handle *h, int on);
+int sdrb_read_x0(sdrb_handle *h, size_t nchunks, double *x0_host);
 const char *sdrb_global_error(void);
 
 #ifdef __cplusplus

@@ -55,6 +55,7 @@ struct sdrb_handle {
     CUtensorMap map_b{};
     size_t tc_smem = 0;
     int num_sms = 148;
+    double2 *x0_buf = nullptr;      // sdrb_keep_x0
 };
 
 namespace {
@@ -375,8 +376,23 @@ int sdrb_create(const sdrb_config *cfg, const sdrb_tables *tab, sdrb_handle **ou
     if (code < 0) return fail(nullptr, SDRB_ERR_ARG, "unknown encoding '%c'", cfg->enc);
     if (cfg->q < 2 || cfg->q > SDRB_MAX_DECIMATION)
         return fail(nullptr, SDRB_ERR_ARG, "decimation %d outside 2..%d", cfg->q, SDRB_MAX_DECIMATION);
-    if (cfg->R < 1 || cfg->N <= cfg->edge + 1 || cfg->max_chunks < 1 || cfg->n_out_sections > 4)
+    if (cfg->R < 1 || cfg->edge < 1 || cfg->N <= cfg->edge + 1 || cfg->max_chunks < 1 || cfg->n_out_sections < 0 ||
+        cfg->n_out_sections > 4)
         return fail(nullptr, SDRB_ERR_ARG, "bad geometry");
+    {   // k_fixup stages (edge+1) head samples and nend = max(rem, edge+1) window samples in s_x[320]
+        const int rem = cfg->N % cfg->q;
+        if (cfg->edge + 1 + std::max(rem, cfg->edge + 1) > 320)
+            return fail(nullptr, SDRB_ERR_ARG, "filter pad %d too long for the fix-up kernel", cfg->edge);
+    }
+    {
+        const void *need[] = {tab->p, tab->P, tab->rho, tab->rho_p, tab->c, tab->zhat, tab->xi, tab->Ec, tab->Oc,
+                              tab->Ppow, tab->pk, tab->Pt, tab->bx, tab->bnd, tab->lam_j, tab->lam_k, tab->mu_k,
+                              tab->T2, tab->T3, tab->T1, tab->Ehead, tab->Eend, tab->PhiF, tab->PhiG, tab->PsiW,
+                              tab->PsiT, tab->psiY, tab->use_nco};
+        for (const void *ptr : need)
+            if (!ptr) return fail(nullptr, SDRB_ERR_ARG, "a required table pointer is NULL");
+        if (cfg->n_out_sections > 0 && !tab->out_sos) return fail(nullptr, SDRB_ERR_ARG, "out_sos is NULL");
+    }
     if (cfg->N / cfg->q < 1) return fail(nullptr, SDRB_ERR_ARG, "chunk shorter than one block");
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
@@ -535,7 +551,7 @@ int sdrb_create(const sdrb_config *cfg, const sdrb_tables *tab, sdrb_handle **ou
     UP(dalloc(h, nch * R * M, &sc.y));
     UP(dalloc(h, (size_t)1, &sc.iq_state));
     if (cudaMemset(sc.iq_state, 0, sizeof(double2)) != cudaSuccess) return bail(fail(h, SDRB_ERR_CUDA, "memset failed"));
-    sc.fftbuf = nullptr; sc.zrow = nullptr; sc.dbg = nullptr;
+    sc.fftbuf = nullptr; sc.zrow = nullptr; sc.dbg = nullptr; sc.x0 = nullptr;
     if (env_int("SDRB_TC_DEBUG", 0)) {
         UP(dalloc(h, (size_t)64 * 16, &sc.dbg));
         cudaMemset(sc.dbg, 0, 64 * 16 * sizeof(unsigned long long));
@@ -751,42 +767,97 @@ int sdrb_read_decimated(sdrb_handle *h, size_t nchunks, double *y_host)
     return SDRB_OK;
 }
 
+}  // extern "C"
+
 // ---------------------------------------------------------------- module-level operators
-static int demod_op(int device, const double *y, int R, int M, double *out, int demod)
+namespace {
+// device allocation freed on every exit path
+struct DevBuf {
+    void *p = nullptr;
+    ~DevBuf() { if (p) cudaFree(p); }
+    cudaError_t alloc(size_t bytes) { return cudaMalloc(&p, bytes ? bytes : 1); }
+    template <typename T> T *as() const { return static_cast<T *>(p); }
+};
+
+int need_device(int device)
 {
-    if (!y || !out || R < 1 || M < 1) return fail(nullptr, SDRB_ERR_ARG, "bad argument");
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
         return fail(nullptr, SDRB_ERR_CUDA, "no CUDA device: libsdrterm_b200 has no CPU fallback");
+    if (device < 0 || device >= ndev) return fail(nullptr, SDRB_ERR_ARG, "bad device ordinal");
     CK(nullptr, cudaSetDevice(device));
+    return 0;
+}
+
+// scipy.signal.resample(r, M) of a real row of h samples as a dense [M][h] matrix (any h, any
+// M >= h): y[k] = sum_m W[k][m] r[m], W[k][m] = (1/h) (1 + 2 sum_{b=1}^{B} c_b cos(b theta)),
+// theta = 2 pi (k/M - m/h), B = floor(h/2), c_B = 1/2 when h is even and M > h (the unpaired
+// bin is split), closed form of the cosine sum in long double.
+std::vector<double> resample_matrix(int h, int M)
+{
+    std::vector<double> W((size_t)M * h);
+    const long double two_pi = 6.283185307179586476925286766559005768L;
+    const int B = h / 2;
+    const bool split = (h % 2 == 0) && M > h;
+    const int nfull = split ? B - 1 : B;                 // bins with weight 1
+    for (int k = 0; k < M; k++)
+        for (int m = 0; m < h; m++) {
+            // reduce the angle exactly in integers first: theta = 2 pi (k h - m M) / (M h)
+            const long long num = ((long long)k * h - (long long)m * M) % ((long long)M * h);
+            const long double th = two_pi * (long double)num / ((long double)M * (long double)h);
+            long double s;
+            const long double sh = sinl(th / 2);
+            if (fabsl(sh) < 1e-18L) s = (long double)nfull;
+            else s = sinl(nfull * th / 2) * cosl((nfull + 1) * th / 2) / sh;   // sum_{b=1}^{nfull} cos(b th)
+            long double v = 1.0L + 2.0L * s;
+            if (split) v += cosl(B * th);                // 2 * (1/2) * cos(B th)
+            W[(size_t)k * h + m] = (double)(v / h);
+        }
+    return W;
+}
+}  // namespace
+
+extern "C" {
+
+static int demod_op(int device, const double *y, int R, int M, double *out, int demod)
+{
+    if (!y || !out || R < 1 || M < 1) return fail(nullptr, SDRB_ERR_ARG, "bad argument");
+    int rc = need_device(device);
+    if (rc) return rc;
     DevPlan pl{};
     pl.M = M; pl.R = R; pl.nsec_out = 0;
     const int h2 = M >> 1;
     pl.fft_ok = (M == 2 * h2) && is_pow2(h2);
     pl.fft_n = pl.fft_ok ? M : 0;
-    if (demod == SDRB_FM && !pl.fft_ok)
-        return fail(nullptr, SDRB_ERR_ARG, "fmDemod operator needs a row length of 2*2^k (got %d)", M);
+    if (demod == SDRB_FM && (M & 1))
+        return fail(nullptr, SDRB_ERR_ARG, "fmDemod pairs samples: the row length must be even (got %d)", M);
     std::vector<double2> tw = make_twiddles(pl.fft_n);
-    double2 *d_tw = nullptr, *d_y = nullptr, *d_fft = nullptr;
-    double *d_out = nullptr, *d_z = nullptr;
+    DevBuf d_tw, d_y, d_out, d_fft, d_z, d_w;
     const size_t dsm = (size_t)M * (2 * sizeof(double2) + sizeof(double));
     pl.demod_in_smem = dsm <= 48 * 1024;
-    CK(nullptr, cudaMalloc(&d_tw, tw.size() * sizeof(double2)));
-    CK(nullptr, cudaMalloc(&d_y, (size_t)R * M * sizeof(double2)));
-    CK(nullptr, cudaMalloc(&d_out, (size_t)R * M * sizeof(double)));
+    CK(nullptr, d_tw.alloc(tw.size() * sizeof(double2)));
+    CK(nullptr, d_y.alloc((size_t)R * M * sizeof(double2)));
+    CK(nullptr, d_out.alloc((size_t)R * M * sizeof(double)));
     if (!pl.demod_in_smem) {
-        CK(nullptr, cudaMalloc(&d_fft, (size_t)R * 2 * M * sizeof(double2)));
-        CK(nullptr, cudaMalloc(&d_z, (size_t)R * M * sizeof(double)));
+        CK(nullptr, d_fft.alloc((size_t)R * 2 * M * sizeof(double2)));
+        CK(nullptr, d_z.alloc((size_t)R * M * sizeof(double)));
     }
-    CK(nullptr, cudaMemcpy(d_tw, tw.data(), tw.size() * sizeof(double2), cudaMemcpyHostToDevice));
-    CK(nullptr, cudaMemcpy(d_y, y, (size_t)R * M * sizeof(double2), cudaMemcpyHostToDevice));
-    pl.tw = d_tw;
+    if (demod == SDRB_FM && !pl.fft_ok) {
+        // any even length: the same dense interpolation the engine uses for non-FFT sizes
+        const std::vector<double> W = resample_matrix(h2, M);
+        CK(nullptr, d_w.alloc(W.size() * sizeof(double)));
+        CK(nullptr, cudaMemcpy(d_w.p, W.data(), W.size() * sizeof(double), cudaMemcpyHostToDevice));
+        pl.fm_interp = d_w.as<double>();
+    }
+    CK(nullptr, cudaMemcpy(d_tw.p, tw.data(), tw.size() * sizeof(double2), cudaMemcpyHostToDevice));
+    CK(nullptr, cudaMemcpy(d_y.p, y, (size_t)R * M * sizeof(double2), cudaMemcpyHostToDevice));
+    pl.tw = d_tw.as<double2>();
     // rows are laid out [R][M]: run as R "rows" of a single chunk
-    k_demod<<<R, 128, pl.demod_in_smem ? dsm : 0>>>(pl, d_y, d_out, d_fft, d_z, 1, demod, 0, 0);
-    cudaError_t e = cudaDeviceSynchronize();
-    if (e == cudaSuccess) e = cudaMemcpy(out, d_out, (size_t)R * M * sizeof(double), cudaMemcpyDeviceToHost);
-    cudaFree(d_tw); cudaFree(d_y); cudaFree(d_out); cudaFree(d_fft); cudaFree(d_z);
-    if (e != cudaSuccess) return fail(nullptr, SDRB_ERR_CUDA, "demod operator failed: %s", cudaGetErrorString(e));
+    k_demod<<<R, 128, pl.demod_in_smem ? dsm : 0>>>(pl, d_y.as<double2>(), d_out.as<double>(), d_fft.as<double2>(),
+                                                    d_z.as<double>(), 1, demod, 0, 0);
+    CK(nullptr, cudaGetLastError());
+    CK(nullptr, cudaDeviceSynchronize());
+    CK(nullptr, cudaMemcpy(out, d_out.p, (size_t)R * M * sizeof(double), cudaMemcpyDeviceToHost));
     return SDRB_OK;
 }
 
@@ -798,21 +869,93 @@ int sdrb_imag_output(int device, const double *y, int R, int M, double *out) { r
 int sdrb_shift_freq(int device, const double *y, const double *shift, int R, int N, double *res)
 {
     if (!y || !shift || !res || R < 1 || N < 1) return fail(nullptr, SDRB_ERR_ARG, "bad argument");
-    int ndev = 0;
-    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
-        return fail(nullptr, SDRB_ERR_CUDA, "no CUDA device: libsdrterm_b200 has no CPU fallback");
-    CK(nullptr, cudaSetDevice(device));
-    double2 *d_y = nullptr, *d_s = nullptr, *d_r = nullptr;
-    CK(nullptr, cudaMalloc(&d_y, (size_t)N * sizeof(double2)));
-    CK(nullptr, cudaMalloc(&d_s, (size_t)R * N * sizeof(double2)));
-    CK(nullptr, cudaMalloc(&d_r, (size_t)R * N * sizeof(double2)));
-    CK(nullptr, cudaMemcpy(d_y, y, (size_t)N * sizeof(double2), cudaMemcpyHostToDevice));
-    CK(nullptr, cudaMemcpy(d_s, shift, (size_t)R * N * sizeof(double2), cudaMemcpyHostToDevice));
-    k_shift<<<148 * 4, 256>>>(d_y, d_s, d_r, R, N);
-    cudaError_t e = cudaDeviceSynchronize();
-    if (e == cudaSuccess) e = cudaMemcpy(res, d_r, (size_t)R * N * sizeof(double2), cudaMemcpyDeviceToHost);
-    cudaFree(d_y); cudaFree(d_s); cudaFree(d_r);
-    if (e != cudaSuccess) return fail(nullptr, SDRB_ERR_CUDA, "shiftFreq operator failed: %s", cudaGetErrorString(e));
+    int rc = need_device(device);
+    if (rc) return rc;
+    DevBuf d_y, d_s, d_r;
+    CK(nullptr, d_y.alloc((size_t)N * sizeof(double2)));
+    CK(nullptr, d_s.alloc((size_t)R * N * sizeof(double2)));
+    CK(nullptr, d_r.alloc((size_t)R * N * sizeof(double2)));
+    CK(nullptr, cudaMemcpy(d_y.p, y, (size_t)N * sizeof(double2), cudaMemcpyHostToDevice));
+    CK(nullptr, cudaMemcpy(d_s.p, shift, (size_t)R * N * sizeof(double2), cudaMemcpyHostToDevice));
+    k_shift<<<148 * 4, 256>>>(d_y.as<double2>(), d_s.as<double2>(), d_r.as<double2>(), R, N);
+    CK(nullptr, cudaGetLastError());
+    CK(nullptr, cudaDeviceSynchronize());
+    CK(nullptr, cudaMemcpy(res, d_r.p, (size_t)R * N * sizeof(double2), cudaMemcpyDeviceToHost));
+    return SDRB_OK;
+}
+
+int sdrb_decode_iq(int device, const void *raw, size_t nsamples, char enc, int swap, double *z_out)
+{
+    const int code = enc_code_of(enc);
+    if (!raw || !z_out || code < 0 || code == ENC_Z) return fail(nullptr, SDRB_ERR_ARG, "bad argument");
+    if (nsamples == 0) return SDRB_OK;
+    int rc = need_device(device);
+    if (rc) return rc;
+    const size_t nbytes = nsamples * 2 * (size_t)itemsize_of(code);
+    DevBuf d_raw, d_z;
+    CK(nullptr, d_raw.alloc(nbytes));
+    CK(nullptr, d_z.alloc(nsamples * sizeof(double2)));
+    CK(nullptr, cudaMemcpy(d_raw.p, raw, nbytes, cudaMemcpyHostToDevice));
+    const unsigned grid = (unsigned)std::min<size_t>((nsamples + 255) / 256, 148 * 8);
+    const uint8_t *r8 = d_raw.as<uint8_t>();
+    double2 *z = d_z.as<double2>();
+    switch (code) {
+    case ENC_b: k_decode<ENC_b><<<grid, 256>>>(r8, z, nsamples, swap); break;
+    case ENC_B: k_decode<ENC_B><<<grid, 256>>>(r8, z, nsamples, swap); break;
+    case ENC_h: k_decode<ENC_h><<<grid, 256>>>(r8, z, nsamples, swap); break;
+    case ENC_H: k_decode<ENC_H><<<grid, 256>>>(r8, z, nsamples, swap); break;
+    case ENC_i: k_decode<ENC_i><<<grid, 256>>>(r8, z, nsamples, swap); break;
+    case ENC_I: k_decode<ENC_I><<<grid, 256>>>(r8, z, nsamples, swap); break;
+    case ENC_f: k_decode<ENC_f><<<grid, 256>>>(r8, z, nsamples, swap); break;
+    default:    k_decode<ENC_d><<<grid, 256>>>(r8, z, nsamples, swap); break;
+    }
+    CK(nullptr, cudaGetLastError());
+    CK(nullptr, cudaDeviceSynchronize());
+    CK(nullptr, cudaMemcpy(z_out, d_z.p, nsamples * sizeof(double2), cudaMemcpyDeviceToHost));
+    return SDRB_OK;
+}
+
+int sdrb_correct_iq(int device, double *z_inout, size_t nsamples, double off_inout[2], double L)
+{
+    if (!z_inout || !off_inout) return fail(nullptr, SDRB_ERR_ARG, "null argument");
+    if (nsamples == 0) return SDRB_OK;
+    int rc = need_device(device);
+    if (rc) return rc;
+    DevBuf d_z, d_off;
+    CK(nullptr, d_z.alloc(nsamples * sizeof(double2)));
+    CK(nullptr, d_off.alloc(sizeof(double2)));
+    CK(nullptr, cudaMemcpy(d_z.p, z_inout, nsamples * sizeof(double2), cudaMemcpyHostToDevice));
+    CK(nullptr, cudaMemcpy(d_off.p, off_inout, sizeof(double2), cudaMemcpyHostToDevice));
+    k_correct_iq<<<1, 1024>>>(d_z.as<double2>(), nsamples, d_off.as<double2>(), L);
+    CK(nullptr, cudaGetLastError());
+    CK(nullptr, cudaDeviceSynchronize());
+    CK(nullptr, cudaMemcpy(z_inout, d_z.p, nsamples * sizeof(double2), cudaMemcpyDeviceToHost));
+    CK(nullptr, cudaMemcpy(off_inout, d_off.p, sizeof(double2), cudaMemcpyDeviceToHost));
+    return SDRB_OK;
+}
+
+int sdrb_keep_x0(sdrb_handle *h, int on)
+{
+    if (!h) return fail(h, SDRB_ERR_ARG, "null argument");
+    if (!h->tc_on) return fail(h, SDRB_ERR_STATE, "block first samples exist only on the tensor-core front end");
+    CK(h, cudaSetDevice(h->cfg.device));
+    CK(h, cudaDeviceSynchronize());
+    if (on && !h->x0_buf) {
+        int rc = dalloc(h, h->max_chunks * (size_t)h->pl.R * h->pl.Mf, &h->x0_buf);
+        if (rc) return rc;
+    }
+    h->sc.x0 = on ? h->x0_buf : nullptr;
+    return SDRB_OK;
+}
+
+int sdrb_read_x0(sdrb_handle *h, size_t nchunks, double *x0_host)
+{
+    if (!h || !x0_host) return fail(h, SDRB_ERR_ARG, "null argument");
+    if (!h->sc.x0) return fail(h, SDRB_ERR_STATE, "block first samples not kept: call sdrb_keep_x0(h, 1) first");
+    if (nchunks > h->last_nchunks) return fail(h, SDRB_ERR_STATE, "only %zu chunks in the last batch", h->last_nchunks);
+    CK(h, cudaSetDevice(h->cfg.device));
+    CK(h, cudaDeviceSynchronize());
+    CK(h, cudaMemcpy(x0_host, h->sc.x0, nchunks * (size_t)h->pl.R * h->pl.Mf * sizeof(double2), cudaMemcpyDeviceToHost));
     return SDRB_OK;
 }
 

@@ -118,7 +118,7 @@ k_finish(const __grid_constant__ DevPlan pl, const __grid_constant__ Scratch sc,
     }
     const int i8 = lane & 7, grp = (lane >> 3) & 1, sub = lane >> 3;
     const double2 p_i = pl.p[i8], P32 = pl.Ppow[(size_t)SDRB_TB * 8 + i8];
-    const int Ls = pl.sos_Lseg, lsh = 31 - __clz(Ls);
+    const int Ls = pl.sos_Lseg, lsh = Ls > 0 ? 31 - __clz(Ls) : 31;   // no output SOS (re/im): no padding
     const int dchunk = (edge + 3) >> 2;                                  // dot-product terms per lane group
     const double lamn = pl.lam_pw[lane], mun = pl.mu_pw[min(32, max(0, edge + 1 - lane))];
 

@@ -29,6 +29,8 @@ struct Scratch {
     double2 *fftbuf;    // [nch*R][2][M] when the demod buffers do not fit shared memory
     double *zrow;       // [nch*R][M]     "
     unsigned long long *dbg;  // optional k_tc timeline (SDRB_TC_DEBUG): [64 tiles][16 events] clock64 of CTA 0
+    double2 *x0;        // optional [nch][R][Mf]: first raw sample of every block as the tensor-core
+                        // front end sees it (exact integers; sdrb_keep_x0, parity tests)
 };
 
 // Shared-memory carve-up of k_main (host mirrors this in sdrb_api.cu: main_smem_bytes()).
@@ -836,4 +838,71 @@ __global__ void k_shift(const double2 *__restrict__ y, const double2 *__restrict
         res[idx] = make_double2(__dadd_rn(__dmul_rn(a.x, b.x), -__dmul_rn(a.y, b.y)),
                                 __dadd_rn(__dmul_rn(a.x, b.y), __dmul_rn(a.y, b.x)));
     }
+}
+
+// read_file.py:100-101  z = y['re'] + 1j*y['im'] on the structured view of the raw bytes.
+template <int ENC>
+__global__ void k_decode(const uint8_t *__restrict__ raw, double2 *__restrict__ z, size_t n, int swap)
+{
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        z[i] = load_sample<ENC>(raw, (long)i, swap);
+}
+
+// read_file.py:65-77 / extra/src/iq_correction.pyx:46-52: z[i] -= off; off += z[i] * L, as the
+// linear recurrence off' = lam off + L z evaluated by one CTA: thread <-> contiguous run, affine
+// maps scanned across the threads, second pass applies the offsets.
+__global__ void __launch_bounds__(1024)
+k_correct_iq(double2 *__restrict__ z, size_t n, double2 *__restrict__ off_io, double L)
+{
+    __shared__ double2 s_a[32];
+    __shared__ double s_m[32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const double lam = 1.0 - L;
+    const size_t per = (n + blockDim.x - 1) / blockDim.x;
+    const size_t i0 = min(n, (size_t)tid * per), i1 = min(n, i0 + per);
+    double2 a = make_double2(0.0, 0.0);
+    double m = 1.0;
+    for (size_t i = i0; i < i1; i++) {
+        const double2 v = z[i];
+        a.x = fma(lam, a.x, L * v.x); a.y = fma(lam, a.y, L * v.y);
+        m *= lam;
+    }
+#pragma unroll
+    for (int lv = 0; lv < 5; lv++) {
+        const double pm = __shfl_up_sync(0xffffffffu, m, 1 << lv);
+        const double2 pa = shfl_up_c(a, 1 << lv);
+        if (lane >= (1 << lv)) { a.x = fma(m, pa.x, a.x); a.y = fma(m, pa.y, a.y); m *= pm; }
+    }
+    if (lane == 31) { s_a[warp] = a; s_m[warp] = m; }
+    __syncthreads();
+    if (warp == 0) {
+        double wm = s_m[lane];
+        double2 wa = s_a[lane];
+#pragma unroll
+        for (int lv = 0; lv < 5; lv++) {
+            const double pm = __shfl_up_sync(0xffffffffu, wm, 1 << lv);
+            const double2 pa = shfl_up_c(wa, 1 << lv);
+            if (lane >= (1 << lv)) { wa.x = fma(wm, pa.x, wa.x); wa.y = fma(wm, pa.y, wa.y); wm *= pm; }
+        }
+        s_a[lane] = wa; s_m[lane] = wm;
+    }
+    __syncthreads();
+    double em = __shfl_up_sync(0xffffffffu, m, 1);
+    double2 ea = shfl_up_c(a, 1);
+    if (lane == 0) { em = 1.0; ea = make_double2(0.0, 0.0); }
+    if (warp > 0) {
+        const double wm = s_m[warp - 1];
+        const double2 wa = s_a[warp - 1];
+        ea.x = fma(em, wa.x, ea.x); ea.y = fma(em, wa.y, ea.y); em *= wm;
+    }
+    const double2 st0 = off_io[0];
+    double2 o = make_double2(fma(em, st0.x, ea.x), fma(em, st0.y, ea.y));
+    for (size_t i = i0; i < i1; i++) {
+        double2 v = z[i];
+        v.x -= o.x; v.y -= o.y;
+        o.x = fma(v.x, L, o.x); o.y = fma(v.y, L, o.y);
+        z[i] = v;
+    }
+    __syncthreads();
+    if (tid == blockDim.x - 1) off_io[0] = o;
 }

@@ -274,6 +274,7 @@ __device__ __forceinline__ void tc_epilogue(const DevPlan &pl, const TcDev &tc, 
                     xr = (int)ce[2 * NCOL]; xi = (int)ce[2 * NCOL + 1];
                 }
                 x0 = make_double2(i32_biased(xr) + tc.cstb[r][34], i32_biased(xi) + tc.cstb[r][35]);
+                if (sc.x0) sc.x0[((size_t)chunk * pl.R + r) * pl.Mf + (size_t)t * SDRB_TB + lane] = x0;
             }
             if (IQ) {
                 const double er = tc_combine<NCOL>(ce, s16, s1, tc.cstb[r][32]);

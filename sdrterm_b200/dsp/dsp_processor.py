@@ -16,6 +16,7 @@ Differences that matter to a caller:
 from __future__ import annotations
 
 import queue as _queue
+import sys
 from sys import stdout
 from typing import Any, Callable
 
@@ -146,13 +147,20 @@ class DspProcessor(DataProcessor):
             enc, swap, ciq, norm = 'Z', False, False, False       # producer already did these
             chunk_bytes = first.size * 16
         else:
-            enc = self._enc
-            if enc is None and self.__fileInfo is not None:
-                enc = np.dtype(self.__fileInfo['bitsPerSample']).char
-                self._swap ^= np.dtype(self.__fileInfo['bitsPerSample']).byteorder == '>'
+            # the header (or host:port => network order) decides dtype and byte order whenever
+            # fileInfo is present, exactly as the reference's reader does (read_file.py:46-49 uses
+            # fileInfo['bitsPerSample'], never -e); -X flips whatever order that is
+            swap = self._swap
+            if self.__fileInfo is not None:
+                dt = np.dtype(self.__fileInfo['bitsPerSample'])
+                enc = dt.char
+                big = dt.byteorder == '>' or (dt.byteorder == '=' and sys.byteorder == 'big')
+                swap = bool(swap) ^ bool(big and dt.itemsize > 1)
+            else:
+                enc = self._enc
             if enc is None:
                 raise ValueError('raw chunks need the sample encoding (enc=... or fileInfo)')
-            swap, ciq, norm = self._swap, self._correctIq, self._normalize
+            ciq, norm = self._correctIq, self._normalize
             chunk_bytes = len(first) if not isinstance(first, np.ndarray) else first.nbytes
         plan = build_plan(self.__fs, enc, self._decimationFactor, self._rowsHz(), simo=self._simo(),
                           swap=swap, correct_iq=ciq, normalize=norm, demod=self._demodName(),
@@ -220,7 +228,9 @@ class DspProcessor(DataProcessor):
 
     def __repr__(self):
         from json import dumps
-        d = {k: v for k, v in self.__dict__.items()
+        # keys lose a trailing 'Str' (vfosStr -> "vfos", the CSV example_simo.sh scrapes; the array
+        # of the same name is skipped), dsp_processor.py:206-217
+        d = {(k[:-3] if 'Str' in k else k): v for k, v in self.__dict__.items()
              if not (v is None or k.startswith('_') or callable(v) or isinstance(v, np.ndarray))}
         if self.__fileInfo is not None:
             d['encoding'] = str(self.__fileInfo.get('bitsPerSample'))

@@ -5,6 +5,7 @@ from __future__ import annotations
 
 import queue as _queue
 import socket
+import sys
 from socketserver import BaseRequestHandler, TCPServer, ThreadingMixIn
 from threading import Event, Thread
 
@@ -60,6 +61,8 @@ class VfoProcessor(DspProcessor):
             for i in range(self._nFreq):
                 self._rowQueue.put(i)
             self._rowQueue.join()
+            # example_simo.sh waits for this line before it starts the stream (:165-170)
+            print('Connection(s) established', file=sys.stderr, flush=True)
 
     def _emit(self, out: np.ndarray, nchunks: int, file) -> None:
         """Row r goes to client r; ``out`` rows already hold big-endian doubles (:84)."""
@@ -87,8 +90,7 @@ class VfoProcessor(DspProcessor):
         with _Server((self.host, self.port), Handler) as server:
             th = Thread(target=server.serve_forever, daemon=True)
             try:
-                from sys import stderr
-                print(f'\nAccepting connections on {server.socket.getsockname()}\n', file=stderr)
+                print(f'\nAccepting connections on {server.socket.getsockname()}\n', file=sys.stderr, flush=True)
                 th.start()
                 self._processData(isDead, buffer)
             except KeyboardInterrupt:

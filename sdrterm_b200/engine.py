@@ -20,7 +20,7 @@ def _dp(a: np.ndarray):
 
 class Engine:
     def __init__(self, plan: Plan, max_chunks: int = 256, device: int = 0, use_tc: bool = True,
-                 keep_decimated: bool = False):
+                 keep_decimated: bool = False, keep_x0: bool = False):
         self.plan = plan
         self.max_chunks = int(max_chunks)
         self.device = int(device)
@@ -95,6 +95,8 @@ class Engine:
         self.M = int(L.sdrb_outputs_per_chunk(self._h))
         if keep_decimated:
             nat.check(L.sdrb_keep_decimated(self._h, 1), self._h)
+        if keep_x0:
+            nat.check(L.sdrb_keep_x0(self._h, 1), self._h)
         self.chunk_bytes = int(L.sdrb_chunk_bytes(self._h))
         self.R = pl.R
 
@@ -173,6 +175,13 @@ class Engine:
         y = np.empty((nchunks, self.R, self.M), dtype=np.complex128)
         nat.check(nat.lib().sdrb_read_decimated(self._h, nchunks, y.ctypes.data), self._h)
         return y
+
+    def block_first_samples(self, nchunks: int) -> np.ndarray:
+        """First raw sample of every block of the last batch as the tensor-core front end decoded it
+        (exact): (nchunks, R, N // q) complex."""
+        x0 = np.empty((nchunks, self.R, self.plan.Mf), dtype=np.complex128)
+        nat.check(nat.lib().sdrb_read_x0(self._h, nchunks, x0.ctypes.data), self._h)
+        return x0
 
     @property
     def iq_state(self) -> complex:

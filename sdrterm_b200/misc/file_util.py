@@ -1,26 +1,78 @@
 """Input description: encoding letter -> numpy dtype, RIFF/RIFX header -> dtype, rate and data
 offset (reference: src/misc/file_util.py:46-195).  Returns the same ``fileInfo`` dictionary keys
 the reference's processors and reader consume (``bitsPerSample``, ``sampRate``, ``dataOffset``,
-``isSocket``)."""
+``isSocket``), and exposes the same public types (``DataType``, ``WaveFormat``, ``ExWaveFormat``)."""
 from __future__ import annotations
 
 import struct
+from enum import Enum
 
 import numpy as np
 
-# file_util.py:46-60: single bytes have no order, the rest are native for files
-ENCODINGS = {'b': '|i1', 'B': '|u1', 'h': '=i2', 'H': '=u2', 'i': '=i4', 'I': '=u4', 'f': '=f4', 'd': '=f8'}
-_WAVE_PCM, _WAVE_FLOAT, _WAVE_EXT = 0x0001, 0x0003, 0xFFFE
-_EX_SIGNED = {0x01: True, 0x02: True, 0x05: False, 0x06: False}        # PCM_S_LE/BE, PCM_U_LE/BE
-_EX_BIG = {0x01: False, 0x02: True, 0x05: False, 0x06: True}
+from .mappable_enum import MappableEnum
+
+
+class WaveFormat(Enum):
+    """``wFormatTag`` values the header parser knows (file_util.py:29-34)."""
+    WAVE_FORMAT_PCM = 0x0001
+    WAVE_FORMAT_IEEE_FLOAT = 0x0003
+    WAVE_FORMAT_ALAW = 0x0006
+    WAVE_FORMAT_MULAW = 0x0007
+    WAVE_FORMAT_EXTENSIBLE = 0xFFFE
+
+
+class ExWaveFormat(Enum):
+    """SubFormat codes of WAVE_FORMAT_EXTENSIBLE (file_util.py:37-43): signedness and byte order."""
+    PCM_S_LE = 0x01
+    PCM_S_BE = 0x02
+    PCM_U_LE = 0x05
+    PCM_U_BE = 0x06
+
+
+class DataType(MappableEnum):
+    """``-e`` letters -> numpy dtype (file_util.py:46-60): single bytes have no order, the rest are
+    native-endian for files; ``str(member)`` is the letter."""
+    b = np.dtype('|i1')
+    B = np.dtype('|u1')
+    h = np.dtype('=i2')
+    H = np.dtype('=u2')
+    i = np.dtype('=i4')
+    I = np.dtype('=u4')  # noqa: E741
+    f = np.dtype('=f4')
+    d = np.dtype('=f8')
+
+    def __str__(self):
+        return self.name
+
+    @classmethod
+    def fromWav(cls, bits: int, aFormat: Enum, bFormat: Enum | None, isRifx: bool) -> np.dtype:
+        """Header fields -> dtype with explicit byte order (file_util.py:62-97).  PCM without a
+        SubFormat: 8 bits unsigned, wider signed; the SubFormat of an extensible header decides
+        signedness and may force big-endian; RIFX forces big-endian."""
+        member, big = None, bool(isRifx)
+        if aFormat == WaveFormat.WAVE_FORMAT_IEEE_FLOAT:
+            member = {32: cls.f, 64: cls.d}.get(bits)
+        elif aFormat in (WaveFormat.WAVE_FORMAT_PCM, WaveFormat.WAVE_FORMAT_EXTENSIBLE):
+            kind = None
+            if isinstance(bFormat, ExWaveFormat):
+                _, kind, order = bFormat.name.split('_')
+                big = big or order == 'BE'
+            table = {8: {'S': cls.b, 'U': cls.B, None: cls.B},
+                     16: {'S': cls.h, 'U': cls.H, None: cls.h},
+                     32: {'S': cls.i, 'U': cls.I, None: cls.i}}.get(bits)
+            member = table[kind] if table is not None else None
+        if member is None:
+            raise ValueError(f'Unsupported format: {aFormat} @ {bits} bits')
+        return member.value.newbyteorder('>' if big else '<')
+
+
+ENCODINGS = {m.name: m.value.str for m in DataType}
 _GUID_TAIL = b'\x00\x00\x00\x00\x10\x00\x80\x00\x00\xAA\x00\x38\x9B\x71'
 
 
 def dtypeOf(enc: str) -> np.dtype:
-    try:
-        return np.dtype(ENCODINGS[enc])
-    except KeyError:
-        raise ValueError(f'unknown encoding {enc!r}; one of {"|".join(ENCODINGS)}') from None
+    """``DataType[enc].value``; an unknown letter is a ``KeyError`` as in the reference."""
+    return DataType[enc].value
 
 
 def parseRawType(file: str | None, fs: int | None, enc: str | None, isSocket: bool = False) -> dict:
@@ -34,26 +86,6 @@ def parseRawType(file: str | None, fs: int | None, enc: str | None, isSocket: bo
     return {'subchunk1Size': 0, 'audioFormat': 0, 'numChannels': 0, 'sampRate': int(fs),
             'byteRate': int(fs), 'blockAlign': 0, 'bitsPerSample': dt, 'dataOffset': 0,
             'isSocket': isSocket}
-
-
-def _wavDtype(bits: int, fmt: int, sub: int | None, rifx: bool) -> np.dtype:
-    big = rifx
-    if fmt == _WAVE_FLOAT:
-        ch = {32: 'f4', 64: 'f8'}.get(bits)
-    elif fmt in (_WAVE_PCM, _WAVE_EXT):
-        signed = None
-        if sub is not None and sub in _EX_SIGNED:
-            signed, big = _EX_SIGNED[sub], rifx or _EX_BIG[sub]
-        if signed is None:
-            signed = bits != 8                                         # 8-bit PCM is unsigned (:66-68)
-        ch = {8: 'i1', 16: 'i2', 32: 'i4'}.get(bits)
-        if ch is not None and not signed:
-            ch = 'u' + ch[1:]
-    else:
-        ch = None
-    if ch is None:
-        raise ValueError(f'Unsupported format: {fmt:#x} @ {bits} bits')
-    return np.dtype(('>' if big else '<') + ch)
 
 
 def checkWavHeader(f, fs: int | None, enc: str | None) -> dict:
@@ -85,16 +117,17 @@ def checkWavHeader(f, fs: int | None, enc: str | None) -> dict:
             raise ValueError('Invalid: Format section not found')
         size, fmt, nch, rate, brate, align, bits = struct.unpack(e + 'IHHIIHH', fh.read(20))
         sub = None
-        if fmt == _WAVE_EXT:
+        if fmt == WaveFormat.WAVE_FORMAT_EXTENSIBLE.value:
             extra, = struct.unpack(e + 'H', fh.read(2))
             fh.read(extra - 16)
-            sub, = struct.unpack(e + 'H', fh.read(2))
+            code, = struct.unpack(e + 'H', fh.read(2))
             if fh.read(14) != _GUID_TAIL:
                 raise ValueError('Invalid: SubFormat GUID malformed')
+            sub = ExWaveFormat(code)                       # unknown codes: ValueError
         info = {'subchunk1Size': size, 'audioFormat': fmt, 'numChannels': nch, 'sampRate': rate,
                 'byteRate': brate, 'blockAlign': align,
-                'bitsPerSample': _wavDtype(bits, fmt, sub, e == '>'), 'isSocket': False,
-                'bitRate': (bits * brate * align) >> 3}
+                'bitsPerSample': DataType.fromWav(bits, WaveFormat(fmt), sub, e == '>'),
+                'isSocket': False, 'bitRate': (bits * brate * align) >> 3}
         pos = fh.tell()
         rest = fh.read(4096)
         k = rest.find(b'data')

@@ -26,6 +26,22 @@ def generateDomain(dataType: str):
     return dom[0], 1 / (-dom[0] + dom[1])
 
 
+def decodeIq(raw, enc: str, swap: bool = False, device: int = 0) -> np.ndarray:
+    """The decode step of the reference's ``feedBuffers`` on its own (read_file.py:100-101:
+    ``y['re'] + 1j*y['im']`` on the ``[('re',T),('im',T)]`` view), run on the device:
+    raw bytes of encoding ``enc`` -> complex128, bit-exact.  ``swap``: stored big-endian."""
+    from .. import _native as nat
+    buf = np.frombuffer(raw, dtype=np.uint8) if not isinstance(raw, np.ndarray) else raw.view(np.uint8).reshape(-1)
+    buf = np.ascontiguousarray(buf)
+    isz = {'b': 1, 'B': 1, 'h': 2, 'H': 2, 'i': 4, 'I': 4, 'f': 4, 'd': 8}[enc]
+    n, r = divmod(buf.size, 2 * isz)
+    if r:
+        raise ValueError(f'{buf.size} bytes are not a whole number of {enc!r} IQ samples')
+    z = np.empty(n, dtype=np.complex128)
+    nat.check(nat.lib().sdrb_decode_iq(device, buf.ctypes.data, n, enc.encode(), int(bool(swap)), z.ctypes.data))
+    return z
+
+
 def chunks(reader, readSize: int = READ_SIZE, isDead=None):
     """Yield whole chunks exactly as the reference's reader presents them: ``readinto`` a reused
     buffer; a short read leaves the previous chunk's tail in place and the whole buffer counts."""

@@ -69,8 +69,7 @@ def main(argv=None) -> int:
     a = buildParser().parse_args(argv)
     fileInfo = checkWavHeader(a.inFile, a.fs, a.enc)           # a WAV header overrides -r / -e
     proc = makeProcessor(a, fileInfo)
-    if a.verbose:
-        print(repr(proc), file=sys.stderr)
+    print(repr(proc), file=sys.stderr, flush=True)          # unconditional: src/sdrterm.py:144
     isDead = _Flag()
     buf = queue.Queue(maxsize=256)
     reader = threading.Thread(target=readFile, daemon=True,

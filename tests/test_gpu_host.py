@@ -150,3 +150,111 @@ def test_module_operators_known_answers():
     assert np.max(np.abs(res - y * sh)) < 1e-15
     with pytest.raises(ValueError):
         dem.amDemod(inp, np.empty((2, 8)))
+
+
+def test_fm_demod_operator_takes_any_even_length():
+    """demodulation.py:35-38 resamples for any n; rows of 2*2^k take the FFT path, everything else
+    the dense resample matrix."""
+    import sdrterm_b200.dsp.demodulation as dem
+    rng = np.random.default_rng(3)
+    for n in (6, 10, 24, 100, 1310, 512):
+        y = rng.normal(size=(2, n)) + 1j * rng.normal(size=(2, n))
+        out = np.empty((2, n))
+        dem.fmDemod(y, out)
+        ref = np.stack([resample(np.angle(r[0::2] * np.conj(r[1::2])), n) for r in y])
+        assert np.max(np.abs(out - ref)) < 1e-11, n
+    with pytest.raises(Exception):
+        dem.fmDemod(rng.normal(size=(1, 7)) + 0j, np.empty((1, 7)))
+
+
+def test_iq_correction_plugin_matches_the_serial_recurrence():
+    """dsp.fast.iq_correction.IQCorrection.correctIq vs the loop of read_file.py:72-77, state
+    carried across calls (the reference's own test allows 10E-2; here 1e-12 relative)."""
+    from sdrterm_b200.dsp.fast.iq_correction import IQCorrection
+    rng = np.random.default_rng(8)
+    fs = 1_024_000
+    c = IQCorrection(fs)
+    off = np.zeros(1, dtype=np.complex128)
+    roff = 0j
+    L = 50 / fs
+    for n in (32768, 1000, 65536):
+        z = (rng.normal(size=n) * 8000 + 37) + 1j * (rng.normal(size=n) * 8000 - 21)
+        ref = z.copy()
+        for i in range(n):
+            ref[i] -= roff
+            roff += ref[i] * L
+        c.correctIq(z, off)
+        assert np.max(np.abs(z - ref)) <= 1e-12 * np.max(np.abs(ref))
+        assert abs(off[0] - roff) <= 1e-12 * max(1.0, abs(roff))
+
+
+def test_cli_simo_prints_the_lines_example_simo_scrapes(tmp_path):
+    """example_simo.sh reads stderr for the repr JSON keys (host, vfos, tunedFreq, decimatedFs),
+    then `Accepting connections on ('<ip>', <port>)`, attaches one client per row and waits for
+    `Connection(s) established` (example_simo.sh:96-118,165-170; src/sdrterm.py:144,
+    vfo_processor.py:78,110).  Run the drop-in CLI as a subprocess the same way."""
+    import json
+    import os
+    import re
+    import subprocess
+    import sys
+    import time
+    import signals
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    body, vfos = signals.c3_bytes(2 * 32768, seed=3)
+    vf = vfos.split(',')[:2]
+    fin = tmp_path / 'in.raw'
+    fin.write_bytes(body)
+    with socket.socket() as s:
+        s.bind(('127.0.0.1', 0))
+        port = s.getsockname()[1]
+    env = dict(os.environ, PYTHONPATH=os.path.join(root, 'src'))
+    proc = subprocess.Popen([sys.executable, '-m', 'sdrterm', '-i', str(fin), '-r', '2400k', '-e', 'h', '-X', '-d', '64',
+                             '-w', '5k', '--simo', f'--vfos={",".join(vf)}', '--vfo-host', f'127.0.0.1:{port}',
+                             '-t', '155685000'],
+                            env=env, cwd=str(tmp_path), stderr=subprocess.PIPE, text=True)
+    lines = []
+    deadline = time.time() + 120
+    while time.time() < deadline:
+        line = proc.stderr.readline()
+        if not line:
+            break
+        lines.append(line)
+        if 'Accepting' in line:
+            break
+    head = ''.join(lines)
+    m = re.search(r"Accepting connections on \('127\.0\.0\.1', (\d+)\)", head)
+    assert m and int(m.group(1)) == port, head
+    d = json.loads(head[head.index('{'):head.rindex('}') + 1])
+    assert d['vfos'] == ','.join(vf) + ',0' and d['host'] == '127.0.0.1' and d['tunedFreq'] == 155685000
+    assert d['decimatedFs'] == 2_400_000 // 64
+    got = {}
+
+    def client(i):
+        c = socket.create_connection(('127.0.0.1', port), timeout=30)
+        buf = b''
+        while True:
+            dta = c.recv(1 << 16)
+            if not dta:
+                break
+            buf += dta
+        got[i] = np.frombuffer(buf[:len(buf) // 8 * 8], dtype='>f8')
+        c.close()
+
+    cl = [threading.Thread(target=client, args=(i,), daemon=True) for i in range(3)]
+    for t in cl:
+        t.start()
+    rest = proc.stderr.read()
+    proc.wait(120)
+    for t in cl:
+        t.join(30)
+    assert 'Connection(s) established' in rest, rest
+    assert proc.returncode == 0
+    kw = dict(fs=2_400_000, enc='h', center=0, dec=64, demod='fm', omega_out=5000, correct_iq=False,
+              vfos=','.join(vf), simo=True, normalize=False, swap=True, big_endian=None)
+    ref = orc.Chain(**kw).run(body)
+    rows = [np.asarray(ref[r], dtype=np.float64) for r in range(3)]
+    assert len(got) == 3
+    for i in range(3):
+        assert got[i].shape == rows[0].shape
+        assert min(rel_err(got[i], r) for r in rows) < TOL

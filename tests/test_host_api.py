@@ -185,3 +185,114 @@ def test_reference_import_names_resolve_to_this_build():
         sys.path.remove(os.path.join(ROOT, 'src'))
         for k in [k for k in sys.modules if k in ('dsp', 'misc', 'sdrterm') or k.startswith(('dsp.', 'misc.'))]:
             del sys.modules[k]
+
+
+def test_datatype_enum_and_from_wav():
+    """file_util.py:46-97: the public types the reference's own test/misc/file_util_test.py imports."""
+    from sdrterm_b200.misc.file_util import DataType, ExWaveFormat, WaveFormat
+    from sdrterm_b200.misc.mappable_enum import MappableEnum
+    assert [m.name for m in DataType] == list('bBhHiIfd')
+    assert str(DataType.h) == 'h' and DataType['H'].value == np.dtype('=u2')
+    assert DataType.dict()['f'] == np.dtype('=f4') and DataType.tuples()[0] == ('b', np.dtype('|i1'))
+    assert MappableEnum.dict() == {} and MappableEnum.tuples() == ()
+    fw = DataType.fromWav
+    assert fw(8, WaveFormat.WAVE_FORMAT_PCM, None, False) == np.dtype('u1')
+    assert fw(16, WaveFormat.WAVE_FORMAT_PCM, None, False) == np.dtype('<i2')
+    assert fw(16, WaveFormat.WAVE_FORMAT_PCM, None, True) == np.dtype('>i2')
+    assert fw(32, WaveFormat.WAVE_FORMAT_EXTENSIBLE, ExWaveFormat.PCM_U_BE, False) == np.dtype('>u4')
+    assert fw(8, WaveFormat.WAVE_FORMAT_EXTENSIBLE, ExWaveFormat.PCM_S_LE, False) == np.dtype('i1')
+    assert fw(64, WaveFormat.WAVE_FORMAT_IEEE_FLOAT, None, True) == np.dtype('>f8')
+    for bad in ((24, WaveFormat.WAVE_FORMAT_PCM), (16, WaveFormat.WAVE_FORMAT_IEEE_FLOAT), (8, WaveFormat.WAVE_FORMAT_ALAW)):
+        with pytest.raises(ValueError):
+            fw(bad[0], bad[1], None, False)
+    with pytest.raises(KeyError):
+        file_util.checkWavHeader(None, 8000, 'q')
+    with pytest.raises(TypeError):
+        file_util.checkWavHeader(None, '2', 'B')
+
+
+def test_repr_json_carries_the_keys_example_simo_scrapes():
+    """example_simo.sh:96-118 greps "host", "vfos" (the CSV, not the array), "tunedFreq" and
+    "decimatedFs" out of repr(processor) (dsp_processor.py:206-217 strips the 'Str' of vfosStr)."""
+    import json
+    p = VfoProcessor(2_400_000, vfoHost='localhost:9123', vfos='-100000,25000', center=-350000, tuned=155685000,
+                     dec=64, omegaOut=5000, fileInfo={'bitsPerSample': np.dtype('>i2')})
+    p.selectOutputFm()
+    d = json.loads(repr(p))
+    assert d['vfos'] == '-100000,25000,0' and 'vfosStr' not in d
+    assert d['host'] == 'localhost' and d['port'] == 9123
+    assert d['tunedFreq'] == 155685000 and d['decimatedFs'] == 2_400_000 // 64 and d['fs'] == 2_400_000
+    assert d['encoding'] == '>i2' or d['encoding'] == 'int16' or 'i2' in d['encoding']
+    q = dsp.DspProcessor(1_024_000, center=15000, dec=64, omegaOut=5000)
+    dq = json.loads(repr(q))
+    assert dq['centerFreq'] == 15000 and dq['decimatedFs'] == 16000
+
+
+class _FakeEngine:
+    made = []
+
+    def __init__(self, plan, **kw):
+        _FakeEngine.made.append(plan)
+
+    def close(self):
+        pass
+
+
+def test_file_info_decides_dtype_and_byte_order_even_when_enc_is_passed(monkeypatch):
+    """IOArgs hands the processor both -e and fileInfo (io_args.py:81-82,111-117); the reader uses
+    fileInfo['bitsPerSample'] only (read_file.py:46-49): a WAV header overrides -e, host:port input
+    is big-endian, -X flips whatever that is."""
+    import sdrterm_b200.engine as engine_mod
+    monkeypatch.setattr(engine_mod, 'Engine', _FakeEngine)
+    raw = bytes(131072)
+
+    def plan_of(**kw):
+        _FakeEngine.made.clear()
+        p = dsp.DspProcessor(1_000_000, dec=64, omegaOut=5000, **kw)
+        p.selectOutputFm()
+        p._makeEngine(raw)
+        return _FakeEngine.made[0]
+
+    pl = plan_of(enc='B', fileInfo={'bitsPerSample': np.dtype('>i2')})
+    assert pl.enc == 'h' and pl.swap is True
+    pl = plan_of(enc='h', fileInfo={'bitsPerSample': np.dtype('>i2')}, swapEndianness=True)
+    assert pl.enc == 'h' and pl.swap is False
+    pl = plan_of(enc='d', fileInfo={'bitsPerSample': np.dtype('<f4')})
+    assert pl.enc == 'f' and pl.swap is False
+    pl = plan_of(enc='h', swapEndianness=True)
+    assert pl.enc == 'h' and pl.swap is True
+    pl = plan_of(fileInfo={'bitsPerSample': np.dtype('u1')}, swapEndianness=False)
+    assert pl.enc == 'B' and pl.swap is False
+    with pytest.raises(ValueError):
+        plan_of()
+
+
+def test_compiled_plugin_seam_is_importable_like_the_reference_expects():
+    """read_file.py:58-63: `from dsp.fast.iq_correction import IQCorrection` must resolve."""
+    src = os.path.join(ROOT, 'src')
+    sys.path.insert(0, src)
+    try:
+        from dsp.fast.iq_correction import IQCorrection
+    finally:
+        sys.path.remove(src)
+    c = IQCorrection(1_024_000)
+    assert c.fs == 1_024_000 and c.impedance == 50 and c.inductance == 50 / 1_024_000
+    c.impedance = 75
+    c.fs = 2_400_000
+    assert c.inductance == 75 / 2_400_000
+    with pytest.raises(TypeError):
+        c.correctIq(np.zeros(4, dtype=np.float64), np.zeros(1, dtype=np.complex128))
+
+
+@pytest.mark.skipif(not os.path.isdir('/root/reference/test'), reason='reference tree not present (GPU box)')
+def test_reference_own_unit_tests_pass_against_the_shims(tmp_path):
+    """The reference's API contract for this path, unmodified: test/misc/file_util_test.py,
+    test/dsp/dsp_processor_test.py and test/misc/read_file_test.py with PYTHONPATH=src."""
+    import subprocess
+    env = dict(os.environ, PYTHONPATH=os.path.join(ROOT, 'src'), NUMBA_CACHE_DIR=str(tmp_path))
+    r = subprocess.run([sys.executable, '-m', 'pytest', '-q', '-p', 'no:cacheprovider',
+                        '/root/reference/test/misc/file_util_test.py',
+                        '/root/reference/test/dsp/dsp_processor_test.py',
+                        '/root/reference/test/misc/read_file_test.py'],
+                       env=env, cwd=str(tmp_path), capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
