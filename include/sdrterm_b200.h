@@ -18,7 +18,7 @@
 extern "C" {
 #endif
 
-#define SDRB_ABI_VERSION 5
+#define SDRB_ABI_VERSION 6
 #define SDRB_TILE_BLOCKS 32
 #define SDRB_NPOLES 8
 #define SDRB_MAX_DECIMATION 256
@@ -90,9 +90,12 @@ typedef struct sdrb_tables {
     const double *T1;        /* [R][ntiles] complex */
     const double *Ehead;     /* [R][edge+1] complex */
     const double *Eend;      /* [R][nend] complex */
-    const double *PhiF, *PhiG;   /* [R][8] complex */
-    const double *PsiW, *PsiT;   /* [2][R][8] complex */
-    const double *psiY;          /* [2][R][TILE_BLOCKS] complex */
+    /* IQ corrector decoupled from the block sums: per row and mode */
+    const double *alpha, *alphaT; /* [R][8] complex */
+    const double *beta, *betaT;   /* [R][8] complex */
+    const double *gamma;          /* [R] complex (0 when --correct-iq is off) */
+    const double *phE;            /* [R] complex: NCO phase at sample q*floor(N/q) */
+    const double *psiY;           /* [2][R][TILE_BLOCKS] complex */
     const uint8_t *use_nco;      /* [R] 0 = no shift for this row (centre == 0, dsp_processor.py:185-187) */
     /* demodulation */
     const double *out_sos;   /* [n_out_sections][6] */
@@ -102,17 +105,20 @@ typedef struct sdrb_tables {
     const double *sos_CA;    /* [sos_Lseg][ns]: c A^i */
     const double *sos_AP;    /* [5][ns][ns]: (A^Lseg)^(2^lv), lv = 0..4 */
     /* tensor-core block front end (plan.py: build_tc); tc_enable == 0 selects the FP64 block
-     * kernel.  The raw stream is the int8 A operand of an exact GEMM against one tc_Bq slice per
-     * row of the bank. */
+     * kernel.  The raw stream is the int8 A operand of an exact GEMM whose rows are super-blocks
+     * of two blocks, against one tc_Bq slice per row of the bank. */
     int32_t tc_enable;
-    int32_t tc_K;            /* bytes per block row = q * 2 * itemsize (128 or 256) */
+    int32_t tc_K;            /* bytes per GEMM row = 2 * q * 2 * itemsize (256 or 512) */
     int32_t tc_isz;          /* bytes per I or Q item */
-    int32_t tc_ncol;         /* digit columns per fixed-point output */
-    int32_t tc_nout;         /* outputs per row = 36: 16 F, 16 G, 2 E, 2 x0 */
-    int32_t tc_npad;         /* GEMM N per row, multiple of 16, <= 256 */
-    int32_t tc_S;            /* fixed-point outputs are integers * 2^-tc_S */
+    int32_t tc_ncol;         /* digit columns per fixed-point output (5) */
+    int32_t tc_nout;         /* fixed-point outputs per row (40) */
+    int32_t tc_npad;         /* GEMM N per row (208) */
+    int32_t tc_S;            /* outputs 0..35 are integers * 2^-tc_S */
+    int32_t tc_S_yl;         /* outputs 36..39 are integers * 2^-tc_S_yl */
+    int32_t tc_nrowc;        /* complex constants per row in tc_rowc */
     const int8_t *tc_Bq;     /* [R][tc_npad][tc_K] coefficient digits */
-    const double *tc_cst;    /* [R][tc_nout] */
+    const double *tc_cst;    /* [R][tc_nout + 4] */
+    const double *tc_rowc;   /* [R][tc_nrowc] complex: epilogue constants (plan.py RC_* layout) */
     uint8_t tc_xor[16];      /* XOR pattern of 16 consecutive stream bytes */
 } sdrb_tables;
 

@@ -16,7 +16,7 @@ LIB_PATH = os.environ.get('SDRB_LIB') or os.path.join(_HERE, 'libsdrterm_b200.so
 HEADER = os.path.join(ROOT, 'include', 'sdrterm_b200.h')
 SOURCES = [os.path.join(_HERE, 'csrc', f) for f in ('sdrb_api.cu', 'sdrb_kernels.cuh', 'sdrb_device.cuh', 'sdrb_tc.cuh', 'sdrb_finish.cuh')]
 
-ABI_VERSION = 5
+ABI_VERSION = 6
 FM, AM, RE, IM = 0, 1, 2, 3
 DEMOD_CODE = {'fm': FM, 'am': AM, 're': RE, 'im': IM}
 
@@ -44,12 +44,13 @@ class Tables(C.Structure):
                 ('lam_q', C.c_double), ('lam_N', C.c_double), ('lam_inv', C.c_double),
                 ('lam_j', _DP), ('lam_k', _DP), ('mu_k', _DP), ('lam_tile', C.c_double * 2), ('RL', C.c_int32),
                 ('run_len', C.c_int32 * 8), ('lam_run', C.c_double * 8), ('T2', _DP), ('T3', _DP), ('T1', _DP),
-                ('Ehead', _DP), ('Eend', _DP), ('PhiF', _DP), ('PhiG', _DP), ('PsiW', _DP),
-                ('PsiT', _DP), ('psiY', _DP), ('use_nco', C.POINTER(C.c_uint8)), ('out_sos', _DP),
+                ('Ehead', _DP), ('Eend', _DP), ('alpha', _DP), ('alphaT', _DP), ('beta', _DP),
+                ('betaT', _DP), ('gamma', _DP), ('phE', _DP), ('psiY', _DP), ('use_nco', C.POINTER(C.c_uint8)), ('out_sos', _DP),
                 ('fm_interp', _DP), ('sos_Lseg', C.c_int32), ('sos_AL', _DP), ('sos_CA', _DP), ('sos_AP', _DP),
                 ('tc_enable', C.c_int32), ('tc_K', C.c_int32), ('tc_isz', C.c_int32),
                 ('tc_ncol', C.c_int32), ('tc_nout', C.c_int32), ('tc_npad', C.c_int32),
-                ('tc_S', C.c_int32), ('tc_Bq', C.POINTER(C.c_int8)), ('tc_cst', _DP),
+                ('tc_S', C.c_int32), ('tc_S_yl', C.c_int32), ('tc_nrowc', C.c_int32),
+                ('tc_Bq', C.POINTER(C.c_int8)), ('tc_cst', _DP), ('tc_rowc', _DP),
                 ('tc_xor', C.c_uint8 * 16)]
 
 

@@ -171,91 +171,84 @@ int make_byte_map(sdrb_handle *h, CUtensorMap *map, const void *base, uint64_t r
     return 0;
 }
 
-template <bool IQ, int NCOL>
-int launch_tc_t(sdrb_handle *h, const CUtensorMap &map_a, size_t nch, int n_mtiles, cudaStream_t st)
+template <bool IQ>
+int launch_tc_t(sdrb_handle *h, const CUtensorMap &map_a, int n_mtiles, int total_wtiles, cudaStream_t st)
 {
     // one row of the bank per CTA: the grid is a whole number of row groups
     const int R = h->pl.R;
     const int slots = std::max(1, std::min(h->num_sms / R, n_mtiles));
-    k_tc<IQ, NCOL><<<slots * R, TC_THREADS, h->tc_smem, st>>>(h->pl, h->tc, h->sc, map_a, h->map_b, (int)nch, n_mtiles);
+    k_tc<IQ><<<slots * R, TC_THREADS, h->tc_smem, st>>>(h->pl, h->tc, h->sc, map_a, h->map_b, n_mtiles, total_wtiles);
     return 0;
 }
 
 int launch_tc(sdrb_handle *h, const uint8_t *raw, size_t nch, cudaStream_t st, bool iq)
 {
-    const uint64_t rows = (uint64_t)nch * h->pl.Mf;
+    // GEMM rows are super-blocks of two blocks: [nch * Mf / 2][K] bytes, 128 rows per MMA tile
+    const uint64_t rows = (uint64_t)nch * h->pl.Mf / 2;
     CUtensorMap map_a;
     int rc = make_byte_map(h, &map_a, raw, rows, (uint32_t)h->tc.K, 128);
     if (rc) return rc;
     const int n_mtiles = (int)((rows + 127) / 128);
-    switch (h->tc.ncol) {
-    case 5: return iq ? launch_tc_t<true, 5>(h, map_a, nch, n_mtiles, st) : launch_tc_t<false, 5>(h, map_a, nch, n_mtiles, st);
-    case 6: return iq ? launch_tc_t<true, 6>(h, map_a, nch, n_mtiles, st) : launch_tc_t<false, 6>(h, map_a, nch, n_mtiles, st);
-    }
-    return fail(h, SDRB_ERR_ARG, "unsupported digit column count %d", h->tc.ncol);
+    const int total_wtiles = (int)(rows / 32);
+    return iq ? launch_tc_t<true>(h, map_a, n_mtiles, total_wtiles, st) : launch_tc_t<false>(h, map_a, n_mtiles, total_wtiles, st);
 }
 
-template <bool IQ, int NCOL>
+template <bool IQ>
 int tc_attr(sdrb_handle *h)
 {
-    CK(h, cudaFuncSetAttribute(k_tc<IQ, NCOL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->tc_smem));
+    CK(h, cudaFuncSetAttribute(k_tc<IQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->tc_smem));
     return 0;
 }
 
-int setup_tc(sdrb_handle *h, const sdrb_tables *tab, const std::vector<double2> &prot)
+int setup_tc(sdrb_handle *h, const sdrb_tables *tab)
 {
     if (!tab->tc_enable || env_int("SDRB_NO_TC", 0)) return 0;
     const int R = h->pl.R;
-    if ((tab->tc_K != 128 && tab->tc_K != 256) || tab->tc_nout != TC_NOUT || tab->tc_ncol < 5 || tab->tc_ncol > 6 ||
-        tab->tc_isz < 1 || tab->tc_isz > 2 || tab->tc_npad > 256 || tab->tc_npad % 16 ||
-        tab->tc_npad < 34 * tab->tc_ncol + 2 * tab->tc_isz || tab->tc_K != h->pl.q * h->pl.sb || h->pl.rem != 0 ||
-        h->pl.cnt_last != SDRB_TB || h->pl.q < h->pl.edge + 1 || h->pl.normalize || !tab->tc_Bq || !tab->tc_cst)
+    if ((tab->tc_K != 256 && tab->tc_K != 512) || tab->tc_nout != TC_NOUT || tab->tc_ncol != TC_NCOL ||
+        tab->tc_isz < 1 || tab->tc_isz > 2 || tab->tc_npad != TC_NPAD || tab->tc_nrowc != TC_NROWC ||
+        tab->tc_K != 2 * h->pl.q * h->pl.sb || h->pl.rem != 0 || h->pl.cnt_last != SDRB_TB || (h->pl.Mf / 2) % 128 ||
+        h->pl.q < h->pl.edge + 1 || h->pl.normalize || !tab->tc_Bq || !tab->tc_cst || !tab->tc_rowc)
         return fail(h, SDRB_ERR_ARG, "tensor-core tables do not match the configuration");
     cudaDeviceProp prop;
     CK(h, cudaGetDeviceProperties(&prop, h->cfg.device));
     h->num_sms = prop.multiProcessorCount;
     if (R > TC_MAX_R) return 0;              // wider banks take the FP64 block kernel
     TcDev &tc = h->tc;
-    tc.K = tab->tc_K; tc.isz = tab->tc_isz; tc.ncol = tab->tc_ncol; tc.nout = tab->tc_nout; tc.npad = tab->tc_npad;
+    tc.K = tab->tc_K; tc.isz = tab->tc_isz;
     tc.nregion = tc.K / 128;
     memcpy(&tc.xor_word, tab->tc_xor, 4);
     for (int i = 0; i < 16; i++)
         if (tab->tc_xor[i] != tab->tc_xor[i & 3]) return fail(h, SDRB_ERR_ARG, "XOR pattern is not 4-periodic");
-    tc.idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(tc.npad >> 3) << 17) | ((128u >> 4) << 24);
+    tc.idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TC_NPAD >> 3) << 17) | ((128u >> 4) << 24);
     tc.scale = ldexp(1.0, -tab->tc_S);
     tc.scale16 = ldexp(1.0, 16 - tab->tc_S);
-    tc.stagger_ns = (uint32_t)env_int("SDRB_TC_STAGGER_NS", 0);
-    // powers 0..8 of the rotating-frame block multipliers (segment carries of the tile scans)
-    std::vector<double2> ppow((size_t)R * 16 * 9);
-    for (int i = 0; i < R * 16; i++) {
-        long double ar = 1.0L, ai = 0.0L;
-        const long double br = prot[i].x, bi = prot[i].y;
-        for (int k = 0; k <= 8; k++) {
-            ppow[(size_t)i * 9 + k] = make_double2((double)ar, (double)ai);
-            const long double nr = ar * br - ai * bi, ni = ar * bi + ai * br;
-            ar = nr; ai = ni;
-        }
-    }
-    int rc = upload(h, ppow.data(), ppow.size(), &tc.prot_pow);
+    tc.scale_yl = ldexp(1.0, -tab->tc_S_yl);
+    tc.scale16_yl = ldexp(1.0, 16 - tab->tc_S_yl);
+    int rc = upload(h, reinterpret_cast<const double2 *>(tab->tc_rowc), (size_t)R * TC_NROWC, &tc.rowc);
     if (rc) return rc;
-    for (int r = 0; r < R; r++) {
-        for (int o = 0; o < TC_NOUT; o++)
-            tc.cstb[r][o] = tab->tc_cst[(size_t)r * TC_NOUT + o] - TC_BIAS32 * (o < 34 ? tc.scale : 1.0);
-        for (int i = 0; i < 8; i++) {
-            tc.phi[r][i] = c2(tab->PhiF, (size_t)r * 8 + i);
-            tc.phi[r][8 + i] = c2(tab->PhiG, (size_t)r * 8 + i);
+    std::vector<double> cstb((size_t)R * (TC_NOUT + 4));
+    for (int r = 0; r < R; r++)
+        for (int o = 0; o < TC_NOUT + 4; o++) {
+            const double sc = o < 36 ? tc.scale : (o < TC_NOUT ? tc.scale_yl : 1.0);
+            cstb[(size_t)r * (TC_NOUT + 4) + o] = tab->tc_cst[(size_t)r * (TC_NOUT + 4) + o] - TC_BIAS32 * sc;
         }
-    }
+    rc = upload(h, cstb.data(), cstb.size(), &tc.cstb);
+    if (rc) return rc;
     const int8_t *d_bq = nullptr;
-    rc = upload(h, tab->tc_Bq, (size_t)R * tc.npad * tc.K, &d_bq);
+    rc = upload(h, tab->tc_Bq, (size_t)R * TC_NPAD * tc.K, &d_bq);
     if (rc) return rc;
-    rc = make_byte_map(h, &h->map_b, d_bq, (uint64_t)R * tc.npad, (uint32_t)tc.K, (uint32_t)tc.npad);
+    rc = make_byte_map(h, &h->map_b, d_bq, (uint64_t)R * TC_NPAD, (uint32_t)tc.K, (uint32_t)TC_NPAD);
     if (rc) return rc;
-    h->tc_smem = tc_smem_bytes(tc.npad, tc.nregion);
-    if (h->tc_smem > 227 * 1024) return fail(h, SDRB_ERR_ARG, "k_tc needs %zu bytes of shared memory", h->tc_smem);
-    if ((rc = tc_attr<true, 5>(h)) || (rc = tc_attr<false, 5>(h)) || (rc = tc_attr<true, 6>(h)) ||
-        (rc = tc_attr<false, 6>(h)))
-        return rc;
+    // the A ring takes whatever shared memory the B slice leaves (227 KB per CTA on sm_100)
+    const size_t cap = 227 * 1024;
+    const size_t fixed = tc_fixed_bytes(tc.nregion);
+    int nstage = fixed < cap ? (int)((cap - fixed) / TC_REGION_BYTES) : 0;
+    nstage = std::min(nstage, env_int("SDRB_TC_ASTAGES", TC_MAX_ASTAGES));
+    nstage = std::min(nstage, TC_MAX_ASTAGES);
+    if (nstage < 2) return fail(h, SDRB_ERR_ARG, "k_tc: no room for the A ring (%zu bytes fixed)", fixed);
+    tc.nstage = nstage;
+    h->tc_smem = tc_smem_bytes(tc.nregion, nstage);
+    if ((rc = tc_attr<true>(h)) || (rc = tc_attr<false>(h))) return rc;
     h->tc_on = true;
     return 0;
 }
@@ -387,8 +380,8 @@ int sdrb_create(const sdrb_config *cfg, const sdrb_tables *tab, sdrb_handle **ou
     {
         const void *need[] = {tab->p, tab->P, tab->rho, tab->rho_p, tab->c, tab->zhat, tab->xi, tab->Ec, tab->Oc,
                               tab->Ppow, tab->pk, tab->Pt, tab->bx, tab->bnd, tab->lam_j, tab->lam_k, tab->mu_k,
-                              tab->T2, tab->T3, tab->T1, tab->Ehead, tab->Eend, tab->PhiF, tab->PhiG, tab->PsiW,
-                              tab->PsiT, tab->psiY, tab->use_nco};
+                              tab->T2, tab->T3, tab->T1, tab->Ehead, tab->Eend, tab->alpha, tab->alphaT, tab->beta,
+                              tab->betaT, tab->gamma, tab->phE, tab->psiY, tab->use_nco};
         for (const void *ptr : need)
             if (!ptr) return fail(nullptr, SDRB_ERR_ARG, "a required table pointer is NULL");
         if (cfg->n_out_sections > 0 && !tab->out_sos) return fail(nullptr, SDRB_ERR_ARG, "out_sos is NULL");
@@ -493,10 +486,26 @@ int sdrb_create(const sdrb_config *cfg, const sdrb_tables *tab, sdrb_handle **ou
     UP(upload(h, reinterpret_cast<const double2 *>(tab->T1), (size_t)R * nt, &pl.T1));
     UP(upload(h, reinterpret_cast<const double2 *>(tab->Ehead), (size_t)R * (pl.edge + 1), &pl.Ehead));
     UP(upload(h, reinterpret_cast<const double2 *>(tab->Eend), (size_t)R * pl.nend, &pl.Eend));
-    UP(upload(h, reinterpret_cast<const double2 *>(tab->PhiF), (size_t)R * 8, &pl.PhiF));
-    UP(upload(h, reinterpret_cast<const double2 *>(tab->PhiG), (size_t)R * 8, &pl.PhiG));
-    UP(upload(h, reinterpret_cast<const double2 *>(tab->PsiW), (size_t)2 * R * 8, &pl.PsiW));
-    UP(upload(h, reinterpret_cast<const double2 *>(tab->PsiT), (size_t)2 * R * 8, &pl.PsiT));
+    UP(upload(h, reinterpret_cast<const double2 *>(tab->alpha), (size_t)R * 8, &pl.alpha));
+    UP(upload(h, reinterpret_cast<const double2 *>(tab->alphaT), (size_t)R * 8, &pl.alphaT));
+    UP(upload(h, reinterpret_cast<const double2 *>(tab->beta), (size_t)R * 8, &pl.beta));
+    UP(upload(h, reinterpret_cast<const double2 *>(tab->betaT), (size_t)R * 8, &pl.betaT));
+    UP(upload(h, reinterpret_cast<const double2 *>(tab->gamma), (size_t)R, &pl.gamma));
+    UP(upload(h, reinterpret_cast<const double2 *>(tab->phE), (size_t)R, &pl.phE));
+    {   // reciprocals and output weights derived from them (host doubles; |beta - 1| << 1)
+        std::vector<double2> binv((size_t)R * 8), binvT((size_t)R * 8), rb((size_t)R * 8), rbT((size_t)R * 8);
+        auto hinv = [](double2 a) { const double d = a.x * a.x + a.y * a.y; return make_double2(a.x / d, -a.y / d); };
+        for (int r = 0; r < R; r++)
+            for (int i = 0; i < 8; i++) {
+                const double2 b = c2(tab->beta, (size_t)r * 8 + i), bT = c2(tab->betaT, (size_t)r * 8 + i);
+                binv[(size_t)r * 8 + i] = hinv(b); binvT[(size_t)r * 8 + i] = hinv(bT);
+                rb[(size_t)r * 8 + i] = hmul(pl.rho[i], b); rbT[(size_t)r * 8 + i] = hmul(pl.rho_p[i], bT);
+            }
+        UP(upload(h, binv.data(), binv.size(), &pl.binv));
+        UP(upload(h, binvT.data(), binvT.size(), &pl.binvT));
+        UP(upload(h, rb.data(), rb.size(), &pl.rb));
+        UP(upload(h, rbT.data(), rbT.size(), &pl.rbT));
+    }
     UP(upload(h, reinterpret_cast<const double2 *>(tab->psiY), (size_t)2 * R * SDRB_TB, &pl.psiY));
     UP(upload(h, prot.data(), prot.size(), &pl.Prot));
     UP(upload(h, tw.data(), tw.size(), &pl.tw));
@@ -560,7 +569,7 @@ int sdrb_create(const sdrb_config *cfg, const sdrb_tables *tab, sdrb_handle **ou
         UP(dalloc(h, nch * R * 2 * M, &sc.fftbuf));
         UP(dalloc(h, nch * R * M, &sc.zrow));
     }
-    UP(setup_tc(h, tab, prot));
+    UP(setup_tc(h, tab));
 #undef UP
     for (int s = 0; s < 2; s++) {
         if (cudaStreamCreateWithFlags(&h->slot[s].stream, cudaStreamNonBlocking) != cudaSuccess ||

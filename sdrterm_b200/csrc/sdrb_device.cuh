@@ -45,11 +45,20 @@ struct DevPlan {
     const double2 *T1;     // [R][ntiles]
     const double2 *Ehead;  // [R][edge+1]
     const double2 *Eend;   // [R][nend]
-    const double2 *PhiF;   // [R][8]
-    const double2 *PhiG;   // [R][8]
-    const double2 *PsiW;   // [2][R][8]
-    const double2 *PsiT;   // [2][R][8]
-    const double2 *psiY;   // [2][R][TB]
+    // IQ corrector decoupled from the modal sums: the front ends sum the UNcorrected
+    // rotated samples; with s[n] = off[n] e^{jwn} the true states are w_i = beta_i W~_i - alpha_i s,
+    // T_i = betaT_i T~_i - alphaT_i s and y = sum rb_i W~_i + sum rbT_i T~_i + g0 u~ - gamma s
+    const double2 *alpha;  // [R][8]  1 / (lam e^{jw} - p_i)
+    const double2 *alphaT; // [R][8]  1 / (1 - p_i lam e^{jw})
+    const double2 *beta;   // [R][8]
+    const double2 *betaT;  // [R][8]
+    const double2 *binv;   // [R][8]  1 / beta_i
+    const double2 *binvT;  // [R][8]  1 / betaT_i
+    const double2 *rb;     // [R][8]  rho_i beta_i
+    const double2 *rbT;    // [R][8]  rho_i / p_i betaT_i
+    const double2 *gamma;  // [R]     0 when the IQ correction is off
+    const double2 *phE;    // [R]     e^{j w q Mf}
+    const double2 *psiY;   // [2][R][TB]  gamma (lam e^{jw})^(q l): tile-start offset -> output of block l
     const double2 *Prot;   // [R][16]  rotating-frame block multipliers (8 forward, 8 backward)
     const double2 *tw;     // [fft_n]  exp(-2 pi i k / fft_n)
     const double *fm_interp;  // [M][M/2] or null

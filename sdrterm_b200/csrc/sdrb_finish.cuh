@@ -91,8 +91,11 @@ k_finish(const __grid_constant__ DevPlan pl, const __grid_constant__ Scratch sc,
             *tbEe = tbEh + 32, *tbPy = tbEe + 32;
     if (R == 1) {
         for (int k = threadIdx.x; k < nt; k += blockDim.x) tbT1[k] = pl.T1[k];
-        for (int k = threadIdx.x; k < 32; k += blockDim.x)
-            tbPsi[k] = (k & 15) < 8 ? pl.PsiW[(size_t)(k >> 4) * 8 + (k & 15)] : pl.PsiT[(size_t)(k >> 4) * 8 + (k & 15) - 8];
+        // tbPsi: per-mode IQ constants of the row: alpha, alphaT | 1/beta, 1/betaT | beta, betaT (lanes 0..7 / 8..15)
+        for (int k = threadIdx.x; k < 16; k += blockDim.x) {
+            tbPsi[k] = k < 8 ? pl.alpha[k] : pl.alphaT[k - 8];
+            tbPsi[16 + k] = k < 8 ? pl.binv[k] : pl.binvT[k - 8];
+        }
         for (int k = threadIdx.x; k < nt * 8; k += blockDim.x) tbPt[k] = pl.Pt[k];
         for (int k = threadIdx.x; k <= edge; k += blockDim.x) { tbEh[k] = pl.Ehead[k]; tbEe[k] = pl.Eend[k]; }
         for (int k = threadIdx.x; k < 64; k += blockDim.x) tbPy[k] = pl.psiY[k];
@@ -182,16 +185,9 @@ k_finish(const __grid_constant__ DevPlan pl, const __grid_constant__ Scratch sc,
 #pragma unroll
             for (int u = 0; u < 8; u++) {
                 const int idx = i0 + u * 32 + lane, t = min(idx >> 4, nt - 1), m = idx & 15;
-                double2 a = av[u];
-                if (iq) {
-                    const int kind = (t == nt - 1) ? 1 : 0;
-                    const double2 o = shfl_c(offr, t);
-                    const double2 psi = R == 1 ? tbPsi[kind * 16 + m]
-                                      : (m < 8 ? pl.PsiW[((size_t)kind * R + r) * 8 + m]
-                                               : pl.PsiT[((size_t)kind * R + r) * 8 + m - 8]);
-                    a = cfma(make_double2(-o.x, -o.y), psi, a);
-                }
-                if (idx < nt * 16) addv[idx] = cmul(T1r[min(t, nt - 1)], a);
+                // the aggregates are sums of the UNcorrected samples: no offset term here (3.3)
+                if (idx < nt * 16) addv[idx] = cmul(T1r[min(t, nt - 1)], av[u]);
+                (void)m;
             }
         }
         FIN_DBG(1);
@@ -255,15 +251,28 @@ k_finish(const __grid_constant__ DevPlan pl, const __grid_constant__ Scratch sc,
         // ---------------------------------------------------------------- 1e. carries across tiles
         // lanes 0..7: forward modal states (Win[t] = state entering tile t); lanes 8..15: anticausal
         // states (Tn[t] = state entering tile t from above)
+        // in the frame of the uncorrected samples (3.3): W~ = (w + alpha s) / beta at n = 0,
+        // T~ = (T + alphaT s) / betaT at n = q*Mf, s = off e^{jwn}; stored pre-scaled by beta / betaT
         double2 st = grp ? accB : accA;
-        if (lane >= 8 && lane < 16) carry[(size_t)nt * 16 + 8 + i8] = st;
+        double2 qal = make_double2(0.0, 0.0), qbe = make_double2(1.0, 0.0), sE = qal;
+        const double2 o0c = shfl_c(offr, 0);
+        if (iq) {
+            const int mi = grp * 8 + i8;
+            qal = R == 1 ? tbPsi[mi] : (grp ? pl.alphaT : pl.alpha)[(size_t)r * 8 + i8];
+            const double2 qbi = R == 1 ? tbPsi[16 + mi] : (grp ? pl.binvT : pl.binv)[(size_t)r * 8 + i8];
+            qbe = (grp ? pl.betaT : pl.beta)[(size_t)r * 8 + i8];
+            sE = cmul(oE, pl.phE[r]);
+            st = cmul(cfma(qal, grp ? sE : o0c, st), qbi);
+        }
+        if (lane >= 8 && lane < 16) carry[(size_t)nt * 16 + 8 + i8] = iq ? cmul(qbe, st) : st;
         for (int tt = 0; tt < nt; tt++) {
             const int t = grp ? nt - 1 - tt : tt;
-            if (lane < 8) carry[(size_t)t * 16 + i8] = st;
+            if (lane < 8) carry[(size_t)t * 16 + i8] = iq ? cmul(qbe, st) : st;
             st = cfma(P32, st, addv[t * 16 + grp * 8 + i8]);
-            if (lane >= 8 && lane < 16) carry[(size_t)t * 16 + 8 + i8] = st;
+            if (lane >= 8 && lane < 16) carry[(size_t)t * 16 + 8 + i8] = iq ? cmul(qbe, st) : st;
         }
-        if (lane < 8) carry[(size_t)nt * 16 + i8] = st;
+        if (lane < 8) carry[(size_t)nt * 16 + i8] = iq ? cmul(qbe, st) : st;
+        if (iq) st = csub(cmul(qbe, st), cmul(qal, sE));    // lanes 0..7: the TRUE forward state at q*Mf
         FIN_DBG(5);
         // ---------------------------------------------------------------- 1f. boundary vector zeta
         {

@@ -39,7 +39,7 @@ __host__ __device__ inline size_t main_tile_bytes(int rowb, bool iq)
     size_t b = (size_t)SDRB_TB * rowb;                       // raw tile, padded rows
     b = (b + 15) & ~(size_t)15;
     b += 2 * SDRB_TB * sizeof(double2);                      // cl[32], blkagg[32]
-    if (iq) b += (size_t)SDRB_TB * 4 * 2 * sizeof(double2);  // runA[32][4][2]
+    (void)iq;
     return b;
 }
 __host__ __device__ inline size_t main_warp_bytes()
@@ -103,7 +103,8 @@ k_main(const __grid_constant__ DevPlan pl, Scratch sc, const uint8_t *__restrict
         double2 *blkagg = cl + SDRB_TB;
         double2 excl = make_double2(0.0, 0.0);
         if (IQ) {
-            double2 *runA = blkagg + SDRB_TB;
+            // IQ-EMA aggregate of every block (the samples themselves stay uncorrected: the
+            // corrector enters through the decoupled terms)
             for (int g = 0; g < 4; g++) {
                 const int b = 8 * g + nq;
                 const unsigned char *rowp = tb + (size_t)b * rowb;
@@ -131,10 +132,6 @@ k_main(const __grid_constant__ DevPlan pl, Scratch sc, const uint8_t *__restrict
                     const double2 v = shfl_c(agg_d, base + (7 - i));
                     A[i + 1] = make_double2(fma(pl.lam_run[i], A[i].x, v.x), fma(pl.lam_run[i], A[i].y, v.y));
                 }
-                const double2 As = kq == 0 ? A[0] : kq == 1 ? A[1] : kq == 2 ? A[2] : A[3];   // at ascending-run start
-                const double2 Ae = kq == 0 ? A[8] : kq == 1 ? A[7] : kq == 2 ? A[6] : A[5];   // at descending-run end
-                runA[(b * 4 + kq) * 2] = As;
-                runA[(b * 4 + kq) * 2 + 1] = Ae;
                 if (kq == 0) blkagg[b] = A[8];
             }
             __syncwarp();
@@ -164,17 +161,12 @@ k_main(const __grid_constant__ DevPlan pl, Scratch sc, const uint8_t *__restrict
         const int cnt = (t == pl.ntiles - 1) ? pl.cnt_last : SDRB_TB;
         const unsigned char *tb = smem_raw + (size_t)tl * tileb;
         const double2 *cl = reinterpret_cast<const double2 *>(tb + (((size_t)SDRB_TB * rowb + 15) & ~(size_t)15));
-        const double2 *runA = cl + 2 * SDRB_TB;
         const double2 *T2r = pl.T2 + (size_t)r * q;
         const bool nco = pl.use_nco[r] != 0;
-        const double2 phFu = pl.PhiF[(size_t)r * 8 + m], phFl = pl.PhiF[(size_t)r * 8 + m + 4];
-        const double2 phGu = pl.PhiG[(size_t)r * 8 + m], phGl = pl.PhiG[(size_t)r * 8 + m + 4];
 
         for (int g = 0; g < 4; g++) {
             const int bB = 8 * g + nq;
             const unsigned char *rowp = tb + (size_t)bB * rowb;
-            double2 acc_a = make_double2(0.0, 0.0), acc_d = make_double2(0.0, 0.0);
-            if (IQ) { acc_a = runA[(bB * 4 + kq) * 2]; acc_d = runA[(bB * 4 + kq) * 2 + 1]; }
             double Sr0 = 0, Sr1 = 0, Si0 = 0, Si1 = 0, Dr0 = 0, Dr1 = 0, Di0 = 0, Di1 = 0;
             for (int s = 0; s < pl.RL; s++) {
                 const int j = a0 + s;
@@ -183,21 +175,12 @@ k_main(const __grid_constant__ DevPlan pl, Scratch sc, const uint8_t *__restrict
                 if (valid) {
                     const int jm = q - 1 - j;
                     const bool mid = (j == jm);
-                    double2 za = decode_sample<ENC>(pl, rowp, j);
-                    if (IQ) {
-                        const double2 z = za;
-                        za.x = fma(-pl.Liq, acc_a.x, z.x); za.y = fma(-pl.Liq, acc_a.y, z.y);
-                        acc_a.x = fma(pl.lam, acc_a.x, z.x); acc_a.y = fma(pl.lam, acc_a.y, z.y);
-                    }
-                    if (s == 0 && kq == 0) x0s[bB] = za;          // first sample of the block
+                    const double2 za = decode_sample<ENC>(pl, rowp, j);
+                    if (s == 0 && kq == 0) x0s[bB] = za;          // first (raw) sample of the block
                     const double2 ua = nco ? cmul(__ldg(T2r + j), za) : za;
                     if (mid) { a = ua; }
                     else {
-                        double2 zb = decode_sample<ENC>(pl, rowp, jm);
-                        if (IQ) {
-                            acc_d.x = (acc_d.x - zb.x) * pl.lam_inv; acc_d.y = (acc_d.y - zb.y) * pl.lam_inv;
-                            zb.x = fma(-pl.Liq, acc_d.x, zb.x); zb.y = fma(-pl.Liq, acc_d.y, zb.y);
-                        }
+                        const double2 zb = decode_sample<ENC>(pl, rowp, jm);
                         const double2 ub = nco ? cmul(__ldg(T2r + jm), zb) : zb;
                         a = cadd(ua, ub); d = csub(ua, ub);
                     }
@@ -219,17 +202,7 @@ k_main(const __grid_constant__ DevPlan pl, Scratch sc, const uint8_t *__restrict
                 double Sup, Slo, Dup, Dlo;
                 if (e == 0) { Sup = Sr - oS; Slo = Sr + oS; Dup = Dr - oD; Dlo = Dr + oD; }
                 else        { Sup = oS + Sr; Slo = oS - Sr; Dup = oD + Dr; Dlo = oD - Dr; }
-                double Fu = Sup + Dup, Gu = Sup - Dup, Fl = Slo + Dlo, Gl = Slo - Dlo;
-                if (IQ) {
-                    const double2 cb = cl[b];
-                    if (e == 0) {
-                        Fu -= fma(cb.x, phFu.x, -cb.y * phFu.y); Fl -= fma(cb.x, phFl.x, -cb.y * phFl.y);
-                        Gu -= fma(cb.x, phGu.x, -cb.y * phGu.y); Gl -= fma(cb.x, phGl.x, -cb.y * phGl.y);
-                    } else {
-                        Fu -= fma(cb.x, phFu.y, cb.y * phFu.x); Fl -= fma(cb.x, phFl.y, cb.y * phFl.x);
-                        Gu -= fma(cb.x, phGu.y, cb.y * phGu.x); Gl -= fma(cb.x, phGl.y, cb.y * phGl.x);
-                    }
-                }
+                const double Fu = Sup + Dup, Gu = Sup - Dup, Fl = Slo + Dlo, Gl = Slo - Dlo;
                 xb[(2 * m + e) * SDRB_XSTRIDE + b] = Fu;
                 xb[(2 * (m + 4) + e) * SDRB_XSTRIDE + b] = Fl;
                 xb[(2 * (8 + m) + e) * SDRB_XSTRIDE + b] = Gu;
@@ -262,13 +235,17 @@ k_main(const __grid_constant__ DevPlan pl, Scratch sc, const uint8_t *__restrict
             for (int i = 0; i < 8; i++) {
                 const double2 Wv = make_double2(xb[(2 * i) * SDRB_XSTRIDE + lane], xb[(2 * i + 1) * SDRB_XSTRIDE + lane]);
                 const double2 Tv = make_double2(xb[(2 * (8 + i)) * SDRB_XSTRIDE + lane], xb[(2 * (8 + i) + 1) * SDRB_XSTRIDE + lane]);
-                sw = cfma(pl.rho[i], Wv, sw);
-                sT = cfma(pl.rho_p[i], Tv, sT);
+                sw = cfma(pl.rb[(size_t)r * 8 + i], Wv, sw);
+                sT = cfma(pl.rbT[(size_t)r * 8 + i], Tv, sT);
             }
             const double2 epsb = cconj(pl.T3[(size_t)r * (SDRB_TB + 1) + 1]);
-            const double2 x0 = csub(x0s[lane], cl[lane]);
+            const double2 x0 = x0s[lane];
             double2 ys = cfma(epsb, sw, sT);
             ys.x = fma(pl.g0, x0.x, ys.x); ys.y = fma(pl.g0, x0.y, ys.y);
+            if (IQ) {                                  // - gamma * (tile-local offset at this block)
+                const double2 gm = pl.gamma[r], o = cl[lane];
+                ys = cfma(make_double2(-gm.x, -gm.y), o, ys);
+            }
             const double2 yp = cmul(pl.T3[(size_t)r * (SDRB_TB + 1) + lane], ys);
             sc.ypart[((size_t)chunk * pl.R + r) * pl.Mf + (size_t)t * SDRB_TB + lane] = yp;
         }
@@ -580,19 +557,21 @@ k_fixup(const __grid_constant__ DevPlan pl, Scratch sc, const uint8_t *__restric
             const double2 ext = csub(cscale(2.0, x0), s_h[edge - j]);
             w = cfma(p, w, ext);
         }
-        // forward carries across tiles
+        // forward carries across tiles, in the frame of the UNcorrected samples the front ends
+        // summed: W~ = (w + alpha s) / beta with s = off e^{jwn} (n = 0: the chunk-start offset);
+        // the carries are stored pre-scaled by beta for the output stage
+        const double2 al = pl.alpha[(size_t)r * 8 + i], be = pl.beta[(size_t)r * 8 + i];
+        const double2 alT = pl.alphaT[(size_t)r * 8 + i], beT = pl.betaT[(size_t)r * 8 + i];
+        const double2 sE = iq ? cmul(offt[nt], pl.phE[r]) : make_double2(0.0, 0.0);   // rotated offset at q*Mf
+        if (iq) w = cmul(cfma(al, offt[0], w), pl.binv[(size_t)r * 8 + i]);
         for (int t = 0; t < nt; t++) {
-            if (lane < 8) carry[(size_t)t * 16 + i] = w;
+            if (lane < 8) carry[(size_t)t * 16 + i] = iq ? cmul(be, w) : w;
             const int kind = (t == nt - 1) ? 1 : 0;
             const int cnt = kind ? pl.cnt_last : SDRB_TB;
-            double2 add = aggr[(size_t)t * 16 + i];
-            if (iq) {
-                const double2 s = make_double2(-offt[t].x, -offt[t].y);
-                add = cfma(s, pl.PsiW[((size_t)kind * pl.R + r) * 8 + i], add);
-            }
-            w = cfma(pl.Ppow[(size_t)cnt * 8 + i], w, cmul(T1r[t], add));
+            w = cfma(pl.Ppow[(size_t)cnt * 8 + i], w, cmul(T1r[t], aggr[(size_t)t * 16 + i]));
         }
-        if (lane < 8) carry[(size_t)nt * 16 + i] = w;
+        if (iq) w = csub(cmul(be, w), cmul(al, sE));              // back to the true state at q*Mf
+        if (lane < 8) carry[(size_t)nt * 16 + i] = iq ? cfma(al, sE, w) : w;   // = beta W~
         const double2 wEnd = w;
         // end segment: partial block then tail extension
         const int nseq = pl.rem + edge;
@@ -631,19 +610,15 @@ k_fixup(const __grid_constant__ DevPlan pl, Scratch sc, const uint8_t *__restric
                 yrow[pl.Mf] = make_double2(fma(pl.g0, xp.x, v.x), fma(pl.g0, xp.y, v.y));
             }
         }
-        // backward carries
+        // backward carries: T~ = (T + alphaT s) / betaT at q*Mf, stored pre-scaled by betaT
         T = Tend;
-        if (lane < 8) carry[(size_t)nt * 16 + 8 + i] = T;
+        if (iq) T = cmul(cfma(alT, sE, T), pl.binvT[(size_t)r * 8 + i]);
+        if (lane < 8) carry[(size_t)nt * 16 + 8 + i] = iq ? cmul(beT, T) : T;
         for (int t = nt - 1; t >= 0; t--) {
             const int kind = (t == nt - 1) ? 1 : 0;
             const int cnt = kind ? pl.cnt_last : SDRB_TB;
-            double2 add = aggr[(size_t)t * 16 + 8 + i];
-            if (iq) {
-                const double2 s = make_double2(-offt[t].x, -offt[t].y);
-                add = cfma(s, pl.PsiT[((size_t)kind * pl.R + r) * 8 + i], add);
-            }
-            T = cfma(pl.Ppow[(size_t)cnt * 8 + i], T, cmul(T1r[t], add));
-            if (lane < 8) carry[(size_t)t * 16 + 8 + i] = T;
+            T = cfma(pl.Ppow[(size_t)cnt * 8 + i], T, cmul(T1r[t], aggr[(size_t)t * 16 + 8 + i]));
+            if (lane < 8) carry[(size_t)t * 16 + 8 + i] = iq ? cmul(beT, T) : T;
         }
     }
     __syncthreads();

@@ -58,8 +58,8 @@ class Engine:
                           ('Ppow', pl.Ppow), ('pk', pl.Pk), ('Pt', pl.Pt), ('bx', pl.bx), ('bnd', pl.bnd), ('lam_j', pl.lam_j),
                           ('lam_k', pl.lam_k), ('mu_k', pl.mu_k), ('T2', pl.T2),
                           ('T3', pl.T3), ('T1', pl.T1), ('Ehead', pl.Ehead), ('Eend', pl.Eend),
-                          ('PhiF', pl.PhiF), ('PhiG', pl.PhiG), ('PsiW', pl.PsiW),
-                          ('PsiT', pl.PsiT), ('psiY', pl.psiY)):
+                          ('alpha', pl.alpha), ('alphaT', pl.alphaT), ('beta', pl.beta),
+                          ('betaT', pl.betaT), ('gamma', pl.gamma), ('phE', pl.phE), ('psiY', pl.psiY)):
             put(name, arr)
         put('out_sos', pl.out_sos if pl.out_sos is not None else np.zeros(6))
         tab.g0, tab.d, tab.k_bnd = m.g0, m.d, int(pl.k_bnd)
@@ -85,6 +85,8 @@ class Engine:
             tc = self.tc
             tab.tc_enable, tab.tc_K, tab.tc_isz = 1, tc.K, tc.isz
             tab.tc_ncol, tab.tc_nout, tab.tc_npad, tab.tc_S = tc.NCOL, tc.nout, tc.Npad, tc.S
+            tab.tc_S_yl, tab.tc_nrowc = tc.S_yl, tc.rowc.shape[1]
+            put('tc_rowc', tc.rowc)
             bq = np.ascontiguousarray(tc.Bq, dtype=np.int8)
             self._keep.append(bq)
             tab.tc_Bq = bq.ctypes.data_as(C.POINTER(C.c_int8))

@@ -126,6 +126,11 @@ def _phasor(w: float, n) -> np.ndarray:
     return (np.cos(ph) + 1j * np.sin(ph)).astype(np.complex128)
 
 
+def _phasor_vec(w: np.ndarray, n: int) -> np.ndarray:
+    """exp(1j*w[r]*n) per row (same 80-bit product as _phasor)."""
+    return np.array([_phasor(wr, n) for wr in w]).reshape(-1)
+
+
 @dataclass
 class Plan:
     # geometry
@@ -182,11 +187,17 @@ class Plan:
     Eend: np.ndarray       # (R, nend)    phases of samples ws..N-1
     ws: int
     nend: int
-    PhiF: np.ndarray       # (R, 8)  sum_j p^(q-1-j) lam^j T2[j]
-    PhiG: np.ndarray       # (R, 8)  sum_j p^j lam^j T2[j]
-    PsiW: np.ndarray       # (2, R, 8)  deferred tile-start offset -> forward aggregate (full / last tile)
-    PsiT: np.ndarray       # (2, R, 8)
-    psiY: np.ndarray       # (2, R, TILE_BLOCKS)
+    # IQ corrector decoupled from the modal sums: with s[n] = off[n] e^{jwn} and
+    # mu = lam e^{jw}, the corrected modal states are w_i = beta_i W~_i - alpha_i s,
+    # T_i = betaT_i T~_i - alphaT_i s with W~, T~ driven by the UNcorrected rotated samples, and
+    # y = sum rho_i beta_i W~_i + sum rho'_i betaT_i T~_i + g0 u~ - gamma s
+    alpha: np.ndarray      # (R, 8)  1 / (mu - p_i)
+    beta: np.ndarray       # (R, 8)  1 + alpha_i L e^{jw}
+    alphaT: np.ndarray     # (R, 8)  1 / (1 - p_i mu)
+    betaT: np.ndarray      # (R, 8)  1 - p_i alphaT_i L e^{jw}
+    gamma: np.ndarray      # (R,)    sum rho_i alpha_i + sum rho'_i alphaT_i + g0  (0 when IQ correction is off)
+    phE: np.ndarray        # (R,)    e^{j w q Mf}: NCO phase at the end of the full blocks
+    psiY: np.ndarray       # (2, R, TILE_BLOCKS)  gamma mu^(q l): tile-start offset -> block l's output
     lam_tile: np.ndarray   # (2,) lam^(q*cnt)
     # demod / output
     demod: str
@@ -300,40 +311,40 @@ def build_plan(fs: int, enc: str, dec: int, rows_hz, *, simo: bool = False, swap
     Ehead = np.stack([_phasor(wr, np.arange(edge + 1)) for wr in w])
     Eend = np.stack([_phasor(wr, ws + np.arange(nend)) for wr in w])
 
-    # IQ / constant-offset block vectors: geometric sums, closed form in high precision
-    PhiF = np.zeros((R, n8), dtype=np.complex128)
-    PhiG = np.zeros((R, n8), dtype=np.complex128)
-    PsiW = np.zeros((2, R, n8), dtype=np.complex128)
-    PsiT = np.zeros((2, R, n8), dtype=np.complex128)
+    # IQ corrector, decoupled (see the Plan fields): per-row constants in high precision
+    alpha = np.zeros((R, n8), dtype=np.complex128)
+    alphaT = np.zeros((R, n8), dtype=np.complex128)
+    beta = np.ones((R, n8), dtype=np.complex128)
+    betaT = np.ones((R, n8), dtype=np.complex128)
+    gamma = np.zeros(R, dtype=np.complex128)
     psiY = np.zeros((2, R, TILE_BLOCKS), dtype=np.complex128)
+    phE = _phasor_vec(w, q * Mf)
     lam_tile = np.array([float(mlam ** (q * TILE_BLOCKS)), float(mlam ** (q * cnt_last))])
     if correct_iq:
         g0 = mp.mpf(modes.g0)
         rho = [mp.mpc(v) for v in modes.rho]
         rho_p = [mp.mpc(v) for v in modes.rho_p]
+        Lmp = mp.mpf(Liq)
         for r in range(R):
-            mu = mlam * mp.expj(mp.mpf(w[r]))              # lam * e^{jw}
+            ejw = mp.expj(mp.mpf(w[r])) if use_nco[r] else mp.mpc(1)
+            mu = mlam * ejw                                 # lam * e^{jw}
+            dist = min(abs(mu - pm[i]) for i in range(n8))
+            if dist < mp.mpf(10) ** -8:
+                raise ValueError('the IQ-offset mode lam*e^{jw} coincides with a pole of the decimation '
+                                 'filter; shift the centre frequency by 1 Hz')
+            a = [1 / (mu - pm[i]) for i in range(n8)]
+            aT = [1 / (1 - pm[i] * mu) for i in range(n8)]
+            b = [1 + a[i] * Lmp * ejw for i in range(n8)]
+            bT = [1 - pm[i] * aT[i] * Lmp * ejw for i in range(n8)]
+            gam = sum(rho[i] * a[i] + rho_p[i] * aT[i] for i in range(n8)) + g0
+            alpha[r] = [_c(v) for v in a]
+            alphaT[r] = [_c(v) for v in aT]
+            beta[r] = [_c(v) for v in b]
+            betaT[r] = [_c(v) for v in bT]
+            gamma[r] = _c(gam)
             muq = mu ** q
-            phiF = [(pm[i] ** q - muq) / (pm[i] - mu) for i in range(n8)]
-            phiG = [(1 - (pm[i] * mu) ** q) / (1 - pm[i] * mu) for i in range(n8)]
-            PhiF[r] = [_c(v) for v in phiF]
-            PhiG[r] = [_c(v) for v in phiG]
-            for kind, cnt in ((0, TILE_BLOCKS), (1, cnt_last)):
-                # block l of the tile sees the deferred offset scaled by muq^l (lam^(ql) T3[l])
-                fl = [[phiF[i] * muq ** l for i in range(n8)] for l in range(cnt)]
-                gl = [[phiG[i] * muq ** l for i in range(n8)] for l in range(cnt)]
-                Wl = [[mp.mpc(0)] * n8]
-                for l in range(cnt):
-                    Wl.append([pm[i] ** q * Wl[l][i] + fl[l][i] for i in range(n8)])
-                Tl = [[mp.mpc(0)] * n8 for _ in range(cnt + 1)]
-                for l in range(cnt - 1, -1, -1):
-                    Tl[l] = [pm[i] ** q * Tl[l + 1][i] + gl[l][i] for i in range(n8)]
-                PsiW[kind, r] = [_c(v) for v in Wl[cnt]]
-                PsiT[kind, r] = [_c(v) for v in Tl[0]]
-                for l in range(cnt):
-                    y = sum(rho[i] * Wl[l][i] + rho_p[i] * Tl[l][i] for i in range(n8)) \
-                        + g0 * muq ** l
-                    psiY[kind, r, l] = _c(y)
+            for l in range(TILE_BLOCKS):
+                psiY[0, r, l] = psiY[1, r, l] = _c(gam * muq ** l)
 
     out_sos = None
     if demod in ('fm', 'am'):
@@ -370,48 +381,69 @@ def build_plan(fs: int, enc: str, dec: int, rows_hz, *, simo: bool = False, swap
                 modes=modes, P=P, Ec=Ec, Oc=Oc, Ppow=Ppow, Pk=Pk, Pt=Pt, bx=bx, lam_k=lam_k, mu_k=mu_k, bnd=bnd, k_bnd=k_bnd,
                 correct_iq=bool(correct_iq), Liq=Liq, lam=lam, lam_j=lam_j, lam_q=lam_q, lam_N=lam_N, lam_inv=lam_inv, RL=RL, run_len=run_len, lam_run=lam_run,
                 norm=norm, w=w, use_nco=use_nco, T2=T2, T3=T3, T1=T1, Ehead=Ehead, Eend=Eend,
-                ws=ws, nend=nend, PhiF=PhiF, PhiG=PhiG, PsiW=PsiW, PsiT=PsiT, psiY=psiY,
+                ws=ws, nend=nend, alpha=alpha, beta=beta, alphaT=alphaT, betaT=betaT, gamma=gamma, phE=phE, psiY=psiY,
                 lam_tile=lam_tile, demod=demod, out_sos=out_sos,
                 big_endian_out=bool(simo if big_endian_out is None else big_endian_out),
                 fm_interp=fm_interp, sos_Lseg=sos_Lseg, sos_AL=sos_AL, sos_CA=sos_CA, sos_AP=sos_AP)
 
 
 # ------------------------------------------------------------------------------------------------
-# Tensor-core block front end (k_tc): the per-block modal sums as ONE exact int8 GEMM over the raw
-# bytes.  Every quantity the block kernel needs from a block of q samples is a real-linear
-# functional of the block's integer samples -- decode, byte order, the block-local IQ correction
-# (a linear EMA), the NCO and the 16 modal sums F_i, G_i -- so it is a row of a coefficient matrix
-# applied to the block's bytes.  The coefficients are rounded once to ND*8-bit fixed point and cut
-# into balanced base-256 digits; with the data bytes as the other int8 operand every product and
-# every int32 column sum is exact, and the columns are recombined in int64/FP64.
+# Tensor-core block front end (k_tc): the block sums AND the block-local part of the outputs as ONE
+# exact int8 GEMM over the raw bytes.
 #
-# Outputs per row (one GEMM N-slice of Npad columns per row r):
-#   o = 0..15   F_i   (Re, Im interleaved, poles 0..7)       ND digits, NCOL = ND + isz - 1 columns
-#   o = 16..31  G_i                                          "
-#   o = 32, 33  E = sum_j lam^(q-1-j) z_j  (IQ-EMA block aggregate)   "
-#   o = 34, 35  x0 = the block's first sample (Re, Im)       1 digit, isz columns
-# ND = 5 (40-bit coefficients) already sits on the FP64 floor of the chain (4e-13 vs the oracle;
-# ND = 4 gives 2e-11 .. 2e-10, ND = 6 and 7 change nothing) -- measured with tests/emulator.py.
-TC_ND = 5                 # coefficient digits (40-bit fixed point)
-TC_MODE_OUTPUTS = 32      # 8 poles x {F, G} x {re, im} per row
-TC_NOUT = 36
+# Rows of the GEMM are SUPER-BLOCKS of SB = 2 consecutive blocks (K = 2 q sb bytes, 256 or 512).
+# Every quantity the epilogue needs from a super-block is a real-linear functional of its integer
+# samples -- decode, byte order, the NCO phasor and the modal weights -- i.e. a row of a
+# coefficient matrix applied to its bytes.  The coefficients are rounded once to 40-bit fixed
+# point (one common binary scale) and cut into ND = 5 balanced base-256 digits; with the raw bytes
+# as the other int8 operand every product and every int32 column sum is exact.
+#
+# Outputs per row of the bank (N slice of Npad = 208 columns), NCOL = 5 digit columns each:
+#   o =  0..15  F~_i = sum_j p_i^(2q-1-j) e^{jwj} z_j     (Re, Im interleaved, poles 0..7)
+#   o = 16..31  G~_i = sum_j p_i^j e^{jwj} z_j
+#   o = 32..35  E_a = sum_{j<q} lam^(q-1-j) z_j,  E_ab = sum_{j<2q} lam^(2q-1-j) z_j   (IQ-EMA aggregates)
+#   o = 36..39  yl_a, yl_b: the part of the two block outputs that is local to the super-block
+#               (g0 z_0 + sum_i rho'_i betaT_i G~_i  /  sum_i rho_i beta_i F~a_i + rho'_i betaT_i G~b_i + g0 u_q)
+#   columns 200.. : x0_a, x0_b = first raw sample of either block, unit coefficients (exact decode
+#               check, sdrb_keep_x0), isz columns per component
+# 16-bit samples: digit s of a coefficient meets the high byte in column s and the low byte in
+# column s+1; the low byte's coefficient is re-rounded to 4 digits (round(A/256)) so that no sixth
+# column is needed -- the low byte carries 1/256 of the weight, so its coefficient needs 8 bits
+# less for the same absolute error (measured: the chain stays at its FP64 floor).
+TC_ND = 5                 # coefficient digits = digit columns per output
+TC_SB = 2                 # blocks per GEMM row
+TC_NOUT = 40
+TC_NPAD = 208
+TC_X0COL = 200
+TC_NROWC = 200            # complex constants per row for the epilogue (TcTables.rowc)
 
 
 @dataclass
 class TcTables:
-    K: int                 # bytes per block row = q * 2 * itemsize
+    K: int                 # bytes per GEMM row = SB * q * 2 * itemsize
     isz: int               # bytes per I or Q item
     ND: int
-    NCOL: int              # digit columns per ND-digit output = ND + isz - 1
-    nout: int              # outputs per row (36)
-    Npad: int              # GEMM N per row (multiple of 16, <= 256)
+    NCOL: int              # digit columns per output (== ND)
+    SB: int
+    nout: int
+    Npad: int
     R: int
     xor_mask: np.ndarray   # (16,) uint8, XOR pattern of one 16-byte group of the raw stream
     Bq: np.ndarray         # (R, Npad, K) int8 coefficient digits
-    S: int                 # common binary scale of the ND-digit outputs: value = integer * 2^-S
-    cst: np.ndarray        # (R, nout) response to the constant the XOR removed
-    col0: np.ndarray       # (nout,) first column of each output
-    ncols: np.ndarray      # (nout,) columns of each output
+    S: int                 # outputs 0..35 are integers * 2^-S
+    S_yl: int              # outputs 36..39 (yl_a, yl_b: small coefficients, their own finer scale) * 2^-S_yl
+    cst: np.ndarray        # (R, nout + 4) response to the constant the XOR removed (last 4: x0 columns)
+    rowc: np.ndarray       # (R, TC_NROWC) complex epilogue constants, see build_tc
+    col_l1: int            # max over columns of sum_k |digit|: bounds every int32 column sum
+
+
+# layout of TcTables.rowc (complex entries)
+RC_CA, RC_CB, RC_DA, RC_DB = 0, 8, 16, 24     # output weights on the forward / backward scan states
+RC_GAM, RC_GAMQ = 32, 33                      # gamma, gamma e^{jwq}
+RC_AGGF = 34                                  # T3x[15]: forward tile aggregate -> tile frame
+RC_ROT = 36                                   # [16] T3x[l] = e^{jw 2q l}
+RC_POW = 52                                   # [16 modes][9] powers 0..8 of the scan multipliers
+RC_END = RC_POW + 16 * 9
 
 
 def _balanced_digits(A: int, nd: int):
@@ -429,9 +461,9 @@ def tc_supported(pl: Plan) -> bool:
     """Shapes the tensor-core front end handles; everything else takes the FP64 block kernel."""
     if pl.enc not in ('b', 'B', 'h', 'H') or pl.norm is not None:
         return False
-    K = pl.q * 2 * _ITEMSIZE[pl.enc]
-    return (K in (128, 256) and pl.rem == 0 and pl.Mf % TILE_BLOCKS == 0 and 1 <= pl.R <= 32
-            and pl.q >= pl.edge + 1)
+    K = TC_SB * pl.q * 2 * _ITEMSIZE[pl.enc]
+    return (K in (256, 512) and pl.rem == 0 and pl.Mf % TILE_BLOCKS == 0
+            and (pl.Mf // TC_SB) % 128 == 0 and 1 <= pl.R <= 32 and pl.q >= pl.edge + 1)
 
 
 def build_tc(pl: Plan, nd: int = TC_ND) -> TcTables | None:
@@ -439,21 +471,19 @@ def build_tc(pl: Plan, nd: int = TC_ND) -> TcTables | None:
         return None
     mp.mp.dps = 50
     q, R = pl.q, pl.R
+    q2 = TC_SB * q
     isz = _ITEMSIZE[pl.enc]
     sb = 2 * isz
-    K = q * sb
+    K = q2 * sb
     signed = pl.enc in ('b', 'h')
     stored_le = not pl.swap
-    ncol = nd + isz - 1
+    ncol = nd
     nout = TC_NOUT
-    ncols = np.array([ncol] * 34 + [isz, isz])
-    col0 = np.concatenate([[0], np.cumsum(ncols)[:-1]])
-    npad = -(-int(ncols.sum()) // 16) * 16
-    if not 5 <= ncol <= 6:
-        raise ValueError(f'{nd} digits of {isz}-byte items need {ncol} columns per output; k_tc takes 5 or 6')
     pm = pl.modes.mp_p
-    L = mp.mpf(pl.Liq)
-    lam = mp.mpf(1) - L
+    lam = mp.mpf(1) - mp.mpf(pl.Liq)
+    g0 = mp.mpf(pl.modes.g0)
+    rho = [mp.mpc(v) for v in pl.modes.rho]
+    rho_p = [mp.mpc(v) for v in pl.modes.rho_p]
 
     # byte bookkeeping of one sample: (component, significance, xored?) per byte
     info = []
@@ -463,66 +493,113 @@ def build_tc(pl: Plan, nd: int = TC_ND) -> TcTables | None:
         xored = not (signed and w == isz - 1)
         info.append((cpt, w, xored))
     xor_mask = np.array([0x80 if info[b % sb][2] else 0 for b in range(16)], dtype=np.uint8)
-    offs = sum(128 * 256 ** w for (cpt, w, x) in info if cpt == 0 and x)   # same for I and Q
-
-    def fold_iq(c):
-        """c'_j = c_j - L * sum_{j'>j} c_j' lam^(j'-1-j): the block-local EMA correction (zero
-        offset at the block start) moved from the samples onto the coefficients."""
-        out = [None] * q
-        s = mp.mpc(0)
-        for j in range(q - 1, -1, -1):
-            out[j] = c[j] - L * s
-            s = c[j] + lam * s
-        return out
 
     allrows = []   # [r][o] -> list over j of (coef on I_j, coef on Q_j), real mp numbers
+    rowc = np.zeros((R, TC_NROWC), dtype=np.complex128)
     for r in range(R):
         rows = []
-        T2 = [mp.mpc(complex(v)) for v in pl.T2[r]] if pl.use_nco[r] else [mp.mpc(1)] * q
-        for md in range(16):
-            i = md % 8
-            if md < 8:
-                c = [pm[i] ** (q - 1 - j) * T2[j] for j in range(q)]
-            else:
-                c = [pm[i] ** j * T2[j] for j in range(q)]
-            if pl.correct_iq:
-                c = fold_iq(c)
+        if pl.use_nco[r]:
+            T2x = [mp.mpc(complex(v)) for v in _phasor(pl.w[r], np.arange(q2))]
+        else:
+            T2x = [mp.mpc(1)] * q2
+        rb = [rho[i] * mp.mpc(complex(pl.beta[r, i])) for i in range(8)]
+        rbT = [rho_p[i] * mp.mpc(complex(pl.betaT[r, i])) for i in range(8)]
+        cplx = []
+        for i in range(8):
+            cplx.append([pm[i] ** (q2 - 1 - j) * T2x[j] for j in range(q2)])
+        for i in range(8):
+            cplx.append([pm[i] ** j * T2x[j] for j in range(q2)])
+        for c in cplx:
             rows.append([(mp.re(v), -mp.im(v)) for v in c])    # Re(c*(I+jQ)) = cr I - ci Q
             rows.append([(mp.im(v), mp.re(v)) for v in c])     # Im(c*(I+jQ)) = ci I + cr Q
-        e = [lam ** (q - 1 - j) for j in range(q)]
-        rows.append([(v, mp.mpf(0)) for v in e])
-        rows.append([(mp.mpf(0), v) for v in e])
+        ea = [lam ** (q - 1 - j) if j < q else mp.mpf(0) for j in range(q2)]
+        eab = [lam ** (q2 - 1 - j) for j in range(q2)]
+        for e in (ea, eab):
+            rows.append([(v, mp.mpf(0)) for v in e])
+            rows.append([(mp.mpf(0), v) for v in e])
+        yla = [sum(rbT[i] * pm[i] ** j for i in range(8)) * T2x[j] + (g0 if j == 0 else 0) for j in range(q2)]
+        ylb = []
+        for j in range(q2):
+            if j < q:
+                ylb.append(sum(rb[i] * pm[i] ** (q - 1 - j) for i in range(8)) * T2x[j])
+            else:
+                ylb.append((sum(rbT[i] * pm[i] ** (j - q) for i in range(8)) + (g0 if j == q else 0)) * T2x[j])
+        for c in (yla, ylb):
+            rows.append([(mp.re(v), -mp.im(v)) for v in c])
+            rows.append([(mp.im(v), mp.re(v)) for v in c])
         allrows.append(rows)
 
-    # one binary scale for every ND-digit output of every row: the combine constants of the
-    # kernel are then compile-time-like scalars (costs < 1 bit on the smaller coefficient rows)
-    lim = 127 * 256 ** (nd - 1)
-    amax = max(max(abs(a), abs(b)) for rows in allrows for row in rows for a, b in row)
-    S = int(mp.floor(mp.log(lim / amax, 2)))
+        # ---- epilogue constants of this row (k_tc: tc_epilogue; tests/emulator.py: emu_main_tc)
+        eps2 = T2x[q] * T2x[q]                                 # e^{jw 2q}
+        P2 = [pm[i] ** q2 for i in range(8)]
+        Pq = [pm[i] ** q for i in range(8)]
+        ce = mp.conj(eps2)
+        for i in range(8):
+            rowc[r, RC_CA + i] = _c(rb[i] * ce)                # y_a += ca_i A_i
+            rowc[r, RC_CB + i] = _c(rbT[i] * P2[i] * eps2)     # y_a += cb_i B_i
+            rowc[r, RC_DA + i] = _c(rb[i] * Pq[i] * ce)        # y_b += da_i A_i
+            rowc[r, RC_DB + i] = _c(rbT[i] * Pq[i] * eps2)     # y_b += db_i B_i
+        gam = mp.mpc(complex(pl.gamma[r]))
+        rowc[r, RC_GAM] = _c(gam)
+        rowc[r, RC_GAMQ] = _c(gam * T2x[q])
+        for l in range(16):
+            rowc[r, RC_ROT + l] = _c(eps2 ** l)
+        rowc[r, RC_AGGF] = _c(eps2 ** 15)
+        for i in range(8):
+            for k in range(9):
+                rowc[r, RC_POW + i * 9 + k] = _c((ce * P2[i]) ** k)            # forward scan multiplier
+                rowc[r, RC_POW + (8 + i) * 9 + k] = _c((eps2 * P2[i]) ** k)    # backward
 
-    Bq = np.zeros((R, npad, K), dtype=np.int8)
-    cst = np.zeros((R, nout))
+    # one binary scale for the modal sums and E of every row, a finer one for the local outputs
+    # (their coefficients are ~1/75 of the modal ones and enter y with weight 1, not rho)
+    lim = 127 * 256 ** (nd - 1)
+    amax = max(max(abs(a), abs(b)) for rows in allrows for row in rows[:36] for a, b in row)
+    ayl = max(max(abs(a), abs(b)) for rows in allrows for row in rows[36:] for a, b in row)
+    S_hi = [int(mp.floor(mp.log(lim / amax, 2))), int(mp.floor(mp.log(lim / ayl, 2)))]   # top-byte coefficient = round(c 2^S_hi)
+    S, S_yl = (v - 8 * (isz - 1) for v in S_hi)       # output integer V = value * 2^S
+
+    Bq = np.zeros((R, TC_NPAD, K), dtype=np.int8)
     for r in range(R):
         for o, row in enumerate(allrows[r]):
-            tot = 0
+            c0 = ncol * o
             for j, ab in enumerate(row):
                 for cpt in (0, 1):
-                    A = int(mp.nint(ab[cpt] * mp.mpf(2) ** S))
-                    tot += A
-                    dig = _balanced_digits(A, nd)
+                    A = int(mp.nint(ab[cpt] * mp.mpf(2) ** S_hi[o >= 36]))
                     for bb, (c2_, w, _x) in enumerate(info):
                         if c2_ != cpt:
                             continue
-                        sh = isz - 1 - w
-                        for s_, dv in enumerate(dig):
-                            Bq[r, col0[o] + s_ + sh, j * sb + bb] = dv
-            cst[r, o] = float(mp.mpf(tot * offs) * mp.mpf(2) ** (-S))
-        # x0: the first sample of the block, exact (coefficient 1 on its own bytes)
-        for cpt in (0, 1):
-            o = 34 + cpt
-            for bb, (c2_, w, _x) in enumerate(info):
-                if c2_ == cpt:
-                    Bq[r, col0[o] + (isz - 1 - w), bb] = 1
-            cst[r, o] = float(offs)
-    return TcTables(K=K, isz=isz, ND=nd, NCOL=ncol, nout=nout, Npad=npad, R=R, xor_mask=xor_mask,
-                    Bq=Bq, S=S, cst=cst, col0=col0, ncols=ncols)
+                        if w == isz - 1:                       # top (or only) byte: all nd digits
+                            for s_, dv in enumerate(_balanced_digits(A, nd)):
+                                Bq[r, c0 + s_, j * sb + bb] = dv
+                        else:                                  # low byte: re-rounded, one digit less
+                            Alo = (A + 128) // 256
+                            for s_, dv in enumerate(_balanced_digits(Alo, nd - 1)):
+                                Bq[r, c0 + 1 + s_, j * sb + bb] = dv
+        # x0_a, x0_b: first sample of either block, exact (coefficient 1 on its own bytes)
+        for blk in (0, 1):
+            for cpt in (0, 1):
+                c0 = TC_X0COL + (2 * blk + cpt) * isz
+                for bb, (c2_, w, _x) in enumerate(info):
+                    if c2_ == cpt:
+                        Bq[r, c0 + (isz - 1 - w), blk * q * sb + bb] = 1
+    # response of every output to the constant the XOR removed (the kernel adds it back): bytes
+    # with the mask set enter the GEMM as (u - 128)
+    xk = np.array([128 if info[k % sb][2] else 0 for k in range(K)], dtype=np.int64)
+    colsum = Bq.astype(np.int64) @ xk                                  # (R, Npad)
+    cst = np.zeros((R, nout + 4))
+    for r in range(R):
+        for o in range(nout):
+            V = 0
+            for t in range(ncol):
+                V = V * 256 + int(colsum[r, ncol * o + t])
+            cst[r, o] = float(mp.mpf(V) * mp.mpf(2) ** (-(S_yl if o >= 36 else S)))
+        for x in range(4):
+            V = 0
+            for t in range(isz):
+                V = V * 256 + int(colsum[r, TC_X0COL + x * isz + t])
+            cst[r, nout + x] = float(V)
+    col_l1 = int(np.abs(Bq.astype(np.int64)).sum(axis=2).max())
+    if col_l1 * 128 * 257 >= 2 ** 31:
+        raise OverflowError('int32 digit-pair sums could overflow for this coefficient set')
+    return TcTables(K=K, isz=isz, ND=nd, NCOL=ncol, SB=TC_SB, nout=nout, Npad=TC_NPAD, R=R, xor_mask=xor_mask,
+                    Bq=Bq, S=S, S_yl=S_yl, cst=cst, rowc=rowc, col_l1=col_l1)

@@ -2,8 +2,10 @@
 (sdrterm_b200/plan.py).  TEST INFRASTRUCTURE: it lets the CPU suite validate the block-modal
 algorithm and every table against the oracle without a GPU.  Structure mirrors the kernels:
 
-  emu_main    <-> k_main   (per chunk x tile [x row]: decode, block-local IQ, NCO, even/odd block
-                            sums, tile-local scans, partial outputs + tile aggregates)
+  emu_main    <-> k_main   (per chunk x tile [x row]: decode, NCO, even/odd block sums of the
+                            UNcorrected samples, IQ-EMA block aggregates, tile-local scans, partial
+                            outputs + tile aggregates; the IQ corrector enters only through the
+                            decoupled terms of DESIGN.md 3.3)
   emu_iq_scan <-> k_iqscan (offset at every tile start, carried across chunks and calls)
   emu_fixup   <-> k_fixup  (head / end segments, cross-tile carries, boundary term -> decimated y)
   emu_demod   <-> k_demod  (fm pair-phase + 2x FFT interpolation | am | re | im, output SOS)
@@ -25,44 +27,6 @@ def decode(pl: Plan, raw: np.ndarray) -> np.ndarray:
         xmin, k = pl.norm
         z = (((1.6 * (z.real - xmin)) * k) - 0.8) + 1j * ((1.6 * z.imag) * k)
     return z
-
-
-def iq_runs(pl: Plan, zb: np.ndarray):
-    """Block-local IQ correction as k_main evaluates it: each block is cut into 8 runs (4 ascending
-    over the first half, 4 over the second); run aggregates are scanned to give the EMA state at
-    every run boundary; the first-half runs then advance the EMA forward from their start, the
-    second-half runs recover it BACKWARD from their end (acc_j = (acc_{j+1} - z_j)/lam), which is
-    the order in which the even/odd pairing consumes the samples."""
-    q, Hq, RL = pl.q, pl.Hq, pl.RL
-    Mf = zb.shape[0]
-    bounds = []
-    for k in range(4):
-        a0, a1 = min(k * RL, Hq), min((k + 1) * RL, Hq)
-        bounds.append((a0, a1))
-    dbounds = [(max(q - a1, Hq), q - a0) for (a0, a1) in bounds]      # per k
-    runs = bounds + [dbounds[3], dbounds[2], dbounds[1], dbounds[0]]   # sample order
-    agg = np.zeros((8, Mf), dtype=np.complex128)
-    for i, (lo, hi) in enumerate(runs):
-        a = np.zeros(Mf, dtype=np.complex128)
-        for j in range(lo, hi):
-            a = pl.lam * a + zb[:, j]
-        agg[i] = a
-        assert hi - lo == pl.run_len[i]
-    A = np.zeros((9, Mf), dtype=np.complex128)
-    for i in range(8):
-        A[i + 1] = pl.lam_run[i] * A[i] + agg[i]
-    zp = np.empty_like(zb)
-    for k in range(4):
-        acc = A[k].copy()
-        for j in range(*bounds[k]):
-            zp[:, j] = zb[:, j] - pl.Liq * acc
-            acc = pl.lam * acc + zb[:, j]
-        acc = A[8 - k].copy()
-        lo, hi = dbounds[k]
-        for j in range(hi - 1, lo - 1, -1):
-            acc = (acc - zb[:, j]) * pl.lam_inv
-            zp[:, j] = zb[:, j] - pl.Liq * acc
-    return zp, A[8]
 
 
 def sos_segments(pl: Plan, z: np.ndarray) -> np.ndarray:
@@ -99,24 +63,17 @@ def sos_segments(pl: Plan, z: np.ndarray) -> np.ndarray:
     return out
 
 
-def emu_main(pl: Plan, z: np.ndarray):
-    """z: decoded chunk (N,).  Returns dict of per-chunk arrays written by the main kernel."""
-    q, Mf, nt = pl.q, pl.Mf, pl.ntiles
-    m = pl.modes
-    zb = z[:q * Mf].reshape(Mf, q)
-    # ---- phase 0: block-local IQ (zero offset at block start)
-    zp = np.empty_like(zb)
-    acc = np.zeros(Mf, dtype=np.complex128)
-    for j in range(q):
-        zp[:, j] = zb[:, j] - pl.Liq * acc
+def block_ema(pl: Plan, zb: np.ndarray) -> np.ndarray:
+    """E_k = sum_j lam^(q-1-j) z_j per block: L*E_k is the offset a block adds from a zero state."""
+    acc = np.zeros(zb.shape[0], dtype=np.complex128)
+    for j in range(zb.shape[1]):
         acc = pl.lam * acc + zb[:, j]
-    blk_agg = pl.Liq * acc                     # offset gained over one block from zero
-    if pl.correct_iq:
-        zp2, acc2 = iq_runs(pl, zb)            # the kernel's run-wise evaluation of the same thing
-        assert np.max(np.abs(zp2 - zp)) <= 1e-13 * max(1.0, np.max(np.abs(zb)))
-        assert np.max(np.abs(acc2 - acc)) <= 1e-12 * max(1.0, np.max(np.abs(acc)))
-        zp = zp2
-    # tile-local block offsets (zero at tile start) and tile aggregates
+    return acc
+
+
+def tile_offsets(pl: Plan, blk_agg: np.ndarray):
+    """Tile-local block offsets (zero at every tile start) and the tile aggregates."""
+    Mf, nt = pl.Mf, pl.ntiles
     off_loc = np.zeros(Mf, dtype=np.complex128)
     tile_agg = np.zeros(nt, dtype=np.complex128)
     for t in range(nt):
@@ -127,12 +84,22 @@ def emu_main(pl: Plan, z: np.ndarray):
             off_loc[k0 + l] = o
             o = pl.lam_q * o + blk_agg[k0 + l]
         tile_agg[t] = o
+    return off_loc, tile_agg
+
+
+def emu_main(pl: Plan, z: np.ndarray):
+    """z: decoded chunk (N,).  Returns dict of per-chunk arrays written by the main kernel."""
+    q, Mf, nt = pl.q, pl.Mf, pl.ntiles
+    m = pl.modes
+    zb = z[:q * Mf].reshape(Mf, q)
+    blk_agg = pl.Liq * block_ema(pl, zb)       # offset gained over one block from zero
+    off_loc, tile_agg = tile_offsets(pl, blk_agg)
     ypart = np.zeros((pl.R, Mf), dtype=np.complex128)
     Wout = np.zeros((pl.R, nt, 8), dtype=np.complex128)
     Tin = np.zeros((pl.R, nt, 8), dtype=np.complex128)
     H = q // 2
     for r in range(pl.R):
-        u = zp * pl.T2[r][None, :]
+        u = zb * pl.T2[r][None, :]               # NCO only: the samples are NOT IQ-corrected here
         a = u[:, :H] + u[:, ::-1][:, :H]
         d = u[:, :H] - u[:, ::-1][:, :H]
         if q & 1:
@@ -152,10 +119,8 @@ def emu_main(pl: Plan, z: np.ndarray):
             D_lo = (d1 + d4) + 1j * (d3 - d2)
             F[:, mm], G[:, mm] = S_up + D_up, S_up - D_up
             F[:, mm + 4], G[:, mm + 4] = S_lo + D_lo, S_lo - D_lo
-        # local IQ offsets, then block rotation
-        F -= off_loc[:, None] * pl.PhiF[r][None, :]
-        G -= off_loc[:, None] * pl.PhiG[r][None, :]
-        x0 = zp[:, 0] - off_loc                  # first sample of each block (T2[0] == 1)
+        rb, rbT = m.rho * pl.beta[r], m.rho_p * pl.betaT[r]
+        x0 = zb[:, 0]                            # first raw sample of each block (T2[0] == 1)
         for t in range(nt):
             k0 = t * TILE_BLOCKS
             cnt = min(TILE_BLOCKS, Mf - k0)
@@ -168,8 +133,8 @@ def emu_main(pl: Plan, z: np.ndarray):
             T = np.zeros((cnt + 1, 8), dtype=np.complex128)
             for l in range(cnt - 1, -1, -1):
                 T[l] = pl.P * T[l + 1] + Gl[l]
-            ypart[r, k0:k0 + cnt] = (W[:cnt] @ m.rho + T[:cnt] @ m.rho_p
-                                      + m.g0 * x0[k0:k0 + cnt] * rot)
+            ypart[r, k0:k0 + cnt] = (W[:cnt] @ rb + T[:cnt] @ rbT
+                                      + (m.g0 * x0[k0:k0 + cnt] - pl.gamma[r] * off_loc[k0:k0 + cnt]) * rot)
             Wout[r, t] = W[cnt]
             Tin[r, t] = T[0]
     return dict(ypart=ypart, Wout=Wout, Tin=Tin, tile_agg=tile_agg)
@@ -226,21 +191,23 @@ def emu_fixup(pl: Plan, z: np.ndarray, mo: dict, off_chunk: complex):
         w = m.zhat * ext[0]
         for j in range(edge):
             w = p * w + ext[j]
-        # forward across tiles
+        # forward across tiles, in the frame of the uncorrected samples: W~ = (w + alpha s) / beta
+        # with s = off e^{jwn} (n = 0: the chunk-start offset itself)
         Win = np.zeros((nt + 1, 8), dtype=np.complex128)
-        Win[0] = w
+        Win[0] = (w + pl.alpha[r] * off_chunk) / pl.beta[r]
         s = -off_tile[:nt]
         for t in range(nt):
             kind = 1 if t == nt - 1 else 0
             cnt = pl.cnt_last if kind else TILE_BLOCKS
-            Win[t + 1] = pl.Ppow[cnt] * Win[t] + pl.T1[r, t] * (mo['Wout'][r, t]
-                                                                + s[t] * pl.PsiW[kind, r])
+            Win[t + 1] = pl.Ppow[cnt] * Win[t] + pl.T1[r, t] * mo['Wout'][r, t]
+        sE = off_tile[nt] * pl.phE[r]              # rotated offset at sample q*Mf
+        w_end = pl.beta[r] * Win[nt] - pl.alpha[r] * sE
         # end segment: partial block (rem samples) + tail extension
         xN1 = xs_e[-1]
         tail = 2 * xN1 - xs_e[-2:-(edge + 2):-1]
         part = xs_e[pl.nend - pl.rem:] if pl.rem else xs_e[:0]
         seq = np.concatenate([part, tail])
-        w = Win[nt].copy()
+        w = w_end.copy()
         wL1 = None
         for i, v in enumerate(seq):
             if i == len(seq) - 1:
@@ -255,16 +222,16 @@ def emu_fixup(pl: Plan, z: np.ndarray, mo: dict, off_chunk: complex):
         Tend = T                                   # anticausal state at n = edge + q*Mf
         if pl.rem:
             k = Mf
-            y[r, k] = (np.sum(m.rho * Win[nt]) + np.sum(m.rho_p * Tend) + m.g0 * part[0]
+            y[r, k] = (np.sum(m.rho * w_end) + np.sum(m.rho_p * Tend) + m.g0 * part[0]
                        + np.sum(pl.bnd[k] * zeta))
         # backward across tiles
         Tn = np.zeros((nt + 1, 8), dtype=np.complex128)
-        Tn[nt] = Tend
+        Tn[nt] = (Tend + pl.alphaT[r] * sE) / pl.betaT[r]
         for t in range(nt - 1, -1, -1):
             kind = 1 if t == nt - 1 else 0
             cnt = pl.cnt_last if kind else TILE_BLOCKS
-            Tn[t] = pl.Ppow[cnt] * Tn[t + 1] + pl.T1[r, t] * (mo['Tin'][r, t]
-                                                              + s[t] * pl.PsiT[kind, r])
+            Tn[t] = pl.Ppow[cnt] * Tn[t + 1] + pl.T1[r, t] * mo['Tin'][r, t]
+        Wc, Tc = pl.beta[r][None, :] * Win, pl.betaT[r][None, :] * Tn      # carries as the kernels keep them
         for t in range(nt):
             kind = 1 if t == nt - 1 else 0
             cnt = pl.cnt_last if kind else TILE_BLOCKS
@@ -272,8 +239,8 @@ def emu_fixup(pl: Plan, z: np.ndarray, mo: dict, off_chunk: complex):
             for l in range(cnt):
                 k = k0 + l
                 v = pl.T1[r, t] * (mo['ypart'][r, k] + s[t] * pl.psiY[kind, r, l])
-                v += np.sum(m.rho * pl.Ppow[l] * Win[t])
-                v += np.sum(m.rho_p * pl.Ppow[cnt - l] * Tn[t + 1])
+                v += np.sum(m.rho * pl.Ppow[l] * Wc[t])
+                v += np.sum(m.rho_p * pl.Ppow[cnt - l] * Tc[t + 1])
                 if k >= pl.k_bnd:
                     v += np.sum(pl.bnd[k] * zeta)
                 y[r, k] = v
@@ -342,83 +309,82 @@ def emu_stream(pl: Plan, stream: bytes, off0: complex = 0j, stale_tail: bool = T
 # ------------------------------------------------------------------------------------------------
 # Tensor-core front end (k_tc): numpy twin.  The int8 GEMM is evaluated exactly in int64.
 def tc_block_values(pl: Plan, tc, raw: np.ndarray, r: int = 0) -> np.ndarray:
-    """raw chunk bytes -> (Mf, nout) float64: the per-block linear functionals of row r as k_tc's
-    epilogue reassembles them from the int32 digit columns."""
-    Mf, K, ncol, nout = pl.Mf, tc.K, tc.NCOL, tc.nout
-    by = np.frombuffer(raw, dtype=np.uint8)[:Mf * K].reshape(Mf, K)
+    """raw chunk bytes -> (Mf/SB, nout + 4) float64: the linear functionals of every super-block of
+    row r as k_tc's epilogue reassembles them from the int32 digit columns (the last 4: x0)."""
+    nsb, K, ncol, nout = pl.Mf // tc.SB, tc.K, tc.NCOL, tc.nout
+    by = np.frombuffer(raw, dtype=np.uint8)[:nsb * K].reshape(nsb, K)
     sby = (by ^ np.tile(tc.xor_mask, K // 16)[None, :]).view(np.int8).astype(np.int64)
     acc = sby @ tc.Bq[r].T.astype(np.int64)                     # exact column sums
-    assert np.max(np.abs(acc)) < 2 ** 31
-    val = np.zeros((Mf, nout))
-    scale = 2.0 ** -tc.S
-    nhi = ncol - 3
+    assert np.max(np.abs(acc)) <= tc.col_l1 * 128 < 2 ** 31
+    val = np.zeros((nsb, nout + 4))
     for o in range(nout):
-        cols = acc[:, tc.col0[o]:tc.col0[o] + tc.ncols[o]]
-        if tc.ncols[o] != ncol:                                 # x0: exact small integer
-            v = np.zeros(Mf, dtype=np.int64)
-            for t in range(cols.shape[1]):
-                v = v * 256 + cols[:, t]
-            val[:, o] = v.astype(np.float64) + tc.cst[r, o]
-            continue
-        vhi = np.zeros(Mf, dtype=np.int64)
-        vlo = np.zeros(Mf, dtype=np.int64)
-        for t in range(nhi):
-            vhi = vhi * 256 + cols[:, t]
-        for t in range(nhi, ncol):
-            vlo = vlo * 256 + cols[:, t]
-        assert np.max(np.abs(vhi)) < 2 ** 51 and np.max(np.abs(vlo)) < 2 ** 51
+        scale = 2.0 ** -(tc.S_yl if o >= 36 else tc.S)
+        c = acc[:, ncol * o:ncol * (o + 1)]
+        mid = c[:, 1] * 256 + c[:, 2]
+        lo = c[:, 3] * 256 + c[:, 4]
+        assert np.max(np.abs(mid)) < 2 ** 31 and np.max(np.abs(lo)) < 2 ** 31      # int32 on the device
+        hi = c[:, 0] * 65536 + mid
+        assert np.max(np.abs(hi)) < 2 ** 51
         # scale is a power of two: both products are exact, the sums round (device: two FMAs)
-        val[:, o] = vhi.astype(np.float64) * (2.0 ** 24 * scale) + (vlo.astype(np.float64) * scale
-                                                                     + tc.cst[r, o])
+        val[:, o] = hi.astype(np.float64) * (2.0 ** 16 * scale) + (lo.astype(np.float64) * scale + tc.cst[r, o])
+    x0c = 5 * nout
+    for x in range(4):
+        v = np.zeros(nsb, dtype=np.int64)
+        for t in range(tc.isz):
+            v = v * 256 + acc[:, x0c + x * tc.isz + t]
+        val[:, nout + x] = v.astype(np.float64) + tc.cst[r, nout + x]
     return val
 
 
 def emu_main_tc(pl: Plan, tc, raw: np.ndarray, z: np.ndarray):
-    """Same outputs as emu_main, with the block sums taken from the int8 GEMM (R == 1 rows only
-    for now).  z (decoded chunk) is used only for the first sample of each block and the tail
-    window, which the kernel decodes from the staged tile."""
+    """Same outputs as emu_main, computed the way k_tc does: GEMM rows are super-blocks of two
+    blocks; per tile (16 super-blocks) the exclusive scan states A (forward) and B (backward) in
+    the frame of each super-block, the two block outputs from the local functionals yl_a / yl_b
+    plus the scan states, the tile aggregates."""
+    from sdrterm_b200 import plan as P_
     q, Mf, nt = pl.q, pl.Mf, pl.ntiles
-    m = pl.modes
-    val = tc_block_values(pl, tc, raw, 0)
     zb = z[:q * Mf].reshape(Mf, q)
-    E = val[:, 32] + 1j * val[:, 33]
-    assert np.array_equal(val[:, 34] + 1j * val[:, 35], zb[:, 0])   # x0 comes out of the GEMM exactly
-    blk_agg = pl.Liq * E
-    off_loc = np.zeros(Mf, dtype=np.complex128)
-    tile_agg = np.zeros(nt, dtype=np.complex128)
-    for t in range(nt):
-        k0 = t * TILE_BLOCKS
-        o = 0j
-        for l in range(TILE_BLOCKS):
-            off_loc[k0 + l] = o
-            o = pl.lam_q * o + blk_agg[k0 + l]
-        tile_agg[t] = o
     ypart = np.zeros((pl.R, Mf), dtype=np.complex128)
     Wout = np.zeros((pl.R, nt, 8), dtype=np.complex128)
     Tin = np.zeros((pl.R, nt, 8), dtype=np.complex128)
+    tile_agg = np.zeros(nt, dtype=np.complex128)
+    lq, lq2 = pl.lam_q, pl.lam_q * pl.lam_q
     for r in range(pl.R):
         v = tc_block_values(pl, tc, raw, r)
+        rc = tc.rowc[r]
         F = v[:, 0:16:2] + 1j * v[:, 1:16:2]
         G = v[:, 16:32:2] + 1j * v[:, 17:32:2]
-        F = F - off_loc[:, None] * pl.PhiF[r][None, :]
-        G = G - off_loc[:, None] * pl.PhiG[r][None, :]
-        x0 = zb[:, 0] - off_loc
+        Ea, Eab = v[:, 32] + 1j * v[:, 33], v[:, 34] + 1j * v[:, 35]
+        yla, ylb = v[:, 36] + 1j * v[:, 37], v[:, 38] + 1j * v[:, 39]
+        assert np.array_equal(v[:, 40] + 1j * v[:, 41], zb[0::2, 0])   # x0 comes out of the GEMM exactly
+        assert np.array_equal(v[:, 42] + 1j * v[:, 43], zb[1::2, 0])
+        ca, cb = rc[P_.RC_CA:P_.RC_CA + 8], rc[P_.RC_CB:P_.RC_CB + 8]
+        da, db = rc[P_.RC_DA:P_.RC_DA + 8], rc[P_.RC_DB:P_.RC_DB + 8]
+        Pm = rc[P_.RC_POW + 9 * np.arange(8) + 1]
+        Pmb = rc[P_.RC_POW + 9 * (8 + np.arange(8)) + 1]
+        rot = rc[P_.RC_ROT:P_.RC_ROT + 16]
         for t in range(nt):
-            k0 = t * TILE_BLOCKS
-            cnt = TILE_BLOCKS
-            rot = pl.T3[r][:cnt]
-            Fl = F[k0:k0 + cnt] * rot[:, None]
-            Gl = G[k0:k0 + cnt] * rot[:, None]
-            W = np.zeros((cnt + 1, 8), dtype=np.complex128)
-            for l in range(cnt):
-                W[l + 1] = pl.P * W[l] + Fl[l]
-            T = np.zeros((cnt + 1, 8), dtype=np.complex128)
-            for l in range(cnt - 1, -1, -1):
-                T[l] = pl.P * T[l + 1] + Gl[l]
-            ypart[r, k0:k0 + cnt] = (W[:cnt] @ m.rho + T[:cnt] @ m.rho_p
-                                      + m.g0 * x0[k0:k0 + cnt] * rot)
-            Wout[r, t] = W[cnt]
-            Tin[r, t] = T[0]
+            s0 = t * 16
+            ea = np.zeros(16, dtype=np.complex128)
+            o = 0j
+            for l in range(16):
+                ea[l] = o
+                o = lq2 * o + pl.Liq * Eab[s0 + l]
+            if r == 0:
+                tile_agg[t] = o
+            eb = lq * ea + pl.Liq * Ea[s0:s0 + 16]
+            A = np.zeros((17, 8), dtype=np.complex128)
+            for l in range(16):
+                A[l + 1] = Pm * A[l] + F[s0 + l]
+            B = np.zeros((17, 8), dtype=np.complex128)           # B[l] = state after super-block l from above
+            for l in range(15, -1, -1):
+                B[l] = Pmb * B[l + 1] + G[s0 + l]
+            ya = yla[s0:s0 + 16] + A[:16] @ ca + B[1:] @ cb - rc[P_.RC_GAM] * ea
+            yb = ylb[s0:s0 + 16] + A[:16] @ da + B[1:] @ db - rc[P_.RC_GAMQ] * eb
+            ypart[r, t * 32:t * 32 + 32:2] = rot * ya
+            ypart[r, t * 32 + 1:t * 32 + 32:2] = rot * yb
+            Wout[r, t] = rc[P_.RC_AGGF] * A[16]
+            Tin[r, t] = B[0]
     return dict(ypart=ypart, Wout=Wout, Tin=Tin, tile_agg=tile_agg)
 
 

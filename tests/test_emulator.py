@@ -1,0 +1,59 @@
+"""CPU: the numpy twins of the CUDA kernels (tests/emulator.py), driven by the SAME plan tables the
+kernels consume, against the oracle.  This validates the host-side table construction -- the modal
+block form, the decoupled IQ-corrector terms and the int8 digit matrices of the
+tensor-core front end (exact integer GEMM emulated in int64) -- without a GPU."""
+import numpy as np
+import pytest
+
+import emulator as emu
+from oracle import oracle as orc
+from sdrterm_b200.plan import build_plan, build_tc
+from util import case_stream, rel_err
+
+TOL = 1e-9
+
+
+def _plan(kw):
+    ch = orc.Chain(**kw)
+    return build_plan(kw['fs'], kw['enc'], kw['dec'], ch.rows, simo=kw['simo'], swap=orc.needs_swap(ch.dt),
+                      correct_iq=kw['correct_iq'], normalize=kw['normalize'], demod=kw['demod'],
+                      omega_out=kw['omega_out'])
+
+
+@pytest.mark.parametrize('name', ['c1_fm_wav_int16', 'c2_am_u8_d50_ceil', 'enc_I_norm_am', 'enc_h_d2_fm'])
+def test_block_kernel_twin_matches_oracle(name):
+    raw, body, kw = case_stream(name)
+    pl = _plan(kw)
+    out, ys, off = emu.emu_stream(pl, body)
+    ch = orc.Chain(**kw)
+    ref = ch.run(body)
+    assert out.shape == ref.shape and rel_err(out, ref) < 1e-11
+    assert abs(off - ch._off[0]) <= 1e-9 * max(1.0, abs(ch._off[0]))
+
+
+@pytest.mark.parametrize('name', ['c1_fm_wav_int16', 'c2_am_u8_d64', 'enc_H_swap_im', 'c3_simo16_int16be'])
+def test_tensor_core_twin_matches_oracle(name):
+    """Super-block GEMM rows, 5 digit columns, re-rounded low-byte coefficients, separate scale of
+    the local outputs: the whole chain stays ~1e-12 from the oracle (tolerance 1e-9)."""
+    raw, body, kw = case_stream(name)
+    pl = _plan(kw)
+    tc = build_tc(pl)
+    assert tc is not None and tc.NCOL == 5 and tc.Npad == 208 and tc.K in (256, 512)
+    assert tc.col_l1 * 128 * 257 < 2 ** 31              # digit-pair sums fit int32 on the device
+    body = body[:len(body) // 131072 * 131072] or body
+    out, ys, off = emu.emu_stream_tc(pl, tc, body)
+    ch = orc.Chain(**kw)
+    ref = ch.run(body)
+    assert out.shape == ref.shape and rel_err(out, ref) < 2e-11
+
+
+def test_iq_decoupling_constants():
+    """w_i = beta_i W~_i - alpha_i s: beta -> 1, gamma -> 0 without --correct-iq; with it, gamma is
+    the two-sided response of the decimation filter to the offset mode lam e^{jw}."""
+    pl0 = build_plan(1_024_000, 'h', 64, [15000], correct_iq=False, demod='fm', omega_out=5000)
+    assert np.all(pl0.beta == 1) and np.all(pl0.alpha == 0) and np.all(pl0.gamma == 0)
+    pl = build_plan(1_024_000, 'h', 64, [0], correct_iq=True, demod='fm', omega_out=5000)
+    # centre 0: the offset mode is (almost) DC, where the low-pass has unit gain (0.05 dB ripple)
+    assert abs(abs(pl.gamma[0]) - 1) < 0.02
+    pl = build_plan(1_024_000, 'h', 64, [200_000], correct_iq=True, demod='fm', omega_out=5000)
+    assert abs(pl.gamma[0]) < 1e-6                      # far in the stop band

@@ -49,10 +49,19 @@ def test_stage_parity_vs_emulator(name):
     """Decimator output chunk by chunk vs tests/emulator.py (same tables, same algorithm)."""
     import emulator as emu
     from gpu_util import run_case
+    from sdrterm_b200.plan import build_tc
     kw, pl, chunks, out, y, off = run_case(name)
-    eo, ey, eoff = emu.emu_stream(pl, chunks.tobytes())
+    tc = build_tc(pl)
+    if tc is not None:      # the tensor-core front end ran: its own twin (same digit matrices)
+        eo, ey, eoff = emu.emu_stream_tc(pl, tc, chunks.tobytes())
+    else:
+        eo, ey, eoff = emu.emu_stream(pl, chunks.tobytes())
     assert rel_err(y, ey) < 1e-11
     assert rel_err(np.asarray(out, dtype=np.float64), eo) < 1e-11
+    if tc is not None:      # and the FP64 block kernel against the general twin
+        kw, pl, chunks, out2, y2, off2 = run_case(name, use_tc=False)
+        eo2, ey2, _ = emu.emu_stream(pl, chunks.tobytes())
+        assert rel_err(y2, ey2) < 1e-11
 
 
 @pytest.mark.parametrize('name', ['c1_fm_wav_int16', 'c2_am_u8_d64', 'c3_simo16_int16be', 'enc_H_swap_im'])
