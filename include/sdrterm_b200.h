@@ -165,6 +165,11 @@ int sdrb_process_device_phases(sdrb_handle *h, const void *raw_dev, size_t nchun
 int sdrb_iq_export_device(sdrb_handle *h, double *dst3_dev, double nsamples, void *stream);
 int sdrb_iq_prefix_device(sdrb_handle *h, const double *gains3_dev, int rank, void *stream);
 
+/* Pre-pass of time-segment sharding for segments longer than one batch: advance the IQ state over
+ * `nchunks` raw HOST chunks exactly as sdrb_process would, without computing any output (the
+ * offset a segment gains from a zero state is what the ranks exchange). */
+int sdrb_iq_gain(sdrb_handle *h, const void *raw_host, size_t nchunks);
+
 /* CUDA-event timing of the kernel groups of the last full sdrb_process_device call: ms[0] = block
  * front end (k_tc / k_main), ms[1] = IQ-offset kernels, ms[2] = k_finish (or k_fixup), ms[3] =
  * k_demod (general path only, 0 otherwise); for bench.py's roofline. */

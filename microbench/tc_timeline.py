@@ -22,14 +22,15 @@ nat.check(nat.lib().sdrb_read_debug(eng._h, buf.ctypes.data), eng._h)
 t = buf.reshape(64, 16).astype(np.int64)
 t0 = t[0, 0]
 names = ['tma_issue', 'xor_start', 'xor_done', 'mma_start', 'mma_issued', 'epi_start', 'tmem_free', 'epi_end',
-         'excl', 'scanA', 'scanBC', 'dot', 'pair']
+         'iq', 'scanF', 'dotF', 'scanB']
 print('tile ' + ' '.join(f'{n:>10s}' for n in names))
-for it in range(2, 32):
-    print(f'{it:4d} ' + ' '.join(f'{(t[it, e] - t0):10d}' for e in range(8)))
+for it in range(3, 32, 3):      # epilogue events are recorded by warp 4 (epilogue group 0: every third tile)
+    print(f'{it:4d} ' + ' '.join(f'{(t[it, e] - t0):10d}' for e in range(12)))
+ev = np.arange(9, 31, 3)
 d = np.diff(t[8:31, 0])
-print('cycles per tile (tma_issue to tma_issue):', d.mean())
-for a, b in ((0, 1), (1, 2), (2, 3), (3, 4), (4, 5), (5, 8), (8, 6), (6, 9), (9, 10), (10, 11), (11, 12), (12, 7), (5, 7), (0, 7)):
-    print(f'{names[a]:>10s} -> {names[b]:<10s}: mean {np.mean(t[8:31, b] - t[8:31, a]):8.0f}')
+print('cycles per MMA tile (tma_issue to tma_issue):', d.mean())
+for a, b in ((0, 1), (1, 2), (2, 3), (3, 4), (4, 5), (5, 6), (6, 8), (8, 9), (9, 10), (10, 11), (11, 7), (5, 7), (0, 7)):
+    print(f'{names[a]:>10s} -> {names[b]:<10s}: mean {np.mean(t[ev, b] - t[ev, a]):8.0f}')
 
 f = t[32:48, :11]          # k_finish events of warp 0 / CTA 0 live in the second half of the buffer
 fn = ['start', '1a loads', '1b iq', '1c nco', '1d dots', '1e tiles', '1f zeta', '2 outputs+phase', '3b fft', '4 sos', '5 store']

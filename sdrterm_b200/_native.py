@@ -60,7 +60,7 @@ EXPORTS = ['sdrb_create', 'sdrb_destroy', 'sdrb_last_error', 'sdrb_outputs_per_c
            'sdrb_fm_demod', 'sdrb_am_demod', 'sdrb_real_output', 'sdrb_imag_output',
            'sdrb_shift_freq', 'sdrb_global_error', 'sdrb_process_device_phases',
            'sdrb_set_profiling', 'sdrb_kernel_times', 'sdrb_keep_decimated', 'sdrb_read_debug', 'sdrb_iq_export_device',
-           'sdrb_iq_prefix_device', 'sdrb_decode_iq', 'sdrb_correct_iq', 'sdrb_keep_x0', 'sdrb_read_x0']
+           'sdrb_iq_prefix_device', 'sdrb_decode_iq', 'sdrb_correct_iq', 'sdrb_keep_x0', 'sdrb_read_x0', 'sdrb_iq_gain']
 
 
 def nvcc_command(out: str = LIB_PATH) -> list[str]:
@@ -122,6 +122,7 @@ def lib():
         L.sdrb_decode_iq.argtypes = [C.c_int, vp, sz, C.c_char, C.c_int, vp]
         L.sdrb_correct_iq.argtypes = [C.c_int, vp, sz, _DP, C.c_double]
         L.sdrb_keep_x0.argtypes = [vp, C.c_int]
+        L.sdrb_iq_gain.argtypes = [vp, vp, sz]
         L.sdrb_read_x0.argtypes = [vp, sz, vp]
         _lib = L
     return _lib

@@ -247,6 +247,8 @@ int setup_tc(sdrb_handle *h, const sdrb_tables *tab)
     nstage = std::min(nstage, TC_MAX_ASTAGES);
     if (nstage < 2) return fail(h, SDRB_ERR_ARG, "k_tc: no room for the A ring (%zu bytes fixed)", fixed);
     tc.nstage = nstage;
+    tc.prefetch_tiles = env_int("SDRB_TC_PREFETCH", 0);
+    if (env_int("SDRB_TC_ABL_NOXOR", 0)) tc.xor_word = 0;      // timing experiment only: wrong results
     h->tc_smem = tc_smem_bytes(tc.nregion, nstage);
     if ((rc = tc_attr<true>(h)) || (rc = tc_attr<false>(h))) return rc;
     h->tc_on = true;
@@ -678,6 +680,46 @@ int sdrb_process(sdrb_handle *h, const void *raw, size_t nchunks, double *out)
             memcpy(out + r * nchunks * M + done * M, tmp.data() + r * n * M, n * M * sizeof(double));
         done += n;
     }
+    return SDRB_OK;
+}
+
+}  // extern "C"
+namespace {
+template <int ENC>
+void launch_iqchunk(sdrb_handle *h, const uint8_t *raw, size_t nch, cudaStream_t st)
+{
+    k_iqchunk<ENC><<<(unsigned)((nch + 7) / 8), 256, 0, st>>>(h->pl, h->sc, raw, (int)nch);
+}
+}  // namespace
+extern "C" {
+
+int sdrb_iq_gain(sdrb_handle *h, const void *raw_host, size_t nchunks)
+{
+    if (!h || !raw_host) return fail(h, SDRB_ERR_ARG, "null argument");
+    if (nchunks == 0 || !h->pl.correct_iq) return SDRB_OK;
+    if (nchunks > h->max_chunks) return fail(h, SDRB_ERR_ARG, "nchunks %zu > max_chunks %zu", nchunks, h->max_chunks);
+    CK(h, cudaSetDevice(h->cfg.device));
+    int rc = ensure_slot(h, 0);
+    if (rc) return rc;
+    Slot &sl = h->slot[0];
+    CK(h, cudaMemcpyAsync(sl.raw, raw_host, nchunks * sdrb_chunk_bytes(h), cudaMemcpyHostToDevice, sl.stream));
+    CK(h, cudaStreamWaitEvent(sl.stream, h->iq_done, 0));
+    switch (h->enc_code) {
+    case ENC_b: launch_iqchunk<ENC_b>(h, sl.raw, nchunks, sl.stream); break;
+    case ENC_B: launch_iqchunk<ENC_B>(h, sl.raw, nchunks, sl.stream); break;
+    case ENC_h: launch_iqchunk<ENC_h>(h, sl.raw, nchunks, sl.stream); break;
+    case ENC_H: launch_iqchunk<ENC_H>(h, sl.raw, nchunks, sl.stream); break;
+    case ENC_i: launch_iqchunk<ENC_i>(h, sl.raw, nchunks, sl.stream); break;
+    case ENC_I: launch_iqchunk<ENC_I>(h, sl.raw, nchunks, sl.stream); break;
+    case ENC_f: launch_iqchunk<ENC_f>(h, sl.raw, nchunks, sl.stream); break;
+    case ENC_d: launch_iqchunk<ENC_d>(h, sl.raw, nchunks, sl.stream); break;
+    default:    launch_iqchunk<ENC_Z>(h, sl.raw, nchunks, sl.stream); break;
+    }
+    k_iqscan_c<<<1, 1024, 0, sl.stream>>>(h->pl, h->sc, (int)nchunks);
+    h->launches += 2;
+    CK(h, cudaGetLastError());
+    CK(h, cudaEventRecord(h->iq_done, sl.stream));
+    CK(h, cudaStreamSynchronize(sl.stream));
     return SDRB_OK;
 }
 

@@ -314,6 +314,36 @@ k_iqgain_w(const __grid_constant__ DevPlan pl, Scratch sc, int nchunks)
     if (lane == nt - 1) sc.gain[c] = a;
 }
 
+// k_iqchunk: warp <-> chunk: the offset a whole chunk gains from a zero state, straight from the raw
+// bytes (decode, normalise, EMA) -> gain[c].  The pre-pass of time-segment sharding for streams
+// longer than one batch (sdrb_iq_gain): no outputs, the raw bytes are read once.
+template <int ENC>
+__global__ void __launch_bounds__(256)
+k_iqchunk(const __grid_constant__ DevPlan pl, Scratch sc, const uint8_t *__restrict__ raw, int nchunks)
+{
+    const int lane = threadIdx.x & 31;
+    const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (c >= nchunks) return;
+    const uint8_t *rawc = raw + (size_t)c * pl.N * pl.sb;
+    // lane <-> contiguous run of ceil(N/32) samples
+    const int per = (pl.N + 31) / 32;
+    const int n0 = min(pl.N, lane * per), n1 = min(pl.N, n0 + per);
+    double2 a = make_double2(0.0, 0.0);
+    double m = 1.0;
+    for (int n = n0; n < n1; n++) {
+        const double2 z = decode_sample<ENC>(pl, rawc, n);
+        a.x = fma(pl.lam, a.x, z.x); a.y = fma(pl.lam, a.y, z.y);
+        m *= pl.lam;
+    }
+#pragma unroll
+    for (int lv = 0; lv < 5; lv++) {
+        const double pm = __shfl_up_sync(0xffffffffu, m, 1 << lv);
+        const double2 pa = shfl_up_c(a, 1 << lv);
+        if (lane >= (1 << lv)) { a.x = fma(m, pa.x, a.x); a.y = fma(m, pa.y, a.y); m *= pm; }
+    }
+    if (lane == 31) sc.gain[c] = make_double2(pl.Liq * a.x, pl.Liq * a.y);
+}
+
 // k_iqscan_c: one CTA of 1024 threads; exclusive scan of the per-chunk maps o -> lam_N o + gain[c]
 // from the handle's IQ state -> start[c] and the new state.  8 chunks per thread and round (their
 // gains are loaded together), warp-shuffle scans, one shared-memory hop across the 32 warps.

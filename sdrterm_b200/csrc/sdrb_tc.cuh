@@ -17,7 +17,7 @@
 // The samples are NOT IQ-corrected here: the corrector is decoupled from the modal sums
 //  and enters as one term per output, -gamma * (rotated offset).
 //
-// Warp roles (384 threads, one CTA per SM, persistent over MMA tiles of 128 super-blocks; a CTA
+// Warp roles (512 threads, one CTA per SM, persistent over MMA tiles of 128 super-blocks; a CTA
 // serves one row r of the VFO bank, blockIdx.x % R):
 //   warp 0      TMA producer (one lane): a ring of 16 KB stages, one 128-byte K slab of a tile each
 //   warp 1      TMEM allocation; tcgen05.mma issue (one lane): 4 MMAs (K = 32) per slab; the MMA's
@@ -26,7 +26,10 @@
 //   warps 2-3   sign fix-up: XOR 0x80 into the bytes that are not the signed top byte, so that
 //               every byte is a valid two's-complement int8 operand (the constant this removes is
 //               added back as cst[o])
-//   warps 4-11  epilogue: warp = 4 + 4*stage + quarter.  `quarter` (= warp % 4) is the TMEM lane
+//   warps 4-15  epilogue: warp = 4 + 4*group + quarter; the three groups take the MMA tiles
+//               round-robin (an epilogue pass is a long chain of dependent FP64 operations: three
+//               tiles in flight per SM hide it, the two TMEM stages are free again as soon as a
+//               group has read its columns).  `quarter` (= warp % 4) is the TMEM lane
 //               quarter = 32 super-blocks (lane <-> super-block) = 2 tiles of 32 blocks:
 //               digit columns -> FP64 (exact up to one rounding), tile-local IQ offsets, forward and
 //               backward modal scans in the rotating frame (lane = (segment of 8 super-blocks,
@@ -45,8 +48,9 @@
 #define TC_NPAD 208                    // GEMM N per row (200 + 8 unit-coefficient x0 columns)
 #define TC_X0COL 200
 #define TC_MAX_R 32                    // rows of the VFO bank this kernel takes
-#define TC_THREADS 384
-#define TC_EPI_WARPS 8
+#define TC_THREADS 512
+#define TC_EPI_WARPS 12
+#define TC_EPI_GROUPS 3                // groups of 4 epilogue warps take the MMA tiles round-robin
 #define TC_XS 33                       // exchange-buffer row stride in double2
 #define TC_STAGES 2                    // TMEM accumulator stages (256 columns apart)
 #define TC_MAX_ASTAGES 8               // shared-memory A ring (TMA -> sign fix-up -> MMA)
@@ -63,7 +67,7 @@
 #define TC_RC_POW 52
 
 struct TcDev {
-    int K, isz, nregion, nstage;
+    int K, isz, nregion, nstage, prefetch_tiles;
     uint32_t xor_word;                 // XOR pattern of 4 consecutive stream bytes
     uint32_t idesc;                    // tcgen05 instruction descriptor (i8 x i8 -> s32, M=128, N=208)
     double scale, scale16;             // 2^-S, 2^(16-S): outputs 0..35
@@ -128,6 +132,13 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map
     asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
                  ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(x), "r"(y), "r"(bar) : "memory");
 }
+// L2 prefetch of one tensor-map box: no shared memory, no barrier -- the bytes in flight between
+// HBM and L2 are then not limited by the depth of the shared-memory ring
+__device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap *map, int x, int y)
+{
+    asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];"
+                 ::"l"(reinterpret_cast<uint64_t>(map)), "r"(x), "r"(y) : "memory");
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
@@ -168,11 +179,24 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t *r)
                  : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
                  : "r"(taddr));
 }
-// 40 consecutive columns = the digit columns of 8 outputs (4 complex values)
-__device__ __forceinline__ void tmem_ld40(uint32_t taddr, uint32_t *r)
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t *r)
 {
-    tmem_ld32(taddr, r);
-    tmem_ld8(taddr + 32, r + 32);
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+                 "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                   "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                 : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld4(uint32_t taddr, uint32_t *r)
+{
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(taddr));
+}
+// 20 consecutive columns = the digit columns of 4 outputs (2 complex values)
+__device__ __forceinline__ void tmem_ld20(uint32_t taddr, uint32_t *r)
+{
+    tmem_ld16(taddr, r);
+    tmem_ld4(taddr + 16, r + 16);
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
@@ -210,17 +234,17 @@ struct TcShared {
     double *sCst;
     uint32_t bar0;
 };
-enum { TCB_FULL_A = 0, TCB_XORED = 1, TCB_A_FREE = 2, TCB_MISC = 3 };   // MISC: MMA_DONE[2], TMEM_FREE[2], BFULL
+enum { TCB_FULL_A = 0, TCB_XORED = 1, TCB_A_FREE = 2, TCB_MISC = 3 };   // MISC: 2,3 TMEM_FREE; 4..6 MMA_DONE; 7 BFULL
 __device__ __forceinline__ uint32_t tc_bar(uint32_t bar0, int kind, int s)
 {
     return bar0 + 8u * (uint32_t)(kind * TC_MAX_ASTAGES + s);
 }
 
-// Four complex values (8 outputs o0..o0+7) from 40 digit columns.
-__device__ __forceinline__ void tc_combine4(const uint32_t *c, const double *cst, int o0, double s16, double s1, double2 *out)
+// Two complex values (4 outputs o0..o0+3) from 20 digit columns.
+__device__ __forceinline__ void tc_combine2(const uint32_t *c, const double *cst, int o0, double s16, double s1, double2 *out)
 {
 #pragma unroll
-    for (int m = 0; m < 4; m++) {
+    for (int m = 0; m < 2; m++) {
         const double2 cs = *reinterpret_cast<const double2 *>(cst + o0 + 2 * m);
         out[m].x = tc_combine(c + 10 * m, s16, s1, cs.x);
         out[m].y = tc_combine(c + 10 * m + 5, s16, s1, cs.y);
@@ -240,27 +264,34 @@ __device__ __forceinline__ void tc_scan(double2 *xs, const double2 *sRow, int la
     double2 *xsp = xs + mode * TC_XS + seg * 8;
     const double2 *pw = sRow + TC_RC_POW + ((BACK ? 8 : 0) + mode) * 9;
     const double2 Pm = pw[1];
-    double2 loc[8];
-    double2 st = make_double2(0.0, 0.0);
+    // positions in scan order: k = 0..7 (forward: j = k, backward: j = 7 - k); two independent
+    // chains over k = 0..3 and k = 4..7 halve the dependent-FMA latency, the second half then
+    // receives the first half's total like a carry
+    double2 v[8], loc[8];
 #pragma unroll
-    for (int jj = 0; jj < 8; jj++) {
-        const int j = BACK ? 7 - jj : jj;
-        const double2 v = xsp[j];
-        loc[j] = st;                                            // exclusive: state before (above) this super-block
-        st = cfma(Pm, st, v);
+    for (int k = 0; k < 8; k++) v[k] = xsp[BACK ? 7 - k : k];
+    double2 sA = make_double2(0.0, 0.0), sB = sA;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        loc[k] = sA;     sA = cfma(Pm, sA, v[k]);               // exclusive: state before this super-block
+        loc[4 + k] = sB; sB = cfma(Pm, sB, v[4 + k]);
     }
+    const double2 st = cfma(pw[4], sA, sB);                     // segment total
     // carry between the two segments of a tile (segments 0,1 = tile 0; 2,3 = tile 1)
     const bool second = BACK ? !(seg & 1) : (seg & 1);          // the segment that receives a carry
     const double2 other = shfl_c(st, lane ^ 8);
     const double2 cin = second ? other : make_double2(0.0, 0.0);
+    const double2 cinB = cfma(pw[4], cin, sA);                  // what enters the second half-chain
     if (second) {
         const double2 tot = cfma(pw[8], cin, st);
         if (BACK) agg_tile[8 + mode] = tot;
         else agg_tile[mode] = cmul(sRow[TC_RC_AGGF], tot);
     }
 #pragma unroll
-    for (int j = 0; j < 8; j++)
-        xsp[j] = cfma(pw[BACK ? 7 - j : j], cin, loc[j]);
+    for (int k = 0; k < 4; k++) {
+        xsp[BACK ? 7 - k : k] = cfma(pw[k], cin, loc[k]);
+        xsp[BACK ? 3 - k : 4 + k] = cfma(pw[k], cinB, loc[4 + k]);
+    }
 }
 
 template <bool IQ>
@@ -268,22 +299,22 @@ __device__ __forceinline__ void tc_epilogue(const DevPlan &pl, const TcDev &tc, 
                                             uint32_t tmem_base, int e, int lane, int r, int slot, int nslots,
                                             int my_iters, int total_wtiles)
 {
-    const int qd = e & 3, g = e >> 2;
+    const int qd = e & 3, grp = e >> 2;                         // TMEM lane quarter, epilogue group
     double2 *xs = sh.sXS + (size_t)e * 8 * TC_XS;
     double2 *xsl = xs + lane;                                   // lane <-> super-block view
     const double2 *sRow = sh.sRow;
     const double *sCst = sh.sCst;
-    const uint32_t bar_done = tc_bar(sh.bar0, TCB_MISC, g);
-    const uint32_t bar_free = tc_bar(sh.bar0, TCB_MISC, 2 + g);
-    const uint32_t trow = tmem_base + ((uint32_t)(32 * qd) << 16) + (uint32_t)(g * 256);
+    const uint32_t bar_done = tc_bar(sh.bar0, TCB_MISC, 4 + grp);
     const int l16 = lane & 15;
     const double s16 = tc.scale16, s1 = tc.scale;
 
-    for (int it = g; it < my_iters; it += 2) {
-        const int u = it >> 1;
+    for (int it = grp, kk = 0; it < my_iters; it += TC_EPI_GROUPS, kk++) {
+        const int g = it & 1;                                   // TMEM accumulator stage of this tile
+        const uint32_t bar_free = tc_bar(sh.bar0, TCB_MISC, 2 + g);
+        const uint32_t trow = tmem_base + ((uint32_t)(32 * qd) << 16) + (uint32_t)(g * 256);
         const int mt = slot + it * nslots;
         const int wt = 4 * mt + qd;                             // warp-tile: 32 super-blocks = 2 tiles
-        if (lane == 0) mbar_wait(bar_done, u & 1);
+        if (lane == 0) mbar_wait(bar_done, kk & 1);
         __syncwarp();
         tc_fence_after();
         if (e == 0 && lane == 0) TC_DBG(sc, it, 5);
@@ -294,37 +325,47 @@ __device__ __forceinline__ void tc_epilogue(const DevPlan &pl, const TcDev &tc, 
         const int gt = 2 * wt + (lane >> 4);
         const int chunk = gt / pl.ntiles, t = gt - chunk * pl.ntiles;
 
-        // ---- TMEM -> registers -> FP64, 40 columns (4 complex values) at a time; the load of the
-        //      next 40 is in flight while the current ones are recombined
-        uint32_t ca[40], cb[40];
-        double2 gq[8], ev[4], v4[4];
-        tmem_ld40(trow, ca);
+        // ---- TMEM -> registers -> FP64, 20 columns (2 complex values) at a time; the load of the
+        //      next 20 is in flight while the current ones are recombined.  The IQ aggregates come
+        //      first so that their warp scan overlaps the remaining loads.
+        uint32_t ca[20], cb[20];
+        double2 gq[8], ev[2], yl[2], v2[2];
+        tmem_ld20(trow + 160, ca);                              // E_a, E_ab
         tmem_ld_wait();
-        tmem_ld40(trow + 40, cb);
-        tc_combine4(ca, sCst, 0, s16, s1, v4);                  // F modes 0..3
+        tmem_ld20(trow, cb);                                    // F 0,1
+        tc_combine2(ca, sCst, 32, s16, s1, ev);
+        // IQ: tile-local offsets at the two block starts of every super-block (zero at the tile
+        // start), tile aggregate
+        double2 exa = make_double2(0.0, 0.0), exb = exa;
+        if (IQ) {
+            double2 inc = make_double2(pl.Liq * ev[1].x, pl.Liq * ev[1].y);
 #pragma unroll
-        for (int m = 0; m < 4; m++) xsl[m * TC_XS] = v4[m];
-        tmem_ld_wait();
-        tmem_ld40(trow + 80, ca);
-        tc_combine4(cb, sCst, 8, s16, s1, v4);                  // F modes 4..7
-#pragma unroll
-        for (int m = 0; m < 4; m++) xsl[(4 + m) * TC_XS] = v4[m];
-        tmem_ld_wait();
-        tmem_ld40(trow + 120, cb);
-        tc_combine4(ca, sCst, 16, s16, s1, gq);                 // G modes 0..3
-        tmem_ld_wait();
-        tmem_ld40(trow + 160, ca);
-        tc_combine4(cb, sCst, 24, s16, s1, gq + 4);             // G modes 4..7
+            for (int i = 0; i < 4; i++) {
+                const double2 tt = shfl_up_c(inc, 1 << i);
+                if (l16 >= (1 << i)) { inc.x = fma(pl.lamq_pow[i + 1], tt.x, inc.x); inc.y = fma(pl.lamq_pow[i + 1], tt.y, inc.y); }
+            }
+            exa = shfl_up_c(inc, 1);
+            if (l16 == 0) exa = make_double2(0.0, 0.0);
+            if (l16 == 15 && r == 0) sc.tile_agg[(size_t)chunk * pl.ntiles + t] = inc;
+            exb = make_double2(fma(pl.lam_q, exa.x, pl.Liq * ev[0].x), fma(pl.lam_q, exa.y, pl.Liq * ev[0].y));
+        }
+#define TC_STEP(CUR, NXT, NEXTCOL, O0, DST)                                                   \
+        tmem_ld_wait();                                                                       \
+        if ((NEXTCOL) >= 0) tmem_ld20(trow + (NEXTCOL), NXT);                                 \
+        tc_combine2(CUR, sCst, O0, s16, s1, DST);
+        TC_STEP(cb, ca, 20, 0, v2)   xsl[0 * TC_XS] = v2[0]; xsl[1 * TC_XS] = v2[1];          // F 0,1
+        TC_STEP(ca, cb, 40, 4, v2)   xsl[2 * TC_XS] = v2[0]; xsl[3 * TC_XS] = v2[1];          // F 2,3
+        TC_STEP(cb, ca, 60, 8, v2)   xsl[4 * TC_XS] = v2[0]; xsl[5 * TC_XS] = v2[1];          // F 4,5
+        TC_STEP(ca, cb, 80, 12, v2)  xsl[6 * TC_XS] = v2[0]; xsl[7 * TC_XS] = v2[1];          // F 6,7
+        TC_STEP(cb, ca, 100, 16, gq)                                                          // G 0,1
+        TC_STEP(ca, cb, 120, 20, gq + 2)
+        TC_STEP(cb, ca, 140, 24, gq + 4)
+        TC_STEP(ca, cb, 180, 28, gq + 6)                                                      // next: yl_a, yl_b
         uint32_t cx[8];
         if (sc.x0) tmem_ld8(trow + TC_X0COL, cx);
         tmem_ld_wait();
-        // E_a, E_ab on the common scale; yl_a, yl_b on their own finer scale
-        ev[0].x = tc_combine(ca, s16, s1, sCst[32]);      ev[0].y = tc_combine(ca + 5, s16, s1, sCst[33]);
-        ev[1].x = tc_combine(ca + 10, s16, s1, sCst[34]); ev[1].y = tc_combine(ca + 15, s16, s1, sCst[35]);
-        ev[2].x = tc_combine(ca + 20, tc.scale16_yl, tc.scale_yl, sCst[36]);
-        ev[2].y = tc_combine(ca + 25, tc.scale16_yl, tc.scale_yl, sCst[37]);
-        ev[3].x = tc_combine(ca + 30, tc.scale16_yl, tc.scale_yl, sCst[38]);
-        ev[3].y = tc_combine(ca + 35, tc.scale16_yl, tc.scale_yl, sCst[39]);
+#undef TC_STEP
+        tc_combine2(cb, sCst, 36, tc.scale16_yl, tc.scale_yl, yl);   // the local outputs have their own finer scale
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_free);
@@ -343,47 +384,42 @@ __device__ __forceinline__ void tc_epilogue(const DevPlan &pl, const TcDev &tc, 
             sc.x0[obase + 1] = make_double2(i32_biased(xr1) + sCst[42], i32_biased(xi1) + sCst[43]);
         }
 
-        // ---- IQ: tile-local offsets at the two block starts of every super-block (zero at the
-        //      tile start), tile aggregate
-        double2 exa = make_double2(0.0, 0.0), exb = exa;
-        if (IQ) {
-            double2 inc = make_double2(pl.Liq * ev[1].x, pl.Liq * ev[1].y);
-#pragma unroll
-            for (int i = 0; i < 4; i++) {
-                const double2 tt = shfl_up_c(inc, 1 << i);
-                if (l16 >= (1 << i)) { inc.x = fma(pl.lamq_pow[i + 1], tt.x, inc.x); inc.y = fma(pl.lamq_pow[i + 1], tt.y, inc.y); }
-            }
-            exa = shfl_up_c(inc, 1);
-            if (l16 == 0) exa = make_double2(0.0, 0.0);
-            if (l16 == 15 && r == 0) sc.tile_agg[(size_t)chunk * pl.ntiles + t] = inc;
-            exb = make_double2(fma(pl.lam_q, exa.x, pl.Liq * ev[0].x), fma(pl.lam_q, exa.y, pl.Liq * ev[0].y));
-        }
-
+        if (e == 0 && lane == 0) TC_DBG(sc, it, 8);
         double2 *agg_tile = sc.agg + (((size_t)chunk * pl.R + r) * pl.ntiles + t) * 16;
         // ---- forward scan (the F sums were parked above), dots with the forward states
         __syncwarp();
         tc_scan<false>(xs, sRow, lane, agg_tile);
         __syncwarp();
-        double2 ya = ev[2], yb = ev[3];
+        if (e == 0 && lane == 0) TC_DBG(sc, it, 9);
+        // four independent accumulation chains per direction (the dependent-FMA latency, not the
+        // FMA count, is what an epilogue warp waits for)
+        double2 ya = yl[0], yb = yl[1], ya2 = make_double2(0.0, 0.0), yb2 = ya2;
 #pragma unroll
-        for (int i = 0; i < 8; i++) {
-            const double2 a = xsl[i * TC_XS];
+        for (int i = 0; i < 8; i += 2) {
+            const double2 a = xsl[i * TC_XS], a2 = xsl[(i + 1) * TC_XS];
             ya = cfma(sRow[TC_RC_CA + i], a, ya);
             yb = cfma(sRow[TC_RC_DA + i], a, yb);
+            ya2 = cfma(sRow[TC_RC_CA + i + 1], a2, ya2);
+            yb2 = cfma(sRow[TC_RC_DA + i + 1], a2, yb2);
         }
         __syncwarp();
+        if (e == 0 && lane == 0) TC_DBG(sc, it, 10);
         // ---- backward scan, dots with the backward states
 #pragma unroll
         for (int m = 0; m < 8; m++) xsl[m * TC_XS] = gq[m];
         __syncwarp();
         tc_scan<true>(xs, sRow, lane, agg_tile);
         __syncwarp();
+        if (e == 0 && lane == 0) TC_DBG(sc, it, 11);
 #pragma unroll
-        for (int i = 0; i < 8; i++) {
-            const double2 b = xsl[i * TC_XS];
+        for (int i = 0; i < 8; i += 2) {
+            const double2 b = xsl[i * TC_XS], b2 = xsl[(i + 1) * TC_XS];
             ya = cfma(sRow[TC_RC_CB + i], b, ya);
             yb = cfma(sRow[TC_RC_DB + i], b, yb);
+            ya2 = cfma(sRow[TC_RC_CB + i + 1], b2, ya2);
+            yb2 = cfma(sRow[TC_RC_DB + i + 1], b2, yb2);
         }
+        ya = cadd(ya, ya2); yb = cadd(yb, yb2);
         __syncwarp();
         if (IQ) {
             const double2 gm = sRow[TC_RC_GAM], gq2 = sRow[TC_RC_GAMQ];
@@ -431,11 +467,11 @@ k_tc(const __grid_constant__ DevPlan pl, const __grid_constant__ TcDev tc, const
             mbar_init(tc_bar(bar0, TCB_XORED, s), 2);
             mbar_init(tc_bar(bar0, TCB_A_FREE, s), 1);
         }
-        for (int s = 0; s < TC_STAGES; s++) {
-            mbar_init(tc_bar(bar0, TCB_MISC, s), 1);            // MMA_DONE
-            mbar_init(tc_bar(bar0, TCB_MISC, 2 + s), 4);        // TMEM_FREE: the 4 warps of the stage
-        }
-        mbar_init(tc_bar(bar0, TCB_MISC, 4), 1);                // BFULL
+        for (int s = 0; s < TC_STAGES; s++)
+            mbar_init(tc_bar(bar0, TCB_MISC, 2 + s), 4);        // TMEM_FREE: the 4 warps that read the stage
+        for (int s = 0; s < TC_EPI_GROUPS; s++)
+            mbar_init(tc_bar(bar0, TCB_MISC, 4 + s), 1);        // MMA_DONE, one per epilogue group
+        mbar_init(tc_bar(bar0, TCB_MISC, 7), 1);                // BFULL
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     for (int i = threadIdx.x; i < TC_NROWC; i += blockDim.x) sh.sRow[i] = tc.rowc[(size_t)r * TC_NROWC + i];
@@ -454,12 +490,17 @@ k_tc(const __grid_constant__ DevPlan pl, const __grid_constant__ TcDev tc, const
     if (warp == 0) {
         // ===================================================================== TMA producer
         if (lane == 0 && my_iters > 0) {
-            mbar_expect_tx(tc_bar(bar0, TCB_MISC, 4), (uint32_t)tc_b_bytes(nreg));
+            mbar_expect_tx(tc_bar(bar0, TCB_MISC, 7), (uint32_t)tc_b_bytes(nreg));
             for (int rg = 0; rg < nreg; rg++)
-                tma_load_2d(smem_u32(sB + (size_t)rg * TC_NPAD * 128), &map_b, rg * 128, r * TC_NPAD, tc_bar(bar0, TCB_MISC, 4));
+                tma_load_2d(smem_u32(sB + (size_t)rg * TC_NPAD * 128), &map_b, rg * 128, r * TC_NPAD, tc_bar(bar0, TCB_MISC, 7));
             int s = 0, ph = 0;
+            const int pfd = tc.prefetch_tiles;                  // MMA tiles the L2 prefetch runs ahead
+            for (int it = 0; it < min(pfd, my_iters); it++)
+                for (int rg = 0; rg < nreg; rg++) tma_prefetch_2d(&map_a, rg * 128, (slot + it * nslots) * 128);
             for (int it = 0; it < my_iters; it++) {
                 const int mt = slot + it * nslots;
+                if (pfd > 0 && it + pfd < my_iters)
+                    for (int rg = 0; rg < nreg; rg++) tma_prefetch_2d(&map_a, rg * 128, (slot + (it + pfd) * nslots) * 128);
                 for (int rg = 0; rg < nreg; rg++) {
                     mbar_wait_sleep(tc_bar(bar0, TCB_A_FREE, s), ph ^ 1);
                     if (rg == 0) TC_DBG(sc, it, 0);
@@ -472,7 +513,7 @@ k_tc(const __grid_constant__ DevPlan pl, const __grid_constant__ TcDev tc, const
     } else if (warp == 1) {
         // ===================================================================== MMA issuer
         if (lane == 0 && my_iters > 0) {
-            mbar_wait_sleep(tc_bar(bar0, TCB_MISC, 4), 0);
+            mbar_wait_sleep(tc_bar(bar0, TCB_MISC, 7), 0);
             int s = 0, ph = 0;
             for (int it = 0; it < my_iters; it++) {
                 const int ts = it & 1, u = it >> 1;              // TMEM stage
@@ -490,7 +531,7 @@ k_tc(const __grid_constant__ DevPlan pl, const __grid_constant__ TcDev tc, const
                     umma_commit(tc_bar(bar0, TCB_A_FREE, s));    // the staged bytes are dead once the MMAs retire
                     if (++s == nstage) { s = 0; ph ^= 1; }
                 }
-                umma_commit(tc_bar(bar0, TCB_MISC, ts));
+                umma_commit(tc_bar(bar0, TCB_MISC, 4 + it % TC_EPI_GROUPS));
                 TC_DBG(sc, it, 4);
             }
         }

@@ -141,6 +141,14 @@ class Engine:
             nat.check(nat.lib().sdrb_process(self._h, buf.ctypes.data, n, out.ctypes.data), self._h)
         return out
 
+    def iq_gain(self, raw) -> None:
+        """Advance the IQ-corrector state over whole raw chunks without producing output."""
+        buf = np.frombuffer(raw, dtype=np.uint8) if not isinstance(raw, np.ndarray) else raw
+        buf = np.ascontiguousarray(buf).view(np.uint8).reshape(-1)
+        n = self._nchunks(buf.size)
+        if n:
+            nat.check(nat.lib().sdrb_iq_gain(self._h, buf.ctypes.data, n), self._h)
+
     def submit(self, slot: int, raw_ptr: int, nchunks: int, out_ptr: int) -> None:
         nat.check(nat.lib().sdrb_submit(self._h, slot, raw_ptr, nchunks, out_ptr), self._h)
 

@@ -1,0 +1,187 @@
+"""Multi-GPU drivers of the chain: one process per GPU, ``torch.distributed`` for the plumbing
+(NCCL on the GPU box, gloo in the CPU tests of the host logic).  The path shards two ways
+ and needs at most one small exchange:
+
+* ``TimeShardedChain`` -- offline files (BASELINE config 5).  Chunks are independent except for
+  the IQ corrector's complex offset (reference src/misc/read_file.py:53), an affine recurrence
+  ``off' = lam off + L z``.  Every rank owns one contiguous time segment on chunk boundaries,
+  runs its block front end from a zero offset, the ranks all-gather the offset each segment
+  *gained* (3 doubles per rank, on the stream, no host round trip), every rank folds the gains of
+  the segments before it into its start offset and finishes.  The raw data is read once.
+* ``RowShardedBank`` -- ``--simo`` banks (configs 3/4; reference src/dsp/vfo_processor.py:42-48,
+  80-84: rows are independent given the raw chunk and go to separate sockets).  Rows are dealt
+  out contiguously and evenly; the ingest rank's raw batch reaches the others as raw BYTES
+  (2*itemsize bytes per sample, not 16) through an NCCL broadcast that is pipelined against the
+  kernels of the previous batch; nothing is gathered, each rank frames its own rows.
+
+``run_file_sharded`` is the product entry point for config 5; bench.py drives the same classes.
+"""
+from __future__ import annotations
+
+import os
+
+import numpy as np
+
+from . import sharding
+from .engine import Engine
+from .plan import Plan, build_plan
+
+CHUNK_BYTES = 131072
+
+
+class TimeShardedChain:
+    """One rank's share of a time-segment sharded stream.  ``step`` processes one device-resident
+    segment of ``nchunks`` chunks; with world == 1 it is a plain ``process_device``."""
+
+    def __init__(self, plan: Plan, max_chunks: int, device: int, dist=None, torch=None):
+        self.plan, self.dist, self.torch = plan, dist, torch
+        self.world = dist.get_world_size() if dist is not None else 1
+        self.rank = dist.get_rank() if dist is not None else 0
+        self.engine = Engine(plan, max_chunks=max_chunks, device=device)
+        if self.world > 1:
+            dev = torch.device('cuda', device)
+            self._mine = torch.zeros(3, dtype=torch.float64, device=dev)
+            self._all = torch.zeros(3 * self.world, dtype=torch.float64, device=dev)
+
+    def step(self, raw_ptr: int, nchunks: int, out_ptr: int, stream: int = 0) -> None:
+        e = self.engine
+        if self.world == 1:
+            e.process_device(raw_ptr, nchunks, out_ptr, stream)
+            return
+        nsamp = nchunks * self.plan.N
+        # block front end + the offset this segment gains from zero; exchange; finish
+        e.process_device_phases(raw_ptr, nchunks, 0, 1 | 2 | 8, stream)
+        e.iq_export_device(self._mine.data_ptr(), nsamp, stream)
+        self.dist.all_gather_into_tensor(self._all, self._mine)
+        e.iq_prefix_device(self._all.data_ptr(), self.rank, stream)
+        e.process_device_phases(raw_ptr, nchunks, out_ptr, 2 | 4, stream)
+
+    def close(self):
+        self.engine.close()
+
+
+def balanced_rows(nrows: int, world: int, rank: int) -> tuple[int, int]:
+    return sharding.row_shard(nrows, world, rank)
+
+
+class RowShardedBank:
+    """One rank's rows of a ``--simo`` bank.  ``rows_hz`` is the full bank (the listed VFO offsets
+    + the centre, reference vfo_processor.py:42-46); this rank builds a plan for its slice only.
+    ``run(batches)`` processes a sequence of raw batches that exist on rank 0 (device tensors);
+    the broadcast of batch i+1 overlaps the kernels of batch i."""
+
+    def __init__(self, fs: int, enc: str, dec: int, rows_hz, max_chunks: int, device: int, dist=None, torch=None,
+                 **plan_kw):
+        self.dist, self.torch = dist, torch
+        self.world = dist.get_world_size() if dist is not None else 1
+        self.rank = dist.get_rank() if dist is not None else 0
+        self.rows_all = [int(f) for f in rows_hz]
+        self.lo, self.hi = balanced_rows(len(self.rows_all), self.world, self.rank)
+        self.rows = self.rows_all[self.lo:self.hi]
+        self.max_chunks = max_chunks
+        self.plan = self.engine = None
+        if self.rows:
+            self.plan = build_plan(fs, enc, dec, self.rows, simo=True, **plan_kw)
+            self.engine = Engine(self.plan, max_chunks=max_chunks, device=device)
+        self.chunk_bytes = CHUNK_BYTES
+        if self.world > 1:
+            dev = torch.device('cuda', device)
+            self._bufs = [torch.empty(max_chunks * CHUNK_BYTES, dtype=torch.uint8, device=dev) for _ in range(2)]
+
+    @property
+    def M(self) -> int:
+        return self.plan.M if self.plan is not None else 0
+
+    def _post(self, i: int, src):
+        """Start the broadcast of batch i (rank 0 copies its batch into the buffer first)."""
+        if self.world == 1:
+            return None
+        b = self._bufs[i & 1]
+        if self.rank == 0:
+            b.copy_(src, non_blocking=True)
+        return self.dist.broadcast(b, src=0, async_op=True)
+
+    def run(self, batches, nchunks: int, outs, stream: int = 0) -> None:
+        """``batches``: list of uint8 device tensors (rank 0; ignored elsewhere, only the count
+        matters); ``outs``: list of (rows, nchunks*M) float64 device tensors of this rank."""
+        n = len(batches)
+        w = self._post(0, batches[0])
+        for i in range(n):
+            if w is not None:
+                w.wait()
+            w = self._post(i + 1, batches[i + 1]) if i + 1 < n else None
+            if self.engine is not None:
+                src = self._bufs[i & 1] if self.world > 1 else batches[i]
+                self.engine.process_device(src.data_ptr(), nchunks, outs[i].data_ptr(), stream)
+
+    def close(self):
+        if self.engine is not None:
+            self.engine.close()
+
+
+def run_file_sharded(path: str, out_path: str | None, *, fs: int, enc: str, dec: int, center: int = 0,
+                     demod: str = 'fm', omega_out: int = 12500, correct_iq: bool = False, swap: bool = False,
+                     data_offset: int = 0, batch_chunks: int = 2048, device: int | None = None, dist=None,
+                     torch=None) -> np.ndarray | None:
+    """BASELINE config 5: an offline IQ file, time-segment sharded over the ranks of ``dist``
+    (``None`` = single process).  Every rank reads ITS segment of the file (whole 131072-byte
+    chunks counted from ``data_offset``; the reference's stale-tail chunk, SURVEY 8-Q5, belongs to
+    the last rank), runs an IQ-gain pre-pass over it when ``correct_iq`` (raw bytes only, no
+    outputs), exchanges the gains, then demodulates its segment batch by batch through the
+    double-buffered host path.  Rank r writes ``out_path + '.part%04d' % r`` (or returns the array
+    when ``out_path`` is None): the concatenation in rank order is the reference's output file."""
+    if torch is None:
+        import torch as _t
+        torch = _t
+    world = dist.get_world_size() if dist is not None else 1
+    rank = dist.get_rank() if dist is not None else 0
+    if device is None:
+        device = int(os.environ.get('LOCAL_RANK', '0'))
+    size = os.path.getsize(path) - data_offset
+    nchunks_total = -(-size // CHUNK_BYTES)
+    first, count = sharding.segment_shard(nchunks_total, world, rank)
+    plan = build_plan(fs, enc, dec, [center], swap=swap, correct_iq=correct_iq, demod=demod, omega_out=omega_out)
+    eng = Engine(plan, max_chunks=batch_chunks, device=device)
+
+    def read_segment():
+        """This rank's chunks as the reference's reused read buffer presents them."""
+        with open(path, 'rb') as fh:
+            fh.seek(data_offset + first * CHUNK_BYTES)
+            raw = np.frombuffer(fh.read(count * CHUNK_BYTES), dtype=np.uint8)
+            if raw.size < count * CHUNK_BYTES:           # short final read: stale tail of the chunk before
+                full = np.empty(count * CHUNK_BYTES, dtype=np.uint8)
+                full[:raw.size] = raw
+                tail0 = raw.size - (raw.size % CHUNK_BYTES)
+                short = raw.size - tail0
+                if tail0 >= CHUNK_BYTES:
+                    prev = raw[tail0 - CHUNK_BYTES:tail0]
+                elif first > 0:
+                    fh.seek(data_offset + (first + count - 2) * CHUNK_BYTES)
+                    prev = np.frombuffer(fh.read(CHUNK_BYTES), dtype=np.uint8)
+                else:
+                    prev = np.zeros(CHUNK_BYTES, dtype=np.uint8)
+                full[tail0 + short:] = prev[short:]
+                raw = full
+        return raw
+
+    raw = read_segment() if count else np.zeros(0, dtype=np.uint8)
+    if correct_iq and world > 1:
+        # pass 1: the offset this segment gains from a zero start (bytes only)
+        eng.iq_state = 0j
+        for b0 in range(0, count, batch_chunks):
+            n = min(batch_chunks, count - b0)
+            eng.iq_gain(raw[b0 * CHUNK_BYTES:(b0 + n) * CHUNK_BYTES])
+        gain = eng.iq_state
+        start = sharding.exchange_iq_gain(dist, torch, gain, count * plan.N, plan.lam,
+                                          device=torch.device('cuda', device) if dist.get_backend() == 'nccl' else None)
+        eng.iq_state = start
+    out = np.empty((1, count * plan.M), dtype=np.float64)
+    for b0 in range(0, count, batch_chunks):
+        n = min(batch_chunks, count - b0)
+        out[:, b0 * plan.M:(b0 + n) * plan.M] = eng.process(raw[b0 * CHUNK_BYTES:(b0 + n) * CHUNK_BYTES])
+    eng.close()
+    if out_path is None:
+        return out
+    with open(out_path + '.part%04d' % rank, 'wb') as fh:
+        fh.write(out[0].tobytes())
+    return None

@@ -17,11 +17,11 @@ import numpy as np
 
 
 def row_shard(nrows: int, world: int, rank: int) -> tuple[int, int]:
-    """Contiguous [start, stop) of the rows owned by ``rank``: ceil(R/world) rows per rank, the
-    tail ranks may own fewer or none."""
-    per = -(-nrows // world)
-    lo = min(nrows, rank * per)
-    return lo, min(nrows, lo + per)
+    """Contiguous [start, stop) of the rows owned by ``rank``, balanced: the row counts of two
+    ranks differ by at most one (17 rows over 8 ranks: 3,2,2,2,2,2,2,2), the larger shares first."""
+    base, extra = divmod(nrows, world)
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
 
 
 def segment_shard(nchunks: int, world: int, rank: int) -> tuple[int, int]:

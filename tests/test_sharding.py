@@ -22,7 +22,9 @@ def test_partitions_cover_everything_once():
         for w in (1, 2, 3, 4, 8):
             rows = [sharding.row_shard(n, w, r) for r in range(w)]
             assert rows[0][0] == 0 and rows[-1][1] == n
-            assert all(rows[i][1] == rows[i + 1][0] or rows[i + 1][0] == n for i in range(w - 1))
+            assert all(rows[i][1] == rows[i + 1][0] for i in range(w - 1))
+            cnt = [b - a for a, b in rows]
+            assert max(cnt) - min(cnt) <= 1 and cnt == sorted(cnt, reverse=True)
             segs = [sharding.segment_shard(n, w, r) for r in range(w)]
             assert sum(c for _, c in segs) == n
             assert all(segs[i][0] + segs[i][1] == segs[i + 1][0] for i in range(w - 1))
