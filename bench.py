@@ -65,12 +65,79 @@ def cpu_chain_rate(nchunks_hint: int, target_s: float, nthreads: int):
     return nch * 32768 / best / 1e6, f'{nch} chunks ({nch * 32768} samples) of the workload, best of 2'
 
 
+def host_threads() -> int:
+    """Cores this process may use.  torchrun exports OMP_NUM_THREADS=1 to its workers; the CPU arm
+    passes its thread count to the oracle explicitly, so that setting never caps it."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
+def python_reference_rate(nch: int):
+    """The UNMODIFIED Python reference (vendored by oracle/make_ref.py into oracle/_ref, git-ignored,
+    shipped with the snapshot) timed in-process the way BASELINE.md section 3 describes: decode +
+    IQ correction (read_file.py:100-103) -> DspProcessor._processChunk -> struct.pack, one thread
+    (scipy's _sosfilt and the numba gufuncs are single-threaded).  None when _ref is absent."""
+    ref = os.path.join(ROOT, 'oracle', '_ref', 'src')
+    if not os.path.isdir(os.path.join(ref, 'dsp')):
+        return None
+    import numpy as np
+    import signals
+    os.environ.setdefault('NUMBA_CACHE_DIR', '/tmp/sdrb_numba_cache')
+    sys.path.insert(0, ref)
+    try:
+        from struct import pack
+        from dsp.dsp_processor import DspProcessor
+        p = DspProcessor(FS, center=CENTER, omegaOut=OMEGA, dec=DEC, fileInfo={'bitsPerSample': np.dtype('<i2')})
+        p.selectOutputFm()
+        body = signals.c1_bytes(nch * 32768, seed=0, header=False)
+        L = 50 / FS
+        off = 0j
+        N = 32768
+        p._generateShift(N)
+        x = np.empty((1, N), dtype=np.complex128)
+        y = np.empty((1, N // DEC), dtype=np.complex128)
+        z = np.empty((1, N // DEC), dtype=np.float64)
+
+        import numba
+
+        @numba.njit(cache=False, fastmath=True)
+        def correct_iq(data, st, ind):                   # read_file.py:67-77, compiled as the reference compiles it
+            for i in range(data.shape[0]):
+                data[i] -= st[0]
+                st[0] += data[i] * ind
+
+        off = np.zeros(1, dtype=np.complex128)
+
+        def chunk(c):
+            v = np.frombuffer(body, dtype=[('re', '<i2'), ('im', '<i2')], count=N, offset=c * CB)
+            zz = v['re'] + 1j * v['im']                  # read_file.py:101
+            correct_iq(zz, off, L)
+            x[0, :] = zz
+            p._processChunk(x, y, z)                     # dsp_processor.py:140-149
+            return pack('@' + (z.size * 'd'), *z.flat)   # dsp_processor.py:162
+
+        chunk(0)                                        # numba JIT warm-up
+        off[0] = 0
+        t0 = time.perf_counter()
+        for c in range(nch):
+            chunk(c)
+        dt = time.perf_counter() - t0
+        return {'value': nch * N / dt / 1e6, 'unit': 'Msamples/s', 'cores': 1, 'kind': 'reference',
+                'sample': f'{nch} chunks ({nch * N} samples), unmodified src/dsp from oracle/_ref, in-process'}
+    except Exception as e:                               # missing numba etc.: report, do not fail the arm
+        return {'unavailable': f'{type(e).__name__}: {e}'}
+    finally:
+        sys.path.remove(ref)
+
+
 def run_reference_arm(args):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
     from oracle import oracle as orc
-    nthreads = orc.max_threads()
+    nthreads = host_threads()
     import numpy as np
     import signals
     kw = dict(fs=FS, enc='h', center=CENTER, dec=DEC, demod='fm', omega_out=OMEGA, correct_iq=True,
@@ -99,6 +166,7 @@ def run_reference_arm(args):
                        'Python reference itself cannot travel to the GPU box'},
             'cpu_baseline': {'value': val, 'unit': 'Msamples/s', 'cores': nthreads, 'kind': 'port',
                              'sample': sample},
+            'reference_python': python_reference_rate(64),
             'e2e': {'value': val, 'unit': 'Msamples/s', 'h2d_bytes_per_step': 0,
                     'd2h_bytes_per_step': 0},
             'gpu_launches': 0}
@@ -237,7 +305,7 @@ def run_cuda_arm(args):
     import torch.distributed as dist
     from sdrterm_b200.engine import Engine
     from sdrterm_b200.plan import build_plan
-    from sdrterm_b200 import sharding
+    from sdrterm_b200 import multigpu
 
     world = int(os.environ.get('WORLD_SIZE', '1'))
     rank = int(os.environ.get('RANK', '0'))
@@ -248,8 +316,6 @@ def run_cuda_arm(args):
     dev = torch.device('cuda', local)
     if world > 1:
         import datetime
-        # keep stdout to the one JSON line (NCCL prints its version banner there at VERSION level)
-        os.environ['NCCL_DEBUG'] = os.environ.get('SDRB_NCCL_DEBUG', 'WARN')
         dist.init_process_group('nccl', device_id=dev, timeout=datetime.timedelta(seconds=180))
     if world != args.gpus and rank == 0:
         print(f'# note: --gpus {args.gpus} but WORLD_SIZE {world}', file=sys.stderr)
@@ -269,24 +335,47 @@ def run_cuda_arm(args):
     nch = args.chunks
     nsamp = nch * 32768
     pl = build_plan(FS, 'h', DEC, [CENTER], correct_iq=True, demod='fm', omega_out=OMEGA)
-    eng = Engine(pl, max_chunks=nch, device=local)
+    # the product's multi-GPU driver (sdrterm_b200/multigpu.py): one contiguous time segment per rank,
+    # IQ-corrector state handed off on the device (no host round trip)
+    chain = multigpu.TimeShardedChain(pl, nch, local, dist if world > 1 else None, torch)
+    eng = chain.engine
     raw = synth_c1_device(torch, nsamp, seed=5 + rank, device=dev)
     out = torch.empty((1, nch * pl.M), dtype=torch.float64, device=dev)
     stream = torch.cuda.current_stream().cuda_stream
-    gain_mine = torch.zeros(3, dtype=torch.float64, device=dev)
-    gain_all = torch.zeros(3 * world, dtype=torch.float64, device=dev)
 
     def step_device():
-        if world == 1:
-            eng.process_device(raw.data_ptr(), nch, out.data_ptr(), stream)
-            return
-        # time-segment sharding: block kernel + offset gain from zero, exchange, finish
-        # (no host round trip: gain export, NCCL all-gather and prefix all run on the stream)
-        eng.process_device_phases(raw.data_ptr(), nch, 0, 1 | 2 | 8, stream)
-        eng.iq_export_device(gain_mine.data_ptr(), nsamp, stream)
-        dist.all_gather_into_tensor(gain_all, gain_mine)
-        eng.iq_prefix_device(gain_all.data_ptr(), rank, stream)
-        eng.process_device_phases(raw.data_ptr(), nch, out.data_ptr(), 2 | 4, stream)
+        chain.step(raw.data_ptr(), nch, out.data_ptr(), stream)
+
+    # ---------------- verify: the sharded result equals one pass over the concatenated stream
+    verify = None
+    if not args.no_verify:
+        vch = min(nch, args.verify_chunks)
+        chain.step(raw.data_ptr(), vch, out.data_ptr(), stream)
+        torch.cuda.synchronize()
+        mine = out[:, :vch * pl.M].clone()
+        if world > 1:
+            allraw = [torch.empty(vch * CB, dtype=torch.uint8, device=dev) for _ in range(world)]
+            dist.all_gather(allraw, raw[:vch * CB].contiguous())
+            allout = [torch.empty_like(mine) for _ in range(world)]
+            dist.all_gather(allout, mine)
+        else:
+            allraw, allout = [raw[:vch * CB]], [mine]
+        if rank == 0:
+            from oracle import oracle as orc          # the checker, outside every timed region
+            whole = torch.cat(allraw)
+            with Engine(pl, max_chunks=world * vch, device=local) as one:
+                ref = torch.empty((1, world * vch * pl.M), dtype=torch.float64, device=dev)
+                one.process_device(whole.data_ptr(), world * vch, ref.data_ptr(), stream)
+                torch.cuda.synchronize()
+            got = torch.cat(allout, dim=1)
+            err = float((got - ref).abs().max() / ref.abs().max())
+            # and the single pass itself against the CPU oracle on the first chunks of the stream
+            och = min(8, world * vch)
+            oref = orc.Chain(fs=FS, enc='h', center=CENTER, dec=DEC, demod='fm', omega_out=OMEGA,
+                             correct_iq=True, nthreads=host_threads()).run_fast(whole[:och * CB].cpu().numpy().tobytes())
+            oerr = float(abs(ref[:, :och * pl.M].cpu().numpy() - oref).max() / abs(oref).max())
+            verify = {'time_sharded_vs_single_pass': err, 'single_pass_vs_oracle': oerr,
+                      'chunks_per_rank': vch, 'tolerance': 1e-9}
 
     clocks = Clocks(local)
     eng.set_profiling(world == 1)
@@ -350,59 +439,101 @@ def run_cuda_arm(args):
     e2e_val = None
     if e2e_ch > 0:
         e2e_val = measure_e2e(torch, Engine, pl, raw, sub, e2e_ch, local, args, barrier, max_over_ranks, world)
-    # ---------------- SIMO (config 3): rows sharded, raw batch broadcast
-    simo = None
-    if args.simo_chunks > 0:
-        import signals
-        offs = signals.vfo_grid(16, 100_000)
-        rows_all = [o for o in offs] + [0]
-        lo, hi = sharding.row_shard(len(rows_all), world, rank)
-        mine = rows_all[lo:hi]
-        sch = args.simo_chunks
-        if mine:
-            pls = build_plan(2_400_000, 'h', 64, mine, simo=True, swap=True, demod='fm', omega_out=5000)
-            engs = Engine(pls, max_chunks=sch, device=local)
-            outs = torch.empty((len(mine), sch * pls.M), dtype=torch.float64, device=dev)
-        raws = synth_c3_device(torch, sch * 32768, 3, dev, offs) if rank == 0 else \
-            torch.empty(sch * CB, dtype=torch.uint8, device=dev)
-        # double-buffered: the broadcast of batch i+1 (NCCL's own stream) overlaps the kernels of
-        # batch i; rank 0 copies its batch into the buffer being broadcast (ingest stand-in)
-        bufs = [torch.empty(sch * CB, dtype=torch.uint8, device=dev) for _ in range(2)] if world > 1 else [raws]
+    # ---------------- SIMO banks (configs 3 and 4): sdrterm_b200.multigpu.RowShardedBank
+    import signals
 
-        def post(i):
-            if world == 1:
-                return None
-            b = bufs[i % len(bufs)]
-            if rank == 0:
-                b.copy_(raws, non_blocking=True)
-            return dist.broadcast(b, src=0, async_op=True)
+    def run_bank(label, fs, enc, rows_all, synth, sch, nsamp_chunk, steps, **plan_kw):
+        bank = multigpu.RowShardedBank(fs, enc, 64, rows_all, sch, local, dist if world > 1 else None, torch,
+                                       demod='fm', **plan_kw)
+        cbk = bank.chunk_bytes
+        leader = bank.rank == bank.leader
+        raws = synth(bank.tg) if leader else torch.empty(sch * cbk, dtype=torch.uint8, device=dev)
+        outs = torch.empty((len(bank.rows), sch * bank.M), dtype=torch.float64, device=dev)
+        # ---- verify: this rank's rows of its segment == the same rows of a one-GPU pass over the
+        #      whole bank on the segment's bytes (run by the group's leader)
+        ver = None
+        if not args.no_verify:
+            vch = min(sch, 16)
+            bank.run([raws[:vch * cbk]], vch, [outs], stream)
+            torch.cuda.synchronize()
+            mine = outs.reshape(-1)[:len(bank.rows) * vch * bank.M].reshape(len(bank.rows), vch * bank.M).clone()
+            full_err = torch.zeros(1, dtype=torch.float64, device=dev)
+            if bank.row_groups > 1:
+                nmax = -(-len(rows_all) // bank.row_groups)
+                pad = torch.zeros((nmax, vch * bank.M), dtype=torch.float64, device=dev)
+                pad[:len(bank.rows)] = mine
+                parts = [torch.empty_like(pad) for _ in range(bank.row_groups)]
+                dist.all_gather(parts, pad, group=bank.group)
+            else:
+                parts = [mine]
+            if leader:
+                plf = build_plan(fs, enc, 64, rows_all, simo=True, demod='fm', **plan_kw)
+                with Engine(plf, max_chunks=vch, device=local) as one:
+                    ref = torch.empty((len(rows_all), vch * plf.M), dtype=torch.float64, device=dev)
+                    one.process_device(raws.data_ptr(), vch, ref.data_ptr(), stream)
+                    torch.cuda.synchronize()
+                from sdrterm_b200 import sharding as shd
+                got = torch.cat([parts[g][:shd.row_shard(len(rows_all), bank.row_groups, g)[1]
+                                          - shd.row_shard(len(rows_all), bank.row_groups, g)[0]]
+                                 for g in range(bank.row_groups)])
+                # framed big-endian: compare the byte patterns' numeric values
+                a = got.view(torch.uint8).reshape(-1, 8).flip(1).contiguous().view(torch.float64)
+                b = ref.view(torch.uint8).reshape(-1, 8).flip(1).contiguous().view(torch.float64)
+                full_err[0] = (a - b).abs().max() / b.abs().max()
+            if world > 1:
+                dist.all_reduce(full_err, op=dist.ReduceOp.MAX)
+            ver = float(full_err.item())
+        batches = [raws] * steps
 
-        def run_simo(nsteps):
-            w = post(0)
-            for i in range(nsteps):
-                if w is not None:
-                    w.wait()
-                w = post(i + 1) if i + 1 < nsteps else None
-                if mine:
-                    engs.process_device(bufs[i % len(bufs)].data_ptr(), sch, outs.data_ptr(), stream)
+        def go(n):
+            bank.run(batches[:n], sch, [outs] * n, stream)
 
-        run_simo(3)
+        go(3)
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        ss = 6
-        run_simo(ss)
+        go(steps)
         e1.record()
         barrier()
-        ms = max_over_ranks(e0.elapsed_time(e1)) / ss
-        in_msps = sch * 32768 / (ms * 1e-3) / 1e6
-        bps = 4 + 8 * len(rows_all) / 64
-        simo = {'workload': 'config 3: 16 VFOs + centre (17 rows), int16 big-endian IQ, fs 2.4 MS/s, '
-                            f'FM, -d 64, {sch} chunks per step; rows sharded over ranks, every raw batch '
-                            'broadcast over NCCL inside the timed region when n_gpus > 1 (double-buffered: '
-                            'the broadcast of the next batch overlaps the kernels of the current one)',
-                'rows': len(rows_all), 'input_msps': in_msps, 'vfo_msps': in_msps * len(rows_all),
-                'ms_per_step': ms, 'bytes_per_sample': bps}
+        ms = max_over_ranks(e0.elapsed_time(e1)) / steps
+        in_msps = bank.time_groups * sch * nsamp_chunk / (ms * 1e-3) / 1e6
+        isz2 = cbk // nsamp_chunk
+        bps = isz2 + 8 * len(rows_all) / 64
+        res = {'workload': label, 'rows': len(rows_all), 'grid': {'row_groups': bank.row_groups, 'time_groups': bank.time_groups},
+               'rows_on_rank0': len(bank.rows), 'chunks_per_step_per_time_group': sch,
+               'input_msps': in_msps, 'vfo_msps': in_msps * len(rows_all), 'ms_per_step': ms, 'bytes_per_sample': bps,
+               'front_end': 'k_tc' if bank.engine.tc is not None else 'k_main', 'verified_max_rel_err': ver}
+        bank.close()
+        return res
+
+    simo = simo4 = None
+    if args.simo_chunks > 0:
+        offs = signals.vfo_grid(16, 100_000)
+        simo = run_bank('config 3: 16 VFOs + centre (17 rows), int16 big-endian IQ, fs 2.4 MS/s, FM, -d 64; ranks on a '
+                        '(row group x time group) grid, the raw batch of a time group broadcast over NCCL inside the '
+                        'timed region (double-buffered against the kernels)',
+                        2_400_000, 'h', [o for o in offs] + [0],
+                        lambda tg: synth_c3_device(torch, args.simo_chunks * 32768, 3 + tg, dev, offs),
+                        args.simo_chunks, 32768, 6, swap=True, omega_out=5000)
+    if args.simo4_chunks > 0:
+        offs4 = signals.vfo_grid(256, 200_000)
+
+        def synth4(tg):
+            g = torch.Generator(device=dev)
+            g.manual_seed(4 + tg)
+            n = args.simo4_chunks * 16384
+            z = 0.05 * torch.randn((n, 2), generator=g, device=dev, dtype=torch.float32)
+            t = torch.arange(n, device=dev, dtype=torch.float64) / 61_440_000
+            for i in (0, 37, 128, 200, 255):         # a few of the 257 carriers (the rate does not depend on the signal)
+                ph = 2 * torch.pi * offs4[i] * t + 0.11 * i
+                z[:, 0] += (0.2 * torch.cos(ph)).float()
+                z[:, 1] += (0.2 * torch.sin(ph)).float()
+            return z.view(torch.uint8).reshape(-1)
+
+        simo4 = run_bank('config 4: 256 VFOs + centre (257 rows) on 61.44 MS/s float32 IQ, FM, -d 64; rows sharded '
+                         'over all ranks, every raw batch broadcast over NCCL inside the timed region',
+                         61_440_000, 'f', [o for o in offs4] + [0], synth4, args.simo4_chunks, 16384, 3,
+                         omega_out=12500)
 
     if rank != 0:
         if world > 1:
@@ -436,12 +567,12 @@ def run_cuda_arm(args):
                 'algorithmic_bytes_per_launch': bytes_per_sample * nsamp,
                 'traffic_source': 'profiles/traffic.json: ncu dram bytes per chunk x chunks per launch',
                 'note': 'dominant kernel = block front end; k_tc = tcgen05 int8 GEMM over the raw bytes + FP64 epilogue (DESIGN.md 3.4)'}
-        if simo is not None:
-            simo['frac_hbm'] = simo['input_msps'] * 1e6 * simo['bytes_per_sample'] / 1e9 / peak
+        for sm in (simo, simo4):
+            if sm is not None:
+                sm['frac_hbm'] = sm['input_msps'] * 1e6 * sm['bytes_per_sample'] / 1e9 / peak / world
     cpu = None
     if world == 1 and not args.no_cpu:
-        from oracle import oracle as orc
-        nth = orc.max_threads()
+        nth = host_threads()
         v, sample = cpu_chain_rate(64, args.cpu_seconds, nth)
         cpu = {'value': v, 'unit': 'Msamples/s', 'cores': nth, 'kind': 'port', 'sample': sample}
     line = {'metric': METRIC, 'value': value, 'unit': 'Msamples/s', 'n_gpus': world, 'steps': args.steps,
@@ -460,6 +591,13 @@ def run_cuda_arm(args):
         line['cpu_baseline'] = cpu
     if simo is not None:
         line['simo'] = simo
+    if simo4 is not None:
+        line['simo_config4'] = simo4
+    if verify is not None:
+        errs = [verify['time_sharded_vs_single_pass'], verify['single_pass_vs_oracle']]
+        errs += [sm['verified_max_rel_err'] for sm in (simo, simo4) if sm is not None and sm['verified_max_rel_err'] is not None]
+        line['verify'] = verify
+        line['verified'] = bool(all(e == e and e <= 1e-9 for e in errs))
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
@@ -475,6 +613,9 @@ def main():
     ap.add_argument('--e2e-chunks', type=int, default=4096)
     ap.add_argument('--e2e-batch', type=int, default=512)
     ap.add_argument('--simo-chunks', type=int, default=512)
+    ap.add_argument('--simo4-chunks', type=int, default=64, help='config 4 (257 rows, float32) chunks per step')
+    ap.add_argument('--no-verify', action='store_true', help='skip the output verification legs')
+    ap.add_argument('--verify-chunks', type=int, default=64)
     ap.add_argument('--ref-chunks', type=int, default=1024, help='chunks per step of the reference arm')
     ap.add_argument('--cpu-seconds', type=float, default=10.0)
     ap.add_argument('--no-cpu', action='store_true')

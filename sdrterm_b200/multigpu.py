@@ -9,10 +9,14 @@
   *gained* (3 doubles per rank, on the stream, no host round trip), every rank folds the gains of
   the segments before it into its start offset and finishes.  The raw data is read once.
 * ``RowShardedBank`` -- ``--simo`` banks (configs 3/4; reference src/dsp/vfo_processor.py:42-48,
-  80-84: rows are independent given the raw chunk and go to separate sockets).  Rows are dealt
-  out contiguously and evenly; the ingest rank's raw batch reaches the others as raw BYTES
+  80-84: rows are independent given the raw chunk and go to separate sockets).  Ranks form a
+  (row group x time group) grid (``bank_grid``): rows are dealt out contiguously and evenly inside
+  a row group, and the leader's raw batch reaches the other ranks of its group as raw BYTES
   (2*itemsize bytes per sample, not 16) through an NCCL broadcast that is pipelined against the
-  kernels of the previous batch; nothing is gathered, each rank frames its own rows.
+  kernels of the previous batch; nothing is gathered, each rank frames its own rows.  A wide bank
+  (config 4: 257 rows) is all row groups; a narrow one (config 3: 17 rows) uses two row groups and
+  spends the remaining ranks on time segments, because every rank of a row group must receive
+  every byte of the segment and NVLink ingress, not the kernels, would otherwise be the limit.
 
 ``run_file_sharded`` is the product entry point for config 5; bench.py drives the same classes.
 """
@@ -60,49 +64,69 @@ class TimeShardedChain:
         self.engine.close()
 
 
-def balanced_rows(nrows: int, world: int, rank: int) -> tuple[int, int]:
-    return sharding.row_shard(nrows, world, rank)
+def bank_grid(nrows: int, world: int, min_rows: int = 8) -> tuple[int, int]:
+    """(row_groups, time_groups) with row_groups * time_groups == world.  Every rank of a row group
+    needs every raw byte of its time segment, so a rank's NVLink ingress is 2*itemsize bytes per
+    input sample whatever the number of row groups: splitting a narrow bank over many ranks makes
+    the broadcast, not the kernels, the limit (17 rows over 8 ranks: 2 rows of compute per 4 bytes
+    received).  Ranks are therefore spent on rows only while a rank keeps >= ``min_rows`` rows, and
+    on time segments beyond that -- a segment's bytes then reach world/time_groups ranks only."""
+    rg = 1
+    while rg * 2 <= world and world % (rg * 2) == 0 and nrows // (rg * 2) >= min_rows:
+        rg *= 2
+    return rg, world // rg
 
 
 class RowShardedBank:
-    """One rank's rows of a ``--simo`` bank.  ``rows_hz`` is the full bank (the listed VFO offsets
-    + the centre, reference vfo_processor.py:42-46); this rank builds a plan for its slice only.
-    ``run(batches)`` processes a sequence of raw batches that exist on rank 0 (device tensors);
-    the broadcast of batch i+1 overlaps the kernels of batch i."""
+    """One rank's share of a ``--simo`` bank on a (row group x time group) grid of ranks.
+    ``rows_hz`` is the full bank (the listed VFO offsets + the centre, reference
+    vfo_processor.py:42-46); rank (tg, rg) owns the rg-th balanced slice of the rows for the
+    tg-th time segment and builds a plan for its slice only.  ``run(batches)`` processes a
+    sequence of raw batches that exist on the time group's leader (rg == 0); the broadcast of
+    batch i+1 to the group overlaps the kernels of batch i.  Nothing is gathered: each rank
+    frames its own rows (one socket per row, vfo_processor.py:80-84)."""
 
     def __init__(self, fs: int, enc: str, dec: int, rows_hz, max_chunks: int, device: int, dist=None, torch=None,
-                 **plan_kw):
+                 min_rows: int = 8, **plan_kw):
         self.dist, self.torch = dist, torch
         self.world = dist.get_world_size() if dist is not None else 1
         self.rank = dist.get_rank() if dist is not None else 0
         self.rows_all = [int(f) for f in rows_hz]
-        self.lo, self.hi = balanced_rows(len(self.rows_all), self.world, self.rank)
+        self.row_groups, self.time_groups = bank_grid(len(self.rows_all), self.world, min_rows)
+        self.tg, self.rg = divmod(self.rank, self.row_groups)
+        self.lo, self.hi = sharding.row_shard(len(self.rows_all), self.row_groups, self.rg)
         self.rows = self.rows_all[self.lo:self.hi]
+        self.leader = self.tg * self.row_groups               # global rank that holds the segment's raw bytes
         self.max_chunks = max_chunks
-        self.plan = self.engine = None
-        if self.rows:
-            self.plan = build_plan(fs, enc, dec, self.rows, simo=True, **plan_kw)
-            self.engine = Engine(self.plan, max_chunks=max_chunks, device=device)
-        self.chunk_bytes = CHUNK_BYTES
-        if self.world > 1:
+        self.plan = build_plan(fs, enc, dec, self.rows, simo=True, **plan_kw)
+        self.engine = Engine(self.plan, max_chunks=max_chunks, device=device)
+        self.chunk_bytes = self.plan.chunk_bytes
+        self.group = None
+        if self.row_groups > 1:
+            # every rank creates every group (torch.distributed requires it), keeps its own
+            for t in range(self.time_groups):
+                g = dist.new_group(list(range(t * self.row_groups, (t + 1) * self.row_groups)))
+                if t == self.tg:
+                    self.group = g
             dev = torch.device('cuda', device)
-            self._bufs = [torch.empty(max_chunks * CHUNK_BYTES, dtype=torch.uint8, device=dev) for _ in range(2)]
+            self._bufs = [torch.empty(max_chunks * self.chunk_bytes, dtype=torch.uint8, device=dev) for _ in range(2)]
 
     @property
     def M(self) -> int:
-        return self.plan.M if self.plan is not None else 0
+        return self.plan.M
 
     def _post(self, i: int, src):
-        """Start the broadcast of batch i (rank 0 copies its batch into the buffer first)."""
-        if self.world == 1:
+        """Start the broadcast of batch i inside the time group (the leader copies its batch into
+        the buffer first)."""
+        if self.row_groups == 1:
             return None
         b = self._bufs[i & 1]
-        if self.rank == 0:
+        if self.rank == self.leader:
             b.copy_(src, non_blocking=True)
-        return self.dist.broadcast(b, src=0, async_op=True)
+        return self.dist.broadcast(b, src=self.leader, group=self.group, async_op=True)
 
     def run(self, batches, nchunks: int, outs, stream: int = 0) -> None:
-        """``batches``: list of uint8 device tensors (rank 0; ignored elsewhere, only the count
+        """``batches``: list of uint8 device tensors (on the leader; elsewhere only the count
         matters); ``outs``: list of (rows, nchunks*M) float64 device tensors of this rank."""
         n = len(batches)
         w = self._post(0, batches[0])
@@ -110,13 +134,11 @@ class RowShardedBank:
             if w is not None:
                 w.wait()
             w = self._post(i + 1, batches[i + 1]) if i + 1 < n else None
-            if self.engine is not None:
-                src = self._bufs[i & 1] if self.world > 1 else batches[i]
-                self.engine.process_device(src.data_ptr(), nchunks, outs[i].data_ptr(), stream)
+            src = self._bufs[i & 1] if self.row_groups > 1 else batches[i]
+            self.engine.process_device(src.data_ptr(), nchunks, outs[i].data_ptr(), stream)
 
     def close(self):
-        if self.engine is not None:
-            self.engine.close()
+        self.engine.close()
 
 
 def run_file_sharded(path: str, out_path: str | None, *, fs: int, enc: str, dec: int, center: int = 0,
