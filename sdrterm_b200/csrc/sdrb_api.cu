@@ -248,7 +248,8 @@ int setup_tc(sdrb_handle *h, const sdrb_tables *tab)
     if (nstage < 2) return fail(h, SDRB_ERR_ARG, "k_tc: no room for the A ring (%zu bytes fixed)", fixed);
     tc.nstage = nstage;
     tc.prefetch_tiles = env_int("SDRB_TC_PREFETCH", 0);
-    if (env_int("SDRB_TC_ABL_NOXOR", 0)) tc.xor_word = 0;      // timing experiment only: wrong results
+    tc.abl = env_int("SDRB_TC_ABL", 0);                        // timing experiments only: wrong results
+    if (tc.abl & 1) tc.xor_word = 0;
     h->tc_smem = tc_smem_bytes(tc.nregion, nstage);
     if ((rc = tc_attr<true>(h)) || (rc = tc_attr<false>(h))) return rc;
     h->tc_on = true;
@@ -296,7 +297,7 @@ int launch_chain_t(sdrb_handle *h, const uint8_t *raw, size_t nch, double *out, 
     mark(2);
     if ((phases & PH_FINISH) && h->finish_on) {
         const size_t items = nch * (size_t)pl.R;
-        const unsigned grid = (unsigned)std::min<size_t>((items + FIN_WARPS - 1) / FIN_WARPS, (size_t)h->num_sms * 3);
+        const unsigned grid = (unsigned)std::min<size_t>((items + FIN_WARPS - 1) / FIN_WARPS, (size_t)h->num_sms * 4);
         k_finish<ENC><<<grid, 32 * FIN_WARPS, h->finish_smem, st>>>(pl, h->sc, raw, out, (int)nch, h->keep_y);
         h->launches++;
         mark(3);

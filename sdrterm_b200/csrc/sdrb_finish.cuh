@@ -28,15 +28,15 @@
 __host__ __device__ inline size_t finish_warp_bytes(int M)
 {
     const int nt = M / SDRB_TB;
-    size_t b = (size_t)(nt + 1) * 16 * sizeof(double2);      // carry
-    b += 2 * (size_t)(M / 4) * sizeof(double2);              // fa, fb (addv aliases them)
+    size_t b = (size_t)(nt + 1) * 16 * sizeof(double2);      // carry; the second FFT buffer fb aliases it (carry is dead by then)
+    b += (size_t)(M / 4) * sizeof(double2);                  // fa (addv aliases it)
     b += (size_t)(M + 32) * sizeof(double);                  // zrow, one pad per segment (seqA, seqB alias its head)
     return b;
 }
 __host__ __device__ inline size_t finish_smem_bytes(int M, int edge)
 {
     const int nt = M / SDRB_TB;
-    const size_t tables = (size_t)(nt + 32 + nt * 8 + 32 + 32 + 64) * sizeof(double2);   // single-row tables
+    const size_t tables = (size_t)(nt + 48 + nt * 8 + 32 + 32 + 64) * sizeof(double2);   // single-row tables
     return (size_t)(M / 2) * sizeof(double2) + (size_t)(edge + 1) * 8 * sizeof(double2) + tables + FIN_WARPS * finish_warp_bytes(M);
 }
 
@@ -72,7 +72,7 @@ __device__ __forceinline__ double fin_demod_scalar(double2 a, int demod)
 }
 
 template <int ENC>
-__global__ void __launch_bounds__(32 * FIN_WARPS, 3)
+__global__ void __launch_bounds__(32 * FIN_WARPS, 4)
 k_finish(const __grid_constant__ DevPlan pl, const __grid_constant__ Scratch sc, const uint8_t *__restrict__ raw,
          double *__restrict__ out, int nchunks, int keep_y)
 {
@@ -87,7 +87,7 @@ k_finish(const __grid_constant__ DevPlan pl, const __grid_constant__ Scratch sc,
     for (int k = threadIdx.x; k < (edge + 1) * 8; k += blockDim.x) pk[k] = pl.pk[k];
     // row tables: resident in shared memory when the bank has one row (the L1 copies are evicted
     // by the streaming ypart / agg reads), read from global memory per item otherwise
-    double2 *tbT1 = pk + (edge + 1) * 8, *tbPsi = tbT1 + nt, *tbPt = tbPsi + 32, *tbEh = tbPt + nt * 8,
+    double2 *tbT1 = pk + (edge + 1) * 8, *tbPsi = tbT1 + nt, *tbPt = tbPsi + 48, *tbEh = tbPt + nt * 8,
             *tbEe = tbEh + 32, *tbPy = tbEe + 32;
     if (R == 1) {
         for (int k = threadIdx.x; k < nt; k += blockDim.x) tbT1[k] = pl.T1[k];
@@ -95,18 +95,20 @@ k_finish(const __grid_constant__ DevPlan pl, const __grid_constant__ Scratch sc,
         for (int k = threadIdx.x; k < 16; k += blockDim.x) {
             tbPsi[k] = k < 8 ? pl.alpha[k] : pl.alphaT[k - 8];
             tbPsi[16 + k] = k < 8 ? pl.binv[k] : pl.binvT[k - 8];
+            tbPsi[32 + k] = k < 8 ? pl.beta[k] : pl.betaT[k - 8];
         }
         for (int k = threadIdx.x; k < nt * 8; k += blockDim.x) tbPt[k] = pl.Pt[k];
         for (int k = threadIdx.x; k <= edge; k += blockDim.x) { tbEh[k] = pl.Ehead[k]; tbEe[k] = pl.Eend[k]; }
         for (int k = threadIdx.x; k < 64; k += blockDim.x) tbPy[k] = pl.psiY[k];
     }
-    unsigned char *wb = smem_raw + (size_t)(h + (edge + 1) * 8 + nt + 32 + nt * 8 + 32 + 32 + 64) * sizeof(double2) +
+    unsigned char *wb = smem_raw + (size_t)(h + (edge + 1) * 8 + nt + 48 + nt * 8 + 32 + 32 + 64) * sizeof(double2) +
                         (size_t)warp * finish_warp_bytes(M);
     double2 *carry = reinterpret_cast<double2 *>(wb);
-    double2 *fa = carry + (size_t)(nt + 1) * 16, *fb = fa + n2;
+    double2 *fa = carry + (size_t)(nt + 1) * 16, *fb = carry;            // fb: only after the outputs (carry dead)
+    // phase-1 scratch overlays fa and the (not yet written) zrow: addv [nt][16], then seqA, seqB
     double2 *addv = fa;                                                  // dead before the FFT buffers are written
-    double2 *seqA = fb + n2, *seqB = seqA + 32;                          // dead before zrow is written
-    double *zrow = reinterpret_cast<double *>(fb + n2);
+    double2 *seqA = fa + (size_t)nt * 16, *seqB = seqA + 32;             // dead before zrow is written
+    double *zrow = reinterpret_cast<double *>(fa + n2);
     __syncthreads();
 
     // lane-invariant tables: this lane's block position l = lane inside every tile
@@ -264,14 +266,16 @@ k_finish(const __grid_constant__ DevPlan pl, const __grid_constant__ Scratch sc,
             sE = cmul(oE, pl.phE[r]);
             st = cmul(cfma(qal, grp ? sE : o0c, st), qbi);
         }
-        if (lane >= 8 && lane < 16) carry[(size_t)nt * 16 + 8 + i8] = iq ? cmul(qbe, st) : st;
+        // (the chain itself stays in the frame of the uncorrected samples; beta / betaT are applied
+        // when the carries are turned into real / imaginary stream states below)
+        if (lane >= 8 && lane < 16) carry[(size_t)nt * 16 + 8 + i8] = st;
         for (int tt = 0; tt < nt; tt++) {
             const int t = grp ? nt - 1 - tt : tt;
-            if (lane < 8) carry[(size_t)t * 16 + i8] = iq ? cmul(qbe, st) : st;
+            if (lane < 8) carry[(size_t)t * 16 + i8] = st;
             st = cfma(P32, st, addv[t * 16 + grp * 8 + i8]);
-            if (lane >= 8 && lane < 16) carry[(size_t)t * 16 + 8 + i8] = iq ? cmul(qbe, st) : st;
+            if (lane >= 8 && lane < 16) carry[(size_t)t * 16 + 8 + i8] = st;
         }
-        if (lane < 8) carry[(size_t)nt * 16 + i8] = iq ? cmul(qbe, st) : st;
+        if (lane < 8) carry[(size_t)nt * 16 + i8] = st;
         if (iq) st = csub(cmul(qbe, st), cmul(qal, sE));    // lanes 0..7: the TRUE forward state at q*Mf
         FIN_DBG(5);
         // ---------------------------------------------------------------- 1f. boundary vector zeta
@@ -291,7 +295,8 @@ k_finish(const __grid_constant__ DevPlan pl, const __grid_constant__ Scratch sc,
             }
             // sosfiltfilt's boundary term c_i p_i^(L-1-n) zeta_i is an anticausal modal response:
             // it rides on the backward carries as X_i = p_i^edge / kappa_i zeta_i at n = edge + q*Mf
-            const double2 X = cmul(pl.bx[i8], cadd(za, zb));
+            double2 X = cmul(pl.bx[i8], cadd(za, zb));
+            if (iq) X = cmul(X, R == 1 ? tbPsi[24 + i8] : pl.binvT[(size_t)r * 8 + i8]);   // into the T~ frame
             __syncwarp();
             for (int t = sub; t < nt; t += 4) {
                 double2 *Tn = carry + (size_t)(t + 1) * 16 + 8 + i8;
@@ -302,7 +307,14 @@ k_finish(const __grid_constant__ DevPlan pl, const __grid_constant__ Scratch sc,
         // carries -> states of the real / imaginary input streams (slots i and i + 4 of each group)
         for (int idx = lane; idx < (nt + 1) * 8; idx += 32) {
             double2 *c = carry + (size_t)(idx >> 2) * 8 + (idx & 3);       // group = (tile, direction)
-            const double2 a = c[0], b = cconj(c[4]);
+            double2 a = c[0], b = c[4];
+            if (iq) {                                                       // beta W~, betaT T~
+                const int d8 = ((idx >> 2) & 1) * 8 + (idx & 3);
+                const double2 b0 = R == 1 ? tbPsi[32 + d8] : (((idx >> 2) & 1) ? pl.betaT : pl.beta)[(size_t)r * 8 + (idx & 3)];
+                const double2 b4 = R == 1 ? tbPsi[32 + d8 + 4] : (((idx >> 2) & 1) ? pl.betaT : pl.beta)[(size_t)r * 8 + (idx & 3) + 4];
+                a = cmul(b0, a); b = cmul(b4, b);
+            }
+            b = cconj(b);
             c[0] = make_double2(0.5 * (a.x + b.x), 0.5 * (a.y + b.y));
             c[4] = make_double2(0.5 * (a.y - b.y), -0.5 * (a.x - b.x));
         }

@@ -68,6 +68,7 @@
 
 struct TcDev {
     int K, isz, nregion, nstage, prefetch_tiles;
+    int abl;                           // timing experiments only (wrong results): 1 no sign fix-up, 2 no scans/outputs, 4 no TMEM reads
     uint32_t xor_word;                 // XOR pattern of 4 consecutive stream bytes
     uint32_t idesc;                    // tcgen05 instruction descriptor (i8 x i8 -> s32, M=128, N=208)
     double scale, scale16;             // 2^-S, 2^(16-S): outputs 0..35
@@ -328,6 +329,12 @@ __device__ __forceinline__ void tc_epilogue(const DevPlan &pl, const TcDev &tc, 
         // ---- TMEM -> registers -> FP64, 20 columns (2 complex values) at a time; the load of the
         //      next 20 is in flight while the current ones are recombined.  The IQ aggregates come
         //      first so that their warp scan overlaps the remaining loads.
+        if (tc.abl & 4) {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_free);
+            continue;
+        }
         uint32_t ca[20], cb[20];
         double2 gq[8], ev[2], yl[2], v2[2];
         tmem_ld20(trow + 160, ca);                              // E_a, E_ab
@@ -370,6 +377,10 @@ __device__ __forceinline__ void tc_epilogue(const DevPlan &pl, const TcDev &tc, 
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_free);
         if (e == 0 && lane == 0) TC_DBG(sc, it, 6);
+        if (tc.abl & 2) {
+            if (gq[0].x + gq[7].y + yl[0].x + exa.x + exb.y == 1.2345e-300) sc.ypart[0] = gq[3];
+            continue;
+        }
 
         const size_t obase = ((size_t)chunk * pl.R + r) * pl.Mf + (size_t)t * SDRB_TB + 2 * l16;
         if (sc.x0) {                                            // exact first samples (parity tests)
