@@ -116,6 +116,7 @@ typedef struct sdrb_tables {
     int32_t tc_S;            /* outputs 0..35 are integers * 2^-tc_S */
     int32_t tc_S_yl;         /* outputs 36..39 are integers * 2^-tc_S_yl */
     int32_t tc_nrowc;        /* complex constants per row in tc_rowc */
+    int32_t tc_a_signed;     /* the GEMM reads the fixed-up raw bytes as signed (b, h) or unsigned (B, H) int8 */
     const int8_t *tc_Bq;     /* [R][tc_npad][tc_K] coefficient digits */
     const double *tc_cst;    /* [R][tc_nout + 4] */
     const double *tc_rowc;   /* [R][tc_nrowc] complex: epilogue constants (plan.py RC_* layout) */
@@ -164,6 +165,13 @@ int sdrb_process_device_phases(sdrb_handle *h, const void *raw_dev, size_t nchun
  * then fold the gains of ranks 0..rank-1 ([world][3] doubles) into this handle's IQ state. */
 int sdrb_iq_export_device(sdrb_handle *h, double *dst3_dev, double nsamples, void *stream);
 int sdrb_iq_prefix_device(sdrb_handle *h, const double *gains3_dev, int rank, void *stream);
+
+/* --smooth-output (src/dsp/dsp_processor.py:159-160): after the output low-pass, every chunk's row of
+ * M outputs is replaced by S applied to it, S = scipy.signal.savgol_filter(I_window, window, 3):
+ * rows 0..h-1 (h = window/2) are the polynomial fit of the first `window` samples, row h the interior
+ * FIR, rows h+1.. the fit of the last `window` samples.  S is [window][window] doubles; window 0
+ * switches smoothing off.  Native-endian output only (the SIMO path of the reference never smooths). */
+int sdrb_set_smooth(sdrb_handle *h, int window, const double *S);
 
 /* Pre-pass of time-segment sharding for segments longer than one batch: advance the IQ state over
  * `nchunks` raw HOST chunks exactly as sdrb_process would, without computing any output (the

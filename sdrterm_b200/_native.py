@@ -49,7 +49,7 @@ class Tables(C.Structure):
                 ('fm_interp', _DP), ('sos_Lseg', C.c_int32), ('sos_AL', _DP), ('sos_CA', _DP), ('sos_AP', _DP),
                 ('tc_enable', C.c_int32), ('tc_K', C.c_int32), ('tc_isz', C.c_int32),
                 ('tc_ncol', C.c_int32), ('tc_nout', C.c_int32), ('tc_npad', C.c_int32),
-                ('tc_S', C.c_int32), ('tc_S_yl', C.c_int32), ('tc_nrowc', C.c_int32),
+                ('tc_S', C.c_int32), ('tc_S_yl', C.c_int32), ('tc_nrowc', C.c_int32), ('tc_a_signed', C.c_int32),
                 ('tc_Bq', C.POINTER(C.c_int8)), ('tc_cst', _DP), ('tc_rowc', _DP),
                 ('tc_xor', C.c_uint8 * 16)]
 
@@ -60,7 +60,7 @@ EXPORTS = ['sdrb_create', 'sdrb_destroy', 'sdrb_last_error', 'sdrb_outputs_per_c
            'sdrb_fm_demod', 'sdrb_am_demod', 'sdrb_real_output', 'sdrb_imag_output',
            'sdrb_shift_freq', 'sdrb_global_error', 'sdrb_process_device_phases',
            'sdrb_set_profiling', 'sdrb_kernel_times', 'sdrb_keep_decimated', 'sdrb_read_debug', 'sdrb_iq_export_device',
-           'sdrb_iq_prefix_device', 'sdrb_decode_iq', 'sdrb_correct_iq', 'sdrb_keep_x0', 'sdrb_read_x0', 'sdrb_iq_gain']
+           'sdrb_iq_prefix_device', 'sdrb_decode_iq', 'sdrb_correct_iq', 'sdrb_keep_x0', 'sdrb_read_x0', 'sdrb_iq_gain', 'sdrb_set_smooth']
 
 
 def nvcc_command(out: str = LIB_PATH) -> list[str]:
@@ -123,6 +123,7 @@ def lib():
         L.sdrb_correct_iq.argtypes = [C.c_int, vp, sz, _DP, C.c_double]
         L.sdrb_keep_x0.argtypes = [vp, C.c_int]
         L.sdrb_iq_gain.argtypes = [vp, vp, sz]
+        L.sdrb_set_smooth.argtypes = [vp, C.c_int, vp]
         L.sdrb_read_x0.argtypes = [vp, sz, vp]
         _lib = L
     return _lib

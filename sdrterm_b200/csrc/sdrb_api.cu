@@ -56,6 +56,8 @@ struct sdrb_handle {
     size_t tc_smem = 0;
     int num_sms = 148;
     double2 *x0_buf = nullptr;      // sdrb_keep_x0
+    int smooth_w = 0;               // --smooth-output window (0 = off)
+    double *smooth_S = nullptr, *smooth_tmp = nullptr;
 };
 
 namespace {
@@ -219,7 +221,8 @@ int setup_tc(sdrb_handle *h, const sdrb_tables *tab)
     memcpy(&tc.xor_word, tab->tc_xor, 4);
     for (int i = 0; i < 16; i++)
         if (tab->tc_xor[i] != tab->tc_xor[i & 3]) return fail(h, SDRB_ERR_ARG, "XOR pattern is not 4-periodic");
-    tc.idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TC_NPAD >> 3) << 17) | ((128u >> 4) << 24);
+    // instruction descriptor: D = s32, A = s8 / u8 (tc_a_signed), B = s8, N, M
+    tc.idesc = (2u << 4) | ((tab->tc_a_signed ? 1u : 0u) << 7) | (1u << 10) | ((uint32_t)(TC_NPAD >> 3) << 17) | ((128u >> 4) << 24);
     tc.scale = ldexp(1.0, -tab->tc_S);
     tc.scale16 = ldexp(1.0, 16 - tab->tc_S);
     tc.scale_yl = ldexp(1.0, -tab->tc_S_yl);
@@ -310,6 +313,13 @@ int launch_chain_t(sdrb_handle *h, const uint8_t *raw, size_t nch, double *out, 
                                                                     (int)nch, pl.demod, 1, pl.be_out);
         h->launches++;
         mark(4);
+    }
+    if ((phases & PH_FINISH) && h->smooth_w > 0 && !pl.be_out) {
+        const size_t nseg = nch * (size_t)pl.R, bytes = nseg * pl.M * sizeof(double);
+        k_savgol<<<(unsigned)std::min<size_t>(nseg, (size_t)h->num_sms * 8), 256, 0, st>>>(out, h->smooth_tmp, h->smooth_S,
+                                                                                        h->smooth_w, pl.M, nseg);
+        CK(h, cudaMemcpyAsync(out, h->smooth_tmp, bytes, cudaMemcpyDeviceToDevice, st));
+        h->launches++;
     }
     CK(h, cudaGetLastError());
     return 0;
@@ -693,6 +703,27 @@ void launch_iqchunk(sdrb_handle *h, const uint8_t *raw, size_t nch, cudaStream_t
 }
 }  // namespace
 extern "C" {
+
+int sdrb_set_smooth(sdrb_handle *h, int window, const double *S)
+{
+    if (!h || window < 0 || (window > 0 && !S)) return fail(h, SDRB_ERR_ARG, "bad argument");
+    if (window > h->pl.M) return fail(h, SDRB_ERR_ARG, "smoothing window %d longer than a chunk's %d outputs", window, h->pl.M);
+    CK(h, cudaSetDevice(h->cfg.device));
+    CK(h, cudaDeviceSynchronize());
+    h->smooth_w = 0;
+    if (window == 0) return SDRB_OK;
+    double *dS = nullptr;
+    int rc = dalloc(h, (size_t)window * window, &dS);
+    if (rc) return rc;
+    CK(h, cudaMemcpy(dS, S, (size_t)window * window * sizeof(double), cudaMemcpyHostToDevice));
+    if (!h->smooth_tmp) {
+        rc = dalloc(h, h->max_chunks * (size_t)h->pl.R * h->pl.M, &h->smooth_tmp);
+        if (rc) return rc;
+    }
+    h->smooth_S = dS;
+    h->smooth_w = window;
+    return SDRB_OK;
+}
 
 int sdrb_iq_gain(sdrb_handle *h, const void *raw_host, size_t nchunks)
 {

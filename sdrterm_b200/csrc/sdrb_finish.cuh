@@ -65,6 +65,60 @@ __device__ __forceinline__ void fin_fft_pass(const double2 *in, double2 *out, in
     }
 }
 
+// exp(-+2 pi i m / M) for m < M from the half table tw[m], m < M/2 (tw[m + M/2] = -tw[m]).
+__device__ __forceinline__ double2 fin_tw(const double2 *tw, int m, int Mh, bool inverse)
+{
+    const bool neg = m >= Mh;
+    double2 w = tw[neg ? m - Mh : m];
+    if (neg) { w.x = -w.x; w.y = -w.y; }
+    if (inverse) w.y = -w.y;
+    return w;
+}
+
+// Stockham radix-4 pass over n points by one warp: one butterfly per lane and step; the twiddle
+// exp(-+2 pi i k / (4 Ns)) = table entry k * tstride (table base M = 2 * Mh).  Half the passes of
+// the radix-2 version, and each pass is one shared-memory round trip of dependent latency.
+__device__ __forceinline__ void fin_fft_pass4(const double2 *in, double2 *out, int n, int Ns, int tstride,
+                                              bool inverse, const double2 *tw, int Mh, int lane)
+{
+    const int quarter = n >> 2;
+    for (int j = lane; j < quarter; j += 32) {
+        const int k = j & (Ns - 1);
+        const int m = k * tstride;
+        const double2 a = in[j];
+        const double2 b = cmul(fin_tw(tw, m, Mh, inverse), in[j + quarter]);
+        const double2 c = cmul(fin_tw(tw, 2 * m, Mh, inverse), in[j + 2 * quarter]);
+        const double2 d = cmul(fin_tw(tw, 3 * m, Mh, inverse), in[j + 3 * quarter]);
+        const double2 s0 = cadd(a, c), s1 = csub(a, c), s2 = cadd(b, d), s3 = csub(b, d);
+        // -i (b - d) forward, +i (b - d) inverse
+        const double2 r3 = inverse ? make_double2(-s3.y, s3.x) : make_double2(s3.y, -s3.x);
+        const int j0 = ((j - k) << 2) + k;
+        out[j0] = cadd(s0, s2);
+        out[j0 + Ns] = cadd(s1, r3);
+        out[j0 + 2 * Ns] = csub(s0, s2);
+        out[j0 + 3 * Ns] = csub(s1, r3);
+    }
+}
+
+// n-point FFT (n a power of two >= 4) by radix-4 passes and one radix-2 pass if needed; returns
+// the buffer that holds the result.
+__device__ __forceinline__ double2 *fin_fft(double2 *src, double2 *dst, int n, int M, bool inverse,
+                                            const double2 *tw, int lane)
+{
+    int Ns = 1;
+    for (; Ns * 4 <= n; Ns <<= 2) {
+        fin_fft_pass4(src, dst, n, Ns, M / (4 * Ns), inverse, tw, M >> 1, lane);
+        __syncwarp();
+        double2 *tmp = src; src = dst; dst = tmp;
+    }
+    if (Ns < n) {
+        fin_fft_pass(src, dst, n, Ns, M / (2 * Ns), inverse, tw, lane);
+        __syncwarp();
+        double2 *tmp = src; src = dst; dst = tmp;
+    }
+    return src;
+}
+
 __device__ __forceinline__ double fin_demod_scalar(double2 a, int demod)
 {
     if (demod == 1) return hypot(fma(a.x, a.x, -a.y * a.y), 2.0 * a.x * a.y);   // abs(square(z))
@@ -386,12 +440,8 @@ k_finish(const __grid_constant__ DevPlan pl, const __grid_constant__ Scratch sc,
             // even outputs of scipy.signal.resample(ph, 2h) are the phases themselves (already in
             // zrow), the odd ones come from the half-sample-shifted spectrum.  Forward FFT of
             // z[m] = ph[2m] + i ph[2m+1], n2 = h/2 points
-            double2 *src = fa, *dst = fb;
-            for (int Ns = 1; Ns < n2; Ns <<= 1) {
-                fin_fft_pass(src, dst, n2, Ns, M / (2 * Ns), false, tw, lane);
-                __syncwarp();
-                double2 *tmp = src; src = dst; dst = tmp;
-            }
+            double2 *src = fin_fft(fa, fb, n2, M, false, tw, lane);
+            double2 *dst = src == fa ? fb : fa;
             // spectrum of the real row X[k] (k <= h/2) from Z, times the half-sample shift
             // H[k] = exp(i pi k / h), re-packed for the half-length inverse transform
             for (int k = lane; k <= (n2 >> 1); k += 32) {
@@ -418,12 +468,7 @@ k_finish(const __grid_constant__ DevPlan pl, const __grid_constant__ Scratch sc,
                 }
             }
             __syncwarp();
-            { double2 *tmp = src; src = dst; dst = tmp; }
-            for (int Ns = 1; Ns < n2; Ns <<= 1) {
-                fin_fft_pass(src, dst, n2, Ns, M / (2 * Ns), true, tw, lane);
-                __syncwarp();
-                double2 *tmp = src; src = dst; dst = tmp;
-            }
+            src = fin_fft(dst, src, n2, M, true, tw, lane);
             const double sc1 = 1.0 / (double)h;
             for (int m = lane; m < n2; m += 32) {
                 const double2 v = src[m];

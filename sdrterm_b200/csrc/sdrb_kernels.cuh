@@ -911,3 +911,26 @@ k_correct_iq(double2 *__restrict__ z, size_t n, double2 *__restrict__ off_io, do
     __syncthreads();
     if (tid == blockDim.x - 1) off_io[0] = o;
 }
+
+// dsp_processor.py:159-160  z[:] = savgol_filter(z, window, 3) per chunk row of M outputs:
+// out[k] = sum_j S[row(k)][j] x[base(k) + j]; row h = the interior FIR (scipy correlates, i.e. the
+// row already holds the coefficients in sample order), rows < h / > h the polynomial edge fits.
+__global__ void k_savgol(const double *__restrict__ x, double *__restrict__ y, const double *__restrict__ S,
+                         int w, int M, size_t nseg)
+{
+    const int h = w >> 1;
+    for (size_t seg = blockIdx.x; seg < nseg; seg += gridDim.x) {
+        const double *xs = x + seg * M;
+        double *ys = y + seg * M;
+        for (int k = threadIdx.x; k < M; k += blockDim.x) {
+            int row, base;
+            if (k < h) { row = k; base = 0; }
+            else if (k >= M - (w - 1 - h)) { row = w - (M - k); base = M - w; }
+            else { row = h; base = k - h; }
+            const double *sr = S + (size_t)row * w;
+            double acc = 0.0;
+            for (int j = 0; j < w; j++) acc = fma(sr[j], xs[base + j], acc);
+            ys[k] = acc;
+        }
+    }
+}

@@ -37,7 +37,7 @@ def generateEllipFilter(fs: int, deg: int, Wn, btype: str):
 
 class DspProcessor(DataProcessor):
     _FILTER_DEGREE = 3
-    MAX_BATCH = 64          # chunks drained from the queue per device call
+    MAX_BATCH = 512         # chunks drained from the queue per device batch (64 MiB of raw input)
 
     def __init__(self, fs: int, center: int = 0, omegaOut: int = 0, tuned: int = 0, dec: int = 2,
                  smooth: bool = False, fileInfo: dict | None = None, **kwargs):
@@ -166,7 +166,10 @@ class DspProcessor(DataProcessor):
                           swap=swap, correct_iq=ciq, normalize=norm, demod=self._demodName(),
                           omega_out=self.omegaOut, chunk_bytes=chunk_bytes)
         self._chunkBytes = chunk_bytes
-        return Engine(plan, max_chunks=self.MAX_BATCH, device=self._device)
+        # --smooth-output (dsp_processor.py:159-160): standard mode only, the SIMO override of
+        # _transformData never smooths (vfo_processor.py:80-84)
+        smooth = int(self.smooth) if (self.smooth and not self._simo()) else 0
+        return Engine(plan, max_chunks=self.MAX_BATCH, device=self._device, smooth=smooth)
 
     @staticmethod
     def _asBytes(chunk) -> np.ndarray:
@@ -180,8 +183,23 @@ class DspProcessor(DataProcessor):
         """Standard mode: one stream, native doubles, chunk after chunk (:162)."""
         file.write(out[0].tobytes())
 
+    def _staging(self):
+        """Two pinned host buffers each way (torch is used for exactly this: pinned memory)."""
+        import torch
+        eng = self._engine
+        n = self.MAX_BATCH
+        self._hin = [torch.empty(n * self._chunkBytes, dtype=torch.uint8).pin_memory() for _ in range(2)]
+        self._hout = [torch.empty(eng.R * n * eng.M, dtype=torch.float64).pin_memory() for _ in range(2)]
+
     def _processData(self, isDead, buffer, file=None) -> None:
+        """The consumer loop (dsp_processor.py:164-183), double-buffered: while the device works on
+        batch i (H2D, kernels, D2H on the slot's stream: sdrb_submit), the host drains the queue
+        into the other pinned buffer and frames / writes the output of batch i-1 (sdrb_wait).
+        A batch is whatever the queue holds (at most MAX_BATCH chunks), so a live stream is not
+        held back waiting for a full batch."""
         eof = False
+        pending = None                                   # (slot, nchunks) in flight
+        b = 0
         while not (self._isDead or isDead.value or eof):
             batch = [buffer.get()]
             while len(batch) < self.MAX_BATCH:
@@ -199,11 +217,29 @@ class DspProcessor(DataProcessor):
                 break
             if self._engine is None:
                 self._engine = self._makeEngine(batch[0])
+                self._staging()
             if any(c.size != self._chunkBytes for c in chunks):
                 raise ValueError('chunks must all have the size of the first one')
-            raw = np.concatenate(chunks) if len(chunks) > 1 else chunks[0]
-            out = self._engine.process(raw)
-            self._emit(out, len(chunks), file)
+            slot = b & 1
+            hin = self._hin[slot].numpy()
+            for i, c in enumerate(chunks):
+                hin[i * self._chunkBytes:(i + 1) * self._chunkBytes] = c
+            self._engine.submit(slot, self._hin[slot].data_ptr(), len(chunks), self._hout[slot].data_ptr())
+            if pending is not None:
+                self._drain(pending, file)
+            pending = (slot, len(chunks))
+            b += 1
+        if pending is not None:
+            self._drain(pending, file)
+
+    def _drain(self, pending, file) -> None:
+        slot, n = pending
+        eng = self._engine
+        eng.wait(slot)
+        out = self._hout[slot].numpy()[:eng.R * n * eng.M].reshape(eng.R, n * eng.M)
+        if eng.plan.big_endian_out:
+            out = out.view('>f8')
+        self._emit(out, n, file)
 
     def processData(self, isDead, buffer, f: str | None, *args, **kwargs) -> None:
         with open(f, 'wb') if f is not None else open(stdout.fileno(), 'wb', closefd=False) as file:
@@ -224,6 +260,7 @@ class DspProcessor(DataProcessor):
     def __getstate__(self):
         d = dict(self.__dict__)
         d['_engine'] = None
+        d.pop('_hin', None), d.pop('_hout', None)
         return d
 
     def __repr__(self):

@@ -20,7 +20,7 @@ def _dp(a: np.ndarray):
 
 class Engine:
     def __init__(self, plan: Plan, max_chunks: int = 256, device: int = 0, use_tc: bool = True,
-                 keep_decimated: bool = False, keep_x0: bool = False):
+                 keep_decimated: bool = False, keep_x0: bool = False, smooth: int = 0):
         self.plan = plan
         self.max_chunks = int(max_chunks)
         self.device = int(device)
@@ -85,7 +85,7 @@ class Engine:
             tc = self.tc
             tab.tc_enable, tab.tc_K, tab.tc_isz = 1, tc.K, tc.isz
             tab.tc_ncol, tab.tc_nout, tab.tc_npad, tab.tc_S = tc.NCOL, tc.nout, tc.Npad, tc.S
-            tab.tc_S_yl, tab.tc_nrowc = tc.S_yl, tc.rowc.shape[1]
+            tab.tc_S_yl, tab.tc_nrowc, tab.tc_a_signed = tc.S_yl, tc.rowc.shape[1], int(tc.a_signed)
             put('tc_rowc', tc.rowc)
             bq = np.ascontiguousarray(tc.Bq, dtype=np.int8)
             self._keep.append(bq)
@@ -99,6 +99,8 @@ class Engine:
             nat.check(L.sdrb_keep_decimated(self._h, 1), self._h)
         if keep_x0:
             nat.check(L.sdrb_keep_x0(self._h, 1), self._h)
+        if smooth:
+            self.set_smooth(int(smooth))
         self.chunk_bytes = int(L.sdrb_chunk_bytes(self._h))
         self.R = pl.R
 
@@ -140,6 +142,19 @@ class Engine:
         if n:
             nat.check(nat.lib().sdrb_process(self._h, buf.ctypes.data, n, out.ctypes.data), self._h)
         return out
+
+    def set_smooth(self, window: int, polyorder: int = 3) -> None:
+        """``--smooth-output``: ``scipy.signal.savgol_filter(z, window, 3)`` on every chunk's output
+        row (reference dsp_processor.py:159-160), as one linear map per chunk: the interior FIR row
+        and the two polynomial edge fits (mode='interp'), taken from SciPy itself applied to the
+        identity so that the coefficients are the reference's."""
+        from scipy.signal import savgol_filter
+        w = int(window)
+        if w > self.M:
+            raise ValueError(f'smoothing window {w} longer than a chunk\'s {self.M} outputs')
+        S = np.ascontiguousarray(savgol_filter(np.eye(w), w, polyorder, axis=0), dtype=np.float64)
+        self._keep.append(S)
+        nat.check(nat.lib().sdrb_set_smooth(self._h, w, S.ctypes.data), self._h)
 
     def iq_gain(self, raw) -> None:
         """Advance the IQ-corrector state over whole raw chunks without producing output."""

@@ -429,6 +429,7 @@ class TcTables:
     Npad: int
     R: int
     xor_mask: np.ndarray   # (16,) uint8, XOR pattern of one 16-byte group of the raw stream
+    a_signed: bool         # the GEMM reads the (fixed-up) raw bytes as signed int8; False: as unsigned
     Bq: np.ndarray         # (R, Npad, K) int8 coefficient digits
     S: int                 # outputs 0..35 are integers * 2^-S
     S_yl: int              # outputs 36..39 (yl_a, yl_b: small coefficients, their own finer scale) * 2^-S_yl
@@ -485,12 +486,17 @@ def build_tc(pl: Plan, nd: int = TC_ND) -> TcTables | None:
     rho = [mp.mpc(v) for v in pl.modes.rho]
     rho_p = [mp.mpc(v) for v in pl.modes.rho_p]
 
-    # byte bookkeeping of one sample: (component, significance, xored?) per byte
+    # byte bookkeeping of one sample: (component, significance, xored?) per byte.  The tensor core
+    # reads the whole A operand either as signed or as unsigned int8: unsigned encodings (B, H) go
+    # in as they are (unsigned), 'b' as it is (signed); only signed 16-bit samples mix a signed top
+    # byte with an unsigned low byte -- the low bytes are XOR-ed with 0x80 (u -> u - 128 as int8)
+    # by the kernel's sign fix-up warps and the constant this removes is added back (cst)
+    a_signed = signed
     info = []
     for bb in range(sb):
         cpt, bi = divmod(bb, isz)
         w = bi if stored_le else isz - 1 - bi
-        xored = not (signed and w == isz - 1)
+        xored = signed and w != isz - 1
         info.append((cpt, w, xored))
     xor_mask = np.array([0x80 if info[b % sb][2] else 0 for b in range(16)], dtype=np.uint8)
 
@@ -599,7 +605,9 @@ def build_tc(pl: Plan, nd: int = TC_ND) -> TcTables | None:
                 V = V * 256 + int(colsum[r, TC_X0COL + x * isz + t])
             cst[r, nout + x] = float(V)
     col_l1 = int(np.abs(Bq.astype(np.int64)).sum(axis=2).max())
-    if col_l1 * 128 * 257 >= 2 ** 31:
+    amax_byte = 128 if a_signed else 255
+    if col_l1 * amax_byte * 257 >= 2 ** 31:
         raise OverflowError('int32 digit-pair sums could overflow for this coefficient set')
     return TcTables(K=K, isz=isz, ND=nd, NCOL=ncol, SB=TC_SB, nout=nout, Npad=TC_NPAD, R=R, xor_mask=xor_mask,
+                    a_signed=a_signed,
                     Bq=Bq, S=S, S_yl=S_yl, cst=cst, rowc=rowc, col_l1=col_l1)

@@ -1,5 +1,5 @@
 """``python -m sdrterm`` drop-in: same options as the reference's CLI (src/sdrterm.py:54-107) for
-the demodulation path.  Plots and the smoothing filter are not part of this build.
+the demodulation path.  Plots are not part of this build.
 
 A reader thread feeds raw chunks to the GPU consumer in this process; the reference's two-process
 layout exists to overlap CPU work that no longer happens on the CPU."""
@@ -54,9 +54,7 @@ def makeProcessor(a, fileInfo):
     from .dsp.vfo_processor import VfoProcessor
     if a.dec < 2:
         raise ValueError('Decimation must be at least 2.')
-    if a.smooth_output:
-        raise ValueError('--smooth-output is not part of this build')
-    kw = dict(center=a.center, omegaOut=a.omegaOut, tuned=a.tuned, dec=a.dec, smooth=False,
+    kw = dict(center=a.center, omegaOut=a.omegaOut, tuned=a.tuned, dec=a.dec, smooth=a.smooth_output,
               fileInfo=fileInfo, swapEndianness=a.swap, correctIq=a.correct_iq, normalize=a.normalize)
     fs = fileInfo['sampRate']
     proc = VfoProcessor(fs, vfoHost=a.vfo_host, vfos=a.vfos, **kw) if a.simo else DspProcessor(fs, **kw)

@@ -313,9 +313,10 @@ def tc_block_values(pl: Plan, tc, raw: np.ndarray, r: int = 0) -> np.ndarray:
     row r as k_tc's epilogue reassembles them from the int32 digit columns (the last 4: x0)."""
     nsb, K, ncol, nout = pl.Mf // tc.SB, tc.K, tc.NCOL, tc.nout
     by = np.frombuffer(raw, dtype=np.uint8)[:nsb * K].reshape(nsb, K)
-    sby = (by ^ np.tile(tc.xor_mask, K // 16)[None, :]).view(np.int8).astype(np.int64)
+    fixed = by ^ np.tile(tc.xor_mask, K // 16)[None, :]           # the sign fix-up warps
+    sby = (fixed.view(np.int8) if tc.a_signed else fixed).astype(np.int64)   # the GEMM's view of the bytes
     acc = sby @ tc.Bq[r].T.astype(np.int64)                     # exact column sums
-    assert np.max(np.abs(acc)) <= tc.col_l1 * 128 < 2 ** 31
+    assert np.max(np.abs(acc)) <= tc.col_l1 * (128 if tc.a_signed else 255) < 2 ** 31
     val = np.zeros((nsb, nout + 4))
     for o in range(nout):
         scale = 2.0 ** -(tc.S_yl if o >= 36 else tc.S)

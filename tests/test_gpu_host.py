@@ -258,3 +258,21 @@ def test_cli_simo_prints_the_lines_example_simo_scrapes(tmp_path):
     for i in range(3):
         assert got[i].shape == rows[0].shape
         assert min(rel_err(got[i], r) for r in rows) < TOL
+
+
+@pytest.mark.parametrize('window', [5, 11, 32])
+def test_cli_smooth_output_matches_savgol_per_chunk(tmp_path, window):
+    """--smooth-output N: dsp_processor.py:159-160 applies savgol_filter(z, N, 3) to every chunk's
+    output row after the output low-pass (standard mode only)."""
+    from scipy.signal import savgol_filter
+    from sdrterm_b200.sdrterm import main
+    raw, body, kw = case_stream('c1_fm_wav_int16')
+    fin, fout = tmp_path / 'in.wav', tmp_path / 'out.bin'
+    fin.write_bytes(raw)
+    assert main(['-i', str(fin), '-o', str(fout), '-c', '15k', '-w', '5k', '-d', '64', '--correct-iq',
+                 '--smooth-output', str(window)]) == 0
+    got = np.frombuffer(fout.read_bytes(), dtype='=f8')
+    g = load_golden('c1_fm_wav_int16')['out'][0]
+    M = 512
+    ref = np.concatenate([savgol_filter(g[c * M:(c + 1) * M], window, 3) for c in range(g.size // M)])
+    assert got.shape == ref.shape and rel_err(got, ref) < TOL
