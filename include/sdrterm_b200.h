@@ -167,11 +167,13 @@ int sdrb_iq_export_device(sdrb_handle *h, double *dst3_dev, double nsamples, voi
 int sdrb_iq_prefix_device(sdrb_handle *h, const double *gains3_dev, int rank, void *stream);
 
 /* --smooth-output (src/dsp/dsp_processor.py:159-160): after the output low-pass, every chunk's row of
- * M outputs is replaced by S applied to it, S = scipy.signal.savgol_filter(I_window, window, 3):
- * rows 0..h-1 (h = window/2) are the polynomial fit of the first `window` samples, row h the interior
- * FIR, rows h+1.. the fit of the last `window` samples.  S is [window][window] doubles; window 0
- * switches smoothing off.  Native-endian output only (the SIMO path of the reference never smooths). */
-int sdrb_set_smooth(sdrb_handle *h, int window, const double *S);
+ * M outputs goes through scipy.signal.savgol_filter(z, window, 3) as three linear maps taken from
+ * SciPy itself: outputs 0..nhead-1 = head rows applied to the first `window` samples, outputs
+ * M-ntail..M-1 = tail rows applied to the last `window` samples, every other output k = the FIR row
+ * applied to samples k+lo .. k+lo+window-1.  `tab` is [nhead + 1 + ntail][window] doubles (head rows,
+ * FIR row, tail rows); window 0 switches smoothing off.  Native-endian output only (the SIMO path of
+ * the reference never smooths). */
+int sdrb_set_smooth(sdrb_handle *h, int window, int nhead, int ntail, int lo, const double *tab);
 
 /* Pre-pass of time-segment sharding for segments longer than one batch: advance the IQ state over
  * `nchunks` raw HOST chunks exactly as sdrb_process would, without computing any output (the

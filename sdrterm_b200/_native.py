@@ -123,7 +123,7 @@ def lib():
         L.sdrb_correct_iq.argtypes = [C.c_int, vp, sz, _DP, C.c_double]
         L.sdrb_keep_x0.argtypes = [vp, C.c_int]
         L.sdrb_iq_gain.argtypes = [vp, vp, sz]
-        L.sdrb_set_smooth.argtypes = [vp, C.c_int, vp]
+        L.sdrb_set_smooth.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, vp]
         L.sdrb_read_x0.argtypes = [vp, sz, vp]
         _lib = L
     return _lib

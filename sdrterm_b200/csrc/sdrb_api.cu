@@ -56,7 +56,7 @@ struct sdrb_handle {
     size_t tc_smem = 0;
     int num_sms = 148;
     double2 *x0_buf = nullptr;      // sdrb_keep_x0
-    int smooth_w = 0;               // --smooth-output window (0 = off)
+    int smooth_w = 0, smooth_nhead = 0, smooth_ntail = 0, smooth_lo = 0;   // --smooth-output (window 0 = off)
     double *smooth_S = nullptr, *smooth_tmp = nullptr;
 };
 
@@ -317,7 +317,7 @@ int launch_chain_t(sdrb_handle *h, const uint8_t *raw, size_t nch, double *out, 
     if ((phases & PH_FINISH) && h->smooth_w > 0 && !pl.be_out) {
         const size_t nseg = nch * (size_t)pl.R, bytes = nseg * pl.M * sizeof(double);
         k_savgol<<<(unsigned)std::min<size_t>(nseg, (size_t)h->num_sms * 8), 256, 0, st>>>(out, h->smooth_tmp, h->smooth_S,
-                                                                                        h->smooth_w, pl.M, nseg);
+                                                                                        h->smooth_w, h->smooth_nhead, h->smooth_ntail, h->smooth_lo, pl.M, nseg);
         CK(h, cudaMemcpyAsync(out, h->smooth_tmp, bytes, cudaMemcpyDeviceToDevice, st));
         h->launches++;
     }
@@ -704,23 +704,26 @@ void launch_iqchunk(sdrb_handle *h, const uint8_t *raw, size_t nch, cudaStream_t
 }  // namespace
 extern "C" {
 
-int sdrb_set_smooth(sdrb_handle *h, int window, const double *S)
+int sdrb_set_smooth(sdrb_handle *h, int window, int nhead, int ntail, int lo, const double *tab)
 {
-    if (!h || window < 0 || (window > 0 && !S)) return fail(h, SDRB_ERR_ARG, "bad argument");
+    if (!h || window < 0 || (window > 0 && (!tab || nhead < 0 || ntail < 0 || nhead + ntail > h->pl.M)))
+        return fail(h, SDRB_ERR_ARG, "bad argument");
     if (window > h->pl.M) return fail(h, SDRB_ERR_ARG, "smoothing window %d longer than a chunk's %d outputs", window, h->pl.M);
     CK(h, cudaSetDevice(h->cfg.device));
     CK(h, cudaDeviceSynchronize());
     h->smooth_w = 0;
     if (window == 0) return SDRB_OK;
+    const size_t n = (size_t)(nhead + 1 + ntail) * window;
     double *dS = nullptr;
-    int rc = dalloc(h, (size_t)window * window, &dS);
+    int rc = dalloc(h, n, &dS);
     if (rc) return rc;
-    CK(h, cudaMemcpy(dS, S, (size_t)window * window * sizeof(double), cudaMemcpyHostToDevice));
+    CK(h, cudaMemcpy(dS, tab, n * sizeof(double), cudaMemcpyHostToDevice));
     if (!h->smooth_tmp) {
         rc = dalloc(h, h->max_chunks * (size_t)h->pl.R * h->pl.M, &h->smooth_tmp);
         if (rc) return rc;
     }
     h->smooth_S = dS;
+    h->smooth_nhead = nhead; h->smooth_ntail = ntail; h->smooth_lo = lo;
     h->smooth_w = window;
     return SDRB_OK;
 }

@@ -912,24 +912,25 @@ k_correct_iq(double2 *__restrict__ z, size_t n, double2 *__restrict__ off_io, do
     if (tid == blockDim.x - 1) off_io[0] = o;
 }
 
-// dsp_processor.py:159-160  z[:] = savgol_filter(z, window, 3) per chunk row of M outputs:
-// out[k] = sum_j S[row(k)][j] x[base(k) + j]; row h = the interior FIR (scipy correlates, i.e. the
-// row already holds the coefficients in sample order), rows < h / > h the polynomial edge fits.
-__global__ void k_savgol(const double *__restrict__ x, double *__restrict__ y, const double *__restrict__ S,
-                         int w, int M, size_t nseg)
+// dsp_processor.py:159-160  z[:] = savgol_filter(z, window, 3) per chunk row of M outputs, as the
+// three linear maps SciPy uses (tab = head rows | FIR row | tail rows, each `w` long).
+__global__ void k_savgol(const double *__restrict__ x, double *__restrict__ y, const double *__restrict__ tab,
+                         int w, int nhead, int ntail, int lo, int M, size_t nseg)
 {
-    const int h = w >> 1;
     for (size_t seg = blockIdx.x; seg < nseg; seg += gridDim.x) {
         const double *xs = x + seg * M;
         double *ys = y + seg * M;
         for (int k = threadIdx.x; k < M; k += blockDim.x) {
             int row, base;
-            if (k < h) { row = k; base = 0; }
-            else if (k >= M - (w - 1 - h)) { row = w - (M - k); base = M - w; }
-            else { row = h; base = k - h; }
-            const double *sr = S + (size_t)row * w;
+            if (k < nhead) { row = k; base = 0; }
+            else if (k >= M - ntail) { row = nhead + 1 + (k - (M - ntail)); base = M - w; }
+            else { row = nhead; base = k + lo; }
+            const double *sr = tab + (size_t)row * w;
             double acc = 0.0;
-            for (int j = 0; j < w; j++) acc = fma(sr[j], xs[base + j], acc);
+            for (int j = 0; j < w; j++) {
+                const int i = base + j;
+                if (i >= 0 && i < M) acc = fma(sr[j], xs[i], acc);
+            }
             ys[k] = acc;
         }
     }

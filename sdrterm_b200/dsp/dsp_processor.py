@@ -201,7 +201,10 @@ class DspProcessor(DataProcessor):
         pending = None                                   # (slot, nchunks) in flight
         b = 0
         while not (self._isDead or isDead.value or eof):
-            batch = [buffer.get()]
+            first = self._next(isDead, buffer)
+            if first is None:                            # halted while waiting for input
+                break
+            batch = [first]
             while len(batch) < self.MAX_BATCH:
                 try:
                     batch.append(buffer.get_nowait())
@@ -231,6 +234,16 @@ class DspProcessor(DataProcessor):
             b += 1
         if pending is not None:
             self._drain(pending, file)
+
+    def _next(self, isDead, buffer):
+        """Blocking ``buffer.get()`` that still notices the halt flag (the reference's consumer is
+        a process that dies with the signal; this one may be a thread)."""
+        while True:
+            try:
+                return buffer.get(timeout=0.25)
+            except _queue.Empty:
+                if self._isDead or isDead.value:
+                    return None
 
     def _drain(self, pending, file) -> None:
         slot, n = pending

@@ -152,9 +152,20 @@ class Engine:
         w = int(window)
         if w > self.M:
             raise ValueError(f'smoothing window {w} longer than a chunk\'s {self.M} outputs')
-        S = np.ascontiguousarray(savgol_filter(np.eye(w), w, polyorder, axis=0), dtype=np.float64)
-        self._keep.append(S)
-        nat.check(nat.lib().sdrb_set_smooth(self._h, w, S.ctypes.data), self._h)
+        # SciPy applied to the identity of a longer signal gives the three linear maps it uses:
+        # head rows (fit of the first w samples), the interior FIR and where its window sits
+        # relative to the output (even windows are not centred), tail rows
+        L = 4 * w
+        S = savgol_filter(np.eye(L), w, polyorder, axis=0)
+        nhead = ntail = w // 2
+        k0 = 2 * w
+        nz = np.nonzero(S[k0])[0]
+        lo = int(nz[0]) - k0
+        assert nz[-1] - nz[0] + 1 <= w and np.allclose(S[k0 + 1, k0 + 1 + lo:k0 + 1 + lo + w], S[k0, k0 + lo:k0 + lo + w])
+        tab = np.concatenate([S[:nhead, :w], S[k0:k0 + 1, k0 + lo:k0 + lo + w], S[L - ntail:, L - w:]], axis=0)
+        tab = np.ascontiguousarray(tab, dtype=np.float64)
+        self._keep.append(tab)
+        nat.check(nat.lib().sdrb_set_smooth(self._h, w, nhead, ntail, lo, tab.ctypes.data), self._h)
 
     def iq_gain(self, raw) -> None:
         """Advance the IQ-corrector state over whole raw chunks without producing output."""

@@ -487,16 +487,18 @@ def build_tc(pl: Plan, nd: int = TC_ND) -> TcTables | None:
     rho_p = [mp.mpc(v) for v in pl.modes.rho_p]
 
     # byte bookkeeping of one sample: (component, significance, xored?) per byte.  The tensor core
-    # reads the whole A operand either as signed or as unsigned int8: unsigned encodings (B, H) go
-    # in as they are (unsigned), 'b' as it is (signed); only signed 16-bit samples mix a signed top
-    # byte with an unsigned low byte -- the low bytes are XOR-ed with 0x80 (u -> u - 128 as int8)
+    # reads the whole A operand either as signed or as unsigned int8: 'B' goes in as it is
+    # (unsigned), 'b' as it is (signed); 16-bit samples mix a signed top byte with an unsigned low
+    # byte -- the bytes that are not a signed top byte are XOR-ed with 0x80 (u -> u - 128 as int8)
     # by the kernel's sign fix-up warps and the constant this removes is added back (cst)
-    a_signed = signed
+    # (unsigned 16-bit samples take the signed route too, both bytes XOR-ed: as unsigned operands
+    # their worst-case int32 column sums would not be provably safe)
+    a_signed = signed or isz == 2
     info = []
     for bb in range(sb):
         cpt, bi = divmod(bb, isz)
         w = bi if stored_le else isz - 1 - bi
-        xored = signed and w != isz - 1
+        xored = a_signed and not (signed and w == isz - 1)
         info.append((cpt, w, xored))
     xor_mask = np.array([0x80 if info[b % sb][2] else 0 for b in range(16)], dtype=np.uint8)
 

@@ -63,13 +63,56 @@ def makeProcessor(a, fileInfo):
     return proc
 
 
-def main(argv=None) -> int:
+def _pidFile(pid: int):
+    """PID file in the temp directory, announced on stderr (src/sdrterm.py:191-222); returns the
+    function that removes it."""
+    import os
+    import re
+    import tempfile
+    import uuid
+    from datetime import datetime, timezone
+    from .misc.general_util import eprint, vprint
+    iso = re.sub(r'[:\-+T]', '', datetime.now(timezone.utc).isoformat(timespec='seconds'))
+    name = os.path.join(tempfile.gettempdir(), f'{iso}-sdrterm-{uuid.uuid4()}.pid')
+    with open(name, 'w+') as fh:
+        fh.write(str(pid) + '\n')
+    eprint(f'PID file is created: {name}')
+
+    def remove():
+        try:
+            os.unlink(name)
+            vprint(f'PID file: {name} deleted')
+        except OSError:
+            pass
+    return remove
+
+
+def main(argv=None, lifecycle: bool = False) -> int:
+    """``lifecycle``: install the reference's process lifecycle -- PID file, SIGINT/SIGTERM/... set
+    the halt flag that both loops poll (src/sdrterm.py:172-231) -- as ``python -m sdrterm`` does;
+    off when main() is called as a function (signal handlers belong to the main thread)."""
+    import os
+    from .misc import general_util as gu
     a = buildParser().parse_args(argv)
+    if a.verbose > 1:
+        gu.traceOn()
+    elif a.verbose > 0:
+        gu.verboseOn()
+    isDead = _Flag()
+    removePid = None
+    if lifecycle:
+        removePid = _pidFile(os.getpid())
+
+        def stop():
+            gu.tprint('Setting halt condition')
+            isDead.value = 1
+            removePid()
+        gu.setSignalHandlers(os.getpid(), stop)
     fileInfo = checkWavHeader(a.inFile, a.fs, a.enc)           # a WAV header overrides -r / -e
     proc = makeProcessor(a, fileInfo)
+    gu.tprint(f'Started proc Main: {os.getpid()}')
     print(repr(proc), file=sys.stderr, flush=True)          # unconditional: src/sdrterm.py:144
-    isDead = _Flag()
-    buf = queue.Queue(maxsize=256)
+    buf = queue.Queue(maxsize=1024)
     reader = threading.Thread(target=readFile, daemon=True,
                               kwargs=dict(buffers=[buf], isDead=isDead, inFile=a.inFile,
                                           fs=fileInfo['sampRate'], dataOffset=fileInfo['dataOffset'],
@@ -79,8 +122,11 @@ def main(argv=None) -> int:
         proc.processData(isDead, buf, a.outFile)
     finally:
         isDead.value = 1
+        if removePid is not None:
+            removePid()
+        gu.vprint('Main halted')
     return 0
 
 
 if __name__ == '__main__':
-    sys.exit(main())
+    sys.exit(main(lifecycle=True))

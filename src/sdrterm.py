@@ -8,4 +8,4 @@ if _ROOT not in sys.path:
 from sdrterm_b200.sdrterm import buildParser, main, makeProcessor  # noqa: E402,F401
 
 if __name__ == '__main__':
-    sys.exit(main())
+    sys.exit(main(lifecycle=True))

@@ -40,7 +40,7 @@ def test_tensor_core_twin_matches_oracle(name):
     tc = build_tc(pl)
     assert tc is not None and tc.NCOL == 5 and tc.Npad == 208 and tc.K in (256, 512)
     assert tc.col_l1 * (128 if tc.a_signed else 255) * 257 < 2 ** 31   # digit-pair sums fit int32 on the device
-    assert tc.a_signed == (kw['enc'] in 'bh') and bool(tc.xor_mask.any()) == (kw['enc'] == 'h')
+    assert tc.a_signed == (kw['enc'] in 'bhH') and bool(tc.xor_mask.any()) == (kw['enc'] in 'hH')
     body = body[:len(body) // 131072 * 131072] or body
     out, ys, off = emu.emu_stream_tc(pl, tc, body)
     ch = orc.Chain(**kw)

@@ -296,3 +296,39 @@ def test_reference_own_unit_tests_pass_against_the_shims(tmp_path):
                         '/root/reference/test/misc/read_file_test.py'],
                        env=env, cwd=str(tmp_path), capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+def test_cli_lifecycle_pid_file_and_signal(tmp_path):
+    """src/sdrterm.py:172-231: `python -m sdrterm` writes a PID file, announces it, and a SIGTERM
+    sets the halt flag -- both loops stop, the PID file is removed, exit status 0.  No input ever
+    arrives on stdin here, so no device engine is created and this runs without a GPU."""
+    import re
+    import signal
+    import subprocess
+    import time
+    env = dict(os.environ, PYTHONPATH=os.path.join(ROOT, 'src'), TMPDIR=str(tmp_path))
+    p = subprocess.Popen([sys.executable, '-m', 'sdrterm', '-r', '1024k', '-e', 'h', '-d', '64', '-w', '5k', '-vv'],
+                         stdin=subprocess.PIPE, stdout=subprocess.PIPE, stderr=subprocess.PIPE, env=env,
+                         cwd=str(tmp_path), text=True)
+    lines = []
+    deadline = time.time() + 60
+    while time.time() < deadline:
+        line = p.stderr.readline()
+        lines.append(line)
+        if 'decimatedFs' in line:                  # the repr JSON comes after the PID file line
+            break
+    head = ''.join(lines)
+    m = re.search(r'PID file is created: (\S+)', head)
+    assert m, head
+    assert os.path.exists(m.group(1)) and open(m.group(1)).read().strip() == str(p.pid)
+    assert f'Started proc Main: {p.pid}' in head
+    time.sleep(0.5)
+    p.send_signal(signal.SIGTERM)
+    try:
+        out, err = p.communicate(timeout=30)
+    except subprocess.TimeoutExpired:
+        p.kill()
+        raise
+    assert p.returncode == 0, err
+    assert f'pid {p.pid} caught: SIGTERM' in err
+    assert not os.path.exists(m.group(1))
