@@ -265,6 +265,45 @@ def synth_c3_device(torch, nsamples: int, seed: int, device, offs):
     return b.flip(1).contiguous().reshape(-1)
 
 
+# ------------------------------------------------------------------------------ CLI end to end
+def measure_cli(torch, raw_dev, nch_small: int, nch_big: int):
+    """file -> `python -m sdrterm` (the drop-in CLI, a fresh process) -> file, config 1 flags, two
+    file sizes: `wall` is what a user sees for the big file (interpreter start, plan construction in
+    50-digit arithmetic, CUDA context, the run); `steady` is the difference quotient between the two
+    sizes, i.e. the streaming rate once the process is up."""
+    import tempfile
+    import numpy as np
+    import signals
+    res = {}
+    d = '/dev/shm' if os.path.isdir('/dev/shm') else tempfile.gettempdir()
+    env = dict(os.environ, PYTHONPATH=os.path.join(ROOT, 'src'))
+    times = {}
+    try:
+        for nch in (nch_small, nch_big):
+            fin = os.path.join(d, f'sdrb_cli_in_{os.getpid()}_{nch}.wav')
+            fout = os.path.join(d, f'sdrb_cli_out_{os.getpid()}_{nch}.bin')
+            body = raw_dev[:nch * CB].cpu().numpy().tobytes()
+            with open(fin, 'wb') as fh:
+                fh.write(signals.wav_header(FS, 16, len(body)) + body)
+            t0 = time.perf_counter()
+            r = subprocess.run([sys.executable, '-m', 'sdrterm', '-i', fin, '-o', fout, '-c', '15k', '-w', '5k', '-d', '64',
+                                '--correct-iq'], env=env, cwd=d, capture_output=True, text=True, timeout=600)
+            times[nch] = time.perf_counter() - t0
+            nout = os.path.getsize(fout) if os.path.exists(fout) else 0
+            for f in (fin, fout):
+                if os.path.exists(f):
+                    os.unlink(f)
+            if r.returncode != 0 or nout < nch * 512 * 8:
+                return {'unavailable': f'cli exit {r.returncode}, {nout} bytes out: {r.stderr[-300:]}'}
+        res = {'wall_msps': nch_big * 32768 / times[nch_big] / 1e6,
+               'steady_msps': (nch_big - nch_small) * 32768 / max(times[nch_big] - times[nch_small], 1e-6) / 1e6,
+               'seconds': {str(k): v for k, v in times.items()}, 'chunks': [nch_small, nch_big],
+               'note': 'python -m sdrterm -i <wav> -o <file> -c 15k -w 5k -d 64 --correct-iq, files on tmpfs'}
+    except Exception as e:
+        res = {'unavailable': f'{type(e).__name__}: {e}'}
+    return res
+
+
 # ------------------------------------------------------------------------------ CUDA arm
 def measure_e2e(torch, Engine, pl, raw, sub, e2e_ch, local, args, barrier, max_over_ranks, world):
     """Host pinned buffers through sdrb_submit / sdrb_wait, H2D and D2H inside the timed region."""
@@ -439,6 +478,9 @@ def run_cuda_arm(args):
     e2e_val = None
     if e2e_ch > 0:
         e2e_val = measure_e2e(torch, Engine, pl, raw, sub, e2e_ch, local, args, barrier, max_over_ranks, world)
+    cli = None
+    if world == 1 and args.cli_chunks > 0:
+        cli = measure_cli(torch, raw, max(64, args.cli_chunks // 8), args.cli_chunks)
     # ---------------- SIMO banks (configs 3 and 4): sdrterm_b200.multigpu.RowShardedBank
     import signals
 
@@ -589,6 +631,8 @@ def run_cuda_arm(args):
         line['roofline'] = roof
     if cpu is not None:
         line['cpu_baseline'] = cpu
+    if cli is not None:
+        line['cli_e2e'] = cli
     if simo is not None:
         line['simo'] = simo
     if simo4 is not None:
@@ -614,6 +658,7 @@ def main():
     ap.add_argument('--e2e-batch', type=int, default=512)
     ap.add_argument('--simo-chunks', type=int, default=512)
     ap.add_argument('--simo4-chunks', type=int, default=64, help='config 4 (257 rows, float32) chunks per step')
+    ap.add_argument('--cli-chunks', type=int, default=4096, help='chunks of the larger file of the CLI end-to-end leg (0 = skip)')
     ap.add_argument('--no-verify', action='store_true', help='skip the output verification legs')
     ap.add_argument('--verify-chunks', type=int, default=64)
     ap.add_argument('--ref-chunks', type=int, default=1024, help='chunks per step of the reference arm')
