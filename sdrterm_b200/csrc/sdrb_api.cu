@@ -300,7 +300,7 @@ int launch_chain_t(sdrb_handle *h, const uint8_t *raw, size_t nch, double *out, 
     mark(2);
     if ((phases & PH_FINISH) && h->finish_on) {
         const size_t items = nch * (size_t)pl.R;
-        const unsigned grid = (unsigned)std::min<size_t>((items + FIN_WARPS - 1) / FIN_WARPS, (size_t)h->num_sms * 4);
+        const unsigned grid = (unsigned)std::min<size_t>((items + FIN_WARPS - 1) / FIN_WARPS, (size_t)h->num_sms * 2);
         k_finish<ENC><<<grid, 32 * FIN_WARPS, h->finish_smem, st>>>(pl, h->sc, raw, out, (int)nch, h->keep_y);
         h->launches++;
         mark(3);

@@ -20,7 +20,7 @@
 #pragma once
 #include "sdrb_kernels.cuh"
 
-#define FIN_WARPS 4
+#define FIN_WARPS 8      // two CTAs of eight warps per SM: the per-CTA table set-up is paid twice per SM, not four times
 #define FIN_DBG(ev) do { if (sc.dbg && blockIdx.x == 0 && warp == 0 && lane == 0 && nit < 16) sc.dbg[512 + nit * 16 + (ev)] = clock64(); } while (0)
 
 // Per-warp shared memory (bytes); per CTA: twiddles exp(-2 pi i k / M) (k < M/2) and the pole
@@ -126,7 +126,7 @@ __device__ __forceinline__ double fin_demod_scalar(double2 a, int demod)
 }
 
 template <int ENC>
-__global__ void __launch_bounds__(32 * FIN_WARPS, 4)
+__global__ void __launch_bounds__(32 * FIN_WARPS, 2)
 k_finish(const __grid_constant__ DevPlan pl, const __grid_constant__ Scratch sc, const uint8_t *__restrict__ raw,
          double *__restrict__ out, int nchunks, int keep_y)
 {

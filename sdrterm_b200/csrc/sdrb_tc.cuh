@@ -133,6 +133,20 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map
     asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
                  ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(x), "r"(y), "r"(bar) : "memory");
 }
+// L2 policies: the raw stream is read exactly once (evict first), while ypart / agg are read back
+// by k_finish a moment later (evict last) -- 100 MB of intermediates then survive in the 126 MB L2
+// instead of being flushed by the 1 GiB of raw bytes streaming past them.
+#define TC_L2_EVICT_FIRST 0x12F0000000000000ull
+#define TC_L2_EVICT_LAST 0x14F0000000000000ull
+__device__ __forceinline__ void tma_load_2d_hint(uint32_t dst, const CUtensorMap *map, int x, int y, uint32_t bar, uint64_t policy)
+{
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%2, %3}], [%4], %5;"
+                 ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(x), "r"(y), "r"(bar), "l"(policy) : "memory");
+}
+__device__ __forceinline__ void st_keep_l2(double2 *p, double2 v)
+{
+    asm volatile("st.global.L2::cache_hint.v2.f64 [%0], {%1, %2}, %3;" ::"l"(p), "d"(v.x), "d"(v.y), "l"(TC_L2_EVICT_LAST) : "memory");
+}
 // L2 prefetch of one tensor-map box: no shared memory, no barrier -- the bytes in flight between
 // HBM and L2 are then not limited by the depth of the shared-memory ring
 __device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap *map, int x, int y)
@@ -285,8 +299,8 @@ __device__ __forceinline__ void tc_scan(double2 *xs, const double2 *sRow, int la
     const double2 cinB = cfma(pw[4], cin, sA);                  // what enters the second half-chain
     if (second) {
         const double2 tot = cfma(pw[8], cin, st);
-        if (BACK) agg_tile[8 + mode] = tot;
-        else agg_tile[mode] = cmul(sRow[TC_RC_AGGF], tot);
+        if (BACK) st_keep_l2(agg_tile + 8 + mode, tot);
+        else st_keep_l2(agg_tile + mode, cmul(sRow[TC_RC_AGGF], tot));
     }
 #pragma unroll
     for (int k = 0; k < 4; k++) {
@@ -439,8 +453,8 @@ __device__ __forceinline__ void tc_epilogue(const DevPlan &pl, const TcDev &tc, 
         }
         const double2 rot = sRow[TC_RC_ROT + l16];
         double2 *yp = sc.ypart + obase;
-        yp[0] = cmul(rot, ya);
-        yp[1] = cmul(rot, yb);
+        st_keep_l2(yp, cmul(rot, ya));
+        st_keep_l2(yp + 1, cmul(rot, yb));
         if (e == 0 && lane == 0) TC_DBG(sc, it, 7);
     }
 }
@@ -516,7 +530,8 @@ k_tc(const __grid_constant__ DevPlan pl, const __grid_constant__ TcDev tc, const
                     mbar_wait_sleep(tc_bar(bar0, TCB_A_FREE, s), ph ^ 1);
                     if (rg == 0) TC_DBG(sc, it, 0);
                     mbar_expect_tx(tc_bar(bar0, TCB_FULL_A, s), TC_REGION_BYTES);
-                    tma_load_2d(smem_u32(sA + (size_t)s * TC_REGION_BYTES), &map_a, rg * 128, mt * 128, tc_bar(bar0, TCB_FULL_A, s));
+                    tma_load_2d_hint(smem_u32(sA + (size_t)s * TC_REGION_BYTES), &map_a, rg * 128, mt * 128, tc_bar(bar0, TCB_FULL_A, s),
+                                     TC_L2_EVICT_FIRST);
                     if (++s == nstage) { s = 0; ph ^= 1; }
                 }
             }

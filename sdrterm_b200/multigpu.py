@@ -115,25 +115,26 @@ class RowShardedBank:
     def M(self) -> int:
         return self.plan.M
 
-    def _post(self, i: int, src):
+    def _post(self, i: int, src, nbytes: int):
         """Start the broadcast of batch i inside the time group (the leader copies its batch into
         the buffer first)."""
         if self.row_groups == 1:
             return None
-        b = self._bufs[i & 1]
+        b = self._bufs[i & 1][:nbytes]
         if self.rank == self.leader:
-            b.copy_(src, non_blocking=True)
+            b.copy_(src[:nbytes], non_blocking=True)
         return self.dist.broadcast(b, src=self.leader, group=self.group, async_op=True)
 
     def run(self, batches, nchunks: int, outs, stream: int = 0) -> None:
         """``batches``: list of uint8 device tensors (on the leader; elsewhere only the count
         matters); ``outs``: list of (rows, nchunks*M) float64 device tensors of this rank."""
         n = len(batches)
-        w = self._post(0, batches[0])
+        nbytes = nchunks * self.chunk_bytes
+        w = self._post(0, batches[0], nbytes)
         for i in range(n):
             if w is not None:
                 w.wait()
-            w = self._post(i + 1, batches[i + 1]) if i + 1 < n else None
+            w = self._post(i + 1, batches[i + 1], nbytes) if i + 1 < n else None
             src = self._bufs[i & 1] if self.row_groups > 1 else batches[i]
             self.engine.process_device(src.data_ptr(), nchunks, outs[i].data_ptr(), stream)
 

@@ -130,3 +130,69 @@ def test_two_rank_gloo_matches_single_process():
     serial3 = orc.Chain(**kw3).run(raw3)
     got3 = sharding.concat_rows([r[6] for r in res])
     assert got3.shape == serial3.shape and np.array_equal(got3, serial3)
+
+
+def test_bank_grid_spends_ranks_on_rows_only_while_a_rank_keeps_enough_of_them():
+    from sdrterm_b200.multigpu import bank_grid
+    assert [bank_grid(17, w) for w in (1, 2, 4, 8)] == [(1, 1), (2, 1), (2, 2), (2, 4)]      # config 3
+    assert [bank_grid(257, w) for w in (1, 2, 4, 8)] == [(1, 1), (2, 1), (4, 1), (8, 1)]     # config 4
+    for rows in (1, 3, 17, 33, 257):
+        for w in (1, 2, 4, 8):
+            rg, tg = bank_grid(rows, w)
+            assert rg * tg == w and (rg == 1 or rows // rg >= 8)
+
+
+class _FakeEngine:
+    """Stands in for the device engine: records what each call was given (host logic under test)."""
+    log = []
+
+    def __init__(self, plan, max_chunks=1, device=0, **kw):
+        self.plan, self.max_chunks = plan, max_chunks
+        self.iq_state = 0j
+
+    def process(self, raw):
+        raw = np.ascontiguousarray(raw).view(np.uint8).reshape(-1)
+        _FakeEngine.log.append(raw.copy())
+        n = raw.size // CB
+        return np.zeros((1, n * self.plan.M))
+
+    def iq_gain(self, raw):
+        pass
+
+    def close(self):
+        pass
+
+
+@pytest.mark.parametrize('nbytes', [7 * CB, 6 * CB + 1000, 3 * CB + 1])
+def test_run_file_sharded_hands_every_rank_its_chunks_with_the_stale_tail(tmp_path, monkeypatch, nbytes):
+    """Host logic of config 5 (no GPU): the segments of all ranks, in rank order, are exactly the
+    chunks the reference's reused read buffer would present, offset by dataOffset."""
+    from gpu_util import chunked
+    from sdrterm_b200 import multigpu
+    monkeypatch.setattr(multigpu, 'Engine', _FakeEngine)
+    rng = np.random.default_rng(1)
+    body = rng.integers(0, 256, nbytes, dtype=np.uint8).tobytes()
+    path = tmp_path / 'in.raw'
+    path.write_bytes(b'HEAD' * 10 + body)
+
+    class FakeDist:
+        def __init__(self, rank, world):
+            self.rank, self.world = rank, world
+
+        def get_world_size(self):
+            return self.world
+
+        def get_rank(self):
+            return self.rank
+
+    for world in (1, 2, 3):
+        got = []
+        for rank in range(world):
+            _FakeEngine.log.clear()
+            out = multigpu.run_file_sharded(str(path), None, fs=1_024_000, enc='h', dec=64, center=15000, omega_out=5000,
+                                            data_offset=40, batch_chunks=2, device=0,
+                                            dist=FakeDist(rank, world) if world > 1 else None, torch=torch)
+            got += list(_FakeEngine.log)
+            assert out.shape[1] % 512 == 0
+        allb = np.concatenate(got) if got else np.zeros(0, dtype=np.uint8)
+        assert np.array_equal(allb, chunked(body).reshape(-1)), (world, nbytes)
