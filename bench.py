@@ -170,7 +170,7 @@ def run_reference_arm(args):
             'e2e': {'value': val, 'unit': 'Msamples/s', 'h2d_bytes_per_step': 0,
                     'd2h_bytes_per_step': 0},
             'gpu_launches': 0}
-    print(json.dumps(line))
+    emit(line)
 
 
 # ------------------------------------------------------------------------------ clocks sampler
@@ -642,9 +642,32 @@ def run_cuda_arm(args):
         errs += [sm['verified_max_rel_err'] for sm in (simo, simo4) if sm is not None and sm['verified_max_rel_err'] is not None]
         line['verify'] = verify
         line['verified'] = bool(all(e == e and e <= 1e-9 for e in errs))
-    print(json.dumps(line))
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
+
+
+_JSON_FD = None
+
+
+def claim_stdout():
+    """Keep the real stdout for the one JSON line: everything else written to fd 1 from here on
+    (NCCL prints its version banner and its NCCL_DEBUG output there) goes to stderr instead, so no
+    NCCL_DEBUG override is needed to keep the line parseable."""
+    global _JSON_FD
+    if _JSON_FD is None:
+        sys.stdout.flush()
+        _JSON_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line: dict) -> None:
+    data = (json.dumps(line) + '\n').encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, data)
 
 
 def main():
@@ -657,7 +680,7 @@ def main():
     ap.add_argument('--e2e-chunks', type=int, default=4096)
     ap.add_argument('--e2e-batch', type=int, default=512)
     ap.add_argument('--simo-chunks', type=int, default=512)
-    ap.add_argument('--simo4-chunks', type=int, default=64, help='config 4 (257 rows, float32) chunks per step')
+    ap.add_argument('--simo4-chunks', type=int, default=256, help='config 4 (257 rows, float32) chunks per step')
     ap.add_argument('--cli-chunks', type=int, default=8192, help='chunks of the larger file of the CLI end-to-end leg (0 = skip)')
     ap.add_argument('--no-verify', action='store_true', help='skip the output verification legs')
     ap.add_argument('--verify-chunks', type=int, default=64)
@@ -665,6 +688,7 @@ def main():
     ap.add_argument('--cpu-seconds', type=float, default=10.0)
     ap.add_argument('--no-cpu', action='store_true')
     args = ap.parse_args()
+    claim_stdout()
     if args.impl == 'reference':
         run_reference_arm(args)
     else:

@@ -486,21 +486,11 @@ def build_tc(pl: Plan, nd: int = TC_ND) -> TcTables | None:
     rho = [mp.mpc(v) for v in pl.modes.rho]
     rho_p = [mp.mpc(v) for v in pl.modes.rho_p]
 
-    # byte bookkeeping of one sample: (component, significance, xored?) per byte.  The tensor core
-    # reads the whole A operand either as signed or as unsigned int8: 'B' goes in as it is
-    # (unsigned), 'b' as it is (signed); 16-bit samples mix a signed top byte with an unsigned low
-    # byte -- the bytes that are not a signed top byte are XOR-ed with 0x80 (u -> u - 128 as int8)
-    # by the kernel's sign fix-up warps and the constant this removes is added back (cst)
-    # (unsigned 16-bit samples take the signed route too, both bytes XOR-ed: as unsigned operands
-    # their worst-case int32 column sums would not be provably safe)
-    a_signed = signed or isz == 2
+    # byte bookkeeping of one sample: (component, significance) per byte
     info = []
     for bb in range(sb):
         cpt, bi = divmod(bb, isz)
-        w = bi if stored_le else isz - 1 - bi
-        xored = a_signed and not (signed and w == isz - 1)
-        info.append((cpt, w, xored))
-    xor_mask = np.array([0x80 if info[b % sb][2] else 0 for b in range(16)], dtype=np.uint8)
+        info.append((cpt, bi if stored_le else isz - 1 - bi))
 
     allrows = []   # [r][o] -> list over j of (coef on I_j, coef on Q_j), real mp numbers
     rowc = np.zeros((R, TC_NROWC), dtype=np.complex128)
@@ -573,7 +563,7 @@ def build_tc(pl: Plan, nd: int = TC_ND) -> TcTables | None:
             for j, ab in enumerate(row):
                 for cpt in (0, 1):
                     A = int(mp.nint(ab[cpt] * mp.mpf(2) ** S_hi[o >= 36]))
-                    for bb, (c2_, w, _x) in enumerate(info):
+                    for bb, (c2_, w) in enumerate(info):
                         if c2_ != cpt:
                             continue
                         if w == isz - 1:                       # top (or only) byte: all nd digits
@@ -587,12 +577,19 @@ def build_tc(pl: Plan, nd: int = TC_ND) -> TcTables | None:
         for blk in (0, 1):
             for cpt in (0, 1):
                 c0 = TC_X0COL + (2 * blk + cpt) * isz
-                for bb, (c2_, w, _x) in enumerate(info):
+                for bb, (c2_, w) in enumerate(info):
                     if c2_ == cpt:
                         Bq[r, c0 + (isz - 1 - w), blk * q * sb + bb] = 1
-    # response of every output to the constant the XOR removed (the kernel adds it back): bytes
-    # with the mask set enter the GEMM as (u - 128)
-    xk = np.array([128 if info[k % sb][2] else 0 for k in range(K)], dtype=np.int64)
+    # Signedness.  The tensor core reads the whole A operand either as signed or as unsigned int8.
+    # Unsigned 8-bit samples go in as they are when the int32 digit-pair sums are provably safe for
+    # bytes up to 255 (K = 256); 'b' goes in as it is (signed).  Everything else takes the signed
+    # route: the bytes that are not a signed top byte are XOR-ed with 0x80 (u -> u - 128 as int8) by
+    # the kernel's sign fix-up warps, and the response to the constant this removes is added back.
+    col_l1 = int(np.abs(Bq.astype(np.int64)).sum(axis=2).max())
+    a_signed = not (pl.enc == 'B' and col_l1 * 255 * 257 < 2 ** 31)
+    xflag = [a_signed and not (signed and w == isz - 1) for (_c, w) in info]
+    xor_mask = np.array([0x80 if xflag[b % sb] else 0 for b in range(16)], dtype=np.uint8)
+    xk = np.array([128 if xflag[k % sb] else 0 for k in range(K)], dtype=np.int64)
     colsum = Bq.astype(np.int64) @ xk                                  # (R, Npad)
     cst = np.zeros((R, nout + 4))
     for r in range(R):
@@ -606,7 +603,6 @@ def build_tc(pl: Plan, nd: int = TC_ND) -> TcTables | None:
             for t in range(isz):
                 V = V * 256 + int(colsum[r, TC_X0COL + x * isz + t])
             cst[r, nout + x] = float(V)
-    col_l1 = int(np.abs(Bq.astype(np.int64)).sum(axis=2).max())
     amax_byte = 128 if a_signed else 255
     if col_l1 * amax_byte * 257 >= 2 ** 31:
         raise OverflowError('int32 digit-pair sums could overflow for this coefficient set')

@@ -156,3 +156,72 @@ def test_tensor_core_front_end_decodes_exactly(enc, swap):
     ref = z.reshape(nch, N)[:, ::q]
     assert x0.shape == (nch, 1, N // q)
     assert np.array_equal(x0[:, 0, :], ref)
+
+
+@pytest.mark.parametrize('use_tc', [True, False])
+def test_simo_bank_with_iq_correction(use_tc):
+    """--simo together with --correct-iq: the decoupled corrector's per-row constants (alpha, beta,
+    gamma depend on each row's NCO frequency) on both front ends and in the fused finish kernel's
+    R > 1 path; no BASELINE config combines the two, so no golden case does either."""
+    from gpu_util import plan_for
+    from sdrterm_b200.engine import Engine
+    # one FM carrier per row (a row that held only noise would make the FM output ill-conditioned:
+    # the phase of a near-zero pair product), a DC offset for the corrector to remove
+    fs, n = 1_024_000, 3 * 32768
+    rng = np.random.default_rng(31)
+    z = np.zeros(n, dtype=np.complex128)
+    for i, f in enumerate((-5000, 22000, 46000, 15000)):
+        z += signals._fm_carrier(n, fs, f, 800 + 50 * i, 2000, 3000.0, phase0=0.4 * i)
+    z += rng.normal(0, 100, n) + 1j * rng.normal(0, 100, n) + (37 - 21j)
+    body = signals._interleave(z, '<i2', -32768, 32767).tobytes()
+    kw = dict(fs=fs, enc='h', center=15000, dec=64, demod='fm', omega_out=5000, correct_iq=True,
+              vfos='-20000,7000,31000', simo=True, normalize=False, swap=False, big_endian=None)
+    pl = plan_for(kw)
+    assert pl.R == 4 and np.abs(pl.gamma).min() >= 0
+    with Engine(pl, max_chunks=3, use_tc=use_tc) as eng:
+        assert (eng.tc is not None) == use_tc
+        out = eng.process(body)
+        off = eng.iq_state
+    ch = orc.Chain(**kw)
+    ref = ch.run(body)
+    got = np.asarray(out, dtype=np.float64)
+    assert got.shape == ref.shape
+    for r in range(pl.R):
+        assert rel_err(got[r], ref[r]) < TOL, r
+    assert abs(off - ch._off[0]) <= 1e-9 * max(1.0, abs(ch._off[0]))
+
+
+@pytest.mark.parametrize('enc,q,swap', [('b', 128, False), ('B', 128, False), ('h', 32, True), ('H', 64, False)])
+def test_tensor_core_shapes_not_covered_by_the_golden_cases(enc, q, swap):
+    """K = 512 with 8-bit samples (q = 128), K = 256 with 16-bit samples (q = 32), unsigned 16-bit
+    at q = 64: FM with IQ correction against the oracle."""
+    from gpu_util import plan_for
+    from sdrterm_b200.engine import Engine
+    isz = 1 if enc in 'bB' else 2
+    n = 2 * (CB // (2 * isz))
+    body = signals.generic_bytes(enc, n, 41, 1_000_000, 30_000, big_endian=swap)
+    kw = dict(fs=1_000_000, enc=enc, center=30000, dec=q, demod='fm', omega_out=3000, correct_iq=True,
+              vfos=None, simo=False, normalize=False, swap=swap, big_endian=None)
+    pl = plan_for(kw)
+    with Engine(pl, max_chunks=2) as eng:
+        assert eng.tc is not None and eng.tc.K == 2 * q * 2 * isz
+        out = eng.process(body)
+    ref = orc.Chain(**kw).run(body)
+    assert out.shape == ref.shape and rel_err(out, ref) < TOL
+
+
+def test_file_sharded_entry_point_single_process(tmp_path):
+    """multigpu.run_file_sharded (BASELINE config 5's product entry point) with world = 1: a raw
+    int16 file whose size is not a whole number of chunks (stale tail), processed in
+    batches of 2 chunks, equals the oracle over the same stream."""
+    import torch
+    from sdrterm_b200 import multigpu
+    body = signals.c1_bytes(5 * 32768 + 7000, seed=17, header=False)
+    path = tmp_path / 'in.raw'
+    path.write_bytes(body)
+    out = multigpu.run_file_sharded(str(path), None, fs=1_024_000, enc='h', dec=64, center=15000, omega_out=5000,
+                                    correct_iq=True, batch_chunks=2, device=0, dist=None, torch=torch)
+    kw = dict(fs=1_024_000, enc='h', center=15000, dec=64, demod='fm', omega_out=5000, correct_iq=True,
+              vfos=None, simo=False, normalize=False, swap=False, big_endian=None)
+    ref = orc.Chain(**kw).run(body)
+    assert out.shape == ref.shape and rel_err(out, ref) < TOL
