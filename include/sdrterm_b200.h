@@ -192,6 +192,11 @@ int sdrb_kernel_times(sdrb_handle *h, float ms[4]);
 int sdrb_submit(sdrb_handle *h, int slot, const void *raw_host, size_t nchunks, double *out_host);
 int sdrb_wait(sdrb_handle *h, int slot);
 
+/* Page-locked host staging buffers for sdrb_submit (so that a host layer needs nothing but this
+ * library to stream: the drop-in CLI does not import torch). */
+int sdrb_host_alloc(size_t bytes, void **ptr_out);
+int sdrb_host_free(void *ptr);
+
 /* The one piece of state that crosses chunks: the IQ corrector's complex offset
  * (src/misc/read_file.py:53).  Used for time-segment sharding across GPUs. */
 int sdrb_get_iq_state(sdrb_handle *h, double off[2]);

@@ -60,7 +60,7 @@ EXPORTS = ['sdrb_create', 'sdrb_destroy', 'sdrb_last_error', 'sdrb_outputs_per_c
            'sdrb_fm_demod', 'sdrb_am_demod', 'sdrb_real_output', 'sdrb_imag_output',
            'sdrb_shift_freq', 'sdrb_global_error', 'sdrb_process_device_phases',
            'sdrb_set_profiling', 'sdrb_kernel_times', 'sdrb_keep_decimated', 'sdrb_read_debug', 'sdrb_iq_export_device',
-           'sdrb_iq_prefix_device', 'sdrb_decode_iq', 'sdrb_correct_iq', 'sdrb_keep_x0', 'sdrb_read_x0', 'sdrb_iq_gain', 'sdrb_set_smooth']
+           'sdrb_iq_prefix_device', 'sdrb_decode_iq', 'sdrb_correct_iq', 'sdrb_keep_x0', 'sdrb_read_x0', 'sdrb_iq_gain', 'sdrb_set_smooth', 'sdrb_host_alloc', 'sdrb_host_free']
 
 
 def nvcc_command(out: str = LIB_PATH) -> list[str]:
@@ -123,10 +123,38 @@ def lib():
         L.sdrb_correct_iq.argtypes = [C.c_int, vp, sz, _DP, C.c_double]
         L.sdrb_keep_x0.argtypes = [vp, C.c_int]
         L.sdrb_iq_gain.argtypes = [vp, vp, sz]
+        L.sdrb_host_alloc.argtypes = [sz, C.POINTER(vp)]
+        L.sdrb_host_free.argtypes = [vp]
         L.sdrb_set_smooth.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, vp]
         L.sdrb_read_x0.argtypes = [vp, sz, vp]
         _lib = L
     return _lib
+
+
+class PinnedBuffer:
+    """Page-locked host memory from the library (cudaHostAlloc) with a numpy view."""
+
+    def __init__(self, nbytes: int):
+        import numpy as np
+        self.ptr = C.c_void_p()
+        check(lib().sdrb_host_alloc(nbytes, C.byref(self.ptr)))
+        self.nbytes = nbytes
+        self.u8 = np.ctypeslib.as_array((C.c_uint8 * nbytes).from_address(self.ptr.value))
+
+    def view(self, dtype):
+        return self.u8.view(dtype)
+
+    def free(self):
+        if self.ptr:
+            lib().sdrb_host_free(self.ptr)
+            self.ptr = C.c_void_p()
+            self.u8 = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
 
 
 def check(rc: int, handle=None) -> None:

@@ -1020,6 +1020,19 @@ int sdrb_correct_iq(int device, double *z_inout, size_t nsamples, double off_ino
     return SDRB_OK;
 }
 
+int sdrb_host_alloc(size_t bytes, void **ptr_out)
+{
+    if (!ptr_out) return fail(nullptr, SDRB_ERR_ARG, "null argument");
+    CK(nullptr, cudaHostAlloc(ptr_out, bytes ? bytes : 1, cudaHostAllocDefault));
+    return SDRB_OK;
+}
+
+int sdrb_host_free(void *ptr)
+{
+    if (ptr) CK(nullptr, cudaFreeHost(ptr));
+    return SDRB_OK;
+}
+
 int sdrb_keep_x0(sdrb_handle *h, int on)
 {
     if (!h) return fail(h, SDRB_ERR_ARG, "null argument");

@@ -161,7 +161,8 @@ class DspProcessor(DataProcessor):
             if enc is None:
                 raise ValueError('raw chunks need the sample encoding (enc=... or fileInfo)')
             ciq, norm = self._correctIq, self._normalize
-            chunk_bytes = len(first) if not isinstance(first, np.ndarray) else first.nbytes
+            nb = len(first) if not isinstance(first, np.ndarray) else first.nbytes
+            chunk_bytes = 131072 if nb % 131072 == 0 else nb     # the reader may hand over several chunks at once
         plan = build_plan(self.__fs, enc, self._decimationFactor, self._rowsHz(), simo=self._simo(),
                           swap=swap, correct_iq=ciq, normalize=norm, demod=self._demodName(),
                           omega_out=self.omegaOut, chunk_bytes=chunk_bytes)
@@ -184,12 +185,12 @@ class DspProcessor(DataProcessor):
         file.write(out[0].tobytes())
 
     def _staging(self):
-        """Two pinned host buffers each way (torch is used for exactly this: pinned memory)."""
-        import torch
+        """Two page-locked host buffers each way (cudaHostAlloc through the C ABI)."""
+        from .._native import PinnedBuffer
         eng = self._engine
         n = self.MAX_BATCH
-        self._hin = [torch.empty(n * self._chunkBytes, dtype=torch.uint8).pin_memory() for _ in range(2)]
-        self._hout = [torch.empty(eng.R * n * eng.M, dtype=torch.float64).pin_memory() for _ in range(2)]
+        self._hin = [PinnedBuffer(n * self._chunkBytes) for _ in range(2)]
+        self._hout = [PinnedBuffer(eng.R * n * eng.M * 8) for _ in range(2)]
 
     def _processData(self, isDead, buffer, file=None) -> None:
         """The consumer loop (dsp_processor.py:164-183), double-buffered: while the device works on
@@ -205,35 +206,59 @@ class DspProcessor(DataProcessor):
             if first is None:                            # halted while waiting for input
                 break
             batch = [first]
-            while len(batch) < self.MAX_BATCH:
+            have = self._itemChunks(first)
+            while have < self.MAX_BATCH:
                 try:
                     batch.append(buffer.get_nowait())
                 except _queue.Empty:
                     break
+                have += self._itemChunks(batch[-1])
             chunks = []
+            nch = 0
             for c in batch:
                 if c is None or len(c) == 0:          # end-of-stream marker (read_file.py:169-171)
                     eof = True
                     break
-                chunks.append(self._asBytes(c))
-            if not chunks:
-                break
-            if self._engine is None:
-                self._engine = self._makeEngine(batch[0])
-                self._staging()
-            if any(c.size != self._chunkBytes for c in chunks):
-                raise ValueError('chunks must all have the size of the first one')
-            slot = b & 1
-            hin = self._hin[slot].numpy()
-            for i, c in enumerate(chunks):
-                hin[i * self._chunkBytes:(i + 1) * self._chunkBytes] = c
-            self._engine.submit(slot, self._hin[slot].data_ptr(), len(chunks), self._hout[slot].data_ptr())
-            if pending is not None:
-                self._drain(pending, file)
-            pending = (slot, len(chunks))
-            b += 1
+                if self._engine is None:
+                    self._engine = self._makeEngine(c)
+                    self._staging()
+                a = self._asBytes(c)                   # one chunk, or several whole chunks read at once
+                if a.size % self._chunkBytes:
+                    raise ValueError('queue items must be whole chunks of the size of the first one')
+                chunks.append(a)
+                nch += a.size // self._chunkBytes
+            # (a batch of multi-chunk items may exceed MAX_BATCH: split it)
+            pos = 0
+            flat = chunks
+            while flat:
+                slot = b & 1
+                hin = self._hin[slot].u8
+                n = 0
+                while flat and n < self.MAX_BATCH:
+                    a = flat[0]
+                    take = min(a.size // self._chunkBytes - pos, self.MAX_BATCH - n)
+                    hin[n * self._chunkBytes:(n + take) * self._chunkBytes] = \
+                        a[pos * self._chunkBytes:(pos + take) * self._chunkBytes]
+                    n += take
+                    pos += take
+                    if pos * self._chunkBytes == a.size:
+                        flat.pop(0)
+                        pos = 0
+                self._engine.submit(slot, self._hin[slot].ptr.value, n, self._hout[slot].ptr.value)
+                if pending is not None:
+                    self._drain(pending, file)
+                pending = (slot, n)
+                b += 1
         if pending is not None:
             self._drain(pending, file)
+
+    @staticmethod
+    def _itemChunks(c) -> int:
+        """Chunks a queue item holds (1 for the reference's complex payload or a single raw chunk)."""
+        if c is None or isinstance(c, np.ndarray) and np.iscomplexobj(c):
+            return 1
+        nb = c.nbytes if isinstance(c, np.ndarray) else len(c)
+        return max(1, nb // 131072)
 
     def _next(self, isDead, buffer):
         """Blocking ``buffer.get()`` that still notices the halt flag (the reference's consumer is
@@ -249,7 +274,7 @@ class DspProcessor(DataProcessor):
         slot, n = pending
         eng = self._engine
         eng.wait(slot)
-        out = self._hout[slot].numpy()[:eng.R * n * eng.M].reshape(eng.R, n * eng.M)
+        out = self._hout[slot].view(np.float64)[:eng.R * n * eng.M].reshape(eng.R, n * eng.M)
         if eng.plan.big_endian_out:
             out = out.view('>f8')
         self._emit(out, n, file)

@@ -151,7 +151,10 @@ def test_read_file_feeds_queues_and_marks_eof(tmp_path):
     items = []
     while not q.empty():
         items.append(q.get())
-    assert [len(i) for i in items] == [131072, 131072, 0]
+    # a regular file is handed over READ_BATCH chunks per item (whole chunks, stale tail included),
+    # then the empty end-of-stream marker
+    assert [len(i) for i in items] == [2 * 131072, 0]
+    assert bytes(items[0][131072 + 6:131072 + 16]) == b'\x07' * 10      # stale tail of the chunk before (8-Q5)
     with pytest.raises(ValueError):
         read_file.readFile(fs=None, buffers=[q])
 
