@@ -30,9 +30,28 @@ _DEMOD_NAME = {fmDemod: 'fm', amDemod: 'am', realOutput: 're', imagOutput: 'im'}
 
 def generateEllipFilter(fs: int, deg: int, Wn, btype: str):
     """Output low-pass design, SciPy's as in the reference (dsp_processor.py:39-45); design is
-    setup, not hot path, and keeps the coefficients identical to the reference's."""
+    setup, not hot path, and keeps the coefficients identical to the reference's.  The result is
+    kept in the plan cache directory so that a command-line run that finds it does not import
+    scipy.signal at all."""
+    import os
+    root = os.environ.get('SDRB_PLAN_CACHE', os.path.join(os.path.expanduser('~'), '.cache', 'sdrterm_b200'))
+    path = os.path.join(root, f'ellip_{int(fs)}_{int(deg)}_{Wn!r}_{btype}.npy'.replace(os.sep, '_')) if root else None
+    if path:
+        try:
+            return np.load(path)
+        except Exception:
+            pass
     from scipy.signal import ellip
-    return ellip(deg, 1, 30, Wn, btype=btype, analog=False, output='sos', fs=fs)
+    sos = ellip(deg, 1, 30, Wn, btype=btype, analog=False, output='sos', fs=fs)
+    if path:
+        try:
+            os.makedirs(root, exist_ok=True)
+            tmp = f'{path}.{os.getpid()}.tmp.npy'
+            np.save(tmp, sos)
+            os.replace(tmp, path)
+        except OSError:
+            pass
+    return sos
 
 
 class DspProcessor(DataProcessor):
@@ -142,7 +161,7 @@ class DspProcessor(DataProcessor):
 
     def _makeEngine(self, first):
         from ..engine import Engine
-        from ..plan import build_plan
+        from ..plan import cached_plan
         if isinstance(first, np.ndarray) and np.iscomplexobj(first):
             enc, swap, ciq, norm = 'Z', False, False, False       # producer already did these
             chunk_bytes = first.size * 16
@@ -163,14 +182,14 @@ class DspProcessor(DataProcessor):
             ciq, norm = self._correctIq, self._normalize
             nb = len(first) if not isinstance(first, np.ndarray) else first.nbytes
             chunk_bytes = 131072 if nb % 131072 == 0 else nb     # the reader may hand over several chunks at once
-        plan = build_plan(self.__fs, enc, self._decimationFactor, self._rowsHz(), simo=self._simo(),
-                          swap=swap, correct_iq=ciq, normalize=norm, demod=self._demodName(),
-                          omega_out=self.omegaOut, chunk_bytes=chunk_bytes)
+        plan, tc = cached_plan(self.__fs, enc, self._decimationFactor, self._rowsHz(), simo=self._simo(),
+                               swap=swap, correct_iq=ciq, normalize=norm, demod=self._demodName(),
+                               omega_out=self.omegaOut, chunk_bytes=chunk_bytes)
         self._chunkBytes = chunk_bytes
         # --smooth-output (dsp_processor.py:159-160): standard mode only, the SIMO override of
         # _transformData never smooths (vfo_processor.py:80-84)
         smooth = int(self.smooth) if (self.smooth and not self._simo()) else 0
-        return Engine(plan, max_chunks=self.MAX_BATCH, device=self._device, smooth=smooth)
+        return Engine(plan, max_chunks=self.MAX_BATCH, device=self._device, smooth=smooth, tc=tc)
 
     @staticmethod
     def _asBytes(chunk) -> np.ndarray:

@@ -20,7 +20,7 @@ def _dp(a: np.ndarray):
 
 class Engine:
     def __init__(self, plan: Plan, max_chunks: int = 256, device: int = 0, use_tc: bool = True,
-                 keep_decimated: bool = False, keep_x0: bool = False, smooth: int = 0):
+                 keep_decimated: bool = False, keep_x0: bool = False, smooth: int = 0, tc='build'):
         self.plan = plan
         self.max_chunks = int(max_chunks)
         self.device = int(device)
@@ -80,7 +80,8 @@ class Engine:
         tab.lam_tile[0], tab.lam_tile[1] = float(pl.lam_tile[0]), float(pl.lam_tile[1])
         if pl.fm_interp is not None:
             put('fm_interp', pl.fm_interp)
-        self.tc = build_tc(pl) if use_tc else None
+        # tc: prebuilt tensor-core tables (plan.cached_plan), or 'build'
+        self.tc = (build_tc(pl) if isinstance(tc, str) else tc) if use_tc else None
         if self.tc is not None:
             tc = self.tc
             tab.tc_enable, tab.tc_K, tab.tc_isz = 1, tc.K, tc.isz

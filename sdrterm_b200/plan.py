@@ -24,9 +24,18 @@ from __future__ import annotations
 
 from dataclasses import dataclass, field
 
-import mpmath as mp
 import numpy as np
-from scipy import signal as _sig
+
+mp = None          # mpmath and scipy.signal are imported on first use (_heavy): a process that finds
+_sig = None        # its plan in the cache (cached_plan) never pays for them
+
+
+def _heavy():
+    global mp, _sig
+    if mp is None:
+        import mpmath
+        from scipy import signal
+        mp, _sig = mpmath, signal
 
 TILE_BLOCKS = 32          # one warp: lane <-> block
 CHUNK_BYTES = 131072      # src/misc/read_file.py:38
@@ -84,6 +93,7 @@ class FilterModes:
 
 
 def filter_modes(sos: np.ndarray, zi: np.ndarray, dps: int = 50) -> FilterModes:
+    _heavy()
     mp.mp.dps = dps
     A, b, c, d = _cascade_state_space(sos)
     n = A.rows
@@ -224,6 +234,7 @@ def build_plan(fs: int, enc: str, dec: int, rows_hz, *, simo: bool = False, swap
                correct_iq: bool = False, normalize: bool = False, impedance: int = 50,
                demod: str = 'fm', omega_out: int = 12500, chunk_bytes: int = CHUNK_BYTES,
                big_endian_out: bool | None = None) -> Plan:
+    _heavy()
     if dec < 2:
         raise ValueError('Decimation must be at least 2.')
     if enc not in _ITEMSIZE:
@@ -470,6 +481,7 @@ def tc_supported(pl: Plan) -> bool:
 def build_tc(pl: Plan, nd: int = TC_ND) -> TcTables | None:
     if not tc_supported(pl):
         return None
+    _heavy()
     mp.mp.dps = 50
     q, R = pl.q, pl.R
     q2 = TC_SB * q
@@ -609,3 +621,40 @@ def build_tc(pl: Plan, nd: int = TC_ND) -> TcTables | None:
     return TcTables(K=K, isz=isz, ND=nd, NCOL=ncol, SB=TC_SB, nout=nout, Npad=TC_NPAD, R=R, xor_mask=xor_mask,
                     a_signed=a_signed,
                     Bq=Bq, S=S, S_yl=S_yl, cst=cst, rowc=rowc, col_l1=col_l1)
+
+
+# ------------------------------------------------------------------------------------------------
+def cached_plan(*args, **kwargs):
+    """``(build_plan(*args, **kwargs), build_tc(plan))`` through an on-disk cache (directory
+    ``$SDRB_PLAN_CACHE``, default ``~/.cache/sdrterm_b200``; set it to an empty string to switch
+    the cache off).  The tables depend only on the arguments and on this file, so the key is their
+    hash; building them takes seconds of 50-digit arithmetic, which matters to a command-line run
+    and to nothing else."""
+    import hashlib
+    import os
+    import pickle
+    root = os.environ.get('SDRB_PLAN_CACHE', os.path.join(os.path.expanduser('~'), '.cache', 'sdrterm_b200'))
+    path = None
+    if root:
+        with open(__file__, 'rb') as fh:
+            ver = hashlib.sha256(fh.read()).hexdigest()[:16]
+        key = hashlib.sha256(repr((args, sorted(kwargs.items()), ver)).encode()).hexdigest()[:32]
+        path = os.path.join(root, f'plan_{key}.pkl')
+        try:
+            with open(path, 'rb') as fh:
+                return pickle.load(fh)
+        except Exception:
+            pass
+    pl = build_plan(*args, **kwargs)
+    tc = build_tc(pl)
+    pl.modes.mp_p = pl.modes.mp_c = None              # high-precision scratch of the build, not part of the plan
+    if path:
+        try:
+            os.makedirs(root, exist_ok=True)
+            tmp = f'{path}.{os.getpid()}.tmp'
+            with open(tmp, 'wb') as fh:
+                pickle.dump((pl, tc), fh, protocol=pickle.HIGHEST_PROTOCOL)
+            os.replace(tmp, path)
+        except OSError:
+            pass
+    return pl, tc
