@@ -353,6 +353,7 @@ def run_cuda_arm(args):
         raise SystemExit('bench.py: no CUDA device (the CUDA arm has no CPU fallback)')
     torch.cuda.set_device(local)
     dev = torch.device('cuda', local)
+    numa_bound = multigpu.bind_to_gpu_numa_node(local) if not args.no_numa else False
     if world > 1:
         import datetime
         dist.init_process_group('nccl', device_id=dev, timeout=datetime.timedelta(seconds=180))
@@ -625,7 +626,8 @@ def run_cuda_arm(args):
                        'parallelism': 'time-segment sharding, IQ state via all-gather' if world > 1 else 'single GPU'},
             'e2e': None if e2e_val is None else {'value': e2e_val, 'unit': 'Msamples/s', 'h2d_bytes_per_step': e2e_ch * CB,
                     'd2h_bytes_per_step': e2e_ch * pl.M * 8,
-                    'note': f'{e2e_ch} chunks per step in batches of {sub}, double-buffered sdrb_submit/sdrb_wait'},
+                    'note': f'{e2e_ch} chunks per step in batches of {sub}, double-buffered sdrb_submit/sdrb_wait',
+                    'numa_bound': numa_bound},
             'gpu_launches': launches, 'clocks': clocks.summary()}
     if roof is not None:
         line['roofline'] = roof
@@ -682,6 +684,7 @@ def main():
     ap.add_argument('--simo-chunks', type=int, default=512)
     ap.add_argument('--simo4-chunks', type=int, default=256, help='config 4 (257 rows, float32) chunks per step')
     ap.add_argument('--cli-chunks', type=int, default=8192, help='chunks of the larger file of the CLI end-to-end leg (0 = skip)')
+    ap.add_argument('--no-numa', action='store_true', help='do not bind the rank to its GPU\'s NUMA node')
     ap.add_argument('--no-verify', action='store_true', help='skip the output verification legs')
     ap.add_argument('--verify-chunks', type=int, default=64)
     ap.add_argument('--ref-chunks', type=int, default=1024, help='chunks per step of the reference arm')
