@@ -55,6 +55,7 @@ struct sdrb_handle {
     CUtensorMap map_b{};
     size_t tc_smem = 0;
     int num_sms = 148;
+    bool pdl = false;               // programmatic dependent launch inside a step (SDRB_PDL=1)
     double2 *x0_buf = nullptr;      // sdrb_keep_x0
     int smooth_w = 0, smooth_nhead = 0, smooth_ntail = 0, smooth_lo = 0;   // --smooth-output (window 0 = off)
     double *smooth_S = nullptr, *smooth_tmp = nullptr;
@@ -139,6 +140,20 @@ int env_int(const char *name, int dflt);
 int launch_tc(sdrb_handle *h, const uint8_t *raw, size_t nch, cudaStream_t st, bool iq);
 
 enum { PH_MAIN = 1, PH_IQSCAN = 2, PH_FINISH = 4, PH_ALL = 7 };
+
+// Launch with the programmatic stream-serialisation attribute (see pdl_wait in sdrb_device.cuh);
+// SDRB_PDL=1 switches it on (ordinary launches otherwise).
+template <typename... KArgs, typename... Args>
+cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, bool pdl, Args... args)
+{
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
 
 // ------------------------------------------------------------------ tensor-core front end
 typedef CUresult (*encode_tiled_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
@@ -286,8 +301,9 @@ int launch_chain_t(sdrb_handle *h, const uint8_t *raw, size_t nch, double *out, 
         if (h->finish_on && pl.ntiles <= 32) {
             // whole-tile chunks: warp-parallel gains, the chunk scan; k_finish derives the offsets
             // at the tile starts itself
-            k_iqgain_w<<<(unsigned)((nch + 7) / 8), 256, 0, st>>>(pl, h->sc, (int)nch);
-            k_iqscan_c<<<1, 1024, 0, st>>>(pl, h->sc, (int)nch);
+            const bool pdl = h->pdl && (phases & PH_MAIN);        // only right behind the front end of the same call
+            CK(h, launch_pdl(k_iqgain_w, dim3((unsigned)((nch + 7) / 8)), dim3(256), 0, st, pdl, pl, h->sc, (int)nch));
+            CK(h, launch_pdl(k_iqscan_c, dim3(1), dim3(1024), 0, st, h->pdl, pl, h->sc, (int)nch));
             h->launches += 2;
         } else {
             const unsigned gb = (unsigned)((nch + 127) / 128);
@@ -301,7 +317,10 @@ int launch_chain_t(sdrb_handle *h, const uint8_t *raw, size_t nch, double *out, 
     if ((phases & PH_FINISH) && h->finish_on) {
         const size_t items = nch * (size_t)pl.R;
         const unsigned grid = (unsigned)std::min<size_t>((items + FIN_WARPS - 1) / FIN_WARPS, (size_t)h->num_sms * 2);
-        k_finish<ENC><<<grid, 32 * FIN_WARPS, h->finish_smem, st>>>(pl, h->sc, raw, out, (int)nch, h->keep_y);
+        // behind the IQ kernels of the same call (or, without IQ correction, behind the front end)
+        const bool pdl = h->pdl && ((phases & PH_MAIN) || ((phases & PH_IQSCAN) && IQ));
+        CK(h, launch_pdl(k_finish<ENC>, dim3(grid), dim3(32 * FIN_WARPS), h->finish_smem, st, pdl, pl, h->sc, raw, out,
+                         (int)nch, h->keep_y));
         h->launches++;
         mark(3);
         mark(4);
@@ -409,6 +428,7 @@ int sdrb_create(const sdrb_config *cfg, const sdrb_tables *tab, sdrb_handle **ou
     h->cfg = *cfg;
     h->enc_code = code;
     h->max_chunks = (size_t)cfg->max_chunks;
+    h->pdl = env_int("SDRB_PDL", 0) != 0;       // measured neutral on B200: off unless asked for
     int rc = 0;
     auto bail = [&](int c) { std::string e = h->error; sdrb_destroy(h); g_error = e; return c; };
     if (cudaSetDevice(cfg->device) != cudaSuccess) return bail(fail(h, SDRB_ERR_CUDA, "cudaSetDevice failed"));

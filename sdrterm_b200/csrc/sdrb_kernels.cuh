@@ -298,6 +298,8 @@ k_iqgain(const __grid_constant__ DevPlan pl, Scratch sc, const uint8_t *__restri
 __global__ void __launch_bounds__(256)
 k_iqgain_w(const __grid_constant__ DevPlan pl, Scratch sc, int nchunks)
 {
+    pdl_trigger();
+    pdl_wait();                                   // tile_agg comes from the block front end
     const int lane = threadIdx.x & 31;
     const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (c >= nchunks) return;
@@ -356,6 +358,8 @@ k_iqscan_c(const __grid_constant__ DevPlan pl, Scratch sc, int nchunks)
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const double2 *__restrict__ gain = sc.gain;
     double2 *__restrict__ start = sc.start;
+    pdl_trigger();
+    pdl_wait();                                   // gain[] comes from k_iqgain_w / k_iqchunk
     if (tid == 0) s_state = sc.iq_state[0];
     __syncthreads();
     for (int base = 0; base < nchunks; base += 1024 * 8) {

@@ -508,6 +508,7 @@ k_tc(const __grid_constant__ DevPlan pl, const __grid_constant__ TcDev tc, const
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
+    pdl_trigger();                                              // the IQ-offset kernels may queue up behind this one
     const uint32_t tmem_base = tmem_base_s;
     const int my_iters = slot < nslots ? (n_mtiles - slot + nslots - 1) / nslots : 0;
     const int nslab = my_iters * nreg;                          // 16 KB slabs this CTA streams
