@@ -408,7 +408,6 @@ def run_cuda_arm(args):
         else:
             allraw, allout = [raw[:vch * CB]], [mine]
         if rank == 0:
-            from oracle import oracle as orc          # the checker, outside every timed region
             whole = torch.cat(allraw)
             with Engine(pl, max_chunks=world * vch, device=local) as one:
                 ref = torch.empty((1, world * vch * pl.M), dtype=torch.float64, device=dev)
@@ -416,13 +415,8 @@ def run_cuda_arm(args):
                 torch.cuda.synchronize()
             got = torch.cat(allout, dim=1)
             err = float((got - ref).abs().max() / ref.abs().max())
-            # and the single pass itself against the CPU oracle on the first chunks of the stream
-            och = min(8, world * vch)
-            oref = orc.Chain(fs=FS, enc='h', center=CENTER, dec=DEC, demod='fm', omega_out=OMEGA,
-                             correct_iq=True, nthreads=host_threads()).run_fast(whole[:och * CB].cpu().numpy().tobytes())
-            oerr = float(abs(ref[:, :och * pl.M].cpu().numpy() - oref).max() / abs(oref).max())
-            verify = {'time_sharded_vs_single_pass': err, 'single_pass_vs_oracle': oerr,
-                      'chunks_per_rank': vch, 'tolerance': 1e-9}
+            verify = {'time_sharded_vs_single_pass': err, 'chunks_per_rank': vch, 'tolerance': 1e-9,
+                      'note': 'the single pass itself is checked against the CPU oracle by tests/ (-m gpu) and smoke()'}
 
     clocks = Clocks(local)
     eng.set_profiling(world == 1)
@@ -647,7 +641,7 @@ def run_cuda_arm(args):
     if simo4 is not None:
         line['simo_config4'] = simo4
     if verify is not None:
-        errs = [verify['time_sharded_vs_single_pass'], verify['single_pass_vs_oracle']]
+        errs = [verify['time_sharded_vs_single_pass']]
         errs += [sm['verified_max_rel_err'] for sm in (simo, simo4) if sm is not None and sm['verified_max_rel_err'] is not None]
         line['verify'] = verify
         line['verified'] = bool(all(e == e and e <= 1e-9 for e in errs))

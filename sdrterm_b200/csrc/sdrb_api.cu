@@ -697,21 +697,36 @@ int sdrb_process(sdrb_handle *h, const void *raw, size_t nchunks, double *out)
         if (rc) return rc;
         return sdrb_wait(h, 0);
     }
-    // more chunks than one batch holds: rows of `out` are nchunks*M long, so each batch is
-    // staged through a per-batch buffer and scattered row by row
-    std::vector<double> tmp(h->max_chunks * R * M);
-    size_t done = 0;
-    while (done < nchunks) {
-        const size_t n = std::min(h->max_chunks, nchunks - done);
-        int rc = sdrb_submit(h, 0, static_cast<const uint8_t *>(raw) + done * cb, n, tmp.data());
-        if (rc) return rc;
-        rc = sdrb_wait(h, 0);
+    // more chunks than one batch holds: rows of `out` are nchunks*M long, so each batch is staged
+    // through a per-slot buffer and scattered row by row; the two slots alternate, so the H2D of
+    // batch i+1 overlaps the kernels of batch i
+    std::vector<double> tmp[2] = {std::vector<double>(h->max_chunks * R * M), std::vector<double>(h->max_chunks * R * M)};
+    size_t start[2] = {0, 0}, count[2] = {0, 0};
+    auto drain = [&](int s) -> int {
+        if (!count[s]) return 0;
+        int rc = sdrb_wait(h, s);
         if (rc) return rc;
         for (size_t r = 0; r < R; r++)
-            memcpy(out + r * nchunks * M + done * M, tmp.data() + r * n * M, n * M * sizeof(double));
+            memcpy(out + r * nchunks * M + start[s] * M, tmp[s].data() + r * count[s] * M, count[s] * M * sizeof(double));
+        count[s] = 0;
+        return 0;
+    };
+    size_t done = 0;
+    int b = 0;
+    while (done < nchunks) {
+        const int s = b & 1;
+        int rc = drain(s);
+        if (rc) return rc;
+        const size_t n = std::min(h->max_chunks, nchunks - done);
+        rc = sdrb_submit(h, s, static_cast<const uint8_t *>(raw) + done * cb, n, tmp[s].data());
+        if (rc) return rc;
+        start[s] = done; count[s] = n;
         done += n;
+        b++;
     }
-    return SDRB_OK;
+    int rc = drain(b & 1);
+    if (rc) return rc;
+    return drain((b + 1) & 1);
 }
 
 }  // extern "C"
@@ -723,30 +738,6 @@ void launch_iqchunk(sdrb_handle *h, const uint8_t *raw, size_t nch, cudaStream_t
 }
 }  // namespace
 extern "C" {
-
-int sdrb_set_smooth(sdrb_handle *h, int window, int nhead, int ntail, int lo, const double *tab)
-{
-    if (!h || window < 0 || (window > 0 && (!tab || nhead < 0 || ntail < 0 || nhead + ntail > h->pl.M)))
-        return fail(h, SDRB_ERR_ARG, "bad argument");
-    if (window > h->pl.M) return fail(h, SDRB_ERR_ARG, "smoothing window %d longer than a chunk's %d outputs", window, h->pl.M);
-    CK(h, cudaSetDevice(h->cfg.device));
-    CK(h, cudaDeviceSynchronize());
-    h->smooth_w = 0;
-    if (window == 0) return SDRB_OK;
-    const size_t n = (size_t)(nhead + 1 + ntail) * window;
-    double *dS = nullptr;
-    int rc = dalloc(h, n, &dS);
-    if (rc) return rc;
-    CK(h, cudaMemcpy(dS, tab, n * sizeof(double), cudaMemcpyHostToDevice));
-    if (!h->smooth_tmp) {
-        rc = dalloc(h, h->max_chunks * (size_t)h->pl.R * h->pl.M, &h->smooth_tmp);
-        if (rc) return rc;
-    }
-    h->smooth_S = dS;
-    h->smooth_nhead = nhead; h->smooth_ntail = ntail; h->smooth_lo = lo;
-    h->smooth_w = window;
-    return SDRB_OK;
-}
 
 int sdrb_iq_gain(sdrb_handle *h, const void *raw_host, size_t nchunks)
 {
