@@ -739,6 +739,30 @@ void launch_iqchunk(sdrb_handle *h, const uint8_t *raw, size_t nch, cudaStream_t
 }  // namespace
 extern "C" {
 
+int sdrb_set_smooth(sdrb_handle *h, int window, int nhead, int ntail, int lo, const double *tab)
+{
+    if (!h || window < 0 || (window > 0 && (!tab || nhead < 0 || ntail < 0 || nhead + ntail > h->pl.M)))
+        return fail(h, SDRB_ERR_ARG, "bad argument");
+    if (window > h->pl.M) return fail(h, SDRB_ERR_ARG, "smoothing window %d longer than a chunk's %d outputs", window, h->pl.M);
+    CK(h, cudaSetDevice(h->cfg.device));
+    CK(h, cudaDeviceSynchronize());
+    h->smooth_w = 0;
+    if (window == 0) return SDRB_OK;
+    const size_t n = (size_t)(nhead + 1 + ntail) * window;
+    double *dS = nullptr;
+    int rc = dalloc(h, n, &dS);
+    if (rc) return rc;
+    CK(h, cudaMemcpy(dS, tab, n * sizeof(double), cudaMemcpyHostToDevice));
+    if (!h->smooth_tmp) {
+        rc = dalloc(h, h->max_chunks * (size_t)h->pl.R * h->pl.M, &h->smooth_tmp);
+        if (rc) return rc;
+    }
+    h->smooth_S = dS;
+    h->smooth_nhead = nhead; h->smooth_ntail = ntail; h->smooth_lo = lo;
+    h->smooth_w = window;
+    return SDRB_OK;
+}
+
 int sdrb_iq_gain(sdrb_handle *h, const void *raw_host, size_t nchunks)
 {
     if (!h || !raw_host) return fail(h, SDRB_ERR_ARG, "null argument");
