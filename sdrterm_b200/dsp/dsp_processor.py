@@ -34,7 +34,8 @@ def generateEllipFilter(fs: int, deg: int, Wn, btype: str):
     kept in the plan cache directory so that a command-line run that finds it does not import
     scipy.signal at all."""
     import os
-    root = os.environ.get('SDRB_PLAN_CACHE', os.path.join(os.path.expanduser('~'), '.cache', 'sdrterm_b200'))
+    from ..plan import cache_dir
+    root = cache_dir()
     path = os.path.join(root, f'ellip_{int(fs)}_{int(deg)}_{Wn!r}_{btype}.npy'.replace(os.sep, '_')) if root else None
     if path:
         try:

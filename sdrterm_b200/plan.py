@@ -624,16 +624,21 @@ def build_tc(pl: Plan, nd: int = TC_ND) -> TcTables | None:
 
 
 # ------------------------------------------------------------------------------------------------
+def cache_dir() -> str:
+    import os
+    return os.environ.get('SDRB_PLAN_CACHE', os.path.join(os.path.dirname(os.path.abspath(__file__)), '.plan_cache'))
+
+
 def cached_plan(*args, **kwargs):
     """``(build_plan(*args, **kwargs), build_tc(plan))`` through an on-disk cache (directory
-    ``$SDRB_PLAN_CACHE``, default ``~/.cache/sdrterm_b200``; set it to an empty string to switch
-    the cache off).  The tables depend only on the arguments and on this file, so the key is their
+    ``$SDRB_PLAN_CACHE``, default ``.plan_cache`` next to this package; set it to an empty string
+    to switch the cache off; an unwritable directory simply means no caching).  The tables depend only on the arguments and on this file, so the key is their
     hash; building them takes seconds of 50-digit arithmetic, which matters to a command-line run
     and to nothing else."""
     import hashlib
     import os
     import pickle
-    root = os.environ.get('SDRB_PLAN_CACHE', os.path.join(os.path.expanduser('~'), '.cache', 'sdrterm_b200'))
+    root = cache_dir()
     path = None
     if root:
         with open(__file__, 'rb') as fh:
