@@ -192,6 +192,11 @@ int sdrb_kernel_times(sdrb_handle *h, float ms[4]);
 int sdrb_submit(sdrb_handle *h, int slot, const void *raw_host, size_t nchunks, double *out_host);
 int sdrb_wait(sdrb_handle *h, int slot);
 
+/* The persistent kernels (k_tc, k_finish) normally take every SM.  When a collective runs beside
+ * them (the NCCL broadcast of the next raw batch in a row-sharded bank), leave `nsm` SMs free so
+ * that its thread blocks can be scheduled and the transfer really overlaps the kernels. */
+int sdrb_reserve_sms(sdrb_handle *h, int nsm);
+
 /* Page-locked host staging buffers for sdrb_submit (so that a host layer needs nothing but this
  * library to stream: the drop-in CLI does not import torch). */
 int sdrb_host_alloc(size_t bytes, void **ptr_out);

@@ -60,7 +60,7 @@ EXPORTS = ['sdrb_create', 'sdrb_destroy', 'sdrb_last_error', 'sdrb_outputs_per_c
            'sdrb_fm_demod', 'sdrb_am_demod', 'sdrb_real_output', 'sdrb_imag_output',
            'sdrb_shift_freq', 'sdrb_global_error', 'sdrb_process_device_phases',
            'sdrb_set_profiling', 'sdrb_kernel_times', 'sdrb_keep_decimated', 'sdrb_read_debug', 'sdrb_iq_export_device',
-           'sdrb_iq_prefix_device', 'sdrb_decode_iq', 'sdrb_correct_iq', 'sdrb_keep_x0', 'sdrb_read_x0', 'sdrb_iq_gain', 'sdrb_set_smooth', 'sdrb_host_alloc', 'sdrb_host_free']
+           'sdrb_iq_prefix_device', 'sdrb_decode_iq', 'sdrb_correct_iq', 'sdrb_keep_x0', 'sdrb_read_x0', 'sdrb_iq_gain', 'sdrb_set_smooth', 'sdrb_host_alloc', 'sdrb_host_free', 'sdrb_reserve_sms']
 
 
 def nvcc_command(out: str = LIB_PATH) -> list[str]:
@@ -125,6 +125,7 @@ def lib():
         L.sdrb_iq_gain.argtypes = [vp, vp, sz]
         L.sdrb_host_alloc.argtypes = [sz, C.POINTER(vp)]
         L.sdrb_host_free.argtypes = [vp]
+        L.sdrb_reserve_sms.argtypes = [vp, C.c_int]
         L.sdrb_set_smooth.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, vp]
         L.sdrb_read_x0.argtypes = [vp, sz, vp]
         _lib = L

@@ -56,6 +56,7 @@ struct sdrb_handle {
     size_t tc_smem = 0;
     int num_sms = 148;
     bool pdl = false;               // programmatic dependent launch inside a step (SDRB_PDL=1)
+    int reserved_sms = 0;           // SMs the persistent kernels leave free (for a collective running beside them)
     double2 *x0_buf = nullptr;      // sdrb_keep_x0
     int smooth_w = 0, smooth_nhead = 0, smooth_ntail = 0, smooth_lo = 0;   // --smooth-output (window 0 = off)
     double *smooth_S = nullptr, *smooth_tmp = nullptr;
@@ -193,7 +194,7 @@ int launch_tc_t(sdrb_handle *h, const CUtensorMap &map_a, int n_mtiles, int tota
 {
     // one row of the bank per CTA: the grid is a whole number of row groups
     const int R = h->pl.R;
-    const int slots = std::max(1, std::min(h->num_sms / R, n_mtiles));
+    const int slots = std::max(1, std::min((h->num_sms - h->reserved_sms) / R, n_mtiles));
     k_tc<IQ><<<slots * R, TC_THREADS, h->tc_smem, st>>>(h->pl, h->tc, h->sc, map_a, h->map_b, n_mtiles, total_wtiles);
     return 0;
 }
@@ -316,7 +317,7 @@ int launch_chain_t(sdrb_handle *h, const uint8_t *raw, size_t nch, double *out, 
     mark(2);
     if ((phases & PH_FINISH) && h->finish_on) {
         const size_t items = nch * (size_t)pl.R;
-        const unsigned grid = (unsigned)std::min<size_t>((items + FIN_WARPS - 1) / FIN_WARPS, (size_t)h->num_sms * 2);
+        const unsigned grid = (unsigned)std::min<size_t>((items + FIN_WARPS - 1) / FIN_WARPS, (size_t)(h->num_sms - h->reserved_sms) * 2);
         // behind the IQ kernels of the same call (or, without IQ correction, behind the front end)
         const bool pdl = h->pdl && ((phases & PH_MAIN) || ((phases & PH_IQSCAN) && IQ));
         CK(h, launch_pdl(k_finish<ENC>, dim3(grid), dim3(32 * FIN_WARPS), h->finish_smem, st, pdl, pl, h->sc, raw, out,
@@ -867,6 +868,13 @@ int sdrb_read_debug(sdrb_handle *h, unsigned long long *out1024)
     if (!h || !out1024 || !h->sc.dbg) return fail(h, SDRB_ERR_STATE, "no debug buffer");
     CK(h, cudaDeviceSynchronize());
     CK(h, cudaMemcpy(out1024, h->sc.dbg, 64 * 16 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    return SDRB_OK;
+}
+
+int sdrb_reserve_sms(sdrb_handle *h, int nsm)
+{
+    if (!h || nsm < 0 || nsm >= h->num_sms) return fail(h, SDRB_ERR_ARG, "bad argument");
+    h->reserved_sms = nsm;
     return SDRB_OK;
 }
 

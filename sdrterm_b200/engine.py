@@ -199,6 +199,10 @@ class Engine:
         """Fold the all-gathered [world][3] gains of the ranks before ``rank`` into the IQ state."""
         nat.check(nat.lib().sdrb_iq_prefix_device(self._h, gains_ptr, rank, stream), self._h)
 
+    def reserve_sms(self, nsm: int) -> None:
+        """Leave ``nsm`` SMs to a collective that runs beside the persistent kernels."""
+        nat.check(nat.lib().sdrb_reserve_sms(self._h, int(nsm)), self._h)
+
     def set_profiling(self, on: bool) -> None:
         nat.check(nat.lib().sdrb_set_profiling(self._h, int(on)), self._h)
 

@@ -118,6 +118,8 @@ class RowShardedBank:
         self.chunk_bytes = self.plan.chunk_bytes
         self.group = None
         if self.row_groups > 1:
+            # the broadcast of the next batch runs beside this batch's kernels: leave it some SMs
+            self.engine.reserve_sms(int(os.environ.get('SDRB_BCAST_SMS', '8')))
             # every rank creates every group (torch.distributed requires it), keeps its own
             for t in range(self.time_groups):
                 g = dist.new_group(list(range(t * self.row_groups, (t + 1) * self.row_groups)))
