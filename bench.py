@@ -544,6 +544,7 @@ def run_cuda_arm(args):
         isz2 = cbk // nsamp_chunk
         bps = isz2 + 8 * len(rows_all) / 64
         res = {'workload': label, 'rows': len(rows_all), 'grid': {'row_groups': bank.row_groups, 'time_groups': bank.time_groups},
+               'raw_transport': bank.transport,
                'rows_on_rank0': len(bank.rows), 'chunks_per_step_per_time_group': sch,
                'input_msps': in_msps, 'vfo_msps': in_msps * len(rows_all), 'ms_per_step': ms, 'bytes_per_sample': bps,
                'front_end': 'k_tc' if bank.engine.tc is not None else 'k_main', 'verified_max_rel_err': ver}
@@ -554,8 +555,8 @@ def run_cuda_arm(args):
     if args.simo_chunks > 0:
         offs = signals.vfo_grid(16, 100_000)
         simo = run_bank('config 3: 16 VFOs + centre (17 rows), int16 big-endian IQ, fs 2.4 MS/s, FM, -d 64; ranks on a '
-                        '(row group x time group) grid, the raw batch of a time group broadcast over NCCL inside the '
-                        'timed region (double-buffered against the kernels)',
+                        '(row group x time group) grid, the raw batch of a time group sent to its ranks inside the '
+                        'timed region (NVLink peer copies or ncclBroadcast, see raw_transport; pipelined against the kernels)',
                         2_400_000, 'h', [o for o in offs] + [0],
                         lambda tg: synth_c3_device(torch, args.simo_chunks * 32768, 3 + tg, dev, offs),
                         args.simo_chunks, 32768, 6, swap=True, omega_out=5000)
@@ -575,7 +576,7 @@ def run_cuda_arm(args):
             return z.view(torch.uint8).reshape(-1)
 
         simo4 = run_bank('config 4: 256 VFOs + centre (257 rows) on 61.44 MS/s float32 IQ, FM, -d 64; rows sharded '
-                         'over all ranks, every raw batch broadcast over NCCL inside the timed region',
+                         'over the ranks, every raw batch sent to all of them inside the timed region (raw_transport)',
                          61_440_000, 'f', [o for o in offs4] + [0], synth4, args.simo4_chunks, 16384, 3,
                          omega_out=12500)
 

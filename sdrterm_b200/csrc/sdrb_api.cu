@@ -550,15 +550,33 @@ int sdrb_create(const sdrb_config *cfg, const sdrb_tables *tab, sdrb_handle **ou
     if (cfg->demod == SDRB_FM && !pl.fft_ok) UP(upload(h, tab->fm_interp, (size_t)M * h2, &pl.fm_interp));
 
     // launch geometry
-    h->tpc = env_int("SDRB_TPC", R == 1 ? 2 : 1);
-    if (h->tpc > pl.ntiles) h->tpc = pl.ntiles;
-    h->warps = env_int("SDRB_WARPS", R == 1 ? h->tpc : (R >= 8 ? 8 : 4));
-    if (h->tpc < 1) h->tpc = 1;
-    if (h->warps < 1) h->warps = 1;
-    if (h->warps > 8) h->warps = 8;
     auto smem_for = [&](int tpc, int w) {
         return (size_t)tpc * main_tile_bytes(pl.rowb, pl.correct_iq != 0) + (size_t)w * main_warp_bytes();
     };
+    // k_main: a CTA's warps share TPC staged tiles and take (tile, row) items in rounds
+    // (more than one tile per CTA measured slower for banks: 33 rows, TPC 1/2/3 -> 205/191/153 G)
+    const int tpc_auto = R == 1 ? 2 : 1;
+    // warps per CTA for a bank: 8 (two CTAs per SM) when the last round of R items is nearly full,
+    // otherwise 6 (three CTAs per SM) or the count in 4..7 that wastes the fewest slots.  Measured,
+    // float32 q = 64, G VFO*samples/s at 257/129/65/33/17 rows: W=8 234/229/218/205/186,
+    // W=6 226/224/224/219/216 (microbench/bank_rows.py).
+    int warps_auto = R == 1 ? 2 : 4;
+    if (R >= 8) {
+        auto waste = [&](int w) { return (double)((R + w - 1) / w * w) / R; };
+        warps_auto = 8;
+        if (waste(8) > 1.06) {
+            warps_auto = 6;
+            if (waste(6) > 1.25)
+                for (int w = 7; w >= 4; w--)
+                    if (waste(w) < waste(warps_auto) - 0.1) warps_auto = w;
+        }
+    }
+    h->tpc = env_int("SDRB_TPC", tpc_auto);
+    if (h->tpc > pl.ntiles) h->tpc = pl.ntiles;
+    h->warps = env_int("SDRB_WARPS", R == 1 ? h->tpc : warps_auto);
+    if (h->tpc < 1) h->tpc = 1;
+    if (h->warps < 1) h->warps = 1;
+    if (h->warps > 8) h->warps = 8;
     while (h->tpc > 1 && smem_for(h->tpc, h->warps) > 220 * 1024) h->tpc--;
     while (h->warps > 1 && smem_for(h->tpc, h->warps) > 220 * 1024) h->warps--;
     h->main_smem = smem_for(h->tpc, h->warps);

@@ -47,6 +47,28 @@ __host__ __device__ inline size_t main_warp_bytes()
     return (size_t)32 * SDRB_XSTRIDE * sizeof(double) + SDRB_TB * sizeof(double2);  // xb + x0s
 }
 
+// Raw tiles of one CTA -> shared memory, one word of type T per sample: every warp takes four
+// block rows at a time and issues their loads together (rows past the chunk's last block are zero).
+template <typename T>
+__device__ __forceinline__ void stage_rows(unsigned char *tiles, size_t tileb, const uint8_t *rawc, int t0, int ntl,
+                                           int ntiles, int cnt_last, int q, int rowb, int warp, int W, int lane)
+{
+    const int total = ntl * SDRB_TB;
+    for (int r0 = warp * 4; r0 < total; r0 += W * 4) {
+        const int tl = r0 >> 5, row0 = r0 & 31, t = t0 + tl;          // four rows never straddle a tile
+        const int cnt = (t == ntiles - 1) ? cnt_last : SDRB_TB;
+        const T *src = reinterpret_cast<const T *>(rawc) + ((size_t)t * SDRB_TB + row0) * q;
+        unsigned char *dst = tiles + (size_t)tl * tileb + (size_t)row0 * rowb;
+        for (int col = lane; col < q; col += 32) {
+            T v[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) v[u] = (row0 + u < cnt) ? src[(size_t)u * q + col] : T{};
+#pragma unroll
+            for (int u = 0; u < 4; u++) reinterpret_cast<T *>(dst + (size_t)u * rowb)[col] = v[u];
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------ k_main
 // grid.x = nchunks * ceil(ntiles / TPC); block = 32*W threads.  A CTA stages TPC consecutive
 // tiles of one chunk in shared memory (raw bytes, once, shared by all rows); its warps then take
@@ -73,27 +95,12 @@ k_main(const __grid_constant__ DevPlan pl, Scratch sc, const uint8_t *__restrict
     const int a0 = min(kq * pl.RL, pl.Hq), a1 = min((kq + 1) * pl.RL, pl.Hq);
     const int d0 = max(q - a1, pl.Hq), d1 = q - a0;
 
-    // ---------------- stage the raw tiles, then (IQ) run aggregates and block offsets
-    for (int tl = warp; tl < ntl; tl += W) {
-        const int t = t0 + tl;
-        const int cnt = (t == pl.ntiles - 1) ? pl.cnt_last : SDRB_TB;
-        unsigned char *tb = smem_raw + (size_t)tl * tileb;
-        const uint8_t *src = rawc + (size_t)t * SDRB_TB * q * sb;
-        for (int row = 0; row < SDRB_TB; row++) {
-            unsigned char *dst = tb + (size_t)row * rowb;
-            if (row < cnt) {
-                const uint8_t *s = src + (size_t)row * q * sb;
-                for (int col = lane; col < q; col += 32) {
-                    if (sb == 2) *reinterpret_cast<uint16_t *>(dst + col * 2) = *reinterpret_cast<const uint16_t *>(s + col * 2);
-                    else if (sb == 4) *reinterpret_cast<uint32_t *>(dst + col * 4) = *reinterpret_cast<const uint32_t *>(s + col * 4);
-                    else if (sb == 8) *reinterpret_cast<uint2 *>(dst + col * 8) = *reinterpret_cast<const uint2 *>(s + col * 8);
-                    else *reinterpret_cast<uint4 *>(dst + col * 16) = *reinterpret_cast<const uint4 *>(s + col * 16);
-                }
-            } else {
-                for (int col = lane; col < q * sb / 2; col += 32) *reinterpret_cast<uint16_t *>(dst + col * 2) = 0;
-            }
-        }
-    }
+    // ---------------- stage the raw tiles (all warps, four rows in flight per lane), then (IQ) run
+    //                  aggregates and block offsets
+    if (sb == 2) stage_rows<uint16_t>(smem_raw, tileb, rawc, t0, ntl, pl.ntiles, pl.cnt_last, q, rowb, warp, W, lane);
+    else if (sb == 4) stage_rows<uint32_t>(smem_raw, tileb, rawc, t0, ntl, pl.ntiles, pl.cnt_last, q, rowb, warp, W, lane);
+    else if (sb == 8) stage_rows<uint2>(smem_raw, tileb, rawc, t0, ntl, pl.ntiles, pl.cnt_last, q, rowb, warp, W, lane);
+    else stage_rows<uint4>(smem_raw, tileb, rawc, t0, ntl, pl.ntiles, pl.cnt_last, q, rowb, warp, W, lane);
     __syncthreads();
     for (int tl = warp; tl < ntl; tl += W) {
         const int t = t0 + tl;

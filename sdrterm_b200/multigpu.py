@@ -92,21 +92,101 @@ def bank_grid(nrows: int, world: int, min_rows: int = 8) -> tuple[int, int]:
     return rg, world // rg
 
 
+class PeerFanout:
+    """The raw batch of a time group's leader -> every other rank of the group through NVLink peer
+    memory, driven by the leader's copy engines (no SM is taken from the kernels that run beside
+    it; an ``ncclBroadcast`` of the same bytes costs the 17-row bank 25 % of its rate at two GPUs).
+
+    Every receiver owns ``NBUF`` = 3 device buffers and shares them with the leader by CUDA IPC
+    (once, at construction).  Batch i: the leader copies its bytes into slot i % 3 of every peer
+    (one stream per peer), then all ranks of the group meet in a one-word all-reduce D_i on their
+    side streams.  A receiver lets D_i start only when its kernels of batch i-2 are done, so on the
+    leader "D_i complete" means slot (i+1) % 3 is free everywhere, and on a receiver it means batch
+    i has landed.  With three slots D_i does not have to wait for the kernels of batch i-1, so its
+    latency stays off the critical path; the copy of batch i+1 overlaps the kernels of batch i."""
+
+    NBUF = 3
+
+    def __init__(self, dist, torch, group, ranks, leader: int, nbytes: int, device: int):
+        from torch.multiprocessing.reductions import reduce_tensor
+        self.dist, self.torch, self.group = dist, torch, group
+        self.is_leader = dist.get_rank() == leader
+        dev = torch.device('cuda', device)
+        self.bufs = [] if self.is_leader else [torch.empty(nbytes, dtype=torch.uint8, device=dev) for _ in range(self.NBUF)]
+        torch.cuda.synchronize(dev)
+        shared = None if self.is_leader else [reduce_tensor(b) for b in self.bufs]
+        got = [None] * len(ranks)
+        dist.all_gather_object(got, shared, group=group)
+        self.peers = []                                   # leader: [peer][slot] tensors that live on the peer's GPU
+        if self.is_leader:
+            for h in got:
+                if h is not None:
+                    self.peers.append([fn(*a) for fn, a in h])
+        self.side = torch.cuda.Stream(device=dev)
+        self.lanes = [torch.cuda.Stream(device=dev) for _ in self.peers]
+        self.flag = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.read_done = [None] * self.NBUF               # receiver: event after the kernels that read the slot
+        self.last = None
+
+    def begin(self) -> None:
+        """Start of a sequence of batches (numbered from 0 again): every rank's earlier kernels
+        are done before the leader may overwrite a slot."""
+        torch = self.torch
+        self.side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(self.side):
+            self.last = self.dist.all_reduce(self.flag, group=self.group, async_op=True)
+        self.read_done = [None] * self.NBUF
+
+    def post(self, i: int, src, nbytes: int):
+        """Start batch i on its way; returns the work object of D_i (wait() on the compute stream)."""
+        torch = self.torch
+        cur = torch.cuda.current_stream()
+        slot = i % self.NBUF
+        if self.is_leader:
+            for lane, peer in zip(self.lanes, self.peers):
+                lane.wait_stream(cur)                     # the source batch is ready
+                with torch.cuda.stream(lane):
+                    if self.last is not None:
+                        self.last.wait()                  # D_{i-1}: the slot is free on every peer
+                    peer[slot][:nbytes].copy_(src[:nbytes], non_blocking=True)
+                self.side.wait_stream(lane)
+        else:
+            ev = self.read_done[(i - 2) % self.NBUF] if i >= 2 else None
+            if ev is not None:
+                self.side.wait_event(ev)
+        with torch.cuda.stream(self.side):
+            self.last = self.dist.all_reduce(self.flag, group=self.group, async_op=True)
+        return self.last
+
+    def slot(self, i: int):
+        return self.bufs[i % self.NBUF]
+
+    def consumed(self, i: int) -> None:
+        """The kernels that read batch i have been enqueued on the current stream."""
+        if not self.is_leader:
+            ev = self.torch.cuda.Event()
+            ev.record(self.torch.cuda.current_stream())
+            self.read_done[i % self.NBUF] = ev
+
+
 class RowShardedBank:
     """One rank's share of a ``--simo`` bank on a (row group x time group) grid of ranks.
     ``rows_hz`` is the full bank (the listed VFO offsets + the centre, reference
     vfo_processor.py:42-46); rank (tg, rg) owns the rg-th balanced slice of the rows for the
     tg-th time segment and builds a plan for its slice only.  ``run(batches)`` processes a
-    sequence of raw batches that exist on the time group's leader (rg == 0); the broadcast of
-    batch i+1 to the group overlaps the kernels of batch i.  Nothing is gathered: each rank
-    frames its own rows (one socket per row, vfo_processor.py:80-84)."""
+    sequence of raw batches that exist on the time group's leader (rg == 0); batch i+1 travels to
+    the group (``PeerFanout``; ``SDRB_BCAST=nccl`` selects a plain NCCL broadcast instead) while
+    the kernels of batch i run.  Nothing is gathered: each rank frames its own rows (one socket
+    per row, vfo_processor.py:80-84)."""
 
     def __init__(self, fs: int, enc: str, dec: int, rows_hz, max_chunks: int, device: int, dist=None, torch=None,
-                 min_rows: int = 8, **plan_kw):
+                 min_rows: int | None = None, **plan_kw):
         self.dist, self.torch = dist, torch
         self.world = dist.get_world_size() if dist is not None else 1
         self.rank = dist.get_rank() if dist is not None else 0
         self.rows_all = [int(f) for f in rows_hz]
+        if min_rows is None:
+            min_rows = 8
         self.row_groups, self.time_groups = bank_grid(len(self.rows_all), self.world, min_rows)
         self.tg, self.rg = divmod(self.rank, self.row_groups)
         self.lo, self.hi = sharding.row_shard(len(self.rows_all), self.row_groups, self.rg)
@@ -117,26 +197,46 @@ class RowShardedBank:
         self.engine = Engine(self.plan, max_chunks=max_chunks, device=device)
         self.chunk_bytes = self.plan.chunk_bytes
         self.group = None
+        self.fanout = None
+        self.transport = 'none'
         if self.row_groups > 1:
-            # the broadcast of the next batch runs beside this batch's kernels: leave it some SMs
-            self.engine.reserve_sms(int(os.environ.get('SDRB_BCAST_SMS', '8')))
             # every rank creates every group (torch.distributed requires it), keeps its own
             for t in range(self.time_groups):
                 g = dist.new_group(list(range(t * self.row_groups, (t + 1) * self.row_groups)))
                 if t == self.tg:
                     self.group = g
             dev = torch.device('cuda', device)
-            self._bufs = [torch.empty(max_chunks * self.chunk_bytes, dtype=torch.uint8, device=dev) for _ in range(2)]
+            ranks = list(range(self.leader, self.leader + self.row_groups))
+            nbytes = max_chunks * self.chunk_bytes
+            want = os.environ.get('SDRB_BCAST', 'peer')
+            ok = torch.zeros(1, dtype=torch.int32, device=dev)
+            if want == 'peer':
+                try:
+                    self.fanout = PeerFanout(dist, torch, self.group, ranks, self.leader, nbytes, device)
+                    ok += 1
+                except Exception as ex:                       # no CUDA IPC / peer access on this box
+                    import sys
+                    print(f'sdrterm_b200: peer-memory fan-out unavailable ({ex!r}); using ncclBroadcast', file=sys.stderr)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)         # one transport for everybody
+            if int(ok.item()) == 1:
+                self.transport = 'peer'
+            else:
+                self.fanout = None
+                self.transport = 'nccl'
+                # the broadcast runs beside this batch's kernels on SMs: leave it some
+                self.engine.reserve_sms(int(os.environ.get('SDRB_BCAST_SMS', '8')))
+                self._bufs = [torch.empty(nbytes, dtype=torch.uint8, device=dev) for _ in range(2)]
 
     @property
     def M(self) -> int:
         return self.plan.M
 
     def _post(self, i: int, src, nbytes: int):
-        """Start the broadcast of batch i inside the time group (the leader copies its batch into
-        the buffer first)."""
+        """Start batch i on its way to the ranks of the time group."""
         if self.row_groups == 1:
             return None
+        if self.fanout is not None:
+            return self.fanout.post(i, src, nbytes)
         b = self._bufs[i & 1][:nbytes]
         if self.rank == self.leader:
             b.copy_(src[:nbytes], non_blocking=True)
@@ -144,16 +244,26 @@ class RowShardedBank:
 
     def run(self, batches, nchunks: int, outs, stream: int = 0) -> None:
         """``batches``: list of uint8 device tensors (on the leader; elsewhere only the count
-        matters); ``outs``: list of (rows, nchunks*M) float64 device tensors of this rank."""
+        matters); ``outs``: list of (rows, nchunks*M) float64 device tensors of this rank.  The
+        kernels go to ``stream``, which must be the current torch stream."""
         n = len(batches)
         nbytes = nchunks * self.chunk_bytes
+        if self.fanout is not None:
+            self.fanout.begin()
         w = self._post(0, batches[0], nbytes)
         for i in range(n):
             if w is not None:
                 w.wait()
             w = self._post(i + 1, batches[i + 1], nbytes) if i + 1 < n else None
-            src = self._bufs[i & 1] if self.row_groups > 1 else batches[i]
+            if self.row_groups == 1 or (self.fanout is not None and self.rank == self.leader):
+                src = batches[i]
+            elif self.fanout is not None:
+                src = self.fanout.slot(i)
+            else:
+                src = self._bufs[i & 1]
             self.engine.process_device(src.data_ptr(), nchunks, outs[i].data_ptr(), stream)
+            if self.fanout is not None:
+                self.fanout.consumed(i)
 
     def close(self):
         self.engine.close()
