@@ -536,15 +536,18 @@ def run_cuda_arm(args):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
+        tc0 = time.perf_counter()
         go(steps)
+        host_ms = (time.perf_counter() - tc0) * 1e3 / steps      # host time to enqueue one batch (not a rate)
         e1.record()
         barrier()
         ms = max_over_ranks(e0.elapsed_time(e1)) / steps
+        host_ms = max_over_ranks(host_ms)
         in_msps = bank.time_groups * sch * nsamp_chunk / (ms * 1e-3) / 1e6
         isz2 = cbk // nsamp_chunk
         bps = isz2 + 8 * len(rows_all) / 64
         res = {'workload': label, 'rows': len(rows_all), 'grid': {'row_groups': bank.row_groups, 'time_groups': bank.time_groups},
-               'raw_transport': bank.transport,
+               'raw_transport': bank.transport, 'host_enqueue_ms_per_step': host_ms,
                'rows_on_rank0': len(bank.rows), 'chunks_per_step_per_time_group': sch,
                'input_msps': in_msps, 'vfo_msps': in_msps * len(rows_all), 'ms_per_step': ms, 'bytes_per_sample': bps,
                'front_end': 'k_tc' if bank.engine.tc is not None else 'k_main', 'verified_max_rel_err': ver}
@@ -559,7 +562,7 @@ def run_cuda_arm(args):
                         'timed region (NVLink peer copies or ncclBroadcast, see raw_transport; pipelined against the kernels)',
                         2_400_000, 'h', [o for o in offs] + [0],
                         lambda tg: synth_c3_device(torch, args.simo_chunks * 32768, 3 + tg, dev, offs),
-                        args.simo_chunks, 32768, 6, swap=True, omega_out=5000)
+                        args.simo_chunks, 32768, 24, swap=True, omega_out=5000)
     if args.simo4_chunks > 0:
         offs4 = signals.vfo_grid(256, 200_000)
 
@@ -577,7 +580,7 @@ def run_cuda_arm(args):
 
         simo4 = run_bank('config 4: 256 VFOs + centre (257 rows) on 61.44 MS/s float32 IQ, FM, -d 64; rows sharded '
                          'over the ranks, every raw batch sent to all of them inside the timed region (raw_transport)',
-                         61_440_000, 'f', [o for o in offs4] + [0], synth4, args.simo4_chunks, 16384, 3,
+                         61_440_000, 'f', [o for o in offs4] + [0], synth4, args.simo4_chunks, 16384, 12,
                          omega_out=12500)
 
     if rank != 0:
