@@ -443,7 +443,7 @@ int sdrb_create(const sdrb_config *cfg, const sdrb_tables *tab, sdrb_handle **ou
     pl.Hq = (cfg->q + 1) / 2; pl.KS = (pl.Hq + 3) / 4; pl.R = cfg->R;
     pl.RL = tab->RL;
     if (pl.RL != pl.KS) return bail(fail(h, SDRB_ERR_ARG, "RL %d does not match ceil(Hq/4) = %d", pl.RL, pl.KS));
-    pl.sb = 2 * pl.itemsize; pl.rowb = pl.q * pl.sb + (pl.sb <= 4 ? 4 : pl.sb);
+    pl.sb = 2 * pl.itemsize;
     for (int i = 0; i < 8; i++) { pl.run_len[i] = tab->run_len[i]; pl.lam_run[i] = tab->lam_run[i]; }
     pl.lam_inv = tab->lam_inv;
     pl.sos_ns = 2 * cfg->n_out_sections; pl.sos_Lseg = tab->sos_Lseg;
@@ -551,26 +551,15 @@ int sdrb_create(const sdrb_config *cfg, const sdrb_tables *tab, sdrb_handle **ou
 
     // launch geometry
     auto smem_for = [&](int tpc, int w) {
-        return (size_t)tpc * main_tile_bytes(pl.rowb, pl.correct_iq != 0) + (size_t)w * main_warp_bytes();
+        return (size_t)tpc * main_tile_bytes(pl.RL, pl.sb) + (size_t)w * main_warp_bytes();
     };
     // k_main: a CTA's warps share TPC staged tiles and take (tile, row) items in rounds
     // (more than one tile per CTA measured slower for banks: 33 rows, TPC 1/2/3 -> 205/191/153 G)
     const int tpc_auto = R == 1 ? 2 : 1;
-    // warps per CTA for a bank: 8 (two CTAs per SM) when the last round of R items is nearly full,
-    // otherwise 6 (three CTAs per SM) or the count in 4..7 that wastes the fewest slots.  Measured,
-    // float32 q = 64, G VFO*samples/s at 257/129/65/33/17 rows: W=8 234/229/218/205/186,
-    // W=6 226/224/224/219/216 (microbench/bank_rows.py).
-    int warps_auto = R == 1 ? 2 : 4;
-    if (R >= 8) {
-        auto waste = [&](int w) { return (double)((R + w - 1) / w * w) / R; };
-        warps_auto = 8;
-        if (waste(8) > 1.06) {
-            warps_auto = 6;
-            if (waste(6) > 1.25)
-                for (int w = 7; w >= 4; w--)
-                    if (waste(w) < waste(warps_auto) - 0.1) warps_auto = w;
-        }
-    }
+    // warps per CTA for a bank: 8 (two CTAs of 126 registers per SM).  Measured, float32 q = 64,
+    // G VFO*samples/s at 257/65/33 rows: W=8 326/308/290, W=7 306/290/286, W=6 303/291/277,
+    // W=5 311/304/292 (microbench/bank_rows.py).
+    const int warps_auto = R == 1 ? 2 : (R >= 8 ? 8 : 4);
     h->tpc = env_int("SDRB_TPC", tpc_auto);
     if (h->tpc > pl.ntiles) h->tpc = pl.ntiles;
     h->warps = env_int("SDRB_WARPS", R == 1 ? h->tpc : warps_auto);

@@ -14,7 +14,7 @@ struct DevPlan {
     int enc, itemsize, swap, correct_iq, normalize, demod, be_out;
     int q, N, edge, L, Mf, rem, M, ntiles, cnt_last, Hq, KS, R, nend, ws, k_bnd, nsec_out;
     int RL;                // pairs per DMMA k-lane (== KS): lane k owns pairs [k*RL, (k+1)*RL)
-    int sb, rowb;          // bytes per complex sample; padded bytes per block row of the raw tile
+    int sb;                // bytes per complex sample
     int run_len[8];        // samples per run, sample order (4 ascending + 4 descending)
     int sos_ns, sos_Lseg;  // output SOS evaluated in 32 segments of sos_Lseg samples
     int fft_ok;            // FM resample by FFT (M == 2h, h power of two)

@@ -33,39 +33,95 @@ struct Scratch {
                         // front end sees it (exact integers; sdrb_keep_x0, parity tests)
 };
 
-// Shared-memory carve-up of k_main (host mirrors this in sdrb_api.cu: main_smem_bytes()).
-__host__ __device__ inline size_t main_tile_bytes(int rowb, bool iq)
+// Shared-memory carve-up of k_main (host mirrors this in sdrb_api.cu).
+// A raw tile is kept in the order the DMMA fragments consume it: slot (s, g, lane) holds the two
+// raw samples lane = (block 8g + (lane>>2), pair kq*RL + s) multiplies in step s of group g --
+// sample j and its mirror q-1-j -- side by side, so a lane fetches a pair with ONE shared-memory
+// load of 2*sb bytes, conflict-free, and no address arithmetic on the row.  Planes of one s are
+// 256*sb bytes apart plus 16 bytes of skew (the staging stores of a warp walk along s).
+__host__ __device__ inline size_t main_plane_bytes(int sb) { return (size_t)256 * sb + 16; }
+__host__ __device__ inline size_t main_tile_bytes(int RL, int sb)
 {
-    size_t b = (size_t)SDRB_TB * rowb;                       // raw tile, padded rows
-    b = (b + 15) & ~(size_t)15;
-    b += 2 * SDRB_TB * sizeof(double2);                      // cl[32], blkagg[32]
-    (void)iq;
-    return b;
+    return (size_t)RL * main_plane_bytes(sb) + 2 * SDRB_TB * sizeof(double2);   // pairs + cl[32], blkagg[32]
 }
 __host__ __device__ inline size_t main_warp_bytes()
 {
     return (size_t)32 * SDRB_XSTRIDE * sizeof(double) + SDRB_TB * sizeof(double2);  // xb + x0s
 }
 
-// Raw tiles of one CTA -> shared memory, one word of type T per sample: every warp takes four
-// block rows at a time and issues their loads together (rows past the chunk's last block are zero).
+// Raw tiles of one CTA -> shared memory in fragment order, one word of type T per sample: every
+// warp takes four block rows at a time and issues their loads together (rows past the chunk's
+// last block are zero).
 template <typename T>
-__device__ __forceinline__ void stage_rows(unsigned char *tiles, size_t tileb, const uint8_t *rawc, int t0, int ntl,
-                                           int ntiles, int cnt_last, int q, int rowb, int warp, int W, int lane)
+__device__ __forceinline__ void stage_pairs(unsigned char *tiles, size_t tileb, const uint8_t *rawc, int t0, int ntl,
+                                            int ntiles, int cnt_last, int q, int Hq, int RL, int warp, int W, int lane)
 {
     const int total = ntl * SDRB_TB;
+    const size_t plane = main_plane_bytes((int)sizeof(T));
     for (int r0 = warp * 4; r0 < total; r0 += W * 4) {
         const int tl = r0 >> 5, row0 = r0 & 31, t = t0 + tl;          // four rows never straddle a tile
         const int cnt = (t == ntiles - 1) ? cnt_last : SDRB_TB;
         const T *src = reinterpret_cast<const T *>(rawc) + ((size_t)t * SDRB_TB + row0) * q;
-        unsigned char *dst = tiles + (size_t)tl * tileb + (size_t)row0 * rowb;
+        unsigned char *tb = tiles + (size_t)tl * tileb;
         for (int col = lane; col < q; col += 32) {
+            const int slot = col < Hq ? 0 : 1, jj = slot ? q - 1 - col : col;
+            const int kq = jj / RL, sp = jj - kq * RL;
             T v[4];
 #pragma unroll
             for (int u = 0; u < 4; u++) v[u] = (row0 + u < cnt) ? src[(size_t)u * q + col] : T{};
+            T *dst = reinterpret_cast<T *>(tb + (size_t)sp * plane) + ((size_t)(row0 >> 3) * 32 + (row0 & 7) * 4 + kq) * 2 + slot;
 #pragma unroll
-            for (int u = 0; u < 4; u++) reinterpret_cast<T *>(dst + (size_t)u * rowb)[col] = v[u];
+            for (int u = 0; u < 4; u++) dst[u * 8] = v[u];           // next block row: lane slot + 4 = 8 words on
         }
+    }
+}
+
+// The pair of slot (s, g, lane) -> two complex doubles (decode of read_file.py:100-101 from registers).
+template <int ENC>
+__device__ __forceinline__ void load_pair(const DevPlan &pl, const unsigned char *plane_s, int g, int lane, double2 &za, double2 &zb)
+{
+    const int idx = g * 32 + lane;
+    if (ENC == ENC_b || ENC == ENC_B) {
+        const uint32_t v = reinterpret_cast<const uint32_t *>(plane_s)[idx];
+        if (ENC == ENC_b) {
+            za = make_double2((double)(int8_t)(v & 0xff), (double)(int8_t)((v >> 8) & 0xff));
+            zb = make_double2((double)(int8_t)((v >> 16) & 0xff), (double)(int8_t)(v >> 24));
+        } else {
+            za = make_double2((double)(v & 0xff), (double)((v >> 8) & 0xff));
+            zb = make_double2((double)((v >> 16) & 0xff), (double)(v >> 24));
+        }
+    } else if (ENC == ENC_h || ENC == ENC_H) {
+        uint2 v = reinterpret_cast<const uint2 *>(plane_s)[idx];
+        if (pl.swap) { v.x = __byte_perm(v.x, 0, 0x2301); v.y = __byte_perm(v.y, 0, 0x2301); }
+        if (ENC == ENC_h) {
+            za = make_double2((double)(int16_t)(v.x & 0xffff), (double)(int16_t)(v.x >> 16));
+            zb = make_double2((double)(int16_t)(v.y & 0xffff), (double)(int16_t)(v.y >> 16));
+        } else {
+            za = make_double2((double)(v.x & 0xffff), (double)(v.x >> 16));
+            zb = make_double2((double)(v.y & 0xffff), (double)(v.y >> 16));
+        }
+    } else if (ENC == ENC_i || ENC == ENC_I || ENC == ENC_f) {
+        uint4 v = reinterpret_cast<const uint4 *>(plane_s)[idx];
+        if (pl.swap) {
+            v.x = __byte_perm(v.x, 0, 0x0123); v.y = __byte_perm(v.y, 0, 0x0123);
+            v.z = __byte_perm(v.z, 0, 0x0123); v.w = __byte_perm(v.w, 0, 0x0123);
+        }
+        if (ENC == ENC_i) {
+            za = make_double2((double)(int32_t)v.x, (double)(int32_t)v.y); zb = make_double2((double)(int32_t)v.z, (double)(int32_t)v.w);
+        } else if (ENC == ENC_I) {
+            za = make_double2((double)v.x, (double)v.y); zb = make_double2((double)v.z, (double)v.w);
+        } else {
+            za = make_double2((double)__uint_as_float(v.x), (double)__uint_as_float(v.y));
+            zb = make_double2((double)__uint_as_float(v.z), (double)__uint_as_float(v.w));
+        }
+    } else {
+        const unsigned char *p = plane_s + (size_t)idx * 32;
+        za = load_sample<ENC>(p, 0, pl.swap);
+        zb = load_sample<ENC>(p, 1, pl.swap);
+    }
+    if (pl.normalize) {
+        za = normalize_sample(za, pl.norm_xmin, pl.norm_k);
+        zb = normalize_sample(zb, pl.norm_xmin, pl.norm_k);
     }
 }
 
@@ -76,37 +132,38 @@ __device__ __forceinline__ void stage_rows(unsigned char *tiles, size_t tileb, c
 // [k*RL, (k+1)*RL) of block 8g + (lane>>2) in group g (B operand), and accumulates output row
 // lane>>2 for blocks 8g + 2k, 8g + 2k + 1 (C operand).
 template <int ENC, bool IQ>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 2)
 k_main(const __grid_constant__ DevPlan pl, Scratch sc, const uint8_t *__restrict__ raw, int nchunks, int TPC)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, W = blockDim.x >> 5;
-    const int q = pl.q, sb = pl.sb, rowb = pl.rowb;
+    const int q = pl.q, sb = pl.sb, RL = pl.RL;
     const int groups = (pl.ntiles + TPC - 1) / TPC;
     const int chunk = blockIdx.x / groups, tg = blockIdx.x % groups;
     if (chunk >= nchunks) return;
-    const size_t tileb = main_tile_bytes(rowb, IQ);
+    const size_t tileb = main_tile_bytes(RL, sb), plane = main_plane_bytes(sb);
     unsigned char *warp_base = smem_raw + (size_t)TPC * tileb;
     const uint8_t *rawc = raw + (size_t)chunk * pl.N * sb;
     const int t0 = tg * TPC;
     const int ntl = min(TPC, pl.ntiles - t0);
     const int kq = lane & 3, nq = lane >> 2;
-    // this lane's pair range and the two sample runs it owns inside a block
-    const int a0 = min(kq * pl.RL, pl.Hq), a1 = min((kq + 1) * pl.RL, pl.Hq);
-    const int d0 = max(q - a1, pl.Hq), d1 = q - a0;
+    // this lane's pair range inside a block: pairs [a0, a1), i.e. samples j and q-1-j
+    const int a0 = min(kq * RL, pl.Hq), a1 = min((kq + 1) * RL, pl.Hq);
+    const int npair = a1 - a0;                              // valid steps s < npair
+    const int smid = (q & 1) && a1 == pl.Hq ? npair - 1 : -1;   // the step that holds the middle sample of an odd block
 
     // ---------------- stage the raw tiles (all warps, four rows in flight per lane), then (IQ) run
     //                  aggregates and block offsets
-    if (sb == 2) stage_rows<uint16_t>(smem_raw, tileb, rawc, t0, ntl, pl.ntiles, pl.cnt_last, q, rowb, warp, W, lane);
-    else if (sb == 4) stage_rows<uint32_t>(smem_raw, tileb, rawc, t0, ntl, pl.ntiles, pl.cnt_last, q, rowb, warp, W, lane);
-    else if (sb == 8) stage_rows<uint2>(smem_raw, tileb, rawc, t0, ntl, pl.ntiles, pl.cnt_last, q, rowb, warp, W, lane);
-    else stage_rows<uint4>(smem_raw, tileb, rawc, t0, ntl, pl.ntiles, pl.cnt_last, q, rowb, warp, W, lane);
+    if (sb == 2) stage_pairs<uint16_t>(smem_raw, tileb, rawc, t0, ntl, pl.ntiles, pl.cnt_last, q, pl.Hq, RL, warp, W, lane);
+    else if (sb == 4) stage_pairs<uint32_t>(smem_raw, tileb, rawc, t0, ntl, pl.ntiles, pl.cnt_last, q, pl.Hq, RL, warp, W, lane);
+    else if (sb == 8) stage_pairs<uint2>(smem_raw, tileb, rawc, t0, ntl, pl.ntiles, pl.cnt_last, q, pl.Hq, RL, warp, W, lane);
+    else stage_pairs<uint4>(smem_raw, tileb, rawc, t0, ntl, pl.ntiles, pl.cnt_last, q, pl.Hq, RL, warp, W, lane);
     __syncthreads();
     for (int tl = warp; tl < ntl; tl += W) {
         const int t = t0 + tl;
         const int cnt = (t == pl.ntiles - 1) ? pl.cnt_last : SDRB_TB;
         unsigned char *tb = smem_raw + (size_t)tl * tileb;
-        double2 *cl = reinterpret_cast<double2 *>(tb + (((size_t)SDRB_TB * rowb + 15) & ~(size_t)15));
+        double2 *cl = reinterpret_cast<double2 *>(tb + (size_t)RL * plane);
         double2 *blkagg = cl + SDRB_TB;
         double2 excl = make_double2(0.0, 0.0);
         if (IQ) {
@@ -114,15 +171,19 @@ k_main(const __grid_constant__ DevPlan pl, Scratch sc, const uint8_t *__restrict
             // corrector enters through the decoupled terms)
             for (int g = 0; g < 4; g++) {
                 const int b = 8 * g + nq;
-                const unsigned char *rowp = tb + (size_t)b * rowb;
                 double2 agg_a = make_double2(0.0, 0.0), agg_d = make_double2(0.0, 0.0);
-                for (int j = a0; j < a1; j++) {
-                    const double2 z = decode_sample<ENC>(pl, rowp, j);
-                    agg_a.x = fma(pl.lam, agg_a.x, z.x); agg_a.y = fma(pl.lam, agg_a.y, z.y);
+                // ascending run: samples a0 .. a1-1 (the first of each pair)
+                for (int sp = 0; sp < npair; sp++) {
+                    double2 za, zb;
+                    load_pair<ENC>(pl, tb + (size_t)sp * plane, g, lane, za, zb);
+                    agg_a.x = fma(pl.lam, agg_a.x, za.x); agg_a.y = fma(pl.lam, agg_a.y, za.y);
                 }
-                for (int j = d0; j < d1; j++) {
-                    const double2 z = decode_sample<ENC>(pl, rowp, j);
-                    agg_d.x = fma(pl.lam, agg_d.x, z.x); agg_d.y = fma(pl.lam, agg_d.y, z.y);
+                // descending run: the mirrors q-1-j, in sample order = pairs from the last to the first
+                for (int sp = npair - 1; sp >= 0; sp--) {
+                    if (sp == smid) continue;
+                    double2 za, zb;
+                    load_pair<ENC>(pl, tb + (size_t)sp * plane, g, lane, za, zb);
+                    agg_d.x = fma(pl.lam, agg_d.x, zb.x); agg_d.y = fma(pl.lam, agg_d.y, zb.y);
                 }
                 // EMA state at the 9 run boundaries of this block (all four lanes of the block
                 // compute the same chain from the gathered run aggregates)
@@ -167,43 +228,47 @@ k_main(const __grid_constant__ DevPlan pl, Scratch sc, const uint8_t *__restrict
         const int t = t0 + tl;
         const int cnt = (t == pl.ntiles - 1) ? pl.cnt_last : SDRB_TB;
         const unsigned char *tb = smem_raw + (size_t)tl * tileb;
-        const double2 *cl = reinterpret_cast<const double2 *>(tb + (((size_t)SDRB_TB * rowb + 15) & ~(size_t)15));
+        const double2 *cl = reinterpret_cast<const double2 *>(tb + (size_t)RL * plane);
         const double2 *T2r = pl.T2 + (size_t)r * q;
         const bool nco = pl.use_nco[r] != 0;
 
-        for (int g = 0; g < 4; g++) {
-            const int bB = 8 * g + nq;
-            const unsigned char *rowp = tb + (size_t)bB * rowb;
-            double Sr0 = 0, Sr1 = 0, Si0 = 0, Si1 = 0, Dr0 = 0, Dr1 = 0, Di0 = 0, Di1 = 0;
-            for (int s = 0; s < pl.RL; s++) {
-                const int j = a0 + s;
-                const bool valid = j < a1;
-                double2 a = make_double2(0.0, 0.0), d = make_double2(0.0, 0.0);
-                if (valid) {
-                    const int jm = q - 1 - j;
-                    const bool mid = (j == jm);
-                    const double2 za = decode_sample<ENC>(pl, rowp, j);
-                    if (s == 0 && kq == 0) x0s[bB] = za;          // first (raw) sample of the block
-                    const double2 ua = nco ? cmul(__ldg(T2r + j), za) : za;
-                    if (mid) { a = ua; }
-                    else {
-                        const double2 zb = decode_sample<ENC>(pl, rowp, jm);
-                        const double2 ub = nco ? cmul(__ldg(T2r + jm), zb) : zb;
-                        a = cadd(ua, ub); d = csub(ua, ub);
-                    }
-                }
-                const double aE = __ldg(pl.Afrag + (size_t)(2 * s) * 32 + lane);
-                const double aO = __ldg(pl.Afrag + (size_t)(2 * s + 1) * 32 + lane);
-                dmma884(Sr0, Sr1, aE, a.x);
-                dmma884(Si0, Si1, aE, a.y);
-                dmma884(Dr0, Dr1, aO, d.x);
-                dmma884(Di0, Di1, aO, d.y);
+        // step s outside, the four block groups inside: the NCO phasors of the pair and the modal
+        // A fragments are fetched once per step and serve 4 x 4 DMMAs
+        double acc[4][8];
+#pragma unroll
+        for (int g = 0; g < 4; g++)
+#pragma unroll
+            for (int i = 0; i < 8; i++) acc[g][i] = 0.0;
+        for (int sp = 0; sp < RL; sp++) {
+            const bool valid = sp < npair, mid = sp == smid;
+            const int j = a0 + sp;
+            double2 Ta = make_double2(1.0, 0.0), Tb = Ta;
+            if (nco && valid) { Ta = __ldg(T2r + j); Tb = __ldg(T2r + (q - 1 - j)); }
+            const double aE = __ldg(pl.Afrag + (size_t)(2 * sp) * 32 + lane);
+            const double aO = __ldg(pl.Afrag + (size_t)(2 * sp + 1) * 32 + lane);
+            const unsigned char *ps = tb + (size_t)sp * plane;
+#pragma unroll
+            for (int g = 0; g < 4; g++) {
+                double2 za, zb;
+                load_pair<ENC>(pl, ps, g, lane, za, zb);
+                if (sp == 0 && kq == 0) x0s[8 * g + nq] = za;      // first (raw) sample of the block
+                double2 ua = nco ? cmul(Ta, za) : za, ub = nco ? cmul(Tb, zb) : zb;
+                if (mid) ub = make_double2(0.0, 0.0);
+                double2 a = cadd(ua, ub), d = mid ? ub : csub(ua, ub);
+                if (!valid) { a = make_double2(0.0, 0.0); d = a; }
+                dmma884(acc[g][0], acc[g][1], aE, a.x);
+                dmma884(acc[g][2], acc[g][3], aE, a.y);
+                dmma884(acc[g][4], acc[g][5], aO, d.x);
+                dmma884(acc[g][6], acc[g][7], aO, d.y);
             }
-            // combine the four real sums into F/G (part e of poles m and m+4), local IQ, exchange
+        }
+        // combine the four real sums into F/G (part e of poles m and m+4), exchange
+#pragma unroll
+        for (int g = 0; g < 4; g++) {
 #pragma unroll
             for (int i = 0; i < 2; i++) {
                 const int b = 8 * g + 2 * kq + i;
-                const double Sr = i ? Sr1 : Sr0, Si = i ? Si1 : Si0, Dr = i ? Dr1 : Dr0, Di = i ? Di1 : Di0;
+                const double Sr = acc[g][i], Si = acc[g][2 + i], Dr = acc[g][4 + i], Di = acc[g][6 + i];
                 const double oS = __shfl_xor_sync(0xffffffffu, Si, 4);
                 const double oD = __shfl_xor_sync(0xffffffffu, Di, 4);
                 double Sup, Slo, Dup, Dlo;
