@@ -74,6 +74,15 @@ __device__ __forceinline__ void stage_pairs(unsigned char *tiles, size_t tileb, 
             for (int u = 0; u < 4; u++) dst[u * 8] = v[u];           // next block row: lane slot + 4 = 8 words on
         }
     }
+    // slots no sample lands in -- pairs Hq .. 4 RL - 1 and the mirror of an odd block's middle
+    // sample -- are zero: their modal coefficients are zero, so the data only has to be finite
+    const int nempty = 2 * (4 * RL - Hq) + (q & 1);
+    for (int idx = warp * 32 + lane; idx < nempty * SDRB_TB * ntl; idx += W * 32) {
+        const int b = idx & 31, k = (idx >> 5) % nempty, tl = (idx >> 5) / nempty;
+        const int jj = k < 2 * (4 * RL - Hq) ? Hq + (k >> 1) : Hq - 1, slot = k < 2 * (4 * RL - Hq) ? (k & 1) : 1;
+        const int kq = jj / RL, sp = jj - kq * RL;
+        reinterpret_cast<T *>(tiles + (size_t)tl * tileb + (size_t)sp * plane)[((size_t)(b >> 3) * 32 + (b & 7) * 4 + kq) * 2 + slot] = T{};
+    }
 }
 
 // The pair of slot (s, g, lane) -> two complex doubles (decode of read_file.py:100-101 from registers).
@@ -240,10 +249,11 @@ k_main(const __grid_constant__ DevPlan pl, Scratch sc, const uint8_t *__restrict
 #pragma unroll
             for (int i = 0; i < 8; i++) acc[g][i] = 0.0;
         for (int sp = 0; sp < RL; sp++) {
-            const bool valid = sp < npair, mid = sp == smid;
+            // steps past this lane's pairs (and the odd part of a middle sample) carry zero modal
+            // coefficients and zero data: no selects in the loop
             const int j = a0 + sp;
             double2 Ta = make_double2(1.0, 0.0), Tb = Ta;
-            if (nco && valid) { Ta = __ldg(T2r + j); Tb = __ldg(T2r + (q - 1 - j)); }
+            if (nco && sp < npair) { Ta = __ldg(T2r + j); Tb = __ldg(T2r + (q - 1 - j)); }
             const double aE = __ldg(pl.Afrag + (size_t)(2 * sp) * 32 + lane);
             const double aO = __ldg(pl.Afrag + (size_t)(2 * sp + 1) * 32 + lane);
             const unsigned char *ps = tb + (size_t)sp * plane;
@@ -252,10 +262,9 @@ k_main(const __grid_constant__ DevPlan pl, Scratch sc, const uint8_t *__restrict
                 double2 za, zb;
                 load_pair<ENC>(pl, ps, g, lane, za, zb);
                 if (sp == 0 && kq == 0) x0s[8 * g + nq] = za;      // first (raw) sample of the block
-                double2 ua = nco ? cmul(Ta, za) : za, ub = nco ? cmul(Tb, zb) : zb;
-                if (mid) ub = make_double2(0.0, 0.0);
-                double2 a = cadd(ua, ub), d = mid ? ub : csub(ua, ub);
-                if (!valid) { a = make_double2(0.0, 0.0); d = a; }
+                if (pl.normalize && sp == smid) zb = make_double2(0.0, 0.0);   // (a normalised zero is not zero)
+                const double2 ua = nco ? cmul(Ta, za) : za, ub = nco ? cmul(Tb, zb) : zb;
+                const double2 a = cadd(ua, ub), d = csub(ua, ub);
                 dmma884(acc[g][0], acc[g][1], aE, a.x);
                 dmma884(acc[g][2], acc[g][3], aE, a.y);
                 dmma884(acc[g][4], acc[g][5], aO, d.x);
