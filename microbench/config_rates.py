@@ -30,12 +30,17 @@ def run(name, pl, nch, itemsize):
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / reps
+    eng.set_profiling(True)
+    eng.process_device(raw.data_ptr(), nch, out.data_ptr())
+    torch.cuda.synchronize()
+    kt = [round(v, 4) for v in eng.kernel_times()]     # front end | IQ kernels | k_finish or k_fixup | k_demod
+    eng.set_profiling(False)
     nsamp = nch * pl.N
     msps = nsamp / (ms * 1e-3) / 1e6
     bps = 2 * itemsize + 8 * pl.R / pl.q
     print(json.dumps({'config': name, 'front_end': 'k_tc' if eng.tc is not None else 'k_main', 'rows': pl.R,
                       'chunks': nch, 'ms': ms, 'input_msps': msps, 'vfo_msps': msps * pl.R,
-                      'bytes_per_sample': bps, 'frac_hbm': msps * 1e6 * bps / 1e9 / PEAK}))
+                      'bytes_per_sample': bps, 'frac_hbm': msps * 1e6 * bps / 1e9 / PEAK, 'kernel_ms': kt}))
     eng.close()
 
 

@@ -52,9 +52,19 @@ __host__ __device__ inline size_t main_warp_bytes()
 // Raw tiles of one CTA -> shared memory in fragment order, one word of type T per sample: every
 // warp takes four block rows at a time and issues their loads together (rows past the chunk's
 // last block are zero).
+// Stored byte order -> the GPU's, one raw sample (two items) at a time: done once when the tile is
+// staged, not once per row of the bank.
+__device__ __forceinline__ uint16_t swap_items(uint16_t v) { return v; }
+__device__ __forceinline__ uint32_t swap_items(uint32_t v) { return __byte_perm(v, 0, 0x2301); }
+__device__ __forceinline__ uint2 swap_items(uint2 v) { return make_uint2(__byte_perm(v.x, 0, 0x0123), __byte_perm(v.y, 0, 0x0123)); }
+__device__ __forceinline__ uint4 swap_items(uint4 v)
+{
+    return make_uint4(__byte_perm(v.y, 0, 0x0123), __byte_perm(v.x, 0, 0x0123), __byte_perm(v.w, 0, 0x0123), __byte_perm(v.z, 0, 0x0123));
+}
+
 template <typename T>
 __device__ __forceinline__ void stage_pairs(unsigned char *tiles, size_t tileb, const uint8_t *rawc, int t0, int ntl,
-                                            int ntiles, int cnt_last, int q, int Hq, int RL, int warp, int W, int lane)
+                                            int ntiles, int cnt_last, int q, int Hq, int RL, int swap, int warp, int W, int lane)
 {
     const int total = ntl * SDRB_TB;
     const size_t plane = main_plane_bytes((int)sizeof(T));
@@ -69,6 +79,10 @@ __device__ __forceinline__ void stage_pairs(unsigned char *tiles, size_t tileb, 
             T v[4];
 #pragma unroll
             for (int u = 0; u < 4; u++) v[u] = (row0 + u < cnt) ? src[(size_t)u * q + col] : T{};
+            if (swap) {
+#pragma unroll
+                for (int u = 0; u < 4; u++) v[u] = swap_items(v[u]);
+            }
             T *dst = reinterpret_cast<T *>(tb + (size_t)sp * plane) + ((size_t)(row0 >> 3) * 32 + (row0 & 7) * 4 + kq) * 2 + slot;
 #pragma unroll
             for (int u = 0; u < 4; u++) dst[u * 8] = v[u];           // next block row: lane slot + 4 = 8 words on
@@ -85,7 +99,8 @@ __device__ __forceinline__ void stage_pairs(unsigned char *tiles, size_t tileb, 
     }
 }
 
-// The pair of slot (s, g, lane) -> two complex doubles (decode of read_file.py:100-101 from registers).
+// The pair of slot (s, g, lane) -> two complex doubles (decode of read_file.py:100-101 from
+// registers; the byte order was fixed when the tile was staged).
 template <int ENC>
 __device__ __forceinline__ void load_pair(const DevPlan &pl, const unsigned char *plane_s, int g, int lane, double2 &za, double2 &zb)
 {
@@ -100,8 +115,7 @@ __device__ __forceinline__ void load_pair(const DevPlan &pl, const unsigned char
             zb = make_double2((double)((v >> 16) & 0xff), (double)(v >> 24));
         }
     } else if (ENC == ENC_h || ENC == ENC_H) {
-        uint2 v = reinterpret_cast<const uint2 *>(plane_s)[idx];
-        if (pl.swap) { v.x = __byte_perm(v.x, 0, 0x2301); v.y = __byte_perm(v.y, 0, 0x2301); }
+        const uint2 v = reinterpret_cast<const uint2 *>(plane_s)[idx];
         if (ENC == ENC_h) {
             za = make_double2((double)(int16_t)(v.x & 0xffff), (double)(int16_t)(v.x >> 16));
             zb = make_double2((double)(int16_t)(v.y & 0xffff), (double)(int16_t)(v.y >> 16));
@@ -110,11 +124,7 @@ __device__ __forceinline__ void load_pair(const DevPlan &pl, const unsigned char
             zb = make_double2((double)(v.y & 0xffff), (double)(v.y >> 16));
         }
     } else if (ENC == ENC_i || ENC == ENC_I || ENC == ENC_f) {
-        uint4 v = reinterpret_cast<const uint4 *>(plane_s)[idx];
-        if (pl.swap) {
-            v.x = __byte_perm(v.x, 0, 0x0123); v.y = __byte_perm(v.y, 0, 0x0123);
-            v.z = __byte_perm(v.z, 0, 0x0123); v.w = __byte_perm(v.w, 0, 0x0123);
-        }
+        const uint4 v = reinterpret_cast<const uint4 *>(plane_s)[idx];
         if (ENC == ENC_i) {
             za = make_double2((double)(int32_t)v.x, (double)(int32_t)v.y); zb = make_double2((double)(int32_t)v.z, (double)(int32_t)v.w);
         } else if (ENC == ENC_I) {
@@ -125,8 +135,8 @@ __device__ __forceinline__ void load_pair(const DevPlan &pl, const unsigned char
         }
     } else {
         const unsigned char *p = plane_s + (size_t)idx * 32;
-        za = load_sample<ENC>(p, 0, pl.swap);
-        zb = load_sample<ENC>(p, 1, pl.swap);
+        za = load_sample<ENC>(p, 0, 0);
+        zb = load_sample<ENC>(p, 1, 0);
     }
     if (pl.normalize) {
         za = normalize_sample(za, pl.norm_xmin, pl.norm_k);
@@ -163,10 +173,10 @@ k_main(const __grid_constant__ DevPlan pl, Scratch sc, const uint8_t *__restrict
 
     // ---------------- stage the raw tiles (all warps, four rows in flight per lane), then (IQ) run
     //                  aggregates and block offsets
-    if (sb == 2) stage_pairs<uint16_t>(smem_raw, tileb, rawc, t0, ntl, pl.ntiles, pl.cnt_last, q, pl.Hq, RL, warp, W, lane);
-    else if (sb == 4) stage_pairs<uint32_t>(smem_raw, tileb, rawc, t0, ntl, pl.ntiles, pl.cnt_last, q, pl.Hq, RL, warp, W, lane);
-    else if (sb == 8) stage_pairs<uint2>(smem_raw, tileb, rawc, t0, ntl, pl.ntiles, pl.cnt_last, q, pl.Hq, RL, warp, W, lane);
-    else stage_pairs<uint4>(smem_raw, tileb, rawc, t0, ntl, pl.ntiles, pl.cnt_last, q, pl.Hq, RL, warp, W, lane);
+    if (sb == 2) stage_pairs<uint16_t>(smem_raw, tileb, rawc, t0, ntl, pl.ntiles, pl.cnt_last, q, pl.Hq, RL, pl.swap, warp, W, lane);
+    else if (sb == 4) stage_pairs<uint32_t>(smem_raw, tileb, rawc, t0, ntl, pl.ntiles, pl.cnt_last, q, pl.Hq, RL, pl.swap, warp, W, lane);
+    else if (sb == 8) stage_pairs<uint2>(smem_raw, tileb, rawc, t0, ntl, pl.ntiles, pl.cnt_last, q, pl.Hq, RL, pl.swap, warp, W, lane);
+    else stage_pairs<uint4>(smem_raw, tileb, rawc, t0, ntl, pl.ntiles, pl.cnt_last, q, pl.Hq, RL, pl.swap, warp, W, lane);
     __syncthreads();
     for (int tl = warp; tl < ntl; tl += W) {
         const int t = t0 + tl;
@@ -181,18 +191,15 @@ k_main(const __grid_constant__ DevPlan pl, Scratch sc, const uint8_t *__restrict
             for (int g = 0; g < 4; g++) {
                 const int b = 8 * g + nq;
                 double2 agg_a = make_double2(0.0, 0.0), agg_d = make_double2(0.0, 0.0);
-                // ascending run: samples a0 .. a1-1 (the first of each pair)
+                // ascending run = the first samples of the pairs (Horner); descending run = their
+                // mirrors q-1-j, newest last: sum_sp lam^sp zb_sp (one decode pass for both)
+                double wd = 1.0;
                 for (int sp = 0; sp < npair; sp++) {
                     double2 za, zb;
                     load_pair<ENC>(pl, tb + (size_t)sp * plane, g, lane, za, zb);
                     agg_a.x = fma(pl.lam, agg_a.x, za.x); agg_a.y = fma(pl.lam, agg_a.y, za.y);
-                }
-                // descending run: the mirrors q-1-j, in sample order = pairs from the last to the first
-                for (int sp = npair - 1; sp >= 0; sp--) {
-                    if (sp == smid) continue;
-                    double2 za, zb;
-                    load_pair<ENC>(pl, tb + (size_t)sp * plane, g, lane, za, zb);
-                    agg_d.x = fma(pl.lam, agg_d.x, zb.x); agg_d.y = fma(pl.lam, agg_d.y, zb.y);
+                    if (sp != smid) { agg_d.x = fma(wd, zb.x, agg_d.x); agg_d.y = fma(wd, zb.y, agg_d.y); }
+                    wd *= pl.lam;
                 }
                 // EMA state at the 9 run boundaries of this block (all four lanes of the block
                 // compute the same chain from the gathered run aggregates)
@@ -257,12 +264,14 @@ k_main(const __grid_constant__ DevPlan pl, Scratch sc, const uint8_t *__restrict
             const double aE = __ldg(pl.Afrag + (size_t)(2 * sp) * 32 + lane);
             const double aO = __ldg(pl.Afrag + (size_t)(2 * sp + 1) * 32 + lane);
             const unsigned char *ps = tb + (size_t)sp * plane;
+            const bool killb = pl.normalize && sp == smid;         // (a normalised zero is not zero)
+            const bool first = sp == 0 && kq == 0;
 #pragma unroll
             for (int g = 0; g < 4; g++) {
                 double2 za, zb;
                 load_pair<ENC>(pl, ps, g, lane, za, zb);
-                if (sp == 0 && kq == 0) x0s[8 * g + nq] = za;      // first (raw) sample of the block
-                if (pl.normalize && sp == smid) zb = make_double2(0.0, 0.0);   // (a normalised zero is not zero)
+                if (first) x0s[8 * g + nq] = za;                   // first (raw) sample of the block
+                if (killb) zb = make_double2(0.0, 0.0);
                 const double2 ua = nco ? cmul(Ta, za) : za, ub = nco ? cmul(Tb, zb) : zb;
                 const double2 a = cadd(ua, ub), d = csub(ua, ub);
                 dmma884(acc[g][0], acc[g][1], aE, a.x);
@@ -296,14 +305,22 @@ k_main(const __grid_constant__ DevPlan pl, Scratch sc, const uint8_t *__restrict
             const bool fwd = lane < 8;
             const double2 Pm = pl.Prot[(size_t)r * 16 + lane];
             double2 st = make_double2(0.0, 0.0);
-            double *xr = xb + (2 * lane) * SDRB_XSTRIDE, *xi = xr + SDRB_XSTRIDE;
+            // forward lanes: exclusive scan = the inclusive one stored one slot up (slot 0 = 0, slot
+            // cnt is padding or an unused block); backward lanes: inclusive, in place.  The next
+            // input is fetched before the store that may overwrite it.
+            const int dir = fwd ? 1 : -1;
+            double *xr = xb + (2 * lane) * SDRB_XSTRIDE + (fwd ? 0 : cnt - 1), *xi = xr + SDRB_XSTRIDE;
+            double *orr = xr + (fwd ? 1 : 0), *oi = orr + SDRB_XSTRIDE;
+            double2 v = make_double2(*xr, *xi);
+            if (fwd) { *xr = 0.0; *xi = 0.0; }
             for (int step = 0; step < cnt; step++) {
-                const int l = fwd ? step : cnt - 1 - step;
-                const double2 v = make_double2(xr[l], xi[l]);
-                const double2 nst = cfma(Pm, st, v);
-                const double2 o = fwd ? st : nst;
-                xr[l] = o.x; xi[l] = o.y;
-                st = nst;
+                xr += dir; xi += dir;
+                double2 vn = make_double2(0.0, 0.0);
+                if (step + 1 < cnt) vn = make_double2(*xr, *xi);
+                st = cfma(Pm, st, v);
+                *orr = st.x; *oi = st.y;
+                orr += dir; oi += dir;
+                v = vn;
             }
             if (fwd) st = cmul(pl.T3[(size_t)r * (SDRB_TB + 1) + cnt - 1], st);
             sc.agg[(((size_t)chunk * pl.R + r) * pl.ntiles + t) * 16 + lane] = st;
