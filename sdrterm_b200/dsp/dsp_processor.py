@@ -58,6 +58,7 @@ def generateEllipFilter(fs: int, deg: int, Wn, btype: str):
 class DspProcessor(DataProcessor):
     _FILTER_DEGREE = 3
     MAX_BATCH = 512         # chunks drained from the queue per device batch (64 MiB of raw input)
+    _inputPool = None       # misc.read_file.ChunkPool shared with the reader (page-locked read buffers), see useInputPool
 
     def __init__(self, fs: int, center: int = 0, omegaOut: int = 0, tuned: int = 0, dec: int = 2,
                  smooth: bool = False, fileInfo: dict | None = None, **kwargs):
@@ -235,6 +236,7 @@ class DspProcessor(DataProcessor):
                 have += self._itemChunks(batch[-1])
             chunks = []
             nch = 0
+            pool = self._inputPool
             for c in batch:
                 if c is None or len(c) == 0:          # end-of-stream marker (read_file.py:169-171)
                     eof = True
@@ -245,32 +247,55 @@ class DspProcessor(DataProcessor):
                 a = self._asBytes(c)                   # one chunk, or several whole chunks read at once
                 if a.size % self._chunkBytes:
                     raise ValueError('queue items must be whole chunks of the size of the first one')
+                home = pool.owner(a) if pool is not None else None
+                if home is not None and a.size // self._chunkBytes <= self.MAX_BATCH:
+                    # the reader filled a page-locked pool buffer: the device reads it where it
+                    # lies (the staged chunks before it go first, in order)
+                    pending, b = self._flush(chunks, pending, b, file)
+                    chunks = []
+                    slot = b & 1
+                    n = a.size // self._chunkBytes
+                    self._engine.submit(slot, a.ctypes.data, n, self._hout[slot].ptr.value)
+                    if pending is not None:
+                        self._drain(pending, file)
+                    pending = (slot, n, home)
+                    b += 1
+                    continue
                 chunks.append(a)
                 nch += a.size // self._chunkBytes
-            # (a batch of multi-chunk items may exceed MAX_BATCH: split it)
-            pos = 0
-            flat = chunks
-            while flat:
-                slot = b & 1
-                hin = self._hin[slot].u8
-                n = 0
-                while flat and n < self.MAX_BATCH:
-                    a = flat[0]
-                    take = min(a.size // self._chunkBytes - pos, self.MAX_BATCH - n)
-                    hin[n * self._chunkBytes:(n + take) * self._chunkBytes] = \
-                        a[pos * self._chunkBytes:(pos + take) * self._chunkBytes]
-                    n += take
-                    pos += take
-                    if pos * self._chunkBytes == a.size:
-                        flat.pop(0)
-                        pos = 0
-                self._engine.submit(slot, self._hin[slot].ptr.value, n, self._hout[slot].ptr.value)
-                if pending is not None:
-                    self._drain(pending, file)
-                pending = (slot, n)
-                b += 1
+            pending, b = self._flush(chunks, pending, b, file)
         if pending is not None:
             self._drain(pending, file)
+
+    def _flush(self, flat, pending, b, file):
+        """Copy the collected chunks into the pinned staging buffers, MAX_BATCH at a time, and
+        submit them (a batch of multi-chunk items may exceed MAX_BATCH: split it)."""
+        pos = 0
+        while flat:
+            slot = b & 1
+            hin = self._hin[slot].u8
+            n = 0
+            while flat and n < self.MAX_BATCH:
+                a = flat[0]
+                take = min(a.size // self._chunkBytes - pos, self.MAX_BATCH - n)
+                hin[n * self._chunkBytes:(n + take) * self._chunkBytes] = \
+                    a[pos * self._chunkBytes:(pos + take) * self._chunkBytes]
+                n += take
+                pos += take
+                if pos * self._chunkBytes == a.size:
+                    flat.pop(0)
+                    pos = 0
+            self._engine.submit(slot, self._hin[slot].ptr.value, n, self._hout[slot].ptr.value)
+            if pending is not None:
+                self._drain(pending, file)
+            pending = (slot, n, None)
+            b += 1
+        return pending, b
+
+    def useInputPool(self, pool) -> None:
+        """Queue items that are views of ``pool``'s buffers (misc.read_file.ChunkPool) are sent to
+        the device from where they lie and handed back to the pool afterwards."""
+        self._inputPool = pool
 
     @staticmethod
     def _itemChunks(c) -> int:
@@ -291,9 +316,11 @@ class DspProcessor(DataProcessor):
                     return None
 
     def _drain(self, pending, file) -> None:
-        slot, n = pending
+        slot, n, home = pending
         eng = self._engine
         eng.wait(slot)
+        if home is not None:
+            self._inputPool.release(home)                 # the device has the bytes: the reader may refill it
         out = self._hout[slot].view(np.float64)[:eng.R * n * eng.M].reshape(eng.R, n * eng.M)
         if eng.plan.big_endian_out:
             out = out.view('>f8')
@@ -318,7 +345,7 @@ class DspProcessor(DataProcessor):
     def __getstate__(self):
         d = dict(self.__dict__)
         d['_engine'] = None
-        d.pop('_hin', None), d.pop('_hout', None)
+        d.pop('_hin', None), d.pop('_hout', None), d.pop('_inputPool', None)
         return d
 
     def __repr__(self):

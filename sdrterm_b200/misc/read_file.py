@@ -45,18 +45,71 @@ def decodeIq(raw, enc: str, swap: bool = False, device: int = 0) -> np.ndarray:
 READ_BATCH = 64             # chunks fetched per read call when the source has them ready
 
 
-def chunks(reader, readSize: int = READ_SIZE, isDead=None, batch: int = 1):
+class ChunkPool:
+    """A few reusable read buffers of ``nbytes`` each, shared by the reader (``get``) and the
+    consumer (``release`` once the device has the bytes).  With page-locked buffers (``alloc`` =
+    ``sdrterm_b200._native.PinnedBuffer``) a file read lands where the H2D DMA starts: no host copy
+    between ``readinto`` and the device.  The pool is the back-pressure: the reader waits for a
+    free buffer."""
+
+    def __init__(self, nbuf: int, nbytes: int, alloc=None):
+        import queue
+        self.nbytes = nbytes
+        self._free = queue.Queue()
+        self._owners = []                                    # keeps the allocations alive
+        self._ranges = []
+        for _ in range(nbuf):
+            if alloc is None:
+                arr = np.zeros(nbytes, dtype=np.uint8)
+                self._owners.append(arr)
+            else:
+                o = alloc(nbytes)
+                self._owners.append(o)
+                arr = o.u8
+            self._ranges.append((arr.ctypes.data, arr.ctypes.data + nbytes, arr))
+            self._free.put(arr)
+
+    def get(self, isDead=None):
+        import queue
+        while True:
+            try:
+                return self._free.get(timeout=0.25)
+            except queue.Empty:
+                if isDead is not None and isDead.value:
+                    return None
+
+    def owner(self, a):
+        """The pool buffer that holds array ``a`` (None if it is not one of ours)."""
+        if not isinstance(a, np.ndarray):
+            return None
+        p = a.ctypes.data
+        for lo, hi, arr in self._ranges:
+            if lo <= p < hi:
+                return arr
+        return None
+
+    def release(self, arr) -> None:
+        self._free.put(arr)
+
+
+def chunks(reader, readSize: int = READ_SIZE, isDead=None, batch: int = 1, pool: ChunkPool | None = None):
     """Yield whole chunks exactly as the reference's reader presents them: ``readinto`` a reused
     buffer; a short read leaves the previous chunk's tail in place and the whole buffer counts
     (SURVEY 8-Q5).  With ``batch`` > 1 up to that many chunks are fetched per call and yielded as
     one array of k*readSize bytes (one Python-level hand-off per 8 MiB instead of per 128 KiB);
-    the chunk boundaries, and the stale tail of a final short chunk, are the same."""
-    buf = np.zeros(batch * readSize, dtype=np.uint8)
-    view = memoryview(buf)
+    the chunk boundaries, and the stale tail of a final short chunk, are the same.  With a
+    ``pool`` the arrays yielded are views of pool buffers (the consumer releases them); without
+    one they are private copies."""
+    own = np.zeros(batch * readSize, dtype=np.uint8) if pool is None else None
     last = np.zeros(readSize, dtype=np.uint8)            # the reference's buffer starts zeroed
     while isDead is None or not isDead.value:
-        n = reader.readinto(view)
+        buf = own if pool is None else pool.get(isDead)
+        if buf is None:
+            return
+        n = reader.readinto(memoryview(buf)[:batch * readSize])
         if not n:
+            if pool is not None:
+                pool.release(buf)
             return
         full, part = divmod(n, readSize)
         if part:
@@ -65,24 +118,28 @@ def chunks(reader, readSize: int = READ_SIZE, isDead=None, batch: int = 1):
             prev = buf[(full - 1) * readSize:full * readSize] if full else last
             buf[full * readSize + part:(full + 1) * readSize] = prev[part:]
             full += 1
-        out = buf[:full * readSize].copy()
-        last = out[-readSize:]
+        if pool is None:
+            out = buf[:full * readSize].copy()
+            last = out[-readSize:]
+        else:
+            out = buf[:full * readSize]
+            last = out[-readSize:].copy()
         yield out
 
 
 def readFile(bitsPerSample=None, dataOffset: int = 0, fs: int | None = None, buffers=None,
              processes=None, isDead=None, inFile: str | None = None, readSize: int = READ_SIZE,
-             isSocket: bool = False, **_) -> None:
+             isSocket: bool = False, pool: ChunkPool | None = None, **_) -> None:
     """Feed every queue in ``buffers`` with raw chunks until EOF or ``isDead``; then the empty
     end-of-stream marker (read_file.py:169-171)."""
     if fs is None:
         raise ValueError('fs is not specified')
     clients = list(buffers or [])
 
-    def feed(reader, batch=1):
+    def feed(reader, batch=1, pool=None):
         # live sources (sockets, pipes) are handed on chunk by chunk; regular files are read
-        # READ_BATCH chunks at a time
-        for c in chunks(reader, readSize, isDead, batch=batch):
+        # READ_BATCH chunks at a time, into the consumer's pool buffers when there is one
+        for c in chunks(reader, readSize, isDead, batch=batch, pool=pool):
             for q in clients:
                 q.put(c)
 
@@ -105,7 +162,10 @@ def readFile(bitsPerSample=None, dataOffset: int = 0, fs: int | None = None, buf
         with open(inFile if isFile else sys.stdin.fileno(), 'rb', closefd=isFile) as fh:
             if dataOffset and fh.seekable():
                 fh.seek(dataOffset)
-            feed(fh, READ_BATCH if (isFile and fh.seekable()) else 1)   # open(..., 'rb') is already a BufferedReader
+            seekable = isFile and fh.seekable()
+            usePool = pool if (seekable and len(clients) == 1 and pool is not None
+                               and pool.nbytes >= READ_BATCH * readSize) else None
+            feed(fh, READ_BATCH if seekable else 1, usePool)   # open(..., 'rb') is already a BufferedReader
     for q in clients:
         try:
             q.put(b'')

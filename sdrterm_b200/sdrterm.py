@@ -113,10 +113,21 @@ def main(argv=None, lifecycle: bool = False) -> int:
     gu.tprint(f'Started proc Main: {os.getpid()}')
     print(repr(proc), file=sys.stderr, flush=True)          # unconditional: src/sdrterm.py:144
     buf = queue.Queue(maxsize=1024)
+    pool = None
+    if a.inFile and not fileInfo['isSocket'] and os.path.isfile(a.inFile):
+        # a regular file is read READ_BATCH chunks at a time straight into page-locked buffers the
+        # device then reads in place (no host copy between the page cache and the DMA)
+        try:
+            from ._native import PinnedBuffer
+            from .misc.read_file import READ_BATCH, READ_SIZE, ChunkPool
+            pool = ChunkPool(6, READ_BATCH * READ_SIZE, PinnedBuffer)
+            proc.useInputPool(pool)
+        except Exception:
+            pool = None                                     # (no device: the engine will say so)
     reader = threading.Thread(target=readFile, daemon=True,
                               kwargs=dict(buffers=[buf], isDead=isDead, inFile=a.inFile,
                                           fs=fileInfo['sampRate'], dataOffset=fileInfo['dataOffset'],
-                                          isSocket=fileInfo['isSocket']))
+                                          isSocket=fileInfo['isSocket'], pool=pool))
     reader.start()
     try:
         proc.processData(isDead, buf, a.outFile)

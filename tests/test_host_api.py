@@ -335,3 +335,91 @@ def test_cli_lifecycle_pid_file_and_signal(tmp_path):
     assert p.returncode == 0, err
     assert f'pid {p.pid} caught: SIGTERM' in err
     assert not os.path.exists(m.group(1))
+
+
+def test_chunk_pool_reader_yields_views_with_the_same_bytes_and_stale_tail():
+    """With a ChunkPool the reader fills pool buffers in place; chunk boundaries and the stale tail
+    of a short final chunk are what the copying reader produces."""
+    data = bytes(range(256)) * 10 + b'\xee' * 100            # 2660 bytes, readSize 512, batch 2
+    ref = [c.tobytes() for c in read_file.chunks(io.BytesIO(data), readSize=512, batch=2)]
+    pool = read_file.ChunkPool(2, 1024)
+    got = []
+    for c in read_file.chunks(io.BytesIO(data), readSize=512, batch=2, pool=pool):
+        home = pool.owner(c)
+        assert home is not None and c.ctypes.data == home.ctypes.data      # a view, not a copy
+        got.append(c.tobytes())
+        pool.release(home)                                                  # what the consumer does
+    assert got == ref
+    assert pool.owner(np.zeros(8, dtype=np.uint8)) is None
+
+
+class _RecordingEngine:
+    """Stands in for the device: remembers what was submitted from where."""
+    R, M = 1, 4
+
+    class plan:
+        big_endian_out = False
+
+    def __init__(self):
+        self.calls = []
+
+    def submit(self, slot, raw_ptr, n, out_ptr):
+        import ctypes
+        self.calls.append((slot, raw_ptr, n, bytes((ctypes.c_uint8 * 16).from_address(raw_ptr))))
+
+    def wait(self, slot):
+        pass
+
+    def close(self):
+        pass
+
+
+def test_consumer_sends_pool_buffers_in_place_and_hands_them_back(tmp_path):
+    """File input through a ChunkPool: every batch is submitted from the pool buffer itself (no
+    staging copy), in file order, and the buffer returns to the pool after the wait."""
+    import queue
+    import threading
+
+    class Buf:
+        def __init__(self, n):
+            import ctypes
+            self.u8 = np.zeros(n, dtype=np.uint8)
+            self.ptr = ctypes.c_void_p(self.u8.ctypes.data)
+
+        def view(self, dt):
+            return self.u8.view(dt)
+
+    eng = _RecordingEngine()
+
+    class P(dsp.DspProcessor):
+        def _makeEngine(self, c):
+            self._chunkBytes = 131072
+            return eng
+
+        def _staging(self):
+            self._hin = [Buf(self.MAX_BATCH * 131072) for _ in range(2)]
+            self._hout = [Buf(self.MAX_BATCH * 4 * 8) for _ in range(2)]
+
+    nchunks = 3 * read_file.READ_BATCH + 5
+    f = tmp_path / 'in.raw'
+    blob = np.arange(nchunks * 131072 // 4, dtype=np.uint32).view(np.uint8)
+    f.write_bytes(blob.tobytes())
+    pool = read_file.ChunkPool(2, read_file.READ_BATCH * 131072)
+    homes = {r[0] for r in pool._ranges}
+    p = P(1_000_000, dec=64, omegaOut=5000, enc='h')
+    p.useInputPool(pool)
+    q = queue.Queue()
+
+    class Flag:
+        value = 0
+    th = threading.Thread(target=read_file.readFile, kwargs=dict(fs=1_000_000, buffers=[q], isDead=Flag(), inFile=str(f), pool=pool))
+    th.start()
+    with open(tmp_path / 'out.bin', 'wb') as out:
+        p._processData(Flag(), q, out)
+    th.join()
+    assert [c[2] for c in eng.calls] == [read_file.READ_BATCH] * 3 + [5]
+    assert all(c[1] in homes for c in eng.calls)                             # submitted in place
+    assert [c[3] for c in eng.calls] == [blob[i * read_file.READ_BATCH * 131072:][:16].tobytes() for i in range(4)]
+    assert [c[0] for c in eng.calls] == [0, 1, 0, 1]                         # alternating device slots
+    assert pool._free.qsize() == 2                                           # every buffer came back
+    assert '_inputPool' not in repr(p) and 'inputPool' not in p.__getstate__()
