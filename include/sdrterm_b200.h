@@ -234,6 +234,20 @@ int sdrb_shift_freq(int device, const double *y, const double *shift, int R, int
 /* sdrb_fm_demod takes any even row length: 2*2^k rows run the FFT interpolation, other lengths a
  * dense scipy.signal.resample matrix built on the host in extended precision. */
 
+/* The FFT feed of the reference's plot consumers, caller-owned host arrays:
+ *   sdrb_power_spectrum  SpectrumAnalyzerPlot.update, src/plots/spectrum_analyzer_plot.py:75-82:
+ *       shiftFreq(y, shift, y); amp = abs(fftshift(fftn(y, norm='forward'))); amp = log10(amp*amp)
+ *       y: `batch` rows of N complex128 (N a power of two >= 4: every chunk of the standard
+ *       encodings is), shift: N complex128 applied to every row, or NULL; out: batch*N doubles.
+ *   sdrb_stft_db         WaterfallPlot.update, src/plots/waterfall_plot.py:44-51,97-99:
+ *       10*log10(abs(ShortTimeFFT.stft(y))) for fft_mode='centered', phase_shift=None; `win` is the
+ *       ShortTimeFFT's (already scaled) window of nperseg values, slices p = 0..p_num-1 start at
+ *       p*hop - nperseg/2, zero outside the n samples, zero-padded to mfft (power of two <= 4096);
+ *       out: mfft rows of p_num doubles.  shift: n complex128 or NULL. */
+int sdrb_power_spectrum(int device, const double *y, const double *shift, int N, int batch, double *out);
+int sdrb_stft_db(int device, const double *y, const double *shift, int n, const double *win, int nperseg, int hop,
+                 int mfft, int p_num, double *out);
+
 /* The decode step of feedBuffers on its own (src/misc/read_file.py:100-101): the structured view
  * [('re',T),('im',T)] of `raw` -> interleaved complex128, bit-exact for every encoding; `swap` =
  * stored byte order differs from little-endian.  nsamples complex samples in, 2*nsamples doubles out. */

@@ -24,6 +24,10 @@ oracle function        reference (relative to /root/reference)
 ``output_filter``      src/dsp/dsp_processor.py:32-45,116-128,149
 ``frame``              src/dsp/dsp_processor.py:162; src/dsp/vfo_processor.py:84
 ``Chain``              src/misc/read_file.py:119-125 + src/dsp/dsp_processor.py:140-183
+``plot_shift``         src/plots/abstract_plot.py:75,151-152
+``power_spectrum``     src/plots/spectrum_analyzer_plot.py:75-82
+``stft_db``            src/plots/waterfall_plot.py:44-51,97-99 (+ scipy.signal.ShortTimeFFT.stft,
+                       restated slice by slice; pinned against SciPy's own in test_oracle_pins)
 =====================  ==========================================================================
 
 Third-party arithmetic: the decimator and both IIR filters live in SciPy (pyproject.toml:12-18,
@@ -323,6 +327,56 @@ def frame(z: np.ndarray, simo: bool) -> list[bytes]:
     if not simo:
         return [np.ascontiguousarray(z, dtype='=f8').tobytes()]
     return [np.ascontiguousarray(row, dtype='>f8').tobytes() for row in z]
+
+
+# ----------------------------------------------------------------------------- plot feeds
+def plot_shift(center: int, fs: int, n: int) -> np.ndarray:
+    """abstract_plot.py:75 ``_omega = -2j*pi*(offset/fs)`` and :151-152 ``exp(_omega * arange(n))``."""
+    return np.exp(-2j * np.pi * (center / fs) * np.arange(n))
+
+
+def power_spectrum(y: np.ndarray, shift: np.ndarray | None) -> np.ndarray:
+    """spectrum_analyzer_plot.py:75-82: ``shiftFreq(y, shift, y)``;
+    ``amp = abs(fftshift(fftn(y, norm='forward')))``; ``amp = log10(amp * amp)`` on the (1, n) array."""
+    from scipy.fft import fftn, fftshift
+    z = np.array([np.asarray(y, dtype=np.complex128).reshape(-1)])
+    if shift is not None:
+        z = z * np.asarray(shift).reshape(1, -1)
+    amp = abs(fftshift(fftn(z, norm='forward')))
+    with np.errstate(divide='ignore'):
+        return np.log10(amp * amp)[0]
+
+
+def stft_geometry(n: int, nperseg: int = 256, hop: int = 128):
+    """(first sample of slice 0, number of slices) of ``ShortTimeFFT.stft`` on an n-sample row for a
+    window whose half length is a multiple of the hop (the reference's 256 / 128): slice p starts
+    at p*hop - nperseg//2; p runs from 0 to the last slice that still begins inside the row
+    (SciPy's p_min .. p_max(n)-1; checked against SciPy in tests/test_oracle_pins.py)."""
+    mid = nperseg // 2
+    p_max = -(-(n + mid) // hop)
+    while (p_max - 1) * hop - mid >= n:
+        p_max -= 1
+    return -mid, p_max
+
+
+def stft_db(y: np.ndarray, shift: np.ndarray | None, win: np.ndarray, hop: int, mfft: int, p_num: int) -> np.ndarray:
+    """waterfall_plot.py:97-99 ``10. * log10(abs(self._SFT.stft(self._y)))`` after ``shiftFreq``; the
+    transform restated per slice: window * segment (zeros outside the row), zero-padded to mfft,
+    FFT, fftshift ('centered'), no phase shift, window already scaled ('magnitude')."""
+    z = np.asarray(y, dtype=np.complex128).reshape(-1)
+    if shift is not None:
+        z = z * np.asarray(shift).reshape(-1)
+    n, m = z.size, len(win)
+    out = np.empty((mfft, p_num), dtype=np.complex128)
+    for p in range(p_num):
+        seg = np.zeros(mfft, dtype=np.complex128)
+        k0 = p * hop - m // 2
+        lo, hi = max(k0, 0), min(k0 + m, n)
+        if hi > lo:
+            seg[lo - k0:hi - k0] = z[lo:hi] * np.conj(win[lo - k0:hi - k0])
+        out[:, p] = np.fft.fftshift(np.fft.fft(seg))
+    with np.errstate(divide='ignore'):
+        return 10. * np.log10(abs(out))
 
 
 # ----------------------------------------------------------------------------- the chain

@@ -58,7 +58,7 @@ EXPORTS = ['sdrb_create', 'sdrb_destroy', 'sdrb_last_error', 'sdrb_outputs_per_c
            'sdrb_chunk_bytes', 'sdrb_process', 'sdrb_process_device', 'sdrb_submit', 'sdrb_wait',
            'sdrb_get_iq_state', 'sdrb_set_iq_state', 'sdrb_read_decimated', 'sdrb_launch_count',
            'sdrb_fm_demod', 'sdrb_am_demod', 'sdrb_real_output', 'sdrb_imag_output',
-           'sdrb_shift_freq', 'sdrb_global_error', 'sdrb_process_device_phases',
+           'sdrb_shift_freq', 'sdrb_power_spectrum', 'sdrb_stft_db', 'sdrb_global_error', 'sdrb_process_device_phases',
            'sdrb_set_profiling', 'sdrb_kernel_times', 'sdrb_keep_decimated', 'sdrb_read_debug', 'sdrb_iq_export_device',
            'sdrb_iq_prefix_device', 'sdrb_decode_iq', 'sdrb_correct_iq', 'sdrb_keep_x0', 'sdrb_read_x0', 'sdrb_iq_gain', 'sdrb_set_smooth', 'sdrb_host_alloc', 'sdrb_host_free', 'sdrb_reserve_sms']
 
@@ -119,6 +119,8 @@ def lib():
         for name in ('sdrb_fm_demod', 'sdrb_am_demod', 'sdrb_real_output', 'sdrb_imag_output'):
             getattr(L, name).argtypes = [C.c_int, vp, C.c_int, C.c_int, vp]
         L.sdrb_shift_freq.argtypes = [C.c_int, vp, vp, C.c_int, C.c_int, vp]
+        L.sdrb_power_spectrum.argtypes = [C.c_int, vp, vp, C.c_int, C.c_int, vp]
+        L.sdrb_stft_db.argtypes = [C.c_int, vp, vp, C.c_int, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp]
         L.sdrb_decode_iq.argtypes = [C.c_int, vp, sz, C.c_char, C.c_int, vp]
         L.sdrb_correct_iq.argtypes = [C.c_int, vp, sz, _DP, C.c_double]
         L.sdrb_keep_x0.argtypes = [vp, C.c_int]

@@ -13,6 +13,7 @@
 #include "sdrb_kernels.cuh"
 #include "sdrb_tc.cuh"
 #include "sdrb_finish.cuh"
+#include "sdrb_spectrum.cuh"
 
 namespace {
 
@@ -1017,6 +1018,75 @@ int sdrb_shift_freq(int device, const double *y, const double *shift, int R, int
     CK(nullptr, cudaGetLastError());
     CK(nullptr, cudaDeviceSynchronize());
     CK(nullptr, cudaMemcpy(res, d_r.p, (size_t)R * N * sizeof(double2), cudaMemcpyDeviceToHost));
+    return SDRB_OK;
+}
+
+int sdrb_power_spectrum(int device, const double *y, const double *shift, int N, int batch, double *out)
+{
+    if (!y || !out || batch < 1 || N < 4 || (N & (N - 1))) return fail(nullptr, SDRB_ERR_ARG, "power spectrum: N must be a power of two >= 4");
+    int rc = need_device(device);
+    if (rc) return rc;
+    const size_t nb = (size_t)batch * N * sizeof(double2);
+    DevBuf d_a, d_b, d_s, d_o;
+    CK(nullptr, d_a.alloc(nb));
+    CK(nullptr, d_b.alloc(nb));
+    CK(nullptr, d_o.alloc((size_t)batch * N * sizeof(double)));
+    CK(nullptr, cudaMemcpy(d_a.p, y, nb, cudaMemcpyHostToDevice));
+    const double2 *sh = nullptr;
+    if (shift) {
+        // one NCO vector for every row of the batch when batch > 1 shares it: the caller passes N values
+        CK(nullptr, d_s.alloc((size_t)N * sizeof(double2)));
+        CK(nullptr, cudaMemcpy(d_s.p, shift, (size_t)N * sizeof(double2), cudaMemcpyHostToDevice));
+        sh = d_s.as<double2>();
+    }
+    double2 *src = d_a.as<double2>(), *dst = d_b.as<double2>();
+    const dim3 grid4((unsigned)std::min(148 * 8, (N / 4 + 255) / 256), (unsigned)batch);
+    int Ns = 1;
+    for (; Ns * 4 <= N; Ns <<= 2) {
+        k_gfft4<<<grid4, 256>>>(src, dst, sh, N, Ns);
+        sh = nullptr;
+        std::swap(src, dst);
+    }
+    if (Ns < N) {
+        k_gfft2<<<grid4, 256>>>(src, dst, sh, N, Ns);
+        std::swap(src, dst);
+    }
+    k_spectrum_db<<<dim3((unsigned)std::min(148 * 8, (N + 255) / 256), (unsigned)batch), 256>>>(src, d_o.as<double>(), N);
+    CK(nullptr, cudaGetLastError());
+    CK(nullptr, cudaDeviceSynchronize());
+    CK(nullptr, cudaMemcpy(out, d_o.p, (size_t)batch * N * sizeof(double), cudaMemcpyDeviceToHost));
+    return SDRB_OK;
+}
+
+int sdrb_stft_db(int device, const double *y, const double *shift, int n, const double *win, int nperseg, int hop,
+                 int mfft, int p_num, double *out)
+{
+    if (!y || !win || !out || n < 1 || nperseg < 1 || hop < 1 || p_num < 1 || mfft < nperseg || mfft < 4 || mfft > 4096 ||
+        (mfft & (mfft - 1)))
+        return fail(nullptr, SDRB_ERR_ARG, "stft: mfft must be a power of two in 4..4096 and >= nperseg");
+    int rc = need_device(device);
+    if (rc) return rc;
+    DevBuf d_y, d_s, d_w, d_o;
+    CK(nullptr, d_y.alloc((size_t)n * sizeof(double2)));
+    CK(nullptr, d_w.alloc((size_t)nperseg * sizeof(double)));
+    CK(nullptr, d_o.alloc((size_t)mfft * p_num * sizeof(double)));
+    CK(nullptr, cudaMemcpy(d_y.p, y, (size_t)n * sizeof(double2), cudaMemcpyHostToDevice));
+    CK(nullptr, cudaMemcpy(d_w.p, win, (size_t)nperseg * sizeof(double), cudaMemcpyHostToDevice));
+    const double2 *sh = nullptr;
+    if (shift) {
+        CK(nullptr, d_s.alloc((size_t)n * sizeof(double2)));
+        CK(nullptr, cudaMemcpy(d_s.p, shift, (size_t)n * sizeof(double2), cudaMemcpyHostToDevice));
+        sh = d_s.as<double2>();
+    }
+    const int W = 4;
+    const size_t smem = ((size_t)(mfft >> 1) + (size_t)W * 2 * mfft) * sizeof(double2);
+    CK(nullptr, cudaFuncSetAttribute(k_stft_db, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const unsigned grid = (unsigned)std::min(148 * 2, (p_num + W - 1) / W);
+    k_stft_db<<<grid, 32 * W, smem>>>(d_y.as<double2>(), sh, d_w.as<double>(), d_o.as<double>(), n, nperseg, hop,
+                                      nperseg / 2, mfft, p_num);
+    CK(nullptr, cudaGetLastError());
+    CK(nullptr, cudaDeviceSynchronize());
+    CK(nullptr, cudaMemcpy(out, d_o.p, (size_t)mfft * p_num * sizeof(double), cudaMemcpyDeviceToHost));
     return SDRB_OK;
 }
 

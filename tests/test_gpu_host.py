@@ -276,3 +276,67 @@ def test_cli_smooth_output_matches_savgol_per_chunk(tmp_path, window):
     M = 512
     ref = np.concatenate([savgol_filter(g[c * M:(c + 1) * M], window, 3) for c in range(g.size // M)])
     assert got.shape == ref.shape and rel_err(got, ref) < TOL
+
+
+def _db_close(got, want, floor_db, tol):
+    """Decibel-type outputs: compare where the reference is above `floor_db` below its maximum (a
+    bin that is numerically zero has an ill-conditioned logarithm), and the linear values everywhere."""
+    assert got.shape == want.shape
+    top = want.max()
+    big = want > top - floor_db
+    assert np.abs(got[big] - want[big]).max() <= tol
+    return np.abs(got[big] - want[big]).max()
+
+
+@pytest.mark.parametrize('n', [8192, 16384, 32768, 65536])
+def test_power_spectrum_feed_matches_the_plot_arithmetic(n):
+    """SpectrumAnalyzerPlot.update (spectrum_analyzer_plot.py:75-92) on the device:
+    log10(|fftshift(fftn(y*shift, norm='forward'))|^2) and the frequency axis."""
+    from scipy.fft import fftfreq, fftshift
+    from sdrterm_b200.plots import SpectrumFeed, powerSpectrum
+    rng = np.random.default_rng(n)
+    fs, center = 1_024_000, 15_000
+    t = np.arange(n)
+    y = 0.05 * (rng.standard_normal(n) + 1j * rng.standard_normal(n)) + np.exp(2j * np.pi * 0.11 * t) + 0.3
+    feed = SpectrumFeed(fs, center=center)
+    freq, amp = feed.update(y)
+    want = orc.power_spectrum(y, orc.plot_shift(center, fs, n))
+    assert np.array_equal(freq, fftshift(fftfreq(n, 1 / fs)))
+    # linear power, relative to the strongest bin: 1e-12; decibels down to 100 dB below it: 1e-9
+    assert np.abs(10 ** amp - 10 ** want).max() <= 1e-12 * (10 ** want).max()
+    _db_close(amp, want, 10.0, 1e-9)
+    # batch of rows, no shift
+    rows = np.stack([y, y[::-1], 2 * y])
+    got = powerSpectrum(rows)
+    for r in range(3):
+        _db_close(got[r], orc.power_spectrum(rows[r], None), 10.0, 1e-9)
+
+
+def test_power_spectrum_feed_rejects_what_it_cannot_do():
+    from sdrterm_b200._native import SdrbError
+    from sdrterm_b200.plots import powerSpectrum
+    with pytest.raises(SdrbError):
+        powerSpectrum(np.ones(1000, dtype=np.complex128))          # not a power of two
+    with pytest.raises(ValueError):
+        powerSpectrum(np.ones(1024, dtype=np.complex128), shift=np.ones(8))
+
+
+@pytest.mark.parametrize('n', [1000, 16384, 32768])
+def test_waterfall_feed_matches_short_time_fft(n):
+    """WaterfallPlot.update (waterfall_plot.py:90-99) on the device against SciPy's
+    ShortTimeFFT itself (the reference's call) and the oracle's restatement."""
+    from scipy.signal import ShortTimeFFT
+    from sdrterm_b200.plots import WaterfallFeed
+    rng = np.random.default_rng(n)
+    fs, center = 1_024_000, -20_000
+    t = np.arange(n)
+    y = 0.1 * (rng.standard_normal(n) + 1j * rng.standard_normal(n)) + np.exp(2j * np.pi * (0.05 + 1e-6 * t) * t)
+    feed = WaterfallFeed(fs, center=center)
+    img = feed.update(y)
+    S = ShortTimeFFT.from_window(('kaiser', 5), fs, 256, 128, mfft=1024, fft_mode='centered', scale_to='magnitude',
+                                 phase_shift=None)
+    sh = orc.plot_shift(center, fs, n)
+    want = 10. * np.log10(abs(S.stft(y * sh)))
+    assert img.shape == want.shape == (1024, n // 128 + 1 if n % 128 == 0 else S.p_max(n))
+    _db_close(img, want, 60.0, 1e-8)
+    _db_close(img, orc.stft_db(y, sh, S.win, S.hop, 1024, S.p_max(n)), 60.0, 1e-8)

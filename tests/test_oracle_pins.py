@@ -123,3 +123,27 @@ def test_stale_tail_and_chunk_count():
     ch = orc.Chain(**kw)
     out = ch.run(body)
     assert out.shape == (1, 4 * 512)
+
+
+def test_plot_feed_restatements_match_scipy():
+    """the oracle's slice-by-slice STFT equals scipy.signal.ShortTimeFFT.stft with the
+    reference's parameters (waterfall_plot.py:44-51) exactly, its slice count equals SciPy's, and
+    the power spectrum is the reference's expression (spectrum_analyzer_plot.py:77-82)."""
+    from scipy.fft import fftn, fftshift
+    from scipy.signal import ShortTimeFFT
+    rng = np.random.default_rng(5)
+    fs = 1_024_000
+    S = ShortTimeFFT.from_window(('kaiser', 5), fs, 256, 128, mfft=1024, fft_mode='centered', scale_to='magnitude',
+                                 phase_shift=None)
+    for n in (128, 129, 1000, 8192, 32768):
+        assert orc.stft_geometry(n) == (-S.m_num_mid, S.p_max(n) - S.p_min) and S.p_min == 0
+    y = rng.standard_normal(4096) + 1j * rng.standard_normal(4096)
+    sh = orc.plot_shift(15000, fs, y.size)
+    want = 10. * np.log10(abs(S.stft(y * sh)))
+    got = orc.stft_db(y, sh, S.win, S.hop, 1024, S.p_max(y.size))
+    assert got.shape == want.shape == (1024, 33)
+    np.testing.assert_allclose(got, want, rtol=0, atol=1e-9)
+    assert np.array_equal(sh, np.exp(-2j * np.pi * (15000 / fs) * np.arange(y.size)))
+    z = np.array([y * sh])
+    amp = abs(fftshift(fftn(z, norm='forward')))
+    assert np.array_equal(orc.power_spectrum(y, sh), np.log10(amp * amp)[0])
