@@ -7,6 +7,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <mutex>
 #include <vector>
 
 #include "../../include/sdrterm_b200.h"
@@ -916,6 +917,43 @@ struct DevBuf {
     template <typename T> T *as() const { return static_cast<T *>(p); }
 };
 
+// The plot feeds are called once per displayed frame on a few hundred kilobytes: their device and
+// page-locked staging buffers are kept between calls (cudaMalloc / cudaFree cost more than the
+// transform).  One set per device and slot, grown on demand, never shrunk; calls are serialised.
+struct FeedWorkspace {
+    static constexpr int kSlots = 6, kMaxDev = 16;
+    void *dev[kMaxDev][kSlots] = {};
+    size_t dev_cap[kMaxDev][kSlots] = {};
+    void *host[kMaxDev][2] = {};
+    size_t host_cap[kMaxDev][2] = {};
+    std::mutex mu;
+    cudaError_t get(int device, int slot, size_t bytes, void **out)
+    {
+        if (dev_cap[device][slot] < bytes) {
+            if (dev[device][slot]) cudaFree(dev[device][slot]);
+            dev[device][slot] = nullptr; dev_cap[device][slot] = 0;
+            cudaError_t e = cudaMalloc(&dev[device][slot], bytes);
+            if (e != cudaSuccess) return e;
+            dev_cap[device][slot] = bytes;
+        }
+        *out = dev[device][slot];
+        return cudaSuccess;
+    }
+    cudaError_t get_host(int device, int slot, size_t bytes, void **out)
+    {
+        if (host_cap[device][slot] < bytes) {
+            if (host[device][slot]) cudaFreeHost(host[device][slot]);
+            host[device][slot] = nullptr; host_cap[device][slot] = 0;
+            cudaError_t e = cudaHostAlloc(&host[device][slot], bytes, cudaHostAllocDefault);
+            if (e != cudaSuccess) return e;
+            host_cap[device][slot] = bytes;
+        }
+        *out = host[device][slot];
+        return cudaSuccess;
+    }
+};
+FeedWorkspace g_feed;
+
 int need_device(int device)
 {
     int ndev = 0;
@@ -1026,20 +1064,26 @@ int sdrb_power_spectrum(int device, const double *y, const double *shift, int N,
     if (!y || !out || batch < 1 || N < 4 || (N & (N - 1))) return fail(nullptr, SDRB_ERR_ARG, "power spectrum: N must be a power of two >= 4");
     int rc = need_device(device);
     if (rc) return rc;
-    const size_t nb = (size_t)batch * N * sizeof(double2);
-    DevBuf d_a, d_b, d_s, d_o;
-    CK(nullptr, d_a.alloc(nb));
-    CK(nullptr, d_b.alloc(nb));
-    CK(nullptr, d_o.alloc((size_t)batch * N * sizeof(double)));
-    CK(nullptr, cudaMemcpy(d_a.p, y, nb, cudaMemcpyHostToDevice));
+    if (device >= FeedWorkspace::kMaxDev) return fail(nullptr, SDRB_ERR_ARG, "bad device ordinal");
+    std::lock_guard<std::mutex> lock(g_feed.mu);
+    const size_t nb = (size_t)batch * N * sizeof(double2), nout = (size_t)batch * N * sizeof(double);
+    void *pa, *pb, *ps = nullptr, *po, *hin, *hout;
+    CK(nullptr, g_feed.get(device, 0, nb, &pa));
+    CK(nullptr, g_feed.get(device, 1, nb, &pb));
+    CK(nullptr, g_feed.get(device, 2, nout, &po));
+    CK(nullptr, g_feed.get_host(device, 0, nb + (size_t)N * sizeof(double2), &hin));
+    CK(nullptr, g_feed.get_host(device, 1, nout, &hout));
+    // pageable -> page-locked on the host, then asynchronous copies and kernels on one stream
+    std::memcpy(hin, y, nb);
+    CK(nullptr, cudaMemcpyAsync(pa, hin, nb, cudaMemcpyHostToDevice, 0));
     const double2 *sh = nullptr;
     if (shift) {
-        // one NCO vector for every row of the batch when batch > 1 shares it: the caller passes N values
-        CK(nullptr, d_s.alloc((size_t)N * sizeof(double2)));
-        CK(nullptr, cudaMemcpy(d_s.p, shift, (size_t)N * sizeof(double2), cudaMemcpyHostToDevice));
-        sh = d_s.as<double2>();
+        CK(nullptr, g_feed.get(device, 3, (size_t)N * sizeof(double2), &ps));
+        std::memcpy(static_cast<char *>(hin) + nb, shift, (size_t)N * sizeof(double2));
+        CK(nullptr, cudaMemcpyAsync(ps, static_cast<char *>(hin) + nb, (size_t)N * sizeof(double2), cudaMemcpyHostToDevice, 0));
+        sh = static_cast<const double2 *>(ps);
     }
-    double2 *src = d_a.as<double2>(), *dst = d_b.as<double2>();
+    double2 *src = static_cast<double2 *>(pa), *dst = static_cast<double2 *>(pb);
     const dim3 grid4((unsigned)std::min(148 * 8, (N / 4 + 255) / 256), (unsigned)batch);
     int Ns = 1;
     for (; Ns * 4 <= N; Ns <<= 2) {
@@ -1051,10 +1095,11 @@ int sdrb_power_spectrum(int device, const double *y, const double *shift, int N,
         k_gfft2<<<grid4, 256>>>(src, dst, sh, N, Ns);
         std::swap(src, dst);
     }
-    k_spectrum_db<<<dim3((unsigned)std::min(148 * 8, (N + 255) / 256), (unsigned)batch), 256>>>(src, d_o.as<double>(), N);
+    k_spectrum_db<<<dim3((unsigned)std::min(148 * 8, (N + 255) / 256), (unsigned)batch), 256>>>(src, static_cast<double *>(po), N);
     CK(nullptr, cudaGetLastError());
-    CK(nullptr, cudaDeviceSynchronize());
-    CK(nullptr, cudaMemcpy(out, d_o.p, (size_t)batch * N * sizeof(double), cudaMemcpyDeviceToHost));
+    CK(nullptr, cudaMemcpyAsync(hout, po, nout, cudaMemcpyDeviceToHost, 0));
+    CK(nullptr, cudaStreamSynchronize(0));
+    std::memcpy(out, hout, nout);
     return SDRB_OK;
 }
 
@@ -1066,27 +1111,41 @@ int sdrb_stft_db(int device, const double *y, const double *shift, int n, const 
         return fail(nullptr, SDRB_ERR_ARG, "stft: mfft must be a power of two in 4..4096 and >= nperseg");
     int rc = need_device(device);
     if (rc) return rc;
-    DevBuf d_y, d_s, d_w, d_o;
-    CK(nullptr, d_y.alloc((size_t)n * sizeof(double2)));
-    CK(nullptr, d_w.alloc((size_t)nperseg * sizeof(double)));
-    CK(nullptr, d_o.alloc((size_t)mfft * p_num * sizeof(double)));
-    CK(nullptr, cudaMemcpy(d_y.p, y, (size_t)n * sizeof(double2), cudaMemcpyHostToDevice));
-    CK(nullptr, cudaMemcpy(d_w.p, win, (size_t)nperseg * sizeof(double), cudaMemcpyHostToDevice));
+    if (device >= FeedWorkspace::kMaxDev) return fail(nullptr, SDRB_ERR_ARG, "bad device ordinal");
+    std::lock_guard<std::mutex> lock(g_feed.mu);
+    const size_t ny = (size_t)n * sizeof(double2), nw = (size_t)nperseg * sizeof(double), nout = (size_t)mfft * p_num * sizeof(double);
+    void *py, *ps = nullptr, *pw, *po, *hin, *hout;
+    CK(nullptr, g_feed.get(device, 0, ny, &py));
+    CK(nullptr, g_feed.get(device, 4, nw, &pw));
+    CK(nullptr, g_feed.get(device, 5, nout, &po));
+    CK(nullptr, g_feed.get_host(device, 0, 2 * ny + nw, &hin));
+    CK(nullptr, g_feed.get_host(device, 1, nout, &hout));
+    char *h8 = static_cast<char *>(hin);
+    std::memcpy(h8, y, ny);
+    std::memcpy(h8 + 2 * ny, win, nw);
+    CK(nullptr, cudaMemcpyAsync(py, h8, ny, cudaMemcpyHostToDevice, 0));
+    CK(nullptr, cudaMemcpyAsync(pw, h8 + 2 * ny, nw, cudaMemcpyHostToDevice, 0));
     const double2 *sh = nullptr;
     if (shift) {
-        CK(nullptr, d_s.alloc((size_t)n * sizeof(double2)));
-        CK(nullptr, cudaMemcpy(d_s.p, shift, (size_t)n * sizeof(double2), cudaMemcpyHostToDevice));
-        sh = d_s.as<double2>();
+        CK(nullptr, g_feed.get(device, 3, ny, &ps));
+        std::memcpy(h8 + ny, shift, ny);
+        CK(nullptr, cudaMemcpyAsync(ps, h8 + ny, ny, cudaMemcpyHostToDevice, 0));
+        sh = static_cast<const double2 *>(ps);
     }
     const int W = 4;
     const size_t smem = ((size_t)(mfft >> 1) + (size_t)W * 2 * mfft) * sizeof(double2);
-    CK(nullptr, cudaFuncSetAttribute(k_stft_db, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    static size_t smem_set = 0;
+    if (smem > smem_set) {
+        CK(nullptr, cudaFuncSetAttribute(k_stft_db, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        smem_set = smem;
+    }
     const unsigned grid = (unsigned)std::min(148 * 2, (p_num + W - 1) / W);
-    k_stft_db<<<grid, 32 * W, smem>>>(d_y.as<double2>(), sh, d_w.as<double>(), d_o.as<double>(), n, nperseg, hop,
-                                      nperseg / 2, mfft, p_num);
+    k_stft_db<<<grid, 32 * W, smem>>>(static_cast<const double2 *>(py), sh, static_cast<const double *>(pw), static_cast<double *>(po),
+                                      n, nperseg, hop, nperseg / 2, mfft, p_num);
     CK(nullptr, cudaGetLastError());
-    CK(nullptr, cudaDeviceSynchronize());
-    CK(nullptr, cudaMemcpy(out, d_o.p, (size_t)mfft * p_num * sizeof(double), cudaMemcpyDeviceToHost));
+    CK(nullptr, cudaMemcpyAsync(hout, po, nout, cudaMemcpyDeviceToHost, 0));
+    CK(nullptr, cudaStreamSynchronize(0));
+    std::memcpy(out, hout, nout);
     return SDRB_OK;
 }
 
