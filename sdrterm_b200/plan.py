@@ -298,7 +298,7 @@ def build_plan(fs: int, enc: str, dec: int, rows_hz, *, simo: bool = False, swap
     for k in range(4):
         a0, a1 = min(k * RL, Hq), min((k + 1) * RL, Hq)
         run_len[k] = a1 - a0
-        run_len[7 - k] = (q - a0) - max(q - a1, Hq)
+        run_len[7 - k] = max(0, (q - a0) - max(q - a1, Hq))   # (a lane past the last pair of an odd block owns nothing)
     assert run_len.sum() == q
     lam_run = np.array([float(mlam ** int(v)) for v in run_len])
     norm = None

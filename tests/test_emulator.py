@@ -58,3 +58,25 @@ def test_iq_decoupling_constants():
     assert abs(abs(pl.gamma[0]) - 1) < 0.02
     pl = build_plan(1_024_000, 'h', 64, [200_000], correct_iq=True, demod='fm', omega_out=5000)
     assert abs(pl.gamma[0]) < 1e-6                      # far in the stop band
+
+
+@pytest.mark.parametrize('enc,q,demod,iq,norm,center', [
+    ('h', 5, 'am', True, False, 30000), ('B', 25, 'am', True, True, 0), ('f', 63, 'fm', False, False, -20000),
+    ('b', 3, 're', True, False, 10000)])
+def test_odd_decimation_factors(enc, q, demod, iq, norm, center):
+    """An odd block has a middle sample without a mirror and, for the lane past the last pair, an
+    empty descending run (plan.run_len must not go negative): the reference takes any `-d`."""
+    import signals
+    isz = {'b': 1, 'B': 1, 'h': 2, 'f': 4}[enc]
+    n = 2 * (131072 // (2 * isz))
+    body = signals.generic_bytes(enc, n, 17 + q, 1_000_000, center or 40_000, big_endian=False)
+    kw = dict(fs=1_000_000, enc=enc, center=center, dec=q, demod=demod, omega_out=4000, correct_iq=iq,
+              vfos=None, simo=False, normalize=norm, swap=False, big_endian=None)
+    pl = _plan(kw)
+    assert pl.run_len.sum() == q and (pl.run_len >= 0).all()
+    out, ys, off = emu.emu_stream(pl, body)
+    ch = orc.Chain(**kw)
+    ref = ch.run(body)
+    assert out.shape == ref.shape and rel_err(out, ref) < 1e-10
+    if iq:
+        assert abs(off - ch._off[0]) <= 1e-9 * max(1.0, abs(ch._off[0]))

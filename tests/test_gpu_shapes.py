@@ -225,3 +225,35 @@ def test_file_sharded_entry_point_single_process(tmp_path):
               vfos=None, simo=False, normalize=False, swap=False, big_endian=None)
     ref = orc.Chain(**kw).run(body)
     assert out.shape == ref.shape and rel_err(out, ref) < TOL
+
+
+@pytest.mark.parametrize('enc,q,demod,iq,norm,center', [
+    ('h', 5, 'am', True, False, 30000),      # odd block: a middle sample without a mirror
+    ('B', 25, 'am', True, True, 0),          # odd, normalised input (a normalised zero is not zero), no NCO
+    ('f', 63, 'fm', False, False, -20000),   # odd, float32, 4*RL > ceil(q/2): empty pair slots
+    ('b', 3, 're', True, False, 10000),      # the smallest odd block
+    ('i', 50, 'fm', True, False, 15000),     # even but ragged (rem != 0), 32-bit integers
+    ('d', 10, 'am', False, False, 5000),     # float64 samples (16 bytes per sample)
+])
+def test_fp64_block_kernel_odd_and_ragged_blocks(enc, q, demod, iq, norm, center):
+    """k_main keeps the raw tile in fragment order (sample j beside its mirror q-1-j):
+    odd q leaves the middle sample alone in its slot, q with 4*ceil(ceil(q/2)/4) > ceil(q/2) leaves
+    whole slots empty, and a ragged chunk ends in a partial block.  None of the golden cases has an
+    odd q; the oracle handles any."""
+    from gpu_util import plan_for
+    from sdrterm_b200.engine import Engine
+    isz = {'b': 1, 'B': 1, 'h': 2, 'i': 4, 'f': 4, 'd': 8}[enc]
+    n = 3 * (CB // (2 * isz))
+    body = signals.generic_bytes(enc, n, 17 + q, 1_000_000, center or 40_000, big_endian=False)
+    kw = dict(fs=1_000_000, enc=enc, center=center, dec=q, demod=demod, omega_out=4000, correct_iq=iq,
+              vfos=None, simo=False, normalize=norm, swap=False, big_endian=None)
+    pl = plan_for(kw)
+    with Engine(pl, max_chunks=3, keep_decimated=True) as eng:
+        assert eng.tc is None                                   # none of these shapes is a GEMM shape
+        out = eng.process(body)
+        off = eng.iq_state
+    ch = orc.Chain(**kw)
+    ref = ch.run(body)
+    assert out.shape == ref.shape and rel_err(out, ref) < TOL
+    if iq:
+        assert abs(off - ch._off[0]) <= 1e-9 * max(1.0, abs(ch._off[0]))
