@@ -29,9 +29,12 @@ __host__ __device__ inline size_t finish_warp_bytes(int M)
 {
     const int nt = M / SDRB_TB;
     size_t b = (size_t)(nt + 1) * 16 * sizeof(double2);      // carry; the second FFT buffer fb aliases it (carry is dead by then)
-    b += (size_t)(M / 4) * sizeof(double2);                  // fa (addv aliases it)
-    b += (size_t)(M + 32) * sizeof(double);                  // zrow, one pad per segment (seqA, seqB alias its head)
-    return b;
+    size_t rest = (size_t)(M / 4) * sizeof(double2);         // fa
+    rest += (size_t)(M + 32) * sizeof(double);               // zrow, one pad per segment
+    // the phase-1 scratch overlays fa + zrow: addv [nt][16], then seqA[32], seqB[32] -- for rows of
+    // 128 outputs and fewer it is the larger of the two
+    const size_t scratch = ((size_t)nt * 16 + 64) * sizeof(double2);
+    return b + (rest > scratch ? rest : scratch);
 }
 __host__ __device__ inline size_t finish_smem_bytes(int M, int edge)
 {

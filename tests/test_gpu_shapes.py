@@ -257,3 +257,69 @@ def test_fp64_block_kernel_odd_and_ragged_blocks(enc, q, demod, iq, norm, center
     assert out.shape == ref.shape and rel_err(out, ref) < TOL
     if iq:
         assert abs(off - ch._off[0]) <= 1e-9 * max(1.0, abs(ch._off[0]))
+
+
+def _sweep_cases():
+    """A fixed pseudo-random sweep over what the CLI accepts: encoding x byte order x decimation x
+    demodulation x --correct-iq x --normalize-input x centre, single VFO and small banks."""
+    rng = np.random.default_rng(20261018)
+    qs = [6, 7, 9, 12, 20, 31, 33, 48, 100, 127, 130, 200, 256]
+    out = []
+    for i in range(16):
+        enc = 'bBhHiIfd'[i % 8]
+        q = int(qs[int(rng.integers(len(qs)))])
+        demod = ['fm', 'am', 're', 'im'][int(rng.integers(4))]
+        if demod == 'fm' and q < 8:
+            demod = 'am'
+        iq = bool(rng.integers(2))
+        norm = bool(rng.integers(2)) and enc in 'bBhHiI'
+        swap = bool(rng.integers(2)) and enc not in 'bB'
+        center = int(rng.integers(-200, 200)) * 1000
+        simo = i % 5 == 4
+        out.append((enc, q, demod, iq, norm, swap, center, simo))
+    return out
+
+
+@pytest.mark.parametrize('enc,q,demod,iq,norm,swap,center,simo', _sweep_cases())
+def test_option_sweep_against_the_oracle(enc, q, demod, iq, norm, swap, center, simo):
+    from gpu_util import plan_for
+    from sdrterm_b200.engine import Engine
+    isz = {'b': 1, 'B': 1, 'h': 2, 'H': 2, 'i': 4, 'I': 4, 'f': 4, 'd': 8}[enc]
+    n = 2 * (CB // (2 * isz))
+    body = signals.generic_bytes(enc, n, 100 + q, 1_000_000, center or 40_000, big_endian=swap)
+    kw = dict(fs=1_000_000, enc=enc, center=0 if simo else center, dec=q, demod=demod, omega_out=min(4000, 1_000_000 // q // 5), correct_iq=iq,
+              vfos='-30000,25000,110000' if simo else None, simo=simo, normalize=norm, swap=swap, big_endian=None)
+    pl = plan_for(kw)
+    with Engine(pl, max_chunks=2) as eng:
+        out = eng.process(body)
+        off = eng.iq_state
+    ch = orc.Chain(**kw)
+    ref = ch.run(body)
+    got = np.asarray(out, dtype=np.float64)
+    assert got.shape == ref.shape
+    for r in range(pl.R):
+        assert rel_err(got[r], ref[r]) < TOL, (r, rel_err(got[r], ref[r]))
+    if iq:
+        assert abs(off - ch._off[0]) <= 1e-9 * max(1.0, abs(ch._off[0]))
+
+
+@pytest.mark.parametrize('enc,q,demod', [('H', 256, 'fm'), ('I', 128, 'im'), ('i', 256, 'am'), ('d', 128, 'fm'), ('h', 128, 'fm')])
+def test_fused_finish_kernel_on_short_rows(enc, q, demod):
+    """k_finish with rows of 64 / 128 / 256 outputs per chunk (4-byte and wider samples at large
+    -d): its phase-1 scratch overlays the FFT buffer and the output row, and for rows of 128 and
+    fewer the scratch is the larger of the two (the per-warp region was sized for the row only:
+    neighbouring warps raced).  Many chunks, so that all warps of a CTA are busy."""
+    from gpu_util import plan_for
+    from sdrterm_b200.engine import Engine
+    isz = {'h': 2, 'H': 2, 'i': 4, 'I': 4, 'd': 8}[enc]
+    nch = 24
+    n = nch * (CB // (2 * isz))
+    body = signals.generic_bytes(enc, n, 7 + q, 1_000_000, 30_000, big_endian=False)
+    kw = dict(fs=1_000_000, enc=enc, center=30000, dec=q, demod=demod, omega_out=min(4000, 1_000_000 // q // 5), correct_iq=True,
+              vfos=None, simo=False, normalize=False, swap=False, big_endian=None)
+    pl = plan_for(kw)
+    assert pl.M in (64, 128, 256) and pl.rem == 0
+    with Engine(pl, max_chunks=nch) as eng:
+        out = eng.process(body)
+    ref = orc.Chain(**kw).run(body)
+    assert out.shape == ref.shape and rel_err(out, ref) < TOL
