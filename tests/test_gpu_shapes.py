@@ -323,3 +323,58 @@ def test_fused_finish_kernel_on_short_rows(enc, q, demod):
         out = eng.process(body)
     ref = orc.Chain(**kw).run(body)
     assert out.shape == ref.shape and rel_err(out, ref) < TOL
+
+
+def _tc_sweep_cases():
+    """The shapes the tensor-core front end takes (8-bit at -d 64 / 128, 16-bit at -d 32 / 64),
+    crossed with byte order, demodulation, --correct-iq, centre and bank width."""
+    rng = np.random.default_rng(7)
+    shapes = [('b', 64), ('b', 128), ('B', 64), ('B', 128), ('h', 32), ('h', 64), ('H', 32), ('H', 64)]
+    out = []
+    for i in range(12):
+        enc, q = shapes[i % 8]
+        demod = ['fm', 'am', 're', 'im'][int(rng.integers(4))]
+        iq = bool(rng.integers(2))
+        swap = bool(rng.integers(2)) and enc in 'hH'
+        center = int(rng.integers(-300, 300)) * 1000
+        nv = [0, 0, 2, 7, 31][int(rng.integers(5))]
+        out.append((enc, q, demod, iq, swap, center, nv))
+    return out
+
+
+@pytest.mark.parametrize('enc,q,demod,iq,swap,center,nv', _tc_sweep_cases())
+def test_tensor_core_option_sweep_against_the_oracle(enc, q, demod, iq, swap, center, nv):
+    from gpu_util import plan_for
+    from sdrterm_b200.engine import Engine
+    isz = 1 if enc in 'bB' else 2
+    nch = 3
+    n = nch * (CB // (2 * isz))
+    vfos = ','.join(str(int(v)) for v in np.linspace(-400_000, 400_000, nv)) if nv else None
+    if nv and demod == 'fm':
+        # the phase of a row without a carrier is ill-conditioned (|d phi| = |dy| / |y| with y the
+        # stop-band residue): give every row of the bank its own carrier
+        rng = np.random.default_rng(300 + q + nv)
+        kind, lo, hi, amp, dc = {'b': ('i1', -128, 127, 3.5, 0.0), 'B': ('u1', 0, 255, 3.5, 127.5),
+                                 'h': ('i2', -32768, 32767, 900.0, 0.0), 'H': ('u2', 0, 65535, 900.0, 32768.0)}[enc]
+        z = np.full(n, dc * (1 + 1j), dtype=np.complex128)
+        for i, f in enumerate([int(v) for v in np.linspace(-400_000, 400_000, nv)] + [0]):
+            z += signals._fm_carrier(n, 1_000_000, f, 600 + 25 * i, 1_500, amp, phase0=0.2 * i)
+        z = z + amp * 0.05 * (rng.normal(0, 1, n) + 1j * rng.normal(0, 1, n))
+        body = signals._interleave(z, np.dtype(kind).newbyteorder('>' if swap else '<'), lo, hi).tobytes()
+    else:
+        body = signals.generic_bytes(enc, n, 300 + q + nv, 1_000_000, center or 40_000, big_endian=swap)
+    kw = dict(fs=1_000_000, enc=enc, center=0 if nv else center, dec=q, demod=demod, omega_out=3000, correct_iq=iq,
+              vfos=vfos, simo=bool(nv), normalize=False, swap=swap, big_endian=None)
+    pl = plan_for(kw)
+    with Engine(pl, max_chunks=nch) as eng:
+        assert eng.tc is not None and pl.R == (nv + 1 if nv else 1)
+        out = eng.process(body)
+        off = eng.iq_state
+    ch = orc.Chain(**kw)
+    ref = ch.run(body)
+    got = np.asarray(out, dtype=np.float64)
+    assert got.shape == ref.shape
+    for r in range(pl.R):
+        assert rel_err(got[r], ref[r]) < TOL, (r, rel_err(got[r], ref[r]))
+    if iq:
+        assert abs(off - ch._off[0]) <= 1e-9 * max(1.0, abs(ch._off[0]))
