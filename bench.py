@@ -397,6 +397,19 @@ def run_cuda_arm(args):
         if world > 1:
             dist.barrier()
 
+    _align = [None]
+
+    def align_on_device():
+        """N > 1: a one-word all-reduce on the stream right before the start event.  The ranks'
+        host threads leave the barrier up to a millisecond apart; without this the early ranks'
+        start events precede the late rank's first kernel, and the skew is charged to a timed
+        window that is only a few milliseconds long.  With it every rank's start event sits at the
+        same point of the device timeline; the timed region itself is unchanged (K steps)."""
+        if world > 1:
+            if _align[0] is None:
+                _align[0] = torch.zeros(1, dtype=torch.int32, device=dev)
+            dist.all_reduce(_align[0])
+
     def max_over_ranks(v: float) -> float:
         if world == 1:
             return v
@@ -467,6 +480,7 @@ def run_cuda_arm(args):
     l0 = eng.launches
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ktimes = []
+    align_on_device()
     ev0.record()
     for _ in range(args.steps):
         step_device()
@@ -560,6 +574,7 @@ def run_cuda_arm(args):
         go(3)
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        align_on_device()
         e0.record()
         tc0 = time.perf_counter()
         go(steps)
