@@ -209,7 +209,8 @@ class RowShardedBank:
                 g = dist.new_group(list(range(t * self.row_groups, (t + 1) * self.row_groups)))
                 if t == self.tg:
                     self.group = g
-            dev = torch.device('cuda', device)
+            # (CPU tensors only when there is no CUDA device at all: the gloo tests of this host logic)
+            dev = torch.device('cuda', device) if torch.cuda.is_available() else torch.device('cpu')
             ranks = list(range(self.leader, self.leader + self.row_groups))
             nbytes = max_chunks * self.chunk_bytes
             want = os.environ.get('SDRB_BCAST', 'peer')

@@ -196,3 +196,71 @@ def test_run_file_sharded_hands_every_rank_its_chunks_with_the_stale_tail(tmp_pa
             assert out.shape[1] % 512 == 0
         allb = np.concatenate(got) if got else np.zeros(0, dtype=np.uint8)
         assert np.array_equal(allb, chunked(body).reshape(-1)), (world, nbytes)
+
+
+def _bank_worker(rank, world, port, q):
+    """RowShardedBank (the product class) on two gloo ranks with a recording engine: the grid, the
+    row slices and the double-buffered hand-over of the leader's raw batches."""
+    for p in (ROOT, os.path.join(ROOT, 'tests')):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    import ctypes
+    from sdrterm_b200 import multigpu
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port), SDRB_BCAST='nccl')
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+
+    class Rec:
+        seen = []
+
+        def __init__(self, plan, max_chunks=1, device=0, **kw):
+            self.plan, self.tc = plan, None
+
+        def reserve_sms(self, n):
+            pass
+
+        def process_device(self, raw_ptr, nchunks, out_ptr, stream=0):
+            nb = nchunks * self.plan.chunk_bytes
+            Rec.seen.append(bytes((ctypes.c_uint8 * nb).from_address(raw_ptr)))
+
+        def close(self):
+            pass
+
+    try:
+        multigpu.Engine = Rec
+        rows = [-200_000, -100_000, 100_000, 200_000, 0]
+        bank = multigpu.RowShardedBank(2_400_000, 'h', 64, rows, 2, 0, dist, torch, min_rows=2, demod='fm', swap=True,
+                                       omega_out=5000)
+        rng = np.random.default_rng(11)
+        data = [rng.integers(0, 256, 2 * CB, dtype=np.uint8) for _ in range(5)]
+        batches = [torch.from_numpy(d.copy()) if rank == bank.leader else torch.empty(2 * CB, dtype=torch.uint8) for d in data]
+        outs = [torch.empty((len(bank.rows), 2 * bank.M), dtype=torch.float64) for _ in data]
+        bank.run(batches, 2, outs)
+        bank.run(batches[:2], 1, outs[:2])                       # a shorter batch through the same buffers
+        ok = [Rec.seen[i] == data[i].tobytes() for i in range(5)] + [Rec.seen[5 + i] == data[i][:CB].tobytes() for i in range(2)]
+        q.put((rank, bank.row_groups, bank.time_groups, bank.lo, bank.hi, bank.transport, ok, len(Rec.seen)))
+        dist.barrier()
+    except BaseException as e:
+        q.put((rank, repr(e)))
+        raise
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+def test_row_sharded_bank_two_rank_gloo():
+    world, port = 2, _free_port()
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_bank_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=240) for _ in range(world)]
+    assert all(len(r) == 8 for r in res), res
+    res.sort(key=lambda x: x[0])
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    assert [(r[1], r[2]) for r in res] == [(2, 1), (2, 1)]
+    assert [(r[3], r[4]) for r in res] == [(0, 3), (3, 5)]                 # balanced row slices, larger share first
+    assert all(r[5] == 'nccl' for r in res)                                  # the collective transport (gloo here)
+    assert all(all(r[6]) and r[7] == 7 for r in res), res                    # every rank saw the leader's bytes, in order
