@@ -192,6 +192,12 @@ class RowShardedBank:
         if min_rows is None:
             min_rows = 8
         self.row_groups, self.time_groups = bank_grid(len(self.rows_all), self.world, min_rows)
+        if plan_kw.get('correct_iq') and self.time_groups > 1:
+            # the corrector's offset runs through the whole stream (read_file.py:53): time groups
+            # would each start from their own state.  TimeShardedChain has the hand-off; a bank does
+            # not (BASELINE configs 3 and 4 run without --correct-iq), so it must not pretend to.
+            raise NotImplementedError('--correct-iq on a bank spread over time groups needs the IQ-offset hand-off: '
+                                      f'use min_rows <= {max(1, len(self.rows_all) // self.world)} (row groups only)')
         self.tg, self.rg = divmod(self.rank, self.row_groups)
         self.lo, self.hi = sharding.row_shard(len(self.rows_all), self.row_groups, self.rg)
         self.rows = self.rows_all[self.lo:self.hi]

@@ -264,3 +264,20 @@ def test_row_sharded_bank_two_rank_gloo():
     assert [(r[3], r[4]) for r in res] == [(0, 3), (3, 5)]                 # balanced row slices, larger share first
     assert all(r[5] == 'nccl' for r in res)                                  # the collective transport (gloo here)
     assert all(all(r[6]) and r[7] == 7 for r in res), res                    # every rank saw the leader's bytes, in order
+
+
+def test_bank_refuses_iq_correction_across_time_groups():
+    """A bank on time groups has no IQ-offset hand-off: it must say so instead of restarting the
+    corrector in every group."""
+    from sdrterm_b200 import multigpu
+
+    class FakeDist:
+        def get_world_size(self):
+            return 8
+
+        def get_rank(self):
+            return 3
+
+    with pytest.raises(NotImplementedError):
+        multigpu.RowShardedBank(2_400_000, 'h', 64, list(range(-8, 9)), 4, 0, FakeDist(), torch, correct_iq=True, demod='fm',
+                                omega_out=5000)
