@@ -261,6 +261,8 @@ class RowShardedBank:
         matters); ``outs``: list of (rows, nchunks*M) float64 device tensors of this rank.  The
         kernels go to ``stream``, which must be the current torch stream."""
         n = len(batches)
+        if nchunks > self.max_chunks or len(outs) < n:
+            raise ValueError(f'{nchunks} chunks per batch exceed max_chunks = {self.max_chunks}, or too few output tensors')
         nbytes = nchunks * self.chunk_bytes
         if self.fanout is not None:
             self.fanout.begin()
