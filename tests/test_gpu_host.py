@@ -340,3 +340,32 @@ def test_waterfall_feed_matches_short_time_fft(n):
     assert img.shape == want.shape == (1024, n // 128 + 1 if n % 128 == 0 else S.p_max(n))
     _db_close(img, want, 60.0, 1e-8)
     _db_close(img, orc.stft_db(y, sh, S.win, S.hop, 1024, S.p_max(n)), 60.0, 1e-8)
+
+
+@pytest.mark.parametrize('enc,flags,kwx', [
+    ('h', ['-d', '25', '-m', 'am', '--correct-iq'], dict(dec=25, demod='am', correct_iq=True)),
+    ('f', ['-d', '64', '-m', 'fm', '--center-frequency=-20k'], dict(dec=64, demod='fm', center=-20000)),
+    ('H', ['-d', '32', '-m', 're', '-X', '--correct-iq', '-c', '12k'], dict(dec=32, demod='re', swap=True, correct_iq=True, center=12000)),
+    ('b', ['-d', '128', '-m', 'im', '--normalize-input'], dict(dec=128, demod='im', normalize=True)),
+    ('i', ['-d', '128', '-m', 'fm', '--correct-iq'], dict(dec=128, demod='fm', correct_iq=True)),
+    ('d', ['-d', '16', '-m', 'am', '-c', '30k'], dict(dec=16, demod='am', center=30000)),
+])
+def test_cli_option_sweep_on_raw_files(tmp_path, enc, flags, kwx):
+    """Raw files through the CLI (reader thread -> page-locked chunk pool -> double-buffered
+    processor -> file writer) for options the named configs do not combine; 9 chunks plus a short
+    one, so the batches are 9 whole chunks read at once and the stale tail of the last (8-Q5)."""
+    import signals
+    from sdrterm_b200.sdrterm import main
+    isz = {'b': 1, 'h': 2, 'H': 2, 'i': 4, 'f': 4, 'd': 8}[enc]
+    n = 9 * (131072 // (2 * isz)) + 1000
+    swap = bool(kwx.get('swap'))
+    body = signals.generic_bytes(enc, n, 77, 1_000_000, kwx.get('center', 0) or 40_000, big_endian=swap)
+    fin, fout = tmp_path / 'in.raw', tmp_path / 'out.bin'
+    fin.write_bytes(body)
+    assert main(['-i', str(fin), '-o', str(fout), '-r', '1M', '-e', enc, '-w', '3k'] + flags) == 0
+    kw = dict(fs=1_000_000, enc=enc, center=0, dec=2, demod='fm', omega_out=3000, correct_iq=False, vfos=None, simo=False,
+              normalize=False, swap=False, big_endian=None)
+    kw.update(kwx)
+    ref = orc.Chain(**kw).run(body)
+    got = np.frombuffer(fout.read_bytes(), dtype='=f8')
+    assert got.shape == ref[0].shape and rel_err(got, ref[0]) < TOL
