@@ -11,7 +11,7 @@ import ctypes as C
 import numpy as np
 
 from . import _native as nat
-from .plan import Plan, build_tc
+from .plan import Plan, build_tc_or_none
 
 
 def _dp(a: np.ndarray):
@@ -81,7 +81,7 @@ class Engine:
         if pl.fm_interp is not None:
             put('fm_interp', pl.fm_interp)
         # tc: prebuilt tensor-core tables (plan.cached_plan), or 'build'
-        self.tc = (build_tc(pl) if isinstance(tc, str) else tc) if use_tc else None
+        self.tc = (build_tc_or_none(pl) if isinstance(tc, str) else tc) if use_tc else None
         if self.tc is not None:
             tc = self.tc
             tab.tc_enable, tab.tc_K, tab.tc_isz = 1, tc.K, tc.isz

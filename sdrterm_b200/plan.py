@@ -624,6 +624,16 @@ def build_tc(pl: Plan, nd: int = TC_ND) -> TcTables | None:
 
 
 # ------------------------------------------------------------------------------------------------
+def build_tc_or_none(pl: Plan) -> TcTables | None:
+    """``build_tc`` for the shapes it takes; a coefficient set whose int32 digit sums could overflow
+    (not seen: the worst of the swept frequencies uses 54 % of the range) is left to the FP64 block
+    kernel instead of failing the run."""
+    try:
+        return build_tc(pl)
+    except OverflowError:
+        return None
+
+
 def cache_dir() -> str:
     import os
     return os.environ.get('SDRB_PLAN_CACHE', os.path.join(os.path.dirname(os.path.abspath(__file__)), '.plan_cache'))
@@ -651,7 +661,7 @@ def cached_plan(*args, **kwargs):
         except Exception:
             pass
     pl = build_plan(*args, **kwargs)
-    tc = build_tc(pl)
+    tc = build_tc_or_none(pl)
     pl.modes.mp_p = pl.modes.mp_c = None              # high-precision scratch of the build, not part of the plan
     if path:
         try:
