@@ -58,7 +58,8 @@ class TimeShardedChain:
         self.rank = dist.get_rank() if dist is not None else 0
         self.engine = Engine(plan, max_chunks=max_chunks, device=device)
         if self.world > 1:
-            dev = torch.device('cuda', device)
+            # (CPU tensors only when there is no CUDA device at all: the gloo tests of this host logic)
+            dev = torch.device('cuda', device) if torch.cuda.is_available() else torch.device('cpu')
             self._mine = torch.zeros(3, dtype=torch.float64, device=dev)
             self._all = torch.zeros(3 * self.world, dtype=torch.float64, device=dev)
 

@@ -281,3 +281,85 @@ def test_bank_refuses_iq_correction_across_time_groups():
     with pytest.raises(NotImplementedError):
         multigpu.RowShardedBank(2_400_000, 'h', 64, list(range(-8, 9)), 4, 0, FakeDist(), torch, correct_iq=True, demod='fm',
                                 omega_out=5000)
+
+
+def _chain_worker(rank, world, port, q):
+    """TimeShardedChain (the product class) on gloo ranks with an engine stand-in that plays the
+    device side of the IQ hand-off in numpy: export (gain, samples), all-gather, prefix."""
+    for p in (ROOT, os.path.join(ROOT, 'tests')):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    import ctypes
+    from sdrterm_b200 import multigpu
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    lam = 1 - 50 / 1_024_000
+
+    class Plan:
+        N, lam_ = 32768, lam
+
+    class Eng:
+        calls = []
+        start = None
+
+        def __init__(self, plan, max_chunks=1, device=0, **kw):
+            pass
+
+        def process_device(self, *a):
+            Eng.calls.append('all')
+
+        def process_device_phases(self, raw_ptr, nchunks, out_ptr, phases, stream=0):
+            Eng.calls.append(phases)
+
+        def iq_export_device(self, dst_ptr, nsamples, stream=0):
+            g = complex(0.25 * (rank + 1), -0.5 * (rank + 1))          # what this segment "gained"
+            d = (ctypes.c_double * 3).from_address(dst_ptr)
+            d[0], d[1], d[2] = g.real, g.imag, float(nsamples)
+            Eng.calls.append('export')
+
+        def iq_prefix_device(self, gains_ptr, r, stream=0):
+            d = np.array((ctypes.c_double * (3 * world)).from_address(gains_ptr))
+            gains = [complex(d[3 * i], d[3 * i + 1]) for i in range(world)]
+            lens = [int(d[3 * i + 2]) for i in range(world)]
+            Eng.start = sharding.iq_start_offset(gains, lens, lam, r)
+            Eng.calls.append('prefix')
+
+        def close(self):
+            pass
+
+    try:
+        multigpu.Engine = Eng
+        chain = multigpu.TimeShardedChain(Plan(), 4, 0, dist, torch)
+        chain.step(0, 3 + rank, 0)
+        q.put((rank, Eng.calls, Eng.start))
+        dist.barrier()
+    except BaseException as e:
+        q.put((rank, repr(e)))
+        raise
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+def test_time_sharded_chain_three_rank_gloo():
+    world, port = 3, _free_port()
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_chain_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=240) for _ in range(world)]
+    assert all(len(r) == 3 for r in res), res
+    res.sort(key=lambda x: x[0])
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    lam = 1 - 50 / 1_024_000
+    gains = [complex(0.25 * (r + 1), -0.5 * (r + 1)) for r in range(world)]
+    lens = [(3 + r) * 32768 for r in range(world)]
+    off = 0j
+    for r in range(world):
+        # front end + gain from zero (MAIN | IQSCAN | ZERO_IQ), export, all-gather, prefix, IQSCAN | FINISH
+        assert res[r][1] == [1 | 2 | 8, 'export', 'prefix', 2 | 4]
+        assert abs(res[r][2] - off) < 1e-15                      # the offset entering segment r
+        off = lam ** lens[r] * off + gains[r]
