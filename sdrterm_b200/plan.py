@@ -497,6 +497,8 @@ def build_tc(pl: Plan, nd: int = TC_ND) -> TcTables | None:
     g0 = mp.mpf(pl.modes.g0)
     rho = [mp.mpc(v) for v in pl.modes.rho]
     rho_p = [mp.mpc(v) for v in pl.modes.rho_p]
+    # pole powers p_i^n, n <= 2q: the same for every row of the bank (most of the build time otherwise)
+    pw = [[pm[i] ** n for n in range(q2 + 1)] for i in range(8)]
 
     # byte bookkeeping of one sample: (component, significance) per byte
     info = []
@@ -516,9 +518,9 @@ def build_tc(pl: Plan, nd: int = TC_ND) -> TcTables | None:
         rbT = [rho_p[i] * mp.mpc(complex(pl.betaT[r, i])) for i in range(8)]
         cplx = []
         for i in range(8):
-            cplx.append([pm[i] ** (q2 - 1 - j) * T2x[j] for j in range(q2)])
+            cplx.append([pw[i][q2 - 1 - j] * T2x[j] for j in range(q2)])
         for i in range(8):
-            cplx.append([pm[i] ** j * T2x[j] for j in range(q2)])
+            cplx.append([pw[i][j] * T2x[j] for j in range(q2)])
         for c in cplx:
             rows.append([(mp.re(v), -mp.im(v)) for v in c])    # Re(c*(I+jQ)) = cr I - ci Q
             rows.append([(mp.im(v), mp.re(v)) for v in c])     # Im(c*(I+jQ)) = ci I + cr Q
@@ -527,13 +529,13 @@ def build_tc(pl: Plan, nd: int = TC_ND) -> TcTables | None:
         for e in (ea, eab):
             rows.append([(v, mp.mpf(0)) for v in e])
             rows.append([(mp.mpf(0), v) for v in e])
-        yla = [sum(rbT[i] * pm[i] ** j for i in range(8)) * T2x[j] + (g0 if j == 0 else 0) for j in range(q2)]
+        yla = [sum(rbT[i] * pw[i][j] for i in range(8)) * T2x[j] + (g0 if j == 0 else 0) for j in range(q2)]
         ylb = []
         for j in range(q2):
             if j < q:
-                ylb.append(sum(rb[i] * pm[i] ** (q - 1 - j) for i in range(8)) * T2x[j])
+                ylb.append(sum(rb[i] * pw[i][q - 1 - j] for i in range(8)) * T2x[j])
             else:
-                ylb.append((sum(rbT[i] * pm[i] ** (j - q) for i in range(8)) + (g0 if j == q else 0)) * T2x[j])
+                ylb.append((sum(rbT[i] * pw[i][j - q] for i in range(8)) + (g0 if j == q else 0)) * T2x[j])
         for c in (yla, ylb):
             rows.append([(mp.re(v), -mp.im(v)) for v in c])
             rows.append([(mp.im(v), mp.re(v)) for v in c])
@@ -541,8 +543,8 @@ def build_tc(pl: Plan, nd: int = TC_ND) -> TcTables | None:
 
         # ---- epilogue constants of this row (k_tc: tc_epilogue; tests/emulator.py: emu_main_tc)
         eps2 = T2x[q] * T2x[q]                                 # e^{jw 2q}
-        P2 = [pm[i] ** q2 for i in range(8)]
-        Pq = [pm[i] ** q for i in range(8)]
+        P2 = [pw[i][q2] for i in range(8)]
+        Pq = [pw[i][q] for i in range(8)]
         ce = mp.conj(eps2)
         for i in range(8):
             rowc[r, RC_CA + i] = _c(rb[i] * ce)                # y_a += ca_i A_i
