@@ -124,10 +124,14 @@ def main(argv=None, lifecycle: bool = False) -> int:
             proc.useInputPool(pool)
         except Exception:
             pool = None                                     # (no device: the engine will say so)
-    reader = threading.Thread(target=readFile, daemon=True,
-                              kwargs=dict(buffers=[buf], isDead=isDead, inFile=a.inFile,
-                                          fs=fileInfo['sampRate'], dataOffset=fileInfo['dataOffset'],
-                                          isSocket=fileInfo['isSocket'], pool=pool))
+    def halt():
+        isDead.value = 1
+
+    from .misc.keyboard_interruptable_thread import KeyboardInterruptableThread
+    rkw = dict(buffers=[buf], isDead=isDead, inFile=a.inFile, fs=fileInfo['sampRate'],
+               dataOffset=fileInfo['dataOffset'], isSocket=fileInfo['isSocket'], pool=pool)
+    # an exception in the reader (Ctrl-C included) sets the halt condition (src/sdrterm.py:195-231)
+    reader = KeyboardInterruptableThread(halt, target=lambda: readFile(**rkw), name='reader', daemon=True)
     reader.start()
     try:
         proc.processData(isDead, buf, a.outFile)

@@ -290,13 +290,16 @@ def test_compiled_plugin_seam_is_importable_like_the_reference_expects():
 @pytest.mark.skipif(not os.path.isdir('/root/reference/test'), reason='reference tree not present (GPU box)')
 def test_reference_own_unit_tests_pass_against_the_shims(tmp_path):
     """The reference's API contract for this path, unmodified: test/misc/file_util_test.py,
-    test/dsp/dsp_processor_test.py and test/misc/read_file_test.py with PYTHONPATH=src."""
+    test/dsp/dsp_processor_test.py, test/misc/read_file_test.py, io_args_test.py and
+    keyboard_interruptable_thread_test.py with PYTHONPATH=src."""
     import subprocess
     env = dict(os.environ, PYTHONPATH=os.path.join(ROOT, 'src'), NUMBA_CACHE_DIR=str(tmp_path))
     r = subprocess.run([sys.executable, '-m', 'pytest', '-q', '-p', 'no:cacheprovider',
                         '/root/reference/test/misc/file_util_test.py',
                         '/root/reference/test/dsp/dsp_processor_test.py',
-                        '/root/reference/test/misc/read_file_test.py'],
+                        '/root/reference/test/misc/read_file_test.py',
+                        '/root/reference/test/misc/io_args_test.py',
+                        '/root/reference/test/misc/keyboard_interruptable_thread_test.py'],
                        env=env, cwd=str(tmp_path), capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
 
